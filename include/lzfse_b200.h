@@ -1,0 +1,147 @@
+/*
+ * lzfse_b200.h -- C ABI of the B200-native batched LZFSE codec (liblzfse_b200.so).
+ *
+ * Drop-in boundary for lzfse_rust's memory-buffer engine.  Each entry point names the reference
+ * interface it replaces (paths relative to the lzfse_rust v0.2.0 source tree):
+ *
+ *   lzfse_b200_decoder_create/destroy  <->  LzfseDecoder::default() / Drop   src/decode/decoder.rs:16-24
+ *   lzfse_b200_decode_bytes            <->  LzfseDecoder::decode_bytes       src/decode/decoder.rs:61
+ *                                           (and the free fn decode_bytes    src/decode/mod.rs:49)
+ *   lzfse_b200_encoder_create/destroy  <->  LzfseEncoder::default() / Drop   src/encode/encoder.rs:13-18
+ *   lzfse_b200_encode_bytes            <->  LzfseEncoder::encode_bytes       src/encode/encoder.rs:49
+ *                                           (and the free fn encode_bytes    src/encode/mod.rs:58)
+ *   lzfse_b200_{decode,encode}_batch_* <->  NEW: the same call over n independent LZFSE streams
+ *   lzfse_b200_decode_probe_batch_*    <->  decode::probe                    src/decode/probe.rs:11-35
+ *   status codes                       <->  lzfse_rust::Error                src/error/mod.rs:40-61,
+ *                                           FseErrorKind src/fse/error_kind.rs:9-39,
+ *                                           VnErrorKind  src/vn/error_kind.rs:9-16
+ *
+ * Differences from the Rust signatures, all forced by the C boundary:
+ *   - `dst: &mut Vec<u8>` (append, grows) becomes `dst, dst_cap, *dst_len`: the frame is written at
+ *     dst[0..*dst_len).  A Rust wrapper does `dst.reserve(bound)`, passes the spare capacity and
+ *     `set_len`s; see INTEGRATION.md.  Too small a capacity yields LZFSE_B200_BUFFER_OVERFLOW.
+ *   - Match distances may not reach before dst[0] (the reference lets them reach into bytes that were
+ *     already in the Vec, src/lz/writer.rs:156-157).
+ *
+ * All work runs on the GPU.  There is no CPU fallback: without a usable CUDA device every call
+ * returns LZFSE_B200_NO_DEVICE (create) or LZFSE_B200_CUDA_ERROR.
+ *
+ * Threading: a handle is single-caller (`&mut self` in the reference).  Distinct handles may be
+ * used concurrently.  *_device calls enqueue on the given CUDA stream and synchronise it once
+ * internally (to size scratch memory); results are complete when they return.
+ */
+#ifndef LZFSE_B200_H
+#define LZFSE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Per-stream status == lzfse_rust::Error discriminants (0 = Ok). */
+enum lzfse_b200_status {
+    LZFSE_B200_OK = 0,
+    LZFSE_B200_BAD_BLOCK = 1,             /* Error::BadBlock */
+    LZFSE_B200_BAD_BITSTREAM = 2,         /* Error::BadBitStream */
+    LZFSE_B200_BAD_D_VALUE = 3,           /* Error::BadDValue */
+    LZFSE_B200_BAD_READER_STATE = 4,      /* Error::BadReaderState (never produced here) */
+    LZFSE_B200_BUFFER_OVERFLOW = 5,       /* Error::BufferOverflow: dst_cap too small */
+    LZFSE_B200_PAYLOAD_OVERFLOW = 6,      /* Error::PayloadOverflow */
+    LZFSE_B200_PAYLOAD_UNDERFLOW = 7,     /* Error::PayloadUnderflow */
+    LZFSE_B200_FSE_BAD_LITERAL_BITS = 16, /* Error::Fse(FseErrorKind::...) = 16 + discriminant */
+    LZFSE_B200_FSE_BAD_LITERAL_COUNT = 17,
+    LZFSE_B200_FSE_BAD_LITERAL_PAYLOAD = 18,
+    LZFSE_B200_FSE_BAD_LITERAL_STATE = 19,
+    LZFSE_B200_FSE_BAD_LMD_BITS = 20,
+    LZFSE_B200_FSE_BAD_LMD_COUNT = 21,
+    LZFSE_B200_FSE_BAD_LMD_PAYLOAD = 22,
+    LZFSE_B200_FSE_BAD_LMD_STATE = 23,
+    LZFSE_B200_FSE_BAD_PAYLOAD_COUNT = 24,
+    LZFSE_B200_FSE_BAD_RAW_BYTE_COUNT = 25,
+    LZFSE_B200_FSE_BAD_READER_STATE = 26,
+    LZFSE_B200_FSE_BAD_WEIGHT_PAYLOAD = 27,
+    LZFSE_B200_FSE_BAD_WEIGHT_PAYLOAD_COUNT = 28,
+    LZFSE_B200_FSE_WEIGHT_PAYLOAD_OVERFLOW = 29,
+    LZFSE_B200_FSE_WEIGHT_PAYLOAD_UNDERFLOW = 30,
+    LZFSE_B200_VN_BAD_PAYLOAD_COUNT = 32, /* Error::Vn(VnErrorKind::...) = 32 + discriminant */
+    LZFSE_B200_VN_BAD_PAYLOAD = 33,
+    LZFSE_B200_VN_BAD_OPCODE = 34,
+    /* call-level failures (return values only, never per-stream) */
+    LZFSE_B200_INVALID_ARGUMENT = 64,
+    LZFSE_B200_NO_DEVICE = 65,
+    LZFSE_B200_CUDA_ERROR = 66,
+    LZFSE_B200_OUT_OF_MEMORY = 67         /* io::ErrorKind::Other in the reference's encode path */
+};
+
+typedef struct lzfse_b200_decoder lzfse_b200_decoder;
+typedef struct lzfse_b200_encoder lzfse_b200_encoder;
+
+const char *lzfse_b200_version(void);
+const char *lzfse_b200_status_string(int status);
+/* Last CUDA error text seen by this handle's calls ("" if none). */
+const char *lzfse_b200_decoder_last_error(const lzfse_b200_decoder *d);
+const char *lzfse_b200_encoder_last_error(const lzfse_b200_encoder *e);
+
+/* ---- decoder ---------------------------------------------------------------------------- */
+int lzfse_b200_decoder_create(int cuda_device, lzfse_b200_decoder **out);
+void lzfse_b200_decoder_destroy(lzfse_b200_decoder *d);
+
+/* decode_bytes: one frame, host buffers.  Returns the stream's status. */
+int lzfse_b200_decode_bytes(lzfse_b200_decoder *d, const uint8_t *src, size_t src_len, uint8_t *dst,
+                            size_t dst_cap, size_t *dst_len);
+
+/* Batched decode of n independent frames.
+ * Stream i reads  src_base[src_off[i] .. src_off[i]+src_len[i])  and writes its output at
+ * dst_base[dst_off[i] ..), at most dst_cap[i] bytes; out_len[i] and status[i] receive the result.
+ * Output regions of different streams must not overlap.  A failing stream does not disturb others;
+ * its output region's contents are unspecified (as in the reference, src/lz/writer.rs:18,28).
+ * _device: every pointer is device memory on the handle's GPU; `cuda_stream` is a cudaStream_t (or NULL).
+ * _host:   every pointer is host memory; H2D/D2H copies happen inside the call.
+ * Return value: call-level status (LZFSE_B200_OK even if individual streams failed). */
+int lzfse_b200_decode_batch_device(lzfse_b200_decoder *d, const uint8_t *src_base, const uint64_t *src_off,
+                                   const uint64_t *src_len, uint8_t *dst_base, const uint64_t *dst_off,
+                                   const uint64_t *dst_cap, uint64_t *out_len, int32_t *status, size_t n,
+                                   void *cuda_stream);
+int lzfse_b200_decode_batch_host(lzfse_b200_decoder *d, const uint8_t *src_base, const uint64_t *src_off,
+                                 const uint64_t *src_len, uint8_t *dst_base, const uint64_t *dst_off,
+                                 const uint64_t *dst_cap, uint64_t *out_len, int32_t *status, size_t n);
+
+/* Header-only walk: raw_len[i] = sum of the blocks' n_raw_bytes, n_blocks[i] = block count.
+ * (Unlike the reference's dead-code probe, LZVN blocks advance by n_payload_bytes; cf. src/vn/ops.rs:13.) */
+int lzfse_b200_decode_probe_batch_device(lzfse_b200_decoder *d, const uint8_t *src_base, const uint64_t *src_off,
+                                         const uint64_t *src_len, uint64_t *raw_len, uint32_t *n_blocks,
+                                         int32_t *status, size_t n, void *cuda_stream);
+int lzfse_b200_decode_probe_batch_host(lzfse_b200_decoder *d, const uint8_t *src_base, const uint64_t *src_off,
+                                       const uint64_t *src_len, uint64_t *raw_len, uint32_t *n_blocks,
+                                       int32_t *status, size_t n);
+
+/* Kernel launches issued by the last batch call on this handle (bench.py's gpu_launches). */
+uint64_t lzfse_b200_decoder_last_launches(const lzfse_b200_decoder *d);
+
+/* ---- encoder ---------------------------------------------------------------------------- */
+int lzfse_b200_encoder_create(int cuda_device, lzfse_b200_encoder **out);
+void lzfse_b200_encoder_destroy(lzfse_b200_encoder *e);
+
+/* Upper bound of the frame size encode produces for src_len input bytes. */
+size_t lzfse_b200_encode_bound(size_t src_len);
+
+/* encode_bytes: one frame, host buffers. */
+int lzfse_b200_encode_bytes(lzfse_b200_encoder *e, const uint8_t *src, size_t src_len, uint8_t *dst,
+                            size_t dst_cap, size_t *dst_len);
+
+/* Batched encode: n independent inputs -> n independent frames (same layout rules as decode). */
+int lzfse_b200_encode_batch_device(lzfse_b200_encoder *e, const uint8_t *src_base, const uint64_t *src_off,
+                                   const uint64_t *src_len, uint8_t *dst_base, const uint64_t *dst_off,
+                                   const uint64_t *dst_cap, uint64_t *out_len, int32_t *status, size_t n,
+                                   void *cuda_stream);
+int lzfse_b200_encode_batch_host(lzfse_b200_encoder *e, const uint8_t *src_base, const uint64_t *src_off,
+                                 const uint64_t *src_len, uint8_t *dst_base, const uint64_t *dst_off,
+                                 const uint64_t *dst_cap, uint64_t *out_len, int32_t *status, size_t n);
+uint64_t lzfse_b200_encoder_last_launches(const lzfse_b200_encoder *e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

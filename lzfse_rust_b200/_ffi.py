@@ -1,0 +1,57 @@
+"""ctypes loader for liblzfse_b200.so.  Fails loudly: there is no CPU fallback behind this package."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "liblzfse_b200.so")
+
+# Every symbol include/lzfse_b200.h declares (tests check the library exports all of them).
+SYMBOLS = [
+    "lzfse_b200_version", "lzfse_b200_status_string", "lzfse_b200_decoder_last_error", "lzfse_b200_encoder_last_error",
+    "lzfse_b200_decoder_create", "lzfse_b200_decoder_destroy", "lzfse_b200_decode_bytes", "lzfse_b200_decode_batch_device",
+    "lzfse_b200_decode_batch_host", "lzfse_b200_decode_probe_batch_device", "lzfse_b200_decode_probe_batch_host",
+    "lzfse_b200_decoder_last_launches", "lzfse_b200_encoder_create", "lzfse_b200_encoder_destroy", "lzfse_b200_encode_bound",
+    "lzfse_b200_encode_bytes", "lzfse_b200_encode_batch_device", "lzfse_b200_encode_batch_host", "lzfse_b200_encoder_last_launches",
+]
+
+_lib = None
+
+
+def load(build_if_missing=True):
+    """Returns the loaded library; builds it with nvcc when the .so is absent or stale."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if build_if_missing:
+        from . import build as _build
+
+        try:
+            _build.build()
+        except Exception as e:  # no nvcc on this box: use the prebuilt .so if there is one
+            if not os.path.exists(SO_PATH):
+                raise RuntimeError("liblzfse_b200.so is missing and could not be built: %s" % e)
+    if not os.path.exists(SO_PATH):
+        raise RuntimeError("liblzfse_b200.so not found at %s (run python -m lzfse_rust_b200.build)" % SO_PATH)
+    lib = C.CDLL(SO_PATH)
+    vp, u64p, i32p, u32p, szp = C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_size_t)
+    lib.lzfse_b200_version.restype = C.c_char_p
+    lib.lzfse_b200_status_string.restype = C.c_char_p
+    lib.lzfse_b200_status_string.argtypes = [C.c_int]
+    for n in ("decoder", "encoder"):
+        getattr(lib, "lzfse_b200_%s_last_error" % n).restype = C.c_char_p
+        getattr(lib, "lzfse_b200_%s_last_error" % n).argtypes = [vp]
+        getattr(lib, "lzfse_b200_%s_create" % n).argtypes = [C.c_int, C.POINTER(vp)]
+        getattr(lib, "lzfse_b200_%s_destroy" % n).argtypes = [vp]
+        getattr(lib, "lzfse_b200_%s_destroy" % n).restype = None
+        getattr(lib, "lzfse_b200_%s_last_launches" % n).argtypes = [vp]
+        getattr(lib, "lzfse_b200_%s_last_launches" % n).restype = C.c_uint64
+    lib.lzfse_b200_encode_bound.argtypes = [C.c_size_t]
+    lib.lzfse_b200_encode_bound.restype = C.c_size_t
+    for n in ("decode", "encode"):
+        getattr(lib, "lzfse_b200_%s_bytes" % n).argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, szp]
+        getattr(lib, "lzfse_b200_%s_batch_device" % n).argtypes = [vp, vp, u64p, u64p, vp, u64p, u64p, u64p, i32p, C.c_size_t, vp]
+        getattr(lib, "lzfse_b200_%s_batch_host" % n).argtypes = [vp, vp, u64p, u64p, vp, u64p, u64p, u64p, i32p, C.c_size_t]
+    lib.lzfse_b200_decode_probe_batch_device.argtypes = [vp, vp, u64p, u64p, u64p, u32p, i32p, C.c_size_t, vp]
+    lib.lzfse_b200_decode_probe_batch_host.argtypes = [vp, vp, u64p, u64p, u64p, u32p, i32p, C.c_size_t]
+    _lib = lib
+    return lib

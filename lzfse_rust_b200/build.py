@@ -1,0 +1,65 @@
+"""Builds liblzfse_b200.so (CUDA kernels + C-ABI) in-tree for sm_100a with nvcc.
+
+The .so is git-ignored but travels to the GPU box with the repo snapshot.  nvcc cross-compiles
+without a GPU, so this also runs in the CPU-only build container."""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+SO = os.path.join(HERE, "liblzfse_b200.so")
+SOURCES = ["decode.cu", "encode.cu", "api.cu"]
+HEADERS = ["common.cuh", "host_util.h", os.path.join("..", "..", "include", "lzfse_b200.h")]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC,-O2,-Wall", "-Xptxas", "-v", "--use_fast_math",
+]
+
+
+def nvcc():
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def needs_build():
+    if not os.path.exists(SO):
+        return True
+    t = os.path.getmtime(SO)
+    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return SO
+    objs = []
+    log = []
+    for src in SOURCES:
+        obj = os.path.join(CSRC, src.replace(".cu", ".o"))
+        cmd = [nvcc()] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        log.append(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+        if r.returncode != 0:
+            sys.stderr.write(log[-1])
+            raise RuntimeError("nvcc failed on " + src)
+        objs.append(obj)
+    cmd = [nvcc(), "-shared", "-o", SO] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    log.append(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+    if r.returncode != 0:
+        sys.stderr.write(log[-1])
+        raise RuntimeError("link failed")
+    with open(os.path.join(HERE, "build.log"), "w") as f:
+        f.write("\n".join(log))
+    if verbose:
+        print("\n".join(log))
+    return SO
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv, verbose=True)
+    print(SO)

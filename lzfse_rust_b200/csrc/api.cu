@@ -1,0 +1,264 @@
+// api.cu -- C-ABI entry points of liblzfse_b200.so (see include/lzfse_b200.h).
+//
+// Host side of the drop-in boundary: owns the CUDA device scratch (what `LzfseDecoder` / `LzfseEncoder`
+// own as FseCore / HistoryTable, decode/decoder.rs:16-24, encode/encoder.rs:14-18) and sequences the
+// kernels in decode.cu / encode.cu.  No CPU codec lives here: if CUDA is unavailable every call fails.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "common.cuh"
+#include "host_util.h"
+
+namespace lzb {
+// decode.cu
+void launch_scan_count(const uint8_t *, const uint64_t *, const uint64_t *, const uint64_t *, size_t, StreamCounts *, uint32_t *, uint64_t *,
+                       uint32_t *, StreamCounts *, cudaStream_t);
+void launch_scan_fill(const uint8_t *, const uint64_t *, const uint64_t *, const uint64_t *, const uint64_t *, size_t, StreamCounts *, BlockDesc *, FseDesc *,
+                      uint32_t *, cudaStream_t);
+int setup_decode_kernels();
+void launch_fse_stages(const uint8_t *, const uint64_t *, const uint64_t *, const uint64_t *, const uint64_t *, const BlockDesc *, FseDesc *, uint32_t, uint8_t *,
+                       LmdRec *, uint32_t *, uint32_t *, int, cudaStream_t);
+void launch_expand(const uint8_t *, const uint64_t *, const uint64_t *, uint8_t *, const uint64_t *, const uint64_t *, const StreamCounts *, const BlockDesc *,
+                   const FseDesc *, const uint8_t *, const LmdRec *, uint32_t *, size_t, cudaStream_t);
+void launch_finish(const uint32_t *, const uint64_t *, uint64_t *, int32_t *, size_t, cudaStream_t);
+}  // namespace lzb
+
+using namespace lzb;
+
+struct lzfse_b200_decoder {
+    int device = 0;
+    int n_sms = 148;
+    cudaStream_t own_stream = nullptr;
+    std::string last_error;
+    uint64_t launches = 0;
+    // scratch
+    DevBuf counts, err, raw_total, totals_dev, blocks, fse, lits, lmds, work;
+    PinnedBuf totals_host;
+    // staging for the *_host entry points
+    HostStage stage;
+};
+
+namespace {
+
+#define CK LZB_CK
+
+int decode_batch_device_impl(lzfse_b200_decoder *d, const uint8_t *src, const uint64_t *src_off, const uint64_t *src_len, uint8_t *dst,
+                             const uint64_t *dst_off, const uint64_t *dst_cap, uint64_t *out_len, int32_t *status, uint64_t *raw_len,
+                             uint32_t *n_blocks, size_t n, cudaStream_t s, bool probe_only) {
+    d->launches = 0;
+    if (n == 0) return LZFSE_B200_OK;
+    CK(d, d->counts.reserve((n + 1) * sizeof(StreamCounts)));
+    CK(d, d->err.reserve(n * sizeof(uint32_t)));
+    CK(d, d->raw_total.reserve(n * sizeof(uint64_t)));
+    CK(d, d->totals_dev.reserve(sizeof(StreamCounts)));
+    CK(d, d->totals_host.reserve(sizeof(StreamCounts)));
+    CK(d, d->work.reserve(2 * sizeof(uint32_t)));
+    uint64_t *raw_total = raw_len ? raw_len : d->raw_total.as<uint64_t>();
+
+    launch_scan_count(src, src_off, src_len, probe_only ? nullptr : dst_cap, n, d->counts.as<StreamCounts>(), d->err.as<uint32_t>(), raw_total,
+                      n_blocks, d->totals_dev.as<StreamCounts>(), s);
+    d->launches += 2;
+    if (probe_only) {
+        launch_finish(d->err.as<uint32_t>(), raw_total, nullptr, status, n, s);
+        d->launches += 1;
+        CK(d, cudaStreamSynchronize(s));
+        CK(d, cudaGetLastError());
+        return LZFSE_B200_OK;
+    }
+    // The one host round trip: scratch sizes depend on what the headers announce.
+    CK(d, cudaMemcpyAsync(d->totals_host.p, d->totals_dev.p, sizeof(StreamCounts), cudaMemcpyDeviceToHost, s));
+    CK(d, cudaStreamSynchronize(s));
+    const StreamCounts tot = *d->totals_host.as<StreamCounts>();
+    if (tot.n_fse > 0xFFFFFFFFull) { d->last_error = "too many FSE blocks in one batch"; return LZFSE_B200_INVALID_ARGUMENT; }
+    CK(d, d->blocks.reserve((tot.n_blocks + 1) * sizeof(BlockDesc)));
+    CK(d, d->fse.reserve((tot.n_fse + 1) * sizeof(FseDesc)));
+    CK(d, d->lits.reserve(tot.n_literals + 64));
+    CK(d, d->lmds.reserve((tot.n_lmds + 1) * sizeof(LmdRec)));
+    CK(d, cudaMemsetAsync(d->work.p, 0, 2 * sizeof(uint32_t), s));
+
+    launch_scan_fill(src, src_off, src_len, dst_off, dst_cap, n, d->counts.as<StreamCounts>(), d->blocks.as<BlockDesc>(), d->fse.as<FseDesc>(),
+                     d->err.as<uint32_t>(), s);
+    d->launches += 1;
+    if (tot.n_fse) {
+        launch_fse_stages(src, src_off, src_len, dst_off, dst_cap, d->blocks.as<BlockDesc>(), d->fse.as<FseDesc>(), (uint32_t)tot.n_fse,
+                          d->lits.as<uint8_t>(), d->lmds.as<LmdRec>(), d->err.as<uint32_t>(), d->work.as<uint32_t>(), d->n_sms, s);
+        d->launches += 2;
+    }
+    launch_expand(src, src_off, src_len, dst, dst_off, dst_cap, d->counts.as<StreamCounts>(), d->blocks.as<BlockDesc>(), d->fse.as<FseDesc>(),
+                  d->lits.as<uint8_t>(), d->lmds.as<LmdRec>(), d->err.as<uint32_t>(), n, s);
+    launch_finish(d->err.as<uint32_t>(), raw_total, out_len, status, n, s);
+    d->launches += 2;
+    CK(d, cudaGetLastError());
+    CK(d, cudaStreamSynchronize(s));
+    return LZFSE_B200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *lzfse_b200_version(void) { return "lzfse_b200 0.1.0 (sm_100a)"; }
+
+const char *lzfse_b200_status_string(int st) {
+    switch (st) {
+    case LZFSE_B200_OK: return "ok";
+    case LZFSE_B200_BAD_BLOCK: return "bad block";
+    case LZFSE_B200_BAD_BITSTREAM: return "bad bitstream";
+    case LZFSE_B200_BAD_D_VALUE: return "bad D value";
+    case LZFSE_B200_BAD_READER_STATE: return "bad reader state";
+    case LZFSE_B200_BUFFER_OVERFLOW: return "buffer overflow";
+    case LZFSE_B200_PAYLOAD_OVERFLOW: return "bad payload overflow";
+    case LZFSE_B200_PAYLOAD_UNDERFLOW: return "bad payload underflow";
+    case LZFSE_B200_FSE_BAD_LITERAL_BITS: return "FSE: bad literal bits";
+    case LZFSE_B200_FSE_BAD_LITERAL_COUNT: return "FSE: bad literal count";
+    case LZFSE_B200_FSE_BAD_LITERAL_PAYLOAD: return "FSE: bad literal payload";
+    case LZFSE_B200_FSE_BAD_LITERAL_STATE: return "FSE: bad literal state";
+    case LZFSE_B200_FSE_BAD_LMD_BITS: return "FSE: bad LMD bits";
+    case LZFSE_B200_FSE_BAD_LMD_COUNT: return "FSE: bad LMD count";
+    case LZFSE_B200_FSE_BAD_LMD_PAYLOAD: return "FSE: bad LMD payload";
+    case LZFSE_B200_FSE_BAD_LMD_STATE: return "FSE: bad LMD state";
+    case LZFSE_B200_FSE_BAD_PAYLOAD_COUNT: return "FSE: bad payload count";
+    case LZFSE_B200_FSE_BAD_RAW_BYTE_COUNT: return "FSE: bad raw byte count";
+    case LZFSE_B200_FSE_BAD_READER_STATE: return "FSE: bad reader state";
+    case LZFSE_B200_FSE_BAD_WEIGHT_PAYLOAD: return "FSE: bad weight payload";
+    case LZFSE_B200_FSE_BAD_WEIGHT_PAYLOAD_COUNT: return "FSE: bad weight payload count";
+    case LZFSE_B200_FSE_WEIGHT_PAYLOAD_OVERFLOW: return "FSE: weight payload overflow";
+    case LZFSE_B200_FSE_WEIGHT_PAYLOAD_UNDERFLOW: return "FSE: weight payload underflow";
+    case LZFSE_B200_VN_BAD_PAYLOAD_COUNT: return "VN: bad payload count";
+    case LZFSE_B200_VN_BAD_PAYLOAD: return "VN: bad payload";
+    case LZFSE_B200_VN_BAD_OPCODE: return "VN: bad opcode";
+    case LZFSE_B200_INVALID_ARGUMENT: return "invalid argument";
+    case LZFSE_B200_NO_DEVICE: return "no usable CUDA device";
+    case LZFSE_B200_CUDA_ERROR: return "CUDA error";
+    case LZFSE_B200_OUT_OF_MEMORY: return "out of device memory";
+    default: return "unknown status";
+    }
+}
+
+int lzfse_b200_decoder_create(int device, lzfse_b200_decoder **out) {
+    if (!out) return LZFSE_B200_INVALID_ARGUMENT;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) return LZFSE_B200_NO_DEVICE;
+    DeviceGuard g(device);
+    if (!g.ok) return LZFSE_B200_NO_DEVICE;
+    lzfse_b200_decoder *d = new (std::nothrow) lzfse_b200_decoder();
+    if (!d) return LZFSE_B200_OUT_OF_MEMORY;
+    d->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete d; return LZFSE_B200_NO_DEVICE; }
+    d->n_sms = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&d->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete d; return LZFSE_B200_CUDA_ERROR; }
+    if (setup_decode_kernels() != 0) {
+        // no sm_100a image for this device, or not enough shared memory: there is no fallback path
+        cudaStreamDestroy(d->own_stream);
+        delete d;
+        cudaGetLastError();
+        return LZFSE_B200_NO_DEVICE;
+    }
+    *out = d;
+    return LZFSE_B200_OK;
+}
+
+void lzfse_b200_decoder_destroy(lzfse_b200_decoder *d) {
+    if (!d) return;
+    DeviceGuard g(d->device);
+    for (DevBuf *b : {&d->counts, &d->err, &d->raw_total, &d->totals_dev, &d->blocks, &d->fse, &d->lits, &d->lmds, &d->work}) b->release();
+    d->totals_host.release();
+    d->stage.release();
+    if (d->own_stream) cudaStreamDestroy(d->own_stream);
+    delete d;
+}
+
+const char *lzfse_b200_decoder_last_error(const lzfse_b200_decoder *d) { return d ? d->last_error.c_str() : ""; }
+uint64_t lzfse_b200_decoder_last_launches(const lzfse_b200_decoder *d) { return d ? d->launches : 0; }
+
+int lzfse_b200_decode_batch_device(lzfse_b200_decoder *d, const uint8_t *src, const uint64_t *src_off, const uint64_t *src_len, uint8_t *dst,
+                                   const uint64_t *dst_off, const uint64_t *dst_cap, uint64_t *out_len, int32_t *status, size_t n, void *stream) {
+    if (!d || (n && (!src_off || !src_len || !dst_off || !dst_cap || !out_len || !status))) return LZFSE_B200_INVALID_ARGUMENT;
+    DeviceGuard g(d->device);
+    if (!g.ok) return LZFSE_B200_CUDA_ERROR;
+    cudaStream_t s = stream ? (cudaStream_t)stream : d->own_stream;
+    return decode_batch_device_impl(d, src, src_off, src_len, dst, dst_off, dst_cap, out_len, status, nullptr, nullptr, n, s, false);
+}
+
+int lzfse_b200_decode_probe_batch_device(lzfse_b200_decoder *d, const uint8_t *src, const uint64_t *src_off, const uint64_t *src_len,
+                                         uint64_t *raw_len, uint32_t *n_blocks, int32_t *status, size_t n, void *stream) {
+    if (!d || (n && (!src_off || !src_len || !raw_len || !status))) return LZFSE_B200_INVALID_ARGUMENT;
+    DeviceGuard g(d->device);
+    if (!g.ok) return LZFSE_B200_CUDA_ERROR;
+    cudaStream_t s = stream ? (cudaStream_t)stream : d->own_stream;
+    return decode_batch_device_impl(d, src, src_off, src_len, nullptr, nullptr, nullptr, nullptr, status, raw_len, n_blocks, n, s, true);
+}
+
+// Host-buffer variants: stage the bytes on the device (host_util.h), run the device path, copy back.
+int lzfse_b200_decode_batch_host(lzfse_b200_decoder *d, const uint8_t *src, const uint64_t *src_off, const uint64_t *src_len, uint8_t *dst,
+                                 const uint64_t *dst_off, const uint64_t *dst_cap, uint64_t *out_len, int32_t *status, size_t n) {
+    if (!d || (n && (!src || !src_off || !src_len || !dst_off || !dst_cap || !out_len || !status))) return LZFSE_B200_INVALID_ARGUMENT;
+    if (n == 0) return LZFSE_B200_OK;
+    DeviceGuard g(d->device);
+    if (!g.ok) return LZFSE_B200_CUDA_ERROR;
+    cudaStream_t s = d->own_stream;
+    HostStage &st = d->stage;
+    int rc = stage_sources(d, st, src, src_off, src_len, n, 4 * n, s);
+    if (rc) return rc;
+    rc = stage_outputs(d, st, dst_off, dst_cap, n);
+    if (rc) return rc;
+    CK(d, st.desc.reserve(4 * n * sizeof(uint64_t)));
+    CK(d, st.res.reserve(n * (sizeof(uint64_t) + sizeof(int32_t))));
+    CK(d, cudaMemcpyAsync(st.desc.p, st.pin.p, 4 * n * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    uint64_t *dd = st.desc.as<uint64_t>();
+    uint64_t *d_out_len = st.res.as<uint64_t>();
+    int32_t *d_status = reinterpret_cast<int32_t *>(d_out_len + n);
+    rc = decode_batch_device_impl(d, st.src.as<uint8_t>(), dd, dd + n, st.dst.as<uint8_t>(), dd + 2 * n, dd + 3 * n, d_out_len, d_status, nullptr,
+                                  nullptr, n, s, false);
+    if (rc) return rc;
+    CK(d, cudaMemcpyAsync(out_len, d_out_len, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    CK(d, cudaMemcpyAsync(status, d_status, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    CK(d, cudaStreamSynchronize(s));
+    rc = fetch_outputs(d, st, dst, dst_off, out_len, status, n, s);
+    if (rc) return rc;
+    CK(d, cudaStreamSynchronize(s));
+    return LZFSE_B200_OK;
+}
+
+int lzfse_b200_decode_probe_batch_host(lzfse_b200_decoder *d, const uint8_t *src, const uint64_t *src_off, const uint64_t *src_len, uint64_t *raw_len,
+                                       uint32_t *n_blocks, int32_t *status, size_t n) {
+    if (!d || (n && (!src || !src_off || !src_len || !raw_len || !status))) return LZFSE_B200_INVALID_ARGUMENT;
+    if (n == 0) return LZFSE_B200_OK;
+    DeviceGuard g(d->device);
+    if (!g.ok) return LZFSE_B200_CUDA_ERROR;
+    cudaStream_t s = d->own_stream;
+    HostStage &st = d->stage;
+    int rc = stage_sources(d, st, src, src_off, src_len, n, 4 * n, s);
+    if (rc) return rc;
+    CK(d, st.desc.reserve(4 * n * sizeof(uint64_t)));
+    CK(d, cudaMemcpyAsync(st.desc.p, st.pin.p, 2 * n * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    CK(d, st.res.reserve(n * (sizeof(uint64_t) + sizeof(int32_t) + sizeof(uint32_t))));
+    uint64_t *d_raw = st.res.as<uint64_t>();
+    int32_t *d_status = reinterpret_cast<int32_t *>(d_raw + n);
+    uint32_t *d_nb = reinterpret_cast<uint32_t *>(d_status + n);
+    uint64_t *dd = st.desc.as<uint64_t>();
+    rc = decode_batch_device_impl(d, st.src.as<uint8_t>(), dd, dd + n, nullptr, nullptr, nullptr, nullptr, d_status, d_raw, d_nb, n, s, true);
+    if (rc) return rc;
+    CK(d, cudaMemcpyAsync(raw_len, d_raw, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    CK(d, cudaMemcpyAsync(status, d_status, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    if (n_blocks) CK(d, cudaMemcpyAsync(n_blocks, d_nb, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CK(d, cudaStreamSynchronize(s));
+    return LZFSE_B200_OK;
+}
+
+int lzfse_b200_decode_bytes(lzfse_b200_decoder *d, const uint8_t *src, size_t src_len, uint8_t *dst, size_t dst_cap, size_t *dst_len) {
+    if (!d || (!src && src_len) || (!dst && dst_cap)) return LZFSE_B200_INVALID_ARGUMENT;
+    uint64_t so = 0, sl = src_len, doff = 0, dc = dst_cap, ol = 0;
+    int32_t st = 0;
+    static const uint8_t empty = 0;
+    int rc = lzfse_b200_decode_batch_host(d, src ? src : &empty, &so, &sl, dst, &doff, &dc, &ol, &st, 1);
+    if (dst_len) *dst_len = (size_t)ol;
+    return rc ? rc : st;
+}
+
+}  // extern "C"

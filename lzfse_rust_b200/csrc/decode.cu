@@ -1,0 +1,825 @@
+// decode.cu -- batched LZFSE decode kernels for sm_100a.
+//
+// Pipeline (all launches on one CUDA stream, see api.cu):
+//   k_scan<false>   thread / stream   walk block headers, count blocks / literals / LMDs, validate
+//   k_exclusive_scan                   per-stream bases
+//   k_scan<true>    thread / stream   fill BlockDesc[] / FseDesc[]
+//   k_fse_literals  lane / FSE block  weights -> U table in shared memory -> 4-state literal decode
+//   k_fse_lmds      lane / FSE block  weights -> L/M/D table in shared memory -> LMD decode + validation
+//   k_expand        warp / stream     literal placement + match copies, raw and LZVN blocks
+//   k_finish        thread / stream   error key -> status, out_len
+//
+// The entropy stages map one LANE to one block: an FSE stream is a serial chain (the bit position of
+// symbol n+1 depends on symbol n), so the only parallelism is across blocks; a lane-per-block warp
+// keeps all 32 lanes issuing, and the tables are laid out [state][lane] so a warp's 32 lookups hit
+// 32 different banks.  What the reference does in Literals::load / FseCore::decode_internal
+// (fse/literals.rs:49-91, fse/fse_core.rs:91-141) is restated below with every check it makes.
+#include "common.cuh"
+
+namespace lzb {
+
+// ------------------------------------------------------------------------------------------------
+// Frame scan (decode/decoder.rs:72-99 dispatch loop, fse/block.rs:80-136,218-341 header parse + validate)
+// ------------------------------------------------------------------------------------------------
+
+struct FseHeader {
+    uint32_t n_raw, n_literals, n_lit_payload, lit_bits, n_lmds, n_lmd_payload, lmd_bits, n_weight_bytes, header_size;
+    uint16_t lit_state[4], lmd_state[3];
+    bool v1;
+};
+
+__device__ int validate_fse_header(const FseHeader &h) {
+    // LmdParam::validate (fse/block.rs:267-283)
+    uint32_t lmd_limit = 1024 + 8 + (h.n_lmds * kMaxLBits + h.n_lmds * kMaxMBits + h.n_lmds * kMaxDBits + 7) / 8;
+    if (h.n_lmds > kLmdsPerBlock || h.n_lmd_payload < 8 || h.n_lmd_payload > lmd_limit) return LZFSE_B200_FSE_BAD_LMD_COUNT;
+    if (h.lmd_bits > 7) return LZFSE_B200_FSE_BAD_LMD_BITS;
+    if (h.lmd_state[0] >= kLStates || h.lmd_state[1] >= kMStates || h.lmd_state[2] >= kDStates) return LZFSE_B200_FSE_BAD_LMD_STATE;
+    // LiteralParam::validate (fse/block.rs:324-341)
+    if (h.n_literals % 4 != 0 || h.n_literals > kLiteralsPerBlock) return LZFSE_B200_FSE_BAD_LITERAL_COUNT;
+    if (h.n_lit_payload > 1024 + (h.n_literals * kMaxUBits + 7) / 8) return LZFSE_B200_FSE_BAD_LITERAL_COUNT;
+    if (h.lit_bits > 7) return LZFSE_B200_FSE_BAD_LITERAL_BITS;
+    if (h.lit_state[0] >= kUStates || h.lit_state[1] >= kUStates || h.lit_state[2] >= kUStates || h.lit_state[3] >= kUStates)
+        return LZFSE_B200_FSE_BAD_LMD_PAYLOAD;  // sic: the reference reports BadLmdPayload here
+    // FseBlock::validate (fse/block.rs:218-227)
+    if (h.n_raw > h.n_literals + h.n_lmds * kMaxMValue) return LZFSE_B200_FSE_BAD_RAW_BYTE_COUNT;
+    return LZFSE_B200_OK;
+}
+
+__device__ int parse_v2(const uint8_t *s, FseHeader &h) {
+    h.v1 = false;
+    h.n_raw = ld_u32(s + 4);
+    uint64_t p = ld_u64(s + 8);
+    h.n_literals = (uint32_t)(p & 0xFFFFF);
+    h.n_lit_payload = (uint32_t)((p >> 20) & 0xFFFFF);
+    h.n_lmds = (uint32_t)((p >> 40) & 0xFFFFF);
+    h.lit_bits = 7 - (uint32_t)((p >> 60) & 7);
+    p = ld_u64(s + 16);
+    for (int i = 0; i < 4; i++) h.lit_state[i] = (uint16_t)((p >> (10 * i)) & 0x3FF);
+    h.n_lmd_payload = (uint32_t)((p >> 40) & 0xFFFFF);
+    h.lmd_bits = 7 - (uint32_t)((p >> 60) & 7);
+    p = ld_u64(s + 24);
+    uint32_t header_size = (uint32_t)p;
+    h.lmd_state[0] = (uint16_t)((p >> 32) & 0x3FF);
+    h.lmd_state[1] = (uint16_t)((p >> 42) & 0x3FF);
+    h.lmd_state[2] = (uint16_t)((p >> 52) & 0x3FF);
+    h.n_weight_bytes = header_size - kV2HeaderSize;
+    h.header_size = header_size;
+    if (h.n_weight_bytes > kV2WeightBytesMax) return LZFSE_B200_FSE_BAD_WEIGHT_PAYLOAD;
+    return validate_fse_header(h);
+}
+
+__device__ int parse_v1(const uint8_t *s, FseHeader &h) {
+    h.v1 = true;
+    h.n_raw = ld_u32(s + 4);
+    uint32_t n_payload = ld_u32(s + 8);
+    h.n_literals = ld_u32(s + 12);
+    h.n_lmds = ld_u32(s + 16);
+    h.n_lit_payload = ld_u32(s + 20);
+    h.n_lmd_payload = ld_u32(s + 24);
+    h.lit_bits = 0u - ld_u32(s + 28);
+    for (int i = 0; i < 4; i++) h.lit_state[i] = (uint16_t)ld_u16(s + 32 + 2 * i);
+    h.lmd_bits = 0u - ld_u32(s + 40);
+    for (int i = 0; i < 3; i++) h.lmd_state[i] = (uint16_t)ld_u16(s + 44 + 2 * i);
+    h.n_weight_bytes = kV1WeightBytes;
+    h.header_size = kV1HeaderSize + kV1WeightBytes;
+    if (n_payload < h.n_lit_payload + h.n_lmd_payload) return LZFSE_B200_FSE_BAD_PAYLOAD_COUNT;
+    return validate_fse_header(h);
+}
+
+template <bool FILL>
+__global__ void k_scan(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ src_off,
+                       const uint64_t *__restrict__ src_len, const uint64_t *__restrict__ dst_off,
+                       const uint64_t *__restrict__ dst_cap, size_t n, StreamCounts *counts /* in FILL: scanned bases */,
+                       BlockDesc *blocks, FseDesc *fse, uint32_t *err, uint64_t *raw_total, uint32_t *n_blocks_out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint8_t *s = src_base + src_off[i];
+    const uint64_t len = src_len[i];
+    uint64_t pos = 0, raw = 0;
+    uint32_t blk = 0, n_fse = 0;
+    uint64_t n_lit = 0, n_lmd = 0;
+    uint32_t key = kNoError;
+    StreamCounts base;
+    if (FILL) base = counts[i];
+    for (;;) {
+        uint64_t rest = len - pos;
+        uint32_t kb = blk < 0x1FFFFFu ? blk : 0x1FFFFFu;
+        if (rest < 4) { key = err_key(kb, PH_HEADER, LZFSE_B200_PAYLOAD_UNDERFLOW); break; }
+        uint32_t magic = ld_u32(s + pos);
+        if (magic == kMagicEos) {
+            if (rest != 4) key = err_key(kb, PH_HEADER, LZFSE_B200_PAYLOAD_OVERFLOW);
+            break;
+        }
+        BlockDesc bd;
+        bd.src_off = src_off[i] + pos;
+        bd.dst_off = (FILL ? dst_off[i] : 0) + raw;
+        bd.stream = (uint32_t)i;
+        bd.index = blk;
+        bd.fse_idx = 0;
+        bd.pad = 0;
+        bool stop = false;
+        uint64_t blen;
+        if (magic == kMagicRaw) {
+            if (rest < 8) { key = err_key(kb, PH_HEADER, LZFSE_B200_PAYLOAD_UNDERFLOW); break; }
+            bd.n_raw = ld_u32(s + pos + 4);
+            bd.type = BT_RAW;
+            blen = 8ull + bd.n_raw;
+            // raw/block.rs:71-93: copy what is there, then PayloadUnderflow if the input was short.  The
+            // copy is where a too small dst shows up first (C-ABI BufferOverflow).
+            const uint64_t avail = rest - 8 < bd.n_raw ? rest - 8 : bd.n_raw;
+            if (dst_cap != nullptr && raw + avail > dst_cap[i]) { key = err_key(kb, PH_LMD, LZFSE_B200_BUFFER_OVERFLOW); break; }
+            if (rest < blen) { key = err_key(kb, PH_LMD, LZFSE_B200_PAYLOAD_UNDERFLOW); break; }
+        } else if (magic == kMagicVxn) {
+            if (rest < kVnHeaderSize) { key = err_key(kb, PH_HEADER, LZFSE_B200_PAYLOAD_UNDERFLOW); break; }
+            bd.n_raw = ld_u32(s + pos + 4);
+            bd.type = BT_VXN;
+            blen = (uint64_t)kVnHeaderSize + ld_u32(s + pos + 8);
+            if (rest < blen) stop = true;  // the opcode interpreter decides which error this is
+        } else if (magic == kMagicVx2 || magic == kMagicVx1) {
+            const bool v1 = magic == kMagicVx1;
+            const uint32_t hs = v1 ? kV1HeaderSize : kV2HeaderSize;
+            if (rest < hs) { key = err_key(kb, PH_HEADER, LZFSE_B200_PAYLOAD_UNDERFLOW); break; }
+            FseHeader h;
+            int e = v1 ? parse_v1(s + pos, h) : parse_v2(s + pos, h);
+            if (e) { key = err_key(kb, PH_HEADER, e); break; }
+            if (rest - hs < h.n_weight_bytes) { key = err_key(kb, PH_HEADER, LZFSE_B200_PAYLOAD_UNDERFLOW); break; }
+            bd.n_raw = h.n_raw;
+            bd.type = v1 ? BT_VX1 : BT_VX2;
+            bd.fse_idx = (uint32_t)(FILL ? base.n_fse : 0) + n_fse;
+            uint32_t flags = v1 ? FSE_V1 : 0;
+            // fse_core.rs:62-88: each payload is `take`n after the previous stage succeeded.
+            if (rest < (uint64_t)h.header_size + h.n_lit_payload) {
+                flags |= FSE_TRUNC_LIT; stop = true;
+                key = err_key(kb, PH_LIT_TAKE, LZFSE_B200_PAYLOAD_UNDERFLOW);
+            } else if (rest < (uint64_t)h.header_size + h.n_lit_payload + h.n_lmd_payload) {
+                flags |= FSE_TRUNC_LMD; stop = true;
+                key = err_key(kb, PH_LMD_TAKE, LZFSE_B200_PAYLOAD_UNDERFLOW);
+            }
+            blen = (uint64_t)h.header_size + h.n_lit_payload + h.n_lmd_payload;
+            if (FILL) {
+                FseDesc fd;
+                fd.lit_off = base.n_literals + n_lit;
+                fd.lmd_off = base.n_lmds + n_lmd;
+                fd.block = (uint32_t)base.n_blocks + blk;
+                fd.flags = flags;
+                fd.header_size = h.header_size;
+                fd.n_weight_bytes = h.n_weight_bytes;
+                fd.n_literals = h.n_literals; fd.n_lit_payload = h.n_lit_payload; fd.lit_bits = h.lit_bits;
+                fd.n_lmds = h.n_lmds; fd.n_lmd_payload = h.n_lmd_payload; fd.lmd_bits = h.lmd_bits;
+                for (int k = 0; k < 4; k++) fd.lit_state[k] = h.lit_state[k];
+                for (int k = 0; k < 3; k++) fd.lmd_state[k] = h.lmd_state[k];
+                fd.pad = 0; fd.pad2 = 0;
+                fd.n_raw = h.n_raw;
+                fd.ok_lit = 0; fd.ok_lmd = 0;
+                fse[bd.fse_idx] = fd;
+            }
+            n_fse++;
+            n_lit += h.n_literals;
+            n_lmd += h.n_lmds;
+        } else {
+            key = err_key(kb, PH_HEADER, LZFSE_B200_BAD_BLOCK);
+            break;
+        }
+        if (FILL) blocks[base.n_blocks + blk] = bd;
+        raw += bd.n_raw;
+        blk++;
+        pos += blen;
+        if (stop) break;
+    }
+    if (!FILL) {
+        StreamCounts c;
+        c.n_blocks = blk; c.n_fse = n_fse; c.n_literals = n_lit; c.n_lmds = n_lmd;
+        counts[i] = c;
+        err[i] = key;
+        raw_total[i] = raw;
+        if (n_blocks_out) n_blocks_out[i] = blk;
+    }
+}
+
+// Exclusive scan of StreamCounts in place with one CTA; totals[0] receives the grand totals and
+// counts[n] too (so stream i's range is [counts[i], counts[i+1])).
+__global__ void __launch_bounds__(1024) k_exclusive_scan(StreamCounts *counts, size_t n, StreamCounts *totals) {
+    __shared__ StreamCounts part[1024];
+    const size_t per = (n + blockDim.x - 1) / blockDim.x;
+    const size_t lo = (size_t)threadIdx.x * per, hi = lo + per < n ? lo + per : n;
+    StreamCounts acc = {0, 0, 0, 0};
+    for (size_t i = lo; i < hi; i++) {
+        acc.n_blocks += counts[i].n_blocks; acc.n_fse += counts[i].n_fse;
+        acc.n_literals += counts[i].n_literals; acc.n_lmds += counts[i].n_lmds;
+    }
+    part[threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        StreamCounts run = {0, 0, 0, 0};
+        for (unsigned t = 0; t < blockDim.x; t++) {
+            StreamCounts v = part[t];
+            part[t] = run;
+            run.n_blocks += v.n_blocks; run.n_fse += v.n_fse; run.n_literals += v.n_literals; run.n_lmds += v.n_lmds;
+        }
+        *totals = run;
+        counts[n] = run;
+    }
+    __syncthreads();
+    StreamCounts run = part[threadIdx.x];
+    for (size_t i = lo; i < hi; i++) {
+        StreamCounts v = counts[i];
+        counts[i] = run;
+        run.n_blocks += v.n_blocks; run.n_fse += v.n_fse; run.n_literals += v.n_literals; run.n_lmds += v.n_lmds;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Weight payload reader (fse/weights.rs:66-105, fse/weight_encoder.rs:10-20)
+// ------------------------------------------------------------------------------------------------
+struct WeightReader {
+    const uint8_t *p;
+    uint32_t len, i;
+    uint64_t accum;
+    int accum_bits;
+    bool v1;
+    __device__ void init(const uint8_t *ptr, uint32_t n, bool is_v1) { p = ptr; len = n; i = 0; accum = 0; accum_bits = 0; v1 = is_v1; }
+    __device__ uint32_t next() {
+        if (v1) { uint32_t w = ld_u16(p + 2 * i); i++; return w; }
+        while (i != len && accum_bits <= 24) { accum |= (uint64_t)p[i] << accum_bits; accum_bits += 8; i++; }
+        uint32_t u = (uint32_t)accum;
+        uint32_t lo = u & 0x1F, bits, w;
+        // WEIGHTS_BITS_TABLE / WEIGHTS_VALUE_TABLE (fse/constants.rs:115-124) in closed form
+        if ((lo & 1) == 0) { bits = 2; w = (lo >> 1) & 1; }                 // x0: 00 -> 0, 10 -> 1
+        else if ((lo & 3) == 1) { bits = 3; w = 2 + ((lo >> 2) & 1); }      // 001 -> 2, 101 -> 3
+        else if ((lo & 7) == 3) { bits = 5; w = 4 + ((lo >> 3) & 3); }      // xx011 -> 4..7
+        else if ((lo & 15) == 7) { bits = 8; w = 8 + ((u >> 4) & 0xF); }    // xxxx0111
+        else { bits = 14; w = 24 + ((u >> 4) & 0x3FF); }                    // xxxxxxxxxx1111
+        accum >>= bits;
+        accum_bits -= (int)bits;
+        return w;
+    }
+    // Weights::load_v2 tail checks (fse/weights.rs:98-103)
+    __device__ int finish() const {
+        if (v1) return LZFSE_B200_OK;
+        if (accum_bits < 0) return LZFSE_B200_FSE_WEIGHT_PAYLOAD_UNDERFLOW;
+        if (accum_bits >= 8 || i != len) return LZFSE_B200_FSE_WEIGHT_PAYLOAD_OVERFLOW;
+        return LZFSE_B200_OK;
+    }
+};
+
+// Full validation of a block's weight payload: bit accounting, then check_totals (weights.rs:189-201).
+__device__ int validate_weights(const uint8_t *wp, uint32_t n_bytes, bool v1) {
+    WeightReader r;
+    r.init(wp, n_bytes, v1);
+    uint32_t tl = 0, tm = 0, td = 0, tu = 0;
+    for (uint32_t k = 0; k < 20; k++) tl += r.next();
+    for (uint32_t k = 0; k < 20; k++) tm += r.next();
+    for (uint32_t k = 0; k < 64; k++) td += r.next();
+    for (uint32_t k = 0; k < 256; k++) tu += r.next();
+    int e = r.finish();
+    if (e) return e;
+    if (tl <= kLStates && tm <= kMStates && td <= kDStates && tu <= kUStates) return LZFSE_B200_OK;
+    return LZFSE_B200_FSE_BAD_WEIGHT_PAYLOAD;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Backward bit reader over global memory (bits/bit_reader.rs:20-71, bits/bit_src.rs:35-46).
+//
+// The reference keeps (idx, accum_bits) and re-reads 8 unaligned bytes per flush.  Here the cursor is
+// a bit position G relative to a 4-byte aligned base; a 64-bit window holds aligned words
+// [widx, widx+1] and `nxt` prefetches word widx-1, so refills never wait on memory.  P = G - shift0 is
+// the reference's 8*idx + accum_bits.  `dead` reproduces "reads below index 0 yield 0": at a flush
+// point the reference's idx goes negative exactly when P < 57.
+// ------------------------------------------------------------------------------------------------
+struct BitReader {
+    const uint32_t *wbase;   // aligned base; word index 0 holds the slice's first byte
+    const uint8_t *lo, *hi;  // readable byte range (the stream's source bytes)
+    uint64_t buf;
+    uint32_t nxt;
+    int widx;   // index of the low word in buf
+    int rel;    // cursor - 32*widx, kept in (0, 64]
+    int shift0; // bit offset of the slice start inside word 0
+    bool dead;
+
+    __device__ __forceinline__ uint32_t load_word(int idx) const {
+        const uint32_t *a = wbase + idx;
+        const uint8_t *b = reinterpret_cast<const uint8_t *>(a);
+        if (b >= lo && b + 4 <= hi) return __ldg(a);
+        uint32_t v = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (b + k >= lo && b + k < hi) v |= (uint32_t)b[k] << (8 * k);
+        return v;
+    }
+    // slice = [start, start+len), len >= 8; `off` = unused high bits of the last byte.
+    __device__ int init(const uint8_t *start, uint32_t len, uint32_t off, const uint8_t *rlo, const uint8_t *rhi) {
+        lo = rlo; hi = rhi; dead = false;
+        uintptr_t a = reinterpret_cast<uintptr_t>(start);
+        wbase = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+        shift0 = (int)(a & 3) * 8;
+        // BitReader::new: the `off` bits above the cursor must be zero.
+        uint32_t last = start[len - 1];
+        if (off != 0 && (last >> (8 - off)) != 0) return LZFSE_B200_BAD_BITSTREAM;
+        int G = shift0 + (int)len * 8 - (int)off;
+        widx = (G - 1) / 32 - 1;
+        rel = G - 32 * widx;
+        buf = ((uint64_t)load_word(widx + 1) << 32) | load_word(widx);
+        nxt = load_word(widx - 1);
+        return LZFSE_B200_OK;
+    }
+    __device__ __forceinline__ int P() const { return 32 * widx + rel - shift0; }
+    __device__ __forceinline__ void refill() {
+        if (rel < 32) {
+            buf = (buf << 32) | nxt;
+            rel += 32;
+            widx--;
+            nxt = dead ? 0u : load_word(widx - 1);
+        }
+    }
+    __device__ __forceinline__ uint32_t pull(uint32_t n) {  // n <= 32 and rel - n >= 0
+        rel -= (int)n;
+        return (uint32_t)(buf >> rel) & ((n >= 32) ? 0xFFFFFFFFu : ((1u << n) - 1u));
+    }
+    // the reference's `flush`: from here on, once idx < 0, every read yields 0
+    __device__ __forceinline__ void flush_point() {
+        if (!dead && P() < 57) { dead = true; buf = 0; nxt = 0; }
+    }
+    __device__ __forceinline__ bool underflow() const { return P() < 64; }  // BitReader::finalize
+};
+
+// ------------------------------------------------------------------------------------------------
+// Literal stage: lane per block.  U table [1024][32] in shared memory, split into a 16-bit
+// (k << 12 | delta) plane and an 8-bit symbol plane: 3 KiB per lane, 96 KiB per warp, 2 warps per SM.
+// (fse/decoder.rs:299-335 build_u_table, fse/literals.rs:49-91 Literals::load)
+// ------------------------------------------------------------------------------------------------
+constexpr int kLitWarps = 2;
+constexpr size_t kLitSmemPerWarp = 1024 * 32 * 3;
+
+__global__ void __launch_bounds__(kLitWarps * 32, 1)
+k_fse_literals(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ src_off, const uint64_t *__restrict__ src_len,
+               const BlockDesc *__restrict__ blocks, FseDesc *__restrict__ fse, uint32_t n_fse, uint8_t *__restrict__ lit_scratch,
+               uint32_t *err, uint32_t *work_counter) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+    uint16_t *kd = reinterpret_cast<uint16_t *>(smem + warp * kLitSmemPerWarp);
+    uint8_t *sy = smem + warp * kLitSmemPerWarp + 1024 * 32 * 2;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(work_counter, 32u);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (base >= n_fse) break;
+        const uint32_t f = base + lane;
+        if (f < n_fse) {
+            FseDesc fd = fse[f];
+            const BlockDesc bd = blocks[fd.block];
+            const uint8_t *blk = src_base + bd.src_off;
+            const uint8_t *s_lo = src_base + src_off[bd.stream], *s_hi = s_lo + src_len[bd.stream];
+            const bool v1 = fd.flags & FSE_V1;
+            const uint8_t *wp = blk + (v1 ? kV1HeaderSize : kV2HeaderSize);
+            const uint32_t kb = bd.index < 0x1FFFFFu ? bd.index : 0x1FFFFFu;
+            int e = validate_weights(wp, fd.n_weight_bytes, v1);
+            if (e) {
+                atomicMin(&err[bd.stream], err_key(kb, PH_WEIGHTS, e));
+            } else if (!(fd.flags & FSE_TRUNC_LIT)) {
+                // build_u_table, one lane per block, states in order
+                WeightReader r;
+                r.init(wp, fd.n_weight_bytes, v1);
+                for (int k = 0; k < 104; k++) r.next();
+                uint32_t total = 0;
+                for (uint32_t sym = 0; sym < 256; sym++) {
+                    uint32_t w = r.next();
+                    if (w == 0) continue;
+                    uint32_t k = __clz(w) - 21;  // clz(w) - clz(1024)
+                    uint32_t x = (2048u >> k) - w;
+                    for (uint32_t j = 0; j < w; j++) {
+                        uint32_t kk, delta;
+                        if (j < x) { kk = k; delta = ((w + j) << k) - 1024u; }
+                        else { kk = k - 1; delta = (j - x) << (k - 1); }
+                        kd[(total + j) * 32 + lane] = (uint16_t)(delta | (kk << 12));
+                        sy[(total + j) * 32 + lane] = (uint8_t)sym;
+                    }
+                    total += w;
+                }
+                for (uint32_t t = total; t < 1024; t++) { kd[t * 32 + lane] = (uint16_t)t; sy[t * 32 + lane] = 0; }
+
+                // Literals::load.  The slice borrows the 8 bytes before the payload as the BitSrc pad
+                // (fse_core.rs:30-33): it is never consumed by a well-formed stream.
+                BitReader br;
+                int st = br.init(blk + fd.header_size - 8, fd.n_lit_payload + 8, fd.lit_bits, s_lo, s_hi);
+                if (st) {
+                    atomicMin(&err[bd.stream], err_key(kb, PH_LIT, st));
+                } else {
+                    uint32_t s0 = fd.lit_state[0], s1 = fd.lit_state[1], s2 = fd.lit_state[2], s3 = fd.lit_state[3];
+                    uint32_t *out = reinterpret_cast<uint32_t *>(lit_scratch + fd.lit_off);
+                    const uint32_t n_it = fd.n_literals >> 2;
+                    for (uint32_t it = 0; it < n_it; it++) {
+                        br.refill();
+                        uint32_t e0 = kd[s0 * 32 + lane], e1 = kd[s1 * 32 + lane], e2 = kd[s2 * 32 + lane], e3 = kd[s3 * 32 + lane];
+                        uint32_t y0 = sy[s0 * 32 + lane], y1 = sy[s1 * 32 + lane], y2 = sy[s2 * 32 + lane], y3 = sy[s3 * 32 + lane];
+                        s0 = br.pull(e0 >> 12) + (e0 & 0xFFF);
+                        s1 = br.pull(e1 >> 12) + (e1 & 0xFFF);
+                        br.refill();
+                        s2 = br.pull(e2 >> 12) + (e2 & 0xFFF);
+                        s3 = br.pull(e3 >> 12) + (e3 & 0xFFF);
+                        br.flush_point();
+                        out[it] = y0 | (y1 << 8) | (y2 << 16) | (y3 << 24);
+                    }
+                    if (br.underflow()) atomicMin(&err[bd.stream], err_key(kb, PH_LIT, LZFSE_B200_PAYLOAD_UNDERFLOW));
+                    else if (s0 | s1 | s2 | s3) atomicMin(&err[bd.stream], err_key(kb, PH_LIT, LZFSE_B200_FSE_BAD_LMD_PAYLOAD));
+                    else fse[f].ok_lit = 1;
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LMD stage: lane per block.  L/M/D table [384][32] x u32 in shared memory (48 KiB per warp).
+// Entry: delta[0:9] | k[9:13] | v_bits[13:17] | v_base (L/M) or symbol (D) [17:].
+// (fse/decoder.rs:244-292 build_v_table_block, fse/fse_core.rs:91-141 decode_internal)
+// ------------------------------------------------------------------------------------------------
+constexpr int kLmdWarps = 4;
+constexpr size_t kLmdSmemPerWarp = 384 * 32 * 4;
+
+__device__ __forceinline__ uint32_t l_extra(uint32_t s) { return s < 16 ? 0u : (s == 16 ? 2u : (s == 17 ? 3u : (s == 18 ? 5u : 8u))); }
+__device__ __forceinline__ uint32_t l_base(uint32_t s) { return s < 16 ? s : (s == 16 ? 16u : (s == 17 ? 20u : (s == 18 ? 28u : 60u))); }
+__device__ __forceinline__ uint32_t m_extra(uint32_t s) { return s < 16 ? 0u : (s == 16 ? 3u : (s == 17 ? 5u : (s == 18 ? 8u : 11u))); }
+__device__ __forceinline__ uint32_t m_base(uint32_t s) { return s < 16 ? s : (s == 16 ? 16u : (s == 17 ? 24u : (s == 18 ? 56u : 312u))); }
+// D_BASE_VALUE[s] = ((4 + (s & 3)) << (s >> 2)) - 4, D_EXTRA_BITS[s] = s >> 2 (fse/constants.rs:305-321)
+__device__ __forceinline__ uint32_t d_base(uint32_t s) { return ((4u + (s & 3u)) << (s >> 2)) - 4u; }
+
+template <int KIND>  // 0 = L, 1 = M, 2 = D
+__device__ __forceinline__ void build_v_block(WeightReader &r, uint32_t *tab, uint32_t lane, uint32_t n_sym, uint32_t n_states,
+                                              uint32_t offset) {
+    const uint32_t n_clz = __clz(n_states);
+    uint32_t total = 0;
+    for (uint32_t sym = 0; sym < n_sym; sym++) {
+        uint32_t w = r.next();
+        if (w == 0) continue;
+        uint32_t k = __clz(w) - n_clz;
+        uint32_t x = ((n_states << 1) >> k) - w;
+        uint32_t vb = KIND == 0 ? l_extra(sym) : (KIND == 1 ? m_extra(sym) : (sym >> 2));
+        uint32_t hi = KIND == 0 ? l_base(sym) : (KIND == 1 ? m_base(sym) : sym);
+        for (uint32_t j = 0; j < w; j++) {
+            uint32_t kk, delta;
+            if (j < x) { kk = k; delta = ((w + j) << k) - n_states; }
+            else { kk = k - 1; delta = (j - x) << (k - 1); }
+            tab[(offset + total + j) * 32 + lane] = (delta + offset) | (kk << 9) | (vb << 13) | (hi << 17);
+        }
+        total += w;
+    }
+    for (uint32_t t = total; t < n_states; t++) tab[(offset + t) * 32 + lane] = (offset + t);  // latch: k = 0, v_bits = 0, base 0
+}
+
+__global__ void __launch_bounds__(kLmdWarps * 32, 1)
+k_fse_lmds(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ src_off, const uint64_t *__restrict__ src_len,
+           const uint64_t *__restrict__ dst_off, const uint64_t *__restrict__ dst_cap, const BlockDesc *__restrict__ blocks,
+           FseDesc *__restrict__ fse, uint32_t n_fse, LmdRec *__restrict__ lmd_scratch, uint32_t *err, uint32_t *work_counter) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+    uint32_t *tab = reinterpret_cast<uint32_t *>(smem + warp * kLmdSmemPerWarp);
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(work_counter, 32u);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (base >= n_fse) break;
+        const uint32_t f = base + lane;
+        if (f < n_fse) {
+            FseDesc fd = fse[f];
+            const BlockDesc bd = blocks[fd.block];
+            const uint8_t *blk = src_base + bd.src_off;
+            const uint8_t *s_lo = src_base + src_off[bd.stream], *s_hi = s_lo + src_len[bd.stream];
+            const bool v1 = fd.flags & FSE_V1;
+            const uint8_t *wp = blk + (v1 ? kV1HeaderSize : kV2HeaderSize);
+            const uint32_t kb = bd.index < 0x1FFFFFu ? bd.index : 0x1FFFFFu;
+            // The literal stage reports weight errors; this stage only needs to know the tables are sound.
+            if (!(fd.flags & (FSE_TRUNC_LIT | FSE_TRUNC_LMD)) && validate_weights(wp, fd.n_weight_bytes, v1) == 0) {
+                WeightReader r;
+                r.init(wp, fd.n_weight_bytes, v1);
+                build_v_block<0>(r, tab, lane, kLSymbols, kLStates, 0);
+                build_v_block<1>(r, tab, lane, kMSymbols, kMStates, 64);
+                build_v_block<2>(r, tab, lane, kDSymbols, kDStates, 128);
+
+                BitReader br;
+                const uint8_t *payload = blk + fd.header_size + fd.n_lit_payload;
+                int st = br.init(payload, fd.n_lmd_payload, fd.lmd_bits, s_lo, s_hi);
+                if (st) {
+                    atomicMin(&err[bd.stream], err_key(kb, PH_LMD, st));
+                } else {
+                    uint32_t sl = fd.lmd_state[0], sm = 64u + fd.lmd_state[1], sd = 128u + fd.lmd_state[2];
+                    uint32_t lit_index = 0, n_match = 0, D = 0;
+                    uint64_t pos = bd.dst_off - dst_off[bd.stream];  // bytes of this stream already produced
+                    const uint64_t cap = dst_cap[bd.stream];
+                    LmdRec *out = lmd_scratch + fd.lmd_off;
+                    int fail = 0;
+                    for (uint32_t i = 0; i < fd.n_lmds; i++) {
+                        uint32_t el = tab[sl * 32 + lane], em = tab[sm * 32 + lane], ed = tab[sd * 32 + lane];
+                        br.refill();
+                        sl = br.pull((el >> 9) & 15) + (el & 0x1FF);
+                        uint32_t L = (el >> 17) + br.pull((el >> 13) & 15);
+                        sm = br.pull((em >> 9) & 15) + (em & 0x1FF);
+                        uint32_t M = (em >> 17) + br.pull((em >> 13) & 15);
+                        br.refill();
+                        sd = br.pull((ed >> 9) & 15) + (ed & 0x1FF);
+                        uint32_t dp = d_base(ed >> 17) + br.pull((ed >> 13) & 15);
+                        br.flush_point();
+                        if (dp) D = dp;
+                        lit_index += L;
+                        if (lit_index > kLiteralsPerBlock) { fail = LZFSE_B200_FSE_BAD_LMD_PAYLOAD; break; }
+                        if (pos + L > cap) { fail = LZFSE_B200_BUFFER_OVERFLOW; break; }  // the C-ABI's fixed-size Vec
+                        pos += L;
+                        if (M) {
+                            n_match += M;
+                            if (D == 0 || D > pos) { fail = LZFSE_B200_BAD_D_VALUE; break; }  // lz/writer.rs:156-177
+                            if (pos + M > cap) { fail = LZFSE_B200_BUFFER_OVERFLOW; break; }
+                            pos += M;
+                        }
+                        LmdRec rec;
+                        rec.l = (uint16_t)L; rec.m = (uint16_t)M; rec.d = D;
+                        out[i] = rec;
+                    }
+                    if (!fail && br.underflow()) fail = LZFSE_B200_PAYLOAD_UNDERFLOW;
+                    if (!fail && !(lit_index <= fd.n_literals && n_match + lit_index == fd.n_raw && sl == 0 && sm == 64 && sd == 128))
+                        fail = LZFSE_B200_FSE_BAD_LMD_PAYLOAD;
+                    if (fail) atomicMin(&err[bd.stream], err_key(kb, PH_LMD, fail));
+                    else fse[f].ok_lmd = 1;
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Expansion stage: one warp per stream walks its blocks in order.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void warp_copy(uint8_t *dst, const uint8_t *src, uint64_t n, uint32_t lane) {
+    // head: align dst to 16
+    uint64_t head = (16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15;
+    if (head > n) head = n;
+    if (lane < head) dst[lane] = src[lane];
+    dst += head; src += head; n -= head;
+    uint64_t nv = n / 16;
+    if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+        const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
+        uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+        for (uint64_t i = lane; i < nv; i += 32) d4[i] = __ldg(s4 + i);
+    } else {
+        uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+        for (uint64_t i = lane; i < nv; i += 32) {
+            const uint8_t *p = src + i * 16;
+            uint4 v;
+            v.x = ld_u32(p); v.y = ld_u32(p + 4); v.z = ld_u32(p + 8); v.w = ld_u32(p + 12);
+            d4[i] = v;
+        }
+    }
+    uint64_t done = nv * 16;
+    for (uint64_t i = done + lane; i < n; i += 32) dst[i] = src[i];
+}
+
+// LZVN opcode classes (vn/constants.rs:24-72) in closed form.
+enum { OP_SML_L, OP_LRG_L, OP_SML_M, OP_LRG_M, OP_PRE_D, OP_SML_D, OP_MED_D, OP_LRG_D, OP_EOS, OP_UDEF, OP_NOP };
+__device__ __forceinline__ int vn_op(uint32_t b) {
+    uint32_t hi = b >> 4, lo3 = b & 7;
+    if (hi == 0xE) return b == 0xE0 ? OP_LRG_L : OP_SML_L;
+    if (hi == 0xF) return b == 0xF0 ? OP_LRG_M : OP_SML_M;
+    if (hi == 0x7 || hi == 0xD) return OP_UDEF;
+    if (hi == 0xA || hi == 0xB) return OP_MED_D;
+    if (lo3 == 7) return OP_LRG_D;
+    if (lo3 == 6) {
+        if (b == 0x06) return OP_EOS;
+        if (b == 0x0E || b == 0x16) return OP_NOP;
+        if (b < 0x40) return OP_UDEF;
+        return OP_PRE_D;
+    }
+    return OP_SML_D;
+}
+
+// LZVN block, interpreted by one lane (vn/vn_core.rs:51-286).  `stream_out` = first output byte of the
+// stream, `out_pos` = bytes of the stream already produced, `cap_end` = the stream's dst capacity: a write
+// past it is the C-ABI's BufferOverflow (the reference's Vec would grow).  A block that produces more
+// than its header announces can only overwrite later output of its own stream, which then fails.
+__device__ int vn_decode_block(const uint8_t *src, uint64_t src_rest /* bytes from block start to stream end */,
+                               uint8_t *stream_out, uint64_t out_pos, uint64_t cap_end) {
+    uint32_t n_raw = ld_u32(src + 4), n_payload = ld_u32(src + 8), match_distance = 0;
+    uint64_t p = kVnHeaderSize;  // offset inside src
+    for (;;) {
+        const uint64_t src_len = src_rest - p;
+        const uint64_t vlen = src_len < kVnPayloadLimit ? src_len : kVnPayloadLimit;
+        const uint64_t out0 = out_pos;
+        uint64_t used = 0;
+        int res = LZFSE_B200_OK;
+        bool eos = false;
+        if (vlen < 8) res = LZFSE_B200_PAYLOAD_UNDERFLOW;
+        while (res == LZFSE_B200_OK && !eos) {
+            const uint8_t *s = src + p + used;
+            const uint64_t rem = vlen - used;
+            const uint32_t opu = ld_u32(s);
+            uint32_t L = 0, M = 0, D = 0, oplen = 0;
+            const int op = vn_op(opu & 0xFF);
+            switch (op) {
+            case OP_SML_L: L = opu & 0xF; oplen = 1; break;
+            case OP_LRG_L: L = ((opu >> 8) & 0xFF) + 16; oplen = 2; break;
+            case OP_SML_M: M = opu & 0xF; oplen = 1; break;
+            case OP_LRG_M: M = ((opu >> 8) & 0xFF) + 16; oplen = 2; break;
+            case OP_PRE_D: M = ((opu >> 3) & 7) + 3; L = (opu >> 6) & 3; oplen = 1; break;
+            case OP_SML_D: D = ((opu & 7) << 8) | ((opu >> 8) & 0xFF); M = ((opu >> 3) & 7) + 3; L = (opu >> 6) & 3; oplen = 2; break;
+            case OP_MED_D: M = (((opu & 7) << 2) | ((opu >> 8) & 3)) + 3; L = (opu >> 3) & 3; D = (opu >> 10) & 0x3FFF; oplen = 3; break;
+            case OP_LRG_D: M = ((opu >> 3) & 7) + 3; L = (opu >> 6) & 3; D = (opu >> 8) & 0xFFFF; oplen = 3; break;
+            case OP_NOP: oplen = 1; break;
+            case OP_EOS:
+                if (ld_u64(s) != 0x06ull) res = LZFSE_B200_VN_BAD_PAYLOAD;
+                else { used += 8; eos = true; }
+                continue;
+            default: res = LZFSE_B200_VN_BAD_OPCODE; continue;
+            }
+            if (rem - oplen < (uint64_t)L + 8) { res = LZFSE_B200_PAYLOAD_UNDERFLOW; continue; }
+            if (op == OP_SML_D || op == OP_MED_D || op == OP_LRG_D) match_distance = D;
+            if (L) {
+                if (out_pos + L > cap_end) { res = LZFSE_B200_BUFFER_OVERFLOW; continue; }
+                for (uint32_t t = 0; t < L; t++) stream_out[out_pos + t] = s[oplen + t];
+                out_pos += L;
+            }
+            if (M) {
+                if (match_distance == 0 || match_distance > out_pos) { res = LZFSE_B200_BAD_D_VALUE; continue; }
+                if (out_pos + M > cap_end) { res = LZFSE_B200_BUFFER_OVERFLOW; continue; }
+                uint8_t *q = stream_out + out_pos;
+                for (uint32_t t = 0; t < M; t++) q[t] = q[(int64_t)t - (int64_t)match_distance];
+                out_pos += M;
+            }
+            used += oplen + L;
+        }
+        const uint64_t produced = out_pos - out0;
+        if (used > n_payload) return LZFSE_B200_PAYLOAD_UNDERFLOW;
+        if (produced > n_raw) return LZFSE_B200_VN_BAD_PAYLOAD;
+        n_payload -= (uint32_t)used;
+        n_raw -= (uint32_t)produced;
+        const bool cycle = src_len > kVnPayloadLimit;
+        p += used;
+        if (res == LZFSE_B200_OK) {
+            if (n_payload != 0) return LZFSE_B200_PAYLOAD_OVERFLOW;
+            if (n_raw != 0) return LZFSE_B200_VN_BAD_PAYLOAD;
+            return LZFSE_B200_OK;
+        }
+        if (res == LZFSE_B200_PAYLOAD_UNDERFLOW && cycle) continue;
+        return res;
+    }
+}
+
+constexpr uint32_t kShortCopy = 16;  // per-lane copies up to this many bytes; longer ones go warp-wide
+
+// One bvx1/bvx2 block: 32 LMDs per step, one per lane.  (fse_core.rs:108-129, lz/writer.rs:115-180)
+__device__ void expand_fse_block(uint8_t *__restrict__ out /* block's first output byte */, uint64_t block_pos /* stream bytes before it */,
+                                 const uint8_t *__restrict__ lit, const LmdRec *__restrict__ lmds, uint32_t n_lmds, uint32_t lane) {
+    uint32_t out_base = 0, lit_base = 0;  // running offsets inside the block
+    (void)block_pos;
+    for (uint32_t b = 0; b < n_lmds; b += 32) {
+        uint32_t L = 0, M = 0, D = 0;
+        if (b + lane < n_lmds) {
+            LmdRec r = lmds[b + lane];
+            L = r.l; M = r.m; D = r.d;
+        }
+        // inclusive scan of (sum L) << 17 | (sum L+M): 32*315 < 2^14, 32*(315+2359) < 2^17
+        uint32_t v = (L << 17) + (L + M), inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+            if (lane >= (uint32_t)o) inc += t;
+        }
+        const uint32_t exc = inc - v;
+        const uint32_t tot = __shfl_sync(0xFFFFFFFFu, inc, 31);
+        const uint32_t my_out = out_base + (exc & 0x1FFFF);  // where my literals go
+        const uint32_t my_lit = lit_base + (exc >> 17);
+        const uint32_t my_dst = my_out + L;                  // where my match goes
+
+        // ---- literals ----
+        const bool long_l = L > kShortCopy;
+        if (!long_l)
+            for (uint32_t t = 0; t < L; t++) out[my_out + t] = lit[my_lit + t];
+        uint32_t mask = __ballot_sync(0xFFFFFFFFu, long_l);
+        while (mask) {
+            int j = __ffs(mask) - 1;
+            mask &= mask - 1;
+            uint32_t o = __shfl_sync(0xFFFFFFFFu, my_out, j), li = __shfl_sync(0xFFFFFFFFu, my_lit, j), n = __shfl_sync(0xFFFFFFFFu, L, j);
+            for (uint32_t t = lane; t < n; t += 32) out[o + t] = lit[li + t];
+        }
+        __syncwarp();
+
+        // ---- matches ----
+        // A lane may copy on its own when everything it reads was final before this step started
+        // (or is its own output); the rest go one at a time, in order, with the whole warp copying.
+        const uint8_t *src = out + my_dst - D;  // may point before `out` (earlier blocks of the stream)
+        const int64_t src_rel = (int64_t)my_dst - (int64_t)D;
+        const int64_t end_nonself = (src_rel + (int64_t)M < (int64_t)my_dst) ? src_rel + (int64_t)M : (int64_t)my_dst;
+        const bool indep = end_nonself <= (int64_t)out_base;
+        const bool solo = M != 0 && M <= kShortCopy && indep;
+        if (solo)
+            for (uint32_t t = 0; t < M; t++) out[my_dst + t] = src[t];
+        mask = __ballot_sync(0xFFFFFFFFu, M != 0 && !solo);
+        if (mask) __syncwarp();
+        while (mask) {
+            int j = __ffs(mask) - 1;
+            mask &= mask - 1;
+            uint32_t o = __shfl_sync(0xFFFFFFFFu, my_dst, j), d = __shfl_sync(0xFFFFFFFFu, D, j), n = __shfl_sync(0xFFFFFFFFu, M, j);
+            const uint8_t *s = out + o - d;
+            if (d >= n) {
+                for (uint32_t t = lane; t < n; t += 32) out[o + t] = s[t];
+            } else {
+                for (uint32_t t = lane; t < n; t += 32) out[o + t] = s[t % d];  // byte i == byte i mod D of the seed
+            }
+            __syncwarp();
+        }
+        __syncwarp();
+        out_base += tot & 0x1FFFF;
+        lit_base += tot >> 17;
+    }
+}
+
+constexpr int kExpandWarps = 8;
+
+__global__ void __launch_bounds__(kExpandWarps * 32)
+k_expand(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ src_off, const uint64_t *__restrict__ src_len,
+         uint8_t *__restrict__ dst_base, const uint64_t *__restrict__ dst_off, const uint64_t *__restrict__ dst_cap,
+         const StreamCounts *__restrict__ bases,
+         const BlockDesc *__restrict__ blocks, const FseDesc *__restrict__ fse, const uint8_t *__restrict__ lit_scratch,
+         const LmdRec *__restrict__ lmd_scratch, uint32_t *err, size_t n_streams) {
+    const uint32_t lane = lane_id();
+    const size_t stream = (size_t)blockIdx.x * kExpandWarps + (threadIdx.x >> 5);
+    if (stream >= n_streams) return;
+    const uint64_t b0 = bases[stream].n_blocks, b1 = bases[stream + 1].n_blocks;
+    uint8_t *stream_out = dst_base + dst_off[stream];
+    for (uint64_t b = b0; b < b1; b++) {
+        const BlockDesc bd = blocks[b];
+        uint8_t *out = dst_base + bd.dst_off;
+        const uint32_t kb = bd.index < 0x1FFFFFu ? bd.index : 0x1FFFFFu;
+        if (bd.type == BT_RAW) {
+            warp_copy(out, src_base + bd.src_off + 8, bd.n_raw, lane);
+        } else if (bd.type == BT_VXN) {
+            int st = 0;
+            if (lane == 0) {
+                const uint64_t rest = src_off[stream] + src_len[stream] - bd.src_off;
+                const uint64_t pos = bd.dst_off - dst_off[stream];
+                st = vn_decode_block(src_base + bd.src_off, rest, stream_out, pos, dst_cap[stream]);
+                if (st) atomicMin(&err[stream], err_key(kb, PH_LMD, st));
+            }
+            st = __shfl_sync(0xFFFFFFFFu, st, 0);
+            if (st) return;
+        } else {
+            const FseDesc &fd = fse[bd.fse_idx];
+            if (!(fd.ok_lit && fd.ok_lmd)) return;  // the entropy stages already recorded why
+            expand_fse_block(out, bd.dst_off - dst_off[stream], lit_scratch + fd.lit_off, lmd_scratch + fd.lmd_off, fd.n_lmds, lane);
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void k_finish(const uint32_t *__restrict__ err, const uint64_t *__restrict__ raw_total, uint64_t *out_len, int32_t *status, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t k = err[i];
+    int32_t st = k == kNoError ? 0 : (int32_t)(k & 0xFF);
+    status[i] = st;
+    if (out_len) out_len[i] = st == 0 ? raw_total[i] : 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host-side launchers (called from api.cu)
+// ------------------------------------------------------------------------------------------------
+void launch_scan_count(const uint8_t *src, const uint64_t *src_off, const uint64_t *src_len, const uint64_t *dst_cap, size_t n,
+                       StreamCounts *counts, uint32_t *err, uint64_t *raw_total, uint32_t *n_blocks_out, StreamCounts *totals, cudaStream_t s) {
+    if (n == 0) return;
+    const int tb = 128;
+    k_scan<false><<<(unsigned)((n + tb - 1) / tb), tb, 0, s>>>(src, src_off, src_len, nullptr, dst_cap, n, counts, nullptr, nullptr, err, raw_total, n_blocks_out);
+    k_exclusive_scan<<<1, 1024, 0, s>>>(counts, n, totals);
+}
+void launch_scan_fill(const uint8_t *src, const uint64_t *src_off, const uint64_t *src_len, const uint64_t *dst_off, const uint64_t *dst_cap, size_t n,
+                      StreamCounts *bases, BlockDesc *blocks, FseDesc *fse, uint32_t *err, cudaStream_t s) {
+    if (n == 0) return;
+    const int tb = 128;
+    k_scan<true><<<(unsigned)((n + tb - 1) / tb), tb, 0, s>>>(src, src_off, src_len, dst_off, dst_cap, n, bases, blocks, fse, err, nullptr, nullptr);
+}
+int setup_decode_kernels() {
+    cudaError_t e = cudaFuncSetAttribute(k_fse_literals, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kLitWarps * kLitSmemPerWarp));
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(k_fse_lmds, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kLmdWarps * kLmdSmemPerWarp));
+    return (int)e;
+}
+void launch_fse_stages(const uint8_t *src, const uint64_t *src_off, const uint64_t *src_len, const uint64_t *dst_off, const uint64_t *dst_cap,
+                       const BlockDesc *blocks, FseDesc *fse, uint32_t n_fse, uint8_t *lit_scratch, LmdRec *lmd_scratch, uint32_t *err,
+                       uint32_t *work_counters /* 2 zeroed u32 */, int n_sms, cudaStream_t s) {
+    if (n_fse == 0) return;
+    unsigned need_lit = (n_fse + 32 * kLitWarps - 1) / (32 * kLitWarps), need_lmd = (n_fse + 32 * kLmdWarps - 1) / (32 * kLmdWarps);
+    unsigned g_lit = need_lit < (unsigned)n_sms ? need_lit : (unsigned)n_sms;
+    unsigned g_lmd = need_lmd < (unsigned)n_sms ? need_lmd : (unsigned)n_sms;
+    k_fse_literals<<<g_lit, kLitWarps * 32, kLitWarps * kLitSmemPerWarp, s>>>(src, src_off, src_len, blocks, fse, n_fse, lit_scratch, err, work_counters);
+    k_fse_lmds<<<g_lmd, kLmdWarps * 32, kLmdWarps * kLmdSmemPerWarp, s>>>(src, src_off, src_len, dst_off, dst_cap, blocks, fse, n_fse, lmd_scratch, err, work_counters + 1);
+}
+void launch_expand(const uint8_t *src, const uint64_t *src_off, const uint64_t *src_len, uint8_t *dst, const uint64_t *dst_off,
+                   const uint64_t *dst_cap, const StreamCounts *bases, const BlockDesc *blocks, const FseDesc *fse, const uint8_t *lit_scratch,
+                   const LmdRec *lmd_scratch, uint32_t *err, size_t n, cudaStream_t s) {
+    if (n == 0) return;
+    k_expand<<<(unsigned)((n + kExpandWarps - 1) / kExpandWarps), kExpandWarps * 32, 0, s>>>(src, src_off, src_len, dst, dst_off, dst_cap, bases, blocks, fse, lit_scratch, lmd_scratch, err, n);
+}
+void launch_finish(const uint32_t *err, const uint64_t *raw_total, uint64_t *out_len, int32_t *status, size_t n, cudaStream_t s) {
+    if (n == 0) return;
+    const int tb = 256;
+    k_finish<<<(unsigned)((n + tb - 1) / tb), tb, 0, s>>>(err, raw_total, out_len, status, n);
+}
+
+}  // namespace lzb
