@@ -174,8 +174,8 @@ __global__ void k_scan(const uint8_t *__restrict__ src_base, const uint64_t *__r
                 fse[bd.fse_idx] = fd;
             }
             n_fse++;
-            n_lit += h.n_literals;
-            n_lmd += h.n_lmds;
+            n_lit += (h.n_literals + 15) & ~15u;  // 16-byte aligned literal runs
+            n_lmd += (h.n_lmds + 1) & ~1u;        // 16-byte aligned LMD runs
         } else {
             key = err_key(kb, PH_HEADER, LZFSE_B200_BAD_BLOCK);
             break;
@@ -280,67 +280,56 @@ __device__ int validate_weights(const uint8_t *wp, uint32_t n_bytes, bool v1) {
 // ------------------------------------------------------------------------------------------------
 // Backward bit reader over global memory (bits/bit_reader.rs:20-71, bits/bit_src.rs:35-46).
 //
-// The reference keeps (idx, accum_bits) and re-reads 8 unaligned bytes per flush.  Here the cursor is
-// a bit position G relative to a 4-byte aligned base; a 64-bit window holds aligned words
-// [widx, widx+1] and `nxt` prefetches word widx-1, so refills never wait on memory.  P = G - shift0 is
-// the reference's 8*idx + accum_bits.  `dead` reproduces "reads below index 0 yield 0": at a flush
-// point the reference's idx goes negative exactly when P < 57.
+// Like the reference, the reader keeps a bit cursor P (= 8*idx + accum_bits there) and re-reads a 64-bit
+// window ending at P at every flush point: window bits [8*floor((P-57)/8), +64) always hold the next
+// 57 bits.  The read is three aligned 32-bit loads plus two funnel shifts, branch-free, so the lanes of
+// a warp (each at its own bit position) never diverge, and the loads are issued together with the
+// table lookups of the same iteration.  `dead` reproduces "reads below index 0 yield 0": at a flush
+// point the reference's idx is negative exactly when P < 57.
 // ------------------------------------------------------------------------------------------------
-struct BitReader {
-    const uint32_t *wbase;   // aligned base; word index 0 holds the slice's first byte
-    const uint8_t *lo, *hi;  // readable byte range (the stream's source bytes)
-    uint64_t buf;
-    uint32_t nxt;
-    int widx;   // index of the low word in buf
-    int rel;    // cursor - 32*widx, kept in (0, 64]
-    int shift0; // bit offset of the slice start inside word 0
+struct BitWindow {
+    const uint8_t *base;  // slice start
+    uintptr_t pf_lo;      // lowest address worth prefetching (inside the block)
+    int P;                // bit cursor, relative to the slice start
     bool dead;
 
-    __device__ __forceinline__ uint32_t load_word(int idx) const {
-        const uint32_t *a = wbase + idx;
-        const uint8_t *b = reinterpret_cast<const uint8_t *>(a);
-        if (b >= lo && b + 4 <= hi) return __ldg(a);
-        uint32_t v = 0;
-#pragma unroll
-        for (int k = 0; k < 4; k++)
-            if (b + k >= lo && b + k < hi) v |= (uint32_t)b[k] << (8 * k);
-        return v;
-    }
     // slice = [start, start+len), len >= 8; `off` = unused high bits of the last byte.
-    __device__ int init(const uint8_t *start, uint32_t len, uint32_t off, const uint8_t *rlo, const uint8_t *rhi) {
-        lo = rlo; hi = rhi; dead = false;
-        uintptr_t a = reinterpret_cast<uintptr_t>(start);
-        wbase = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
-        shift0 = (int)(a & 3) * 8;
-        // BitReader::new: the `off` bits above the cursor must be zero.
-        uint32_t last = start[len - 1];
+    __device__ __forceinline__ int init(const uint8_t *start, uint32_t len, uint32_t off) {
+        base = start; dead = false;
+        pf_lo = reinterpret_cast<uintptr_t>(start);
+        P = (int)len * 8 - (int)off;
+        uint32_t last = start[len - 1];  // BitReader::new: the `off` bits above the cursor must be zero
         if (off != 0 && (last >> (8 - off)) != 0) return LZFSE_B200_BAD_BITSTREAM;
-        int G = shift0 + (int)len * 8 - (int)off;
-        widx = (G - 1) / 32 - 1;
-        rel = G - 32 * widx;
-        buf = ((uint64_t)load_word(widx + 1) << 32) | load_word(widx);
-        nxt = load_word(widx - 1);
         return LZFSE_B200_OK;
     }
-    __device__ __forceinline__ int P() const { return 32 * widx + rel - shift0; }
-    __device__ __forceinline__ void refill() {
-        if (rel < 32) {
-            buf = (buf << 32) | nxt;
-            rel += 32;
-            widx--;
-            nxt = dead ? 0u : load_word(widx - 1);
-        }
+    // Flush point: returns the window; `cur` = position of the cursor inside it (57..64).
+    __device__ __forceinline__ uint64_t window(int &cur) {
+        if (P < 57) dead = true;
+        const int byte = (P - 57) >> 3;  // the reference's idx: the window's top byte holds bit P-1
+        cur = P - byte * 8;              // 57..64
+        if (dead) return 0;
+        const uintptr_t a = reinterpret_cast<uintptr_t>(base) + (intptr_t)byte;
+        const uint32_t r = (uint32_t)a & 3u;
+        const uint32_t *a4 = reinterpret_cast<const uint32_t *>(a - r);
+        // Each lane walks its own stream, so one lane's L1 miss stalls the whole warp: keep every lane's
+        // next lines resident by prefetching 2 lines below the window (no-op when already cached).
+        const uintptr_t pf = a - r - 256;
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(pf > pf_lo ? pf : pf_lo));
+        const uint32_t w0 = __ldg(a4), w1 = __ldg(a4 + 1);
+        const uint32_t w2 = r ? __ldg(a4 + 2) : 0u;  // never touches a word that holds no slice byte
+        const uint32_t lo = __funnelshift_r(w0, w1, r * 8), hi = __funnelshift_r(w1, w2, r * 8);
+        return ((uint64_t)hi << 32) | lo;
     }
-    __device__ __forceinline__ uint32_t pull(uint32_t n) {  // n <= 32 and rel - n >= 0
-        rel -= (int)n;
-        return (uint32_t)(buf >> rel) & ((n >= 32) ? 0xFFFFFFFFu : ((1u << n) - 1u));
-    }
-    // the reference's `flush`: from here on, once idx < 0, every read yields 0
-    __device__ __forceinline__ void flush_point() {
-        if (!dead && P() < 57) { dead = true; buf = 0; nxt = 0; }
-    }
-    __device__ __forceinline__ bool underflow() const { return P() < 64; }  // BitReader::finalize
+    __device__ __forceinline__ bool underflow() const { return P < 64; }  // BitReader::finalize
 };
+__device__ __forceinline__ uint32_t bits_at(uint64_t win, int pos, uint32_t n) {  // n < 32
+    uint32_t x = (uint32_t)(win >> pos), r;
+    asm("bfe.u32 %0, %1, 0, %2;" : "=r"(r) : "r"(x), "r"(n));
+    return r;
+}
+__device__ __forceinline__ uint32_t byte_of(uint32_t v, int i) {  // one PRMT
+    return __byte_perm(v, 0, 0x4440 | i);
+}
 
 // ------------------------------------------------------------------------------------------------
 // Literal stage: lane per block.  U table [1024][32] in shared memory, split into a 16-bit
@@ -351,8 +340,7 @@ constexpr int kLitWarps = 2;
 constexpr size_t kLitSmemPerWarp = 1024 * 32 * 3;
 
 __global__ void __launch_bounds__(kLitWarps * 32, 1)
-k_fse_literals(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ src_off, const uint64_t *__restrict__ src_len,
-               const BlockDesc *__restrict__ blocks, FseDesc *__restrict__ fse, uint32_t n_fse, uint8_t *__restrict__ lit_scratch,
+k_fse_literals(const uint8_t *__restrict__ src_base, const BlockDesc *__restrict__ blocks, FseDesc *__restrict__ fse, uint32_t n_fse, uint8_t *__restrict__ lit_scratch,
                uint32_t *err, uint32_t *work_counter) {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
@@ -368,7 +356,6 @@ k_fse_literals(const uint8_t *__restrict__ src_base, const uint64_t *__restrict_
             FseDesc fd = fse[f];
             const BlockDesc bd = blocks[fd.block];
             const uint8_t *blk = src_base + bd.src_off;
-            const uint8_t *s_lo = src_base + src_off[bd.stream], *s_hi = s_lo + src_len[bd.stream];
             const bool v1 = fd.flags & FSE_V1;
             const uint8_t *wp = blk + (v1 ? kV1HeaderSize : kV2HeaderSize);
             const uint32_t kb = bd.index < 0x1FFFFFu ? bd.index : 0x1FFFFFu;
@@ -399,26 +386,36 @@ k_fse_literals(const uint8_t *__restrict__ src_base, const uint64_t *__restrict_
 
                 // Literals::load.  The slice borrows the 8 bytes before the payload as the BitSrc pad
                 // (fse_core.rs:30-33): it is never consumed by a well-formed stream.
-                BitReader br;
-                int st = br.init(blk + fd.header_size - 8, fd.n_lit_payload + 8, fd.lit_bits, s_lo, s_hi);
+                BitWindow br;
+                int st = br.init(blk + fd.header_size - 8, fd.n_lit_payload + 8, fd.lit_bits);
                 if (st) {
                     atomicMin(&err[bd.stream], err_key(kb, PH_LIT, st));
                 } else {
                     uint32_t s0 = fd.lit_state[0], s1 = fd.lit_state[1], s2 = fd.lit_state[2], s3 = fd.lit_state[3];
-                    uint32_t *out = reinterpret_cast<uint32_t *>(lit_scratch + fd.lit_off);
+                    uint32_t *out = reinterpret_cast<uint32_t *>(lit_scratch + fd.lit_off);  // 16-byte aligned
                     const uint32_t n_it = fd.n_literals >> 2;
-                    for (uint32_t it = 0; it < n_it; it++) {
-                        br.refill();
-                        uint32_t e0 = kd[s0 * 32 + lane], e1 = kd[s1 * 32 + lane], e2 = kd[s2 * 32 + lane], e3 = kd[s3 * 32 + lane];
-                        uint32_t y0 = sy[s0 * 32 + lane], y1 = sy[s1 * 32 + lane], y2 = sy[s2 * 32 + lane], y3 = sy[s3 * 32 + lane];
-                        s0 = br.pull(e0 >> 12) + (e0 & 0xFFF);
-                        s1 = br.pull(e1 >> 12) + (e1 & 0xFFF);
-                        br.refill();
-                        s2 = br.pull(e2 >> 12) + (e2 & 0xFFF);
-                        s3 = br.pull(e3 >> 12) + (e3 & 0xFFF);
-                        br.flush_point();
-                        out[it] = y0 | (y1 << 8) | (y2 << 16) | (y3 << 24);
+                    // One step = the reference's loop body: 4 literals, states 0..3 in that order, one flush.
+                    auto step = [&]() -> uint32_t {
+                        int cur;
+                        const uint64_t win = br.window(cur);
+                        const uint32_t e0 = kd[s0 * 32 + lane], e1 = kd[s1 * 32 + lane], e2 = kd[s2 * 32 + lane], e3 = kd[s3 * 32 + lane];
+                        const uint32_t y0 = sy[s0 * 32 + lane], y1 = sy[s1 * 32 + lane], y2 = sy[s2 * 32 + lane], y3 = sy[s3 * 32 + lane];
+                        const uint32_t k0 = e0 >> 12, k1 = e1 >> 12, k2 = e2 >> 12, k3 = e3 >> 12;
+                        const int p0 = cur - (int)k0, p1 = p0 - (int)k1, p2 = p1 - (int)k2, p3 = p2 - (int)k3;
+                        s0 = bits_at(win, p0, k0) + (e0 & 0xFFF);
+                        s1 = bits_at(win, p1, k1) + (e1 & 0xFFF);
+                        s2 = bits_at(win, p2, k2) + (e2 & 0xFFF);
+                        s3 = bits_at(win, p3, k3) + (e3 & 0xFFF);
+                        br.P -= cur - p3;
+                        return y0 | (y1 << 8) | (y2 << 16) | (y3 << 24);
+                    };
+                    uint32_t it = 0;
+                    for (; it + 4 <= n_it; it += 4) {
+                        uint4 v;
+                        v.x = step(); v.y = step(); v.z = step(); v.w = step();
+                        __stcg(reinterpret_cast<uint4 *>(out + it), v);
                     }
+                    for (; it < n_it; it++) out[it] = step();
                     if (br.underflow()) atomicMin(&err[bd.stream], err_key(kb, PH_LIT, LZFSE_B200_PAYLOAD_UNDERFLOW));
                     else if (s0 | s1 | s2 | s3) atomicMin(&err[bd.stream], err_key(kb, PH_LIT, LZFSE_B200_FSE_BAD_LMD_PAYLOAD));
                     else fse[f].ok_lit = 1;
@@ -431,16 +428,18 @@ k_fse_literals(const uint8_t *__restrict__ src_base, const uint64_t *__restrict_
 
 // ------------------------------------------------------------------------------------------------
 // LMD stage: lane per block.  L/M/D table [384][32] x u32 in shared memory (48 KiB per warp).
-// Entry: delta[0:9] | k[9:13] | v_bits[13:17] | v_base (L/M) or symbol (D) [17:].
+// Entry bytes: [0] delta (relative to the symbol kind's first state)  [1] k  [2] k + v_bits  [3] symbol,
+// so every field is one byte-extract away.  v_base comes from the symbol in closed form.
 // (fse/decoder.rs:244-292 build_v_table_block, fse/fse_core.rs:91-141 decode_internal)
 // ------------------------------------------------------------------------------------------------
 constexpr int kLmdWarps = 4;
 constexpr size_t kLmdSmemPerWarp = 384 * 32 * 4;
 
 __device__ __forceinline__ uint32_t l_extra(uint32_t s) { return s < 16 ? 0u : (s == 16 ? 2u : (s == 17 ? 3u : (s == 18 ? 5u : 8u))); }
-__device__ __forceinline__ uint32_t l_base(uint32_t s) { return s < 16 ? s : (s == 16 ? 16u : (s == 17 ? 20u : (s == 18 ? 28u : 60u))); }
 __device__ __forceinline__ uint32_t m_extra(uint32_t s) { return s < 16 ? 0u : (s == 16 ? 3u : (s == 17 ? 5u : (s == 18 ? 8u : 11u))); }
-__device__ __forceinline__ uint32_t m_base(uint32_t s) { return s < 16 ? s : (s == 16 ? 16u : (s == 17 ? 24u : (s == 18 ? 56u : 312u))); }
+// L_BASE_VALUE = 0..15,16,20,28,60; M_BASE_VALUE = 0..15,16,24,56,312 (fse/constants.rs:132-134,164-166)
+__device__ __forceinline__ uint32_t l_base(uint32_t s) { return s < 16 ? s : ((0x3C1C1410u >> ((s - 16) * 8)) & 0xFFu); }
+__device__ __forceinline__ uint32_t m_base(uint32_t s) { return s < 16 ? s : (uint32_t)((0x0138003800180010ull >> ((s - 16) * 16)) & 0xFFFFu); }
 // D_BASE_VALUE[s] = ((4 + (s & 3)) << (s >> 2)) - 4, D_EXTRA_BITS[s] = s >> 2 (fse/constants.rs:305-321)
 __device__ __forceinline__ uint32_t d_base(uint32_t s) { return ((4u + (s & 3u)) << (s >> 2)) - 4u; }
 
@@ -455,22 +454,21 @@ __device__ __forceinline__ void build_v_block(WeightReader &r, uint32_t *tab, ui
         uint32_t k = __clz(w) - n_clz;
         uint32_t x = ((n_states << 1) >> k) - w;
         uint32_t vb = KIND == 0 ? l_extra(sym) : (KIND == 1 ? m_extra(sym) : (sym >> 2));
-        uint32_t hi = KIND == 0 ? l_base(sym) : (KIND == 1 ? m_base(sym) : sym);
         for (uint32_t j = 0; j < w; j++) {
             uint32_t kk, delta;
             if (j < x) { kk = k; delta = ((w + j) << k) - n_states; }
             else { kk = k - 1; delta = (j - x) << (k - 1); }
-            tab[(offset + total + j) * 32 + lane] = (delta + offset) | (kk << 9) | (vb << 13) | (hi << 17);
+            tab[(offset + total + j) * 32 + lane] = delta | (kk << 8) | ((kk + vb) << 16) | (sym << 24);
         }
         total += w;
     }
-    for (uint32_t t = total; t < n_states; t++) tab[(offset + t) * 32 + lane] = (offset + t);  // latch: k = 0, v_bits = 0, base 0
+    for (uint32_t t = total; t < n_states; t++) tab[(offset + t) * 32 + lane] = t;  // latch: k = 0, no value bits, symbol 0
 }
 
 __global__ void __launch_bounds__(kLmdWarps * 32, 1)
-k_fse_lmds(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ src_off, const uint64_t *__restrict__ src_len,
-           const uint64_t *__restrict__ dst_off, const uint64_t *__restrict__ dst_cap, const BlockDesc *__restrict__ blocks,
-           FseDesc *__restrict__ fse, uint32_t n_fse, LmdRec *__restrict__ lmd_scratch, uint32_t *err, uint32_t *work_counter) {
+k_fse_lmds(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ dst_off, const uint64_t *__restrict__ dst_cap,
+           const BlockDesc *__restrict__ blocks, FseDesc *__restrict__ fse, uint32_t n_fse, LmdRec *__restrict__ lmd_scratch, uint32_t *err,
+           uint32_t *work_counter) {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
     uint32_t *tab = reinterpret_cast<uint32_t *>(smem + warp * kLmdSmemPerWarp);
@@ -484,7 +482,6 @@ k_fse_lmds(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ sr
             FseDesc fd = fse[f];
             const BlockDesc bd = blocks[fd.block];
             const uint8_t *blk = src_base + bd.src_off;
-            const uint8_t *s_lo = src_base + src_off[bd.stream], *s_hi = s_lo + src_len[bd.stream];
             const bool v1 = fd.flags & FSE_V1;
             const uint8_t *wp = blk + (v1 ? kV1HeaderSize : kV2HeaderSize);
             const uint32_t kb = bd.index < 0x1FFFFFu ? bd.index : 0x1FFFFFu;
@@ -496,46 +493,65 @@ k_fse_lmds(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ sr
                 build_v_block<1>(r, tab, lane, kMSymbols, kMStates, 64);
                 build_v_block<2>(r, tab, lane, kDSymbols, kDStates, 128);
 
-                BitReader br;
-                const uint8_t *payload = blk + fd.header_size + fd.n_lit_payload;
-                int st = br.init(payload, fd.n_lmd_payload, fd.lmd_bits, s_lo, s_hi);
+                BitWindow br;
+                int st = br.init(blk + fd.header_size + fd.n_lit_payload, fd.n_lmd_payload, fd.lmd_bits);
                 if (st) {
                     atomicMin(&err[bd.stream], err_key(kb, PH_LMD, st));
                 } else {
-                    uint32_t sl = fd.lmd_state[0], sm = 64u + fd.lmd_state[1], sd = 128u + fd.lmd_state[2];
+                    uint32_t sl = fd.lmd_state[0], sm = fd.lmd_state[1], sd = fd.lmd_state[2];  // relative states
                     uint32_t lit_index = 0, n_match = 0, D = 0;
-                    uint64_t pos = bd.dst_off - dst_off[bd.stream];  // bytes of this stream already produced
+                    // Stream positions in 32 bits: distances are < 2^18 and a block adds < 2^25, so clamping
+                    // the bytes already produced (and the capacity left) at 2^30 changes no comparison.
+                    const uint64_t pos0 = bd.dst_off - dst_off[bd.stream];
                     const uint64_t cap = dst_cap[bd.stream];
+                    const uint32_t before = (uint32_t)(pos0 < 0x40000000ull ? pos0 : 0x40000000ull);
+                    const uint64_t room64 = cap > pos0 ? cap - pos0 : 0;
+                    const uint32_t room = (uint32_t)(room64 < 0x40000000ull ? room64 : 0x40000000ull);
+                    uint32_t rel = 0;  // bytes this block has produced
                     LmdRec *out = lmd_scratch + fd.lmd_off;
                     int fail = 0;
-                    for (uint32_t i = 0; i < fd.n_lmds; i++) {
-                        uint32_t el = tab[sl * 32 + lane], em = tab[sm * 32 + lane], ed = tab[sd * 32 + lane];
-                        br.refill();
-                        sl = br.pull((el >> 9) & 15) + (el & 0x1FF);
-                        uint32_t L = (el >> 17) + br.pull((el >> 13) & 15);
-                        sm = br.pull((em >> 9) & 15) + (em & 0x1FF);
-                        uint32_t M = (em >> 17) + br.pull((em >> 13) & 15);
-                        br.refill();
-                        sd = br.pull((ed >> 9) & 15) + (ed & 0x1FF);
-                        uint32_t dp = d_base(ed >> 17) + br.pull((ed >> 13) & 15);
-                        br.flush_point();
-                        if (dp) D = dp;
+                    const uint32_t *tl = tab + lane, *tm = tab + 64 * 32 + lane, *td = tab + 128 * 32 + lane;
+                    // One step = one LMD (fse_core.rs:104-131).  Failures are latched, not branched on: the first
+                    // one wins, later (garbage) steps stay inside the tables and the scratch run.
+                    auto step = [&]() -> uint2 {
+                        int cur;
+                        const uint64_t win = br.window(cur);
+                        const uint32_t el = tl[sl * 32], em = tm[sm * 32], ed = td[sd * 32];
+                        const uint32_t kl = byte_of(el, 1), tlb = byte_of(el, 2);
+                        const uint32_t km = byte_of(em, 1), tmb = byte_of(em, 2);
+                        const uint32_t kd_ = byte_of(ed, 1), tdb = byte_of(ed, 2);
+                        const int pl = cur - (int)tlb, pm = pl - (int)tmb, pd = pm - (int)tdb;  // cursor after each symbol
+                        // state bits are pulled first, then the value bits (fse/decoder.rs:214-219)
+                        sl = bits_at(win, cur - (int)kl, kl) + byte_of(el, 0);
+                        const uint32_t L = l_base(el >> 24) + bits_at(win, pl, tlb - kl);
+                        sm = bits_at(win, pl - (int)km, km) + byte_of(em, 0);
+                        const uint32_t M = m_base(em >> 24) + bits_at(win, pm, tmb - km);
+                        sd = bits_at(win, pm - (int)kd_, kd_) + byte_of(ed, 0);
+                        const uint32_t dp = d_base(ed >> 24) + bits_at(win, pd, tdb - kd_);
+                        br.P -= cur - pd;
+                        D = dp ? dp : D;  // lmd/lmd_type.rs:155-159
                         lit_index += L;
-                        if (lit_index > kLiteralsPerBlock) { fail = LZFSE_B200_FSE_BAD_LMD_PAYLOAD; break; }
-                        if (pos + L > cap) { fail = LZFSE_B200_BUFFER_OVERFLOW; break; }  // the C-ABI's fixed-size Vec
-                        pos += L;
-                        if (M) {
-                            n_match += M;
-                            if (D == 0 || D > pos) { fail = LZFSE_B200_BAD_D_VALUE; break; }  // lz/writer.rs:156-177
-                            if (pos + M > cap) { fail = LZFSE_B200_BUFFER_OVERFLOW; break; }
-                            pos += M;
-                        }
-                        LmdRec rec;
-                        rec.l = (uint16_t)L; rec.m = (uint16_t)M; rec.d = D;
-                        out[i] = rec;
+                        rel += L;
+                        int f1 = lit_index > kLiteralsPerBlock ? LZFSE_B200_FSE_BAD_LMD_PAYLOAD
+                                 : (rel > room ? LZFSE_B200_BUFFER_OVERFLOW : 0);  // C-ABI: fixed-size Vec
+                        // lz/writer.rs:156-177: distance 0 or beyond what has been written
+                        const int f2 = (M != 0 && (D == 0 || D > before + rel)) ? LZFSE_B200_BAD_D_VALUE : 0;
+                        n_match += M;
+                        rel += M;
+                        const int f3 = rel > room ? LZFSE_B200_BUFFER_OVERFLOW : 0;
+                        f1 = f1 ? f1 : (f2 ? f2 : f3);
+                        fail = fail ? fail : f1;
+                        return make_uint2(L | (M << 16), D);
+                    };
+                    uint32_t i = 0;
+                    for (; i + 2 <= fd.n_lmds; i += 2) {  // two 8-byte records per 16-byte store (lmd_off is even)
+                        const uint2 r0 = step(), r1 = step();
+                        __stcg(reinterpret_cast<uint4 *>(out + i), make_uint4(r0.x, r0.y, r1.x, r1.y));
                     }
+                    if (i < fd.n_lmds) *reinterpret_cast<uint2 *>(out + i) = step();
+                    if (!fail) { int cur; br.window(cur); }  // the final flush (sets nothing, P unchanged)
                     if (!fail && br.underflow()) fail = LZFSE_B200_PAYLOAD_UNDERFLOW;
-                    if (!fail && !(lit_index <= fd.n_literals && n_match + lit_index == fd.n_raw && sl == 0 && sm == 64 && sd == 128))
+                    if (!fail && !(lit_index <= fd.n_literals && n_match + lit_index == fd.n_raw && sl == 0 && sm == 0 && sd == 0))
                         fail = LZFSE_B200_FSE_BAD_LMD_PAYLOAD;
                     if (fail) atomicMin(&err[bd.stream], err_key(kb, PH_LMD, fail));
                     else fse[f].ok_lmd = 1;
@@ -690,8 +706,15 @@ __device__ void expand_fse_block(uint8_t *__restrict__ out /* block's first outp
 
         // ---- literals ----
         const bool long_l = L > kShortCopy;
-        if (!long_l)
-            for (uint32_t t = 0; t < L; t++) out[my_out + t] = lit[my_lit + t];
+        if (!long_l && L) {  // all loads first, then all stores: no per-byte round trip
+            uint8_t tmp[kShortCopy];
+#pragma unroll
+            for (uint32_t t = 0; t < kShortCopy; t++)
+                if (t < L) tmp[t] = lit[my_lit + t];
+#pragma unroll
+            for (uint32_t t = 0; t < kShortCopy; t++)
+                if (t < L) out[my_out + t] = tmp[t];
+        }
         uint32_t mask = __ballot_sync(0xFFFFFFFFu, long_l);
         while (mask) {
             int j = __ffs(mask) - 1;
@@ -708,9 +731,16 @@ __device__ void expand_fse_block(uint8_t *__restrict__ out /* block's first outp
         const int64_t src_rel = (int64_t)my_dst - (int64_t)D;
         const int64_t end_nonself = (src_rel + (int64_t)M < (int64_t)my_dst) ? src_rel + (int64_t)M : (int64_t)my_dst;
         const bool indep = end_nonself <= (int64_t)out_base;
-        const bool solo = M != 0 && M <= kShortCopy && indep;
-        if (solo)
-            for (uint32_t t = 0; t < M; t++) out[my_dst + t] = src[t];
+        const bool solo = M != 0 && M <= kShortCopy && indep && D >= M;
+        if (solo) {
+            uint8_t tmp[kShortCopy];
+#pragma unroll
+            for (uint32_t t = 0; t < kShortCopy; t++)
+                if (t < M) tmp[t] = src[t];
+#pragma unroll
+            for (uint32_t t = 0; t < kShortCopy; t++)
+                if (t < M) out[my_dst + t] = tmp[t];
+        }
         mask = __ballot_sync(0xFFFFFFFFu, M != 0 && !solo);
         if (mask) __syncwarp();
         while (mask) {
@@ -807,8 +837,8 @@ void launch_fse_stages(const uint8_t *src, const uint64_t *src_off, const uint64
     unsigned need_lit = (n_fse + 32 * kLitWarps - 1) / (32 * kLitWarps), need_lmd = (n_fse + 32 * kLmdWarps - 1) / (32 * kLmdWarps);
     unsigned g_lit = need_lit < (unsigned)n_sms ? need_lit : (unsigned)n_sms;
     unsigned g_lmd = need_lmd < (unsigned)n_sms ? need_lmd : (unsigned)n_sms;
-    k_fse_literals<<<g_lit, kLitWarps * 32, kLitWarps * kLitSmemPerWarp, s>>>(src, src_off, src_len, blocks, fse, n_fse, lit_scratch, err, work_counters);
-    k_fse_lmds<<<g_lmd, kLmdWarps * 32, kLmdWarps * kLmdSmemPerWarp, s>>>(src, src_off, src_len, dst_off, dst_cap, blocks, fse, n_fse, lmd_scratch, err, work_counters + 1);
+    k_fse_literals<<<g_lit, kLitWarps * 32, kLitWarps * kLitSmemPerWarp, s>>>(src, blocks, fse, n_fse, lit_scratch, err, work_counters);
+    k_fse_lmds<<<g_lmd, kLmdWarps * 32, kLmdWarps * kLmdSmemPerWarp, s>>>(src, dst_off, dst_cap, blocks, fse, n_fse, lmd_scratch, err, work_counters + 1);
 }
 void launch_expand(const uint8_t *src, const uint64_t *src_off, const uint64_t *src_len, uint8_t *dst, const uint64_t *dst_off,
                    const uint64_t *dst_cap, const StreamCounts *bases, const BlockDesc *blocks, const FseDesc *fse, const uint8_t *lit_scratch,
