@@ -1,27 +1,829 @@
-// encode.cu -- batched LZFSE encode kernels for sm_100a (placeholder: entry points only).
+// encode.cu -- batched LZFSE encode kernels for sm_100a + the encoder half of the C-ABI.
+//
+// The encoder reproduces lzfse_rust's `encode_bytes` bit for bit (same parse, same blocks, same frames),
+// which is possible on a GPU because the only sequential piece of the reference's front end is the lazy
+// match arbitration: the hash table is fed every position exactly once and in order
+// (encode/frontend_bytes.rs:185-207,336-344), so the candidates a position sees do not depend on the parse.
+//
+// Pipeline (one CUDA stream):
+//   k_enc_prep        thread / stream   block-type policy (frontend_bytes.rs:63-77) + scratch sizing
+//   k_exclusive_scan                    per-stream scratch bases (decode.cu)
+//   k_enc_parse       warp / stream     hash-table match finder (warp-wide candidate compares and batched
+//                                       history inserts), Match::select, FSE block buffering or LZVN opcodes
+//   k_enc_fse_blocks  lane / block      histogram, normalize_m1, weight varints, encode tables, 4-state
+//                                       literal stream, L/M/D stream, bvx2 header
+//   k_enc_assemble    warp / stream     compaction of the blocks into the caller's frame + bvx$
 #include <new>
 #include <string>
 
 #include "common.cuh"
 #include "host_util.h"
 
+namespace lzb {
+
+__global__ void k_exclusive_scan(StreamCounts *counts, size_t n, StreamCounts *totals);  // decode.cu
+
+constexpr uint32_t kEmptyIdx = 0xC0C0C0C0u;  // history reset marker (encode/history.rs:72-83: any idx whose distance is out of range)
+constexpr uint32_t kTableWords = (1u << kHashBits) * kHashWidth;
+
+enum StreamKind : uint32_t { SK_RAW = 0, SK_VN = 1, SK_FSE = 2 };
+
+// Per-stream scratch sizing.  A front-end match becomes 1 + M/2359 packs plus L/315 literal-only packs
+// (fse/buffer.rs:45-97), and matches are at least 4 bytes apart.
+__host__ __device__ inline uint64_t pack_cap(uint64_t len) { return len / 4 + len / 315 + len / 2359 + len / 2048 + 32; }  // + one split pack per block
+__host__ __device__ inline uint64_t block_cap(uint64_t len) { return pack_cap(len) / kLmdsPerBlock + len / kLiteralsPerBlock + 3; }
+// Hard bound of one bvx2 block: header + weights + 10 bits per (padded) literal + 8 + 54 bits per pack.
+__host__ __device__ inline uint64_t block_bound(uint64_t n_lits, uint64_t n_packs) {
+    return 32 + 630 + ((n_lits + 3) / 4 * 4 * 10 + 7) / 8 + 8 + (n_packs * 54 + 7) / 8 + 32;
+}
+__host__ __device__ inline uint64_t out_cap(uint64_t len) {
+    return block_cap(len) * 768 + (len + 4 * block_cap(len)) * 10 / 8 + pack_cap(len) * 54 / 8 + 1024;
+}
+
+struct EncStream {       // per stream, written by prep / parse, read by assemble
+    uint32_t kind;       // StreamKind
+    uint32_t n_blocks;   // FSE blocks produced
+    uint32_t vn_size;    // LZVN: bytes of the finished block (header included) in the out scratch
+    uint32_t pad;
+};
+
+struct EncBlock {        // one bvx2 block to encode (compact list, any order)
+    uint64_t pack_off;   // element offset into the pack scratch
+    uint64_t lit_off;    // byte offset into the literal scratch
+    uint64_t out_off;    // byte offset into the out scratch
+    uint32_t n_packs, n_lits, n_match_bytes;
+    uint32_t out_size;   // filled by k_enc_fse_blocks
+};
+
+// ------------------------------------------------------------------------------------------------
+// prep: policy + sizing.  counts[i] = {packs, literal bytes, block slots, out bytes}
+// ------------------------------------------------------------------------------------------------
+__global__ void k_enc_prep(const uint64_t *__restrict__ src_len, size_t n, EncStream *streams, StreamCounts *counts, int32_t *status) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t len = src_len[i];
+    EncStream st;
+    st.n_blocks = 0; st.vn_size = 0; st.pad = 0;
+    StreamCounts c = {0, 0, 0, 0};
+    status[i] = LZFSE_B200_OK;
+    if (len > 0x7FFFFFFFull) {  // BLOCK_GUIDE repositioning (frontend_bytes.rs:348-375) is out of scope
+        st.kind = SK_RAW;
+        status[i] = LZFSE_B200_INVALID_ARGUMENT;
+    } else if (len > kVnCutoff) {
+        st.kind = SK_FSE;
+        c.n_blocks = pack_cap(len);                  // packs
+        c.n_fse = (len + 31) & ~15ull;               // literal bytes
+        c.n_literals = block_cap(len);               // block slots
+        c.n_lmds = (out_cap(len) + 15) & ~15ull;     // out bytes
+    } else if (len > kRawCutoff) {
+        st.kind = SK_VN;
+        c.n_lmds = (out_cap(len) + 15) & ~15ull;
+    } else {
+        st.kind = SK_RAW;
+    }
+    streams[i] = st;
+    counts[i] = c;
+}
+
+// ------------------------------------------------------------------------------------------------
+// parse: warp per stream
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t hash_u(uint32_t val, bool vn) {  // fse/object.rs:38-43, vn/object.rs:33-47
+    if (vn) val &= 0x00FFFFFFu;
+    return (val * 0x9E3779B1u) >> (32 - kHashBits);
+}
+__device__ __forceinline__ uint32_t lanemask_lt() { uint32_t m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
+
+// Forward match length from `len0`, whole warp: 4 bytes per lane and step (match_kit/match_fast.rs:22-49).
+__device__ __forceinline__ uint32_t warp_match_inc(const uint8_t *src, uint32_t a, uint32_t b, uint32_t len0, uint32_t max, uint32_t lane) {
+    uint32_t len = len0;
+    while (len < max) {
+        const uint32_t off = len + lane * 4;
+        uint32_t x = 0, valid = 0;  // valid = bytes of this lane's word that lie below max
+        if (off < max) {
+            valid = max - off < 4 ? max - off : 4;
+            uint32_t wa = 0, wb = 0;
+            if (valid == 4) { wa = ld_u32(src + a + off); wb = ld_u32(src + b + off); }
+            else for (uint32_t k = 0; k < valid; k++) { wa |= (uint32_t)src[a + off + k] << (8 * k); wb |= (uint32_t)src[b + off + k] << (8 * k); }
+            x = wa ^ wb;
+        }
+        const uint32_t diff = __ballot_sync(0xFFFFFFFFu, x != 0);
+        if (diff) {
+            const int l = __ffs(diff) - 1;
+            const uint32_t xl = __shfl_sync(0xFFFFFFFFu, x, l);
+            return len + l * 4 + ((__ffs(xl) - 1) >> 3);
+        }
+        len += 128;
+    }
+    return max;
+}
+// Backward match length, whole warp, one byte per lane and step (match_kit/match_fast.rs:61-89).
+__device__ __forceinline__ uint32_t warp_match_dec(const uint8_t *src, uint32_t a, uint32_t b, uint32_t max, uint32_t lane) {
+    uint32_t len = 0;
+    while (len < max) {
+        const uint32_t k = len + lane;
+        const bool differ = k < max && src[a - k - 1] != src[b - k - 1];
+        const uint32_t d = __ballot_sync(0xFFFFFFFFu, differ);
+        if (d) return len + (__ffs(d) - 1);
+        len += 32;
+    }
+    return max;
+}
+
+struct Match { uint32_t idx, match_idx, match_len; };
+
+// Per-stream back-end state, identical in every lane (the control flow is warp-uniform).
+struct FseSink {   // fse/buffer.rs + fse/backend.rs:66-96
+    uint2 *packs;            // stream's pack scratch
+    uint8_t *lits;           // stream's literal scratch
+    EncBlock *blocks;        // compact block list
+    uint32_t *block_ids;     // stream's block slot list
+    uint32_t *block_counter;
+    uint64_t pack_base, lit_base, out_base;  // absolute offsets of the stream's scratch
+    uint32_t n_packs_total, n_lits_total;    // appended so far (all blocks)
+    uint32_t blk_pack0, blk_lit0;            // where the open block starts
+    uint32_t n_match_bytes, match_distance;
+    uint32_t n_blocks;
+    uint64_t out_used;
+};
+
+__device__ __forceinline__ void sink_emit_block(FseSink &s, uint32_t lane) {  // emit_block_v2: close the open block
+    if (lane == 0) {
+        EncBlock b;
+        b.pack_off = s.pack_base + s.blk_pack0;
+        b.lit_off = s.lit_base + s.blk_lit0;
+        b.out_off = s.out_base + s.out_used;
+        b.n_packs = s.n_packs_total - s.blk_pack0;
+        b.n_lits = s.n_lits_total - s.blk_lit0;
+        b.n_match_bytes = s.n_match_bytes;
+        b.out_size = 0;
+        const uint32_t id = atomicAdd(s.block_counter, 1u);
+        s.blocks[id] = b;
+        s.block_ids[s.n_blocks] = id;
+    }
+    s.out_used += (block_bound(s.n_lits_total - s.blk_lit0, s.n_packs_total - s.blk_pack0) + 15) & ~15ull;
+    s.n_blocks++;
+    s.blk_pack0 = s.n_packs_total; s.blk_lit0 = s.n_lits_total;
+    s.n_match_bytes = 0; s.match_distance = 0;  // Buffer::reset
+}
+__device__ __forceinline__ void sink_push_pack(FseSink &s, uint32_t l, uint32_t m, uint32_t d, uint32_t lane) {
+    if (lane == 0) s.packs[s.n_packs_total] = make_uint2(l | (m << 16), d);
+    s.n_packs_total++;
+}
+__device__ __forceinline__ void sink_push_l(FseSink &s, uint32_t l, uint32_t lane) {  // Buffer::push_l
+    s.match_distance = 1;
+    sink_push_pack(s, l, 0, 1, lane);
+}
+__device__ __forceinline__ void sink_push_lmd(FseSink &s, uint32_t l, uint32_t m, uint32_t d, uint32_t lane) {  // Buffer::push_lmd
+    if (s.match_distance == d) d = 0; else s.match_distance = d;
+    sink_push_pack(s, l, m, d, lane);
+    s.n_match_bytes += m;
+}
+__device__ __forceinline__ void sink_copy_lits(FseSink &s, const uint8_t *src, uint32_t from, uint32_t n, uint32_t lane) {
+    uint8_t *dst = s.lits + s.n_lits_total;
+    for (uint32_t t = lane; t < n; t += 32) dst[t] = src[from + t];
+    s.n_lits_total += n;
+}
+// Buffer::push (fse/buffer.rs:45-97); returns false when the block is full and must be emitted first.
+__device__ bool sink_buffer_push(FseSink &s, const uint8_t *src, uint32_t &lit_from, uint32_t &lit_len, uint32_t &match_len, uint32_t d, uint32_t lane) {
+    while (lit_len > kMaxLValue) {
+        if (s.n_packs_total - s.blk_pack0 == kLmdsPerBlock) return false;
+        const uint32_t limit = kLiteralsPerBlock - (s.n_lits_total - s.blk_lit0);
+        if (kMaxLValue <= limit) { sink_copy_lits(s, src, lit_from, kMaxLValue, lane); lit_from += kMaxLValue; lit_len -= kMaxLValue; sink_push_l(s, kMaxLValue, lane); }
+        else if (limit != 0) { sink_copy_lits(s, src, lit_from, limit, lane); lit_from += limit; lit_len -= limit; sink_push_l(s, limit, lane); return false; }
+        else return false;
+    }
+    if (s.n_packs_total - s.blk_pack0 == kLmdsPerBlock) return false;
+    uint32_t literal_len = lit_len;
+    const uint32_t limit = kLiteralsPerBlock - (s.n_lits_total - s.blk_lit0);
+    if (literal_len <= limit) { sink_copy_lits(s, src, lit_from, literal_len, lane); lit_from += literal_len; lit_len = 0; }
+    else if (limit != 0) { sink_copy_lits(s, src, lit_from, limit, lane); lit_from += limit; lit_len -= limit; sink_push_l(s, limit, lane); return false; }
+    else return false;
+    while (match_len > kMaxMValue) {
+        sink_push_lmd(s, literal_len, kMaxMValue, d, lane);
+        match_len -= kMaxMValue; literal_len = 0;
+        if (s.n_packs_total - s.blk_pack0 == kLmdsPerBlock) return false;
+    }
+    sink_push_lmd(s, literal_len, match_len, d, lane);
+    match_len = 0;
+    return true;
+}
+__device__ void sink_push_match(FseSink &s, const uint8_t *src, uint32_t lit_from, uint32_t lit_len, uint32_t match_len, uint32_t d, uint32_t lane) {
+    while (!sink_buffer_push(s, src, lit_from, lit_len, match_len, d, lane)) sink_emit_block(s, lane);  // fse/backend.rs:76-90
+}
+
+// LZVN back end (vn/backend.rs:37-136 + vn/opc.rs).  Lane 0 writes the opcode bytes.
+struct VnSink {
+    uint8_t *out;   // stream's out scratch; the 12-byte header is patched at the end
+    uint32_t pos;   // bytes written (header included)
+    uint32_t match_distance, n_literals, n_match_bytes;
+};
+__device__ __forceinline__ void vn_put(VnSink &v, uint32_t opu, uint32_t oplen, const uint8_t *src, uint32_t from, uint32_t n, uint32_t lane) {
+    if (lane == 0) {
+        for (uint32_t k = 0; k < oplen; k++) v.out[v.pos + k] = (uint8_t)(opu >> (8 * k));
+        for (uint32_t k = 0; k < n; k++) v.out[v.pos + oplen + k] = src[from + k];
+    }
+    v.pos += oplen + n;
+}
+__device__ void vn_literal_runs(VnSink &v, const uint8_t *src, uint32_t &from, uint32_t &len, uint32_t keep_below, uint32_t lane) {
+    while (len >= 0x10) {
+        const uint32_t n = len < 0x10F ? len : 0x10F;
+        vn_put(v, 0xE0u | ((n - 0x10) << 8), 2, src, from, n, lane);
+        from += n; len -= n;
+    }
+    if (len >= keep_below && len > 0) { vn_put(v, 0xE0u | len, 1, src, from, len, lane); from += len; len = 0; }
+}
+__device__ void vn_push_match(VnSink &v, const uint8_t *src, uint32_t from, uint32_t lit_len, uint32_t match_len, uint32_t d, uint32_t lane) {
+    v.n_literals += lit_len; v.n_match_bytes += match_len;
+    vn_literal_runs(v, src, from, lit_len, 4, lane);
+    const uint32_t L = lit_len;
+    uint32_t n = 0x0A - 2 * L; if (n > match_len) n = match_len;
+    match_len -= n;
+    if (d == v.match_distance) {
+        if (L == 0) vn_put(v, 0xF0u | n, 1, src, from, 0, lane);                                  // SmlM
+        else vn_put(v, 0x6u | ((n - 3) << 3) | (L << 6), 1, src, from, L, lane);                  // PreD
+    } else if (d < 0x600) {
+        vn_put(v, ((d >> 8) & 7) | ((n - 3) << 3) | (L << 6) | ((d & 0xFF) << 8), 2, src, from, L, lane);  // SmlD
+    } else if (d >= 0x4000 || match_len == 0 || n + match_len > 0x22) {
+        vn_put(v, 0x7u | ((n - 3) << 3) | (L << 6) | (d << 8), 3, src, from, L, lane);            // LrgD
+    } else {
+        const uint32_t m = n - 3;
+        vn_put(v, ((m >> 2) & 7) | (L << 3) | (0x5u << 5) | ((m & 3) << 8) | (d << 10), 3, src, from, L, lane);  // MedD
+    }
+    v.match_distance = d;
+    while (match_len > 0x0F) { const uint32_t lim = match_len < 0x10F ? match_len : 0x10F; vn_put(v, 0xF0u | ((lim - 0x10) << 8), 2, src, from, 0, lane); match_len -= lim; }
+    if (match_len > 0) vn_put(v, 0xF0u | match_len, 1, src, from, 0, lane);
+}
+
+constexpr int kParseWarps = 4;
+
+__global__ void __launch_bounds__(kParseWarps * 32)
+k_enc_parse(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ src_off, const uint64_t *__restrict__ src_len, size_t n_streams,
+            EncStream *streams, const StreamCounts *__restrict__ bases, uint32_t *tables /* one per warp slot */, uint2 *pack_scratch,
+            uint8_t *lit_scratch, uint32_t *block_ids, EncBlock *blocks, uint32_t *block_counter, uint8_t *out_scratch, uint32_t *stream_counter) {
+    const uint32_t lane = lane_id();
+    const uint32_t warp_slot = blockIdx.x * kParseWarps + (threadIdx.x >> 5);
+    uint32_t *table = tables + (size_t)warp_slot * kTableWords;
+    for (;;) {
+        // persistent warps pull streams from a counter; each owns one history table
+        uint32_t si = 0;
+        if (lane == 0) si = atomicAdd(stream_counter, 1u);
+        si = __shfl_sync(0xFFFFFFFFu, si, 0);
+        if (si >= n_streams) break;
+        const uint32_t kind = streams[si].kind;
+        if (kind == SK_RAW) continue;
+        const bool vn = kind == SK_VN;
+        const uint8_t *src = src_base + src_off[si];
+        const uint32_t len = (uint32_t)src_len[si];
+        const uint32_t max_d = vn ? kVnMaxD : kMaxDValue;
+        // HistoryTable::reset
+        for (uint32_t t = lane; t < kTableWords / 4; t += 32) reinterpret_cast<uint4 *>(table)[t] = make_uint4(kEmptyIdx, kEmptyIdx, kEmptyIdx, kEmptyIdx);
+        __syncwarp();
+
+        const StreamCounts base = bases[si];
+        FseSink fs;
+        VnSink vs;
+        if (!vn) {
+            fs.packs = pack_scratch + base.n_blocks; fs.lits = lit_scratch + base.n_fse; fs.blocks = blocks;
+            fs.block_ids = block_ids + base.n_literals; fs.block_counter = block_counter;
+            fs.pack_base = base.n_blocks; fs.lit_base = base.n_fse; fs.out_base = base.n_lmds;
+            fs.n_packs_total = 0; fs.n_lits_total = 0; fs.blk_pack0 = 0; fs.blk_lit0 = 0; fs.n_match_bytes = 0; fs.match_distance = 0;
+            fs.n_blocks = 0; fs.out_used = 0;
+        } else {
+            vs.out = out_scratch + base.n_lmds; vs.pos = kVnHeaderSize; vs.match_distance = 0; vs.n_literals = 0; vs.n_match_bytes = 0;
+        }
+        auto push_match = [&](uint32_t lit_from, uint32_t lit_len, uint32_t match_len, uint32_t d) {
+            if (vn) vn_push_match(vs, src, lit_from, lit_len, match_len, d, lane);
+            else sink_push_match(fs, src, lit_from, lit_len, match_len, d, lane);
+        };
+
+        // FrontendBytes::match_any (encode/frontend_bytes.rs:160-211)
+        const uint32_t end = len - 3;
+        uint32_t index = 0, literal_index = 0;
+        Match pending = {0, 0, 0};
+        for (;;) {
+            const uint32_t val = ld_u32(src + index);
+            uint32_t *bucket = table + hash_u(val, vn) * kHashWidth;
+            const uint4 q = __ldcg(reinterpret_cast<const uint4 *>(bucket));  // History copy before the push
+            __syncwarp();
+            if (lane == 0) __stcg(reinterpret_cast<uint4 *>(bucket), make_uint4(index, q.x, q.y, q.z));  // HistoryTable::push
+            __syncwarp();  // orders the store before the next position's bucket read (shuffles/ballots do not)
+            // find_match (:214-244): newest first, stop at the first candidate out of range
+            const uint32_t qi = lane == 0 ? q.x : (lane == 1 ? q.y : (lane == 2 ? q.z : q.w));
+            uint32_t unit = 0;  // match_us: 4, 3 (LZVN only) or 0
+            bool in_range = false;
+            if (lane < 4) {
+                in_range = (index - qi) <= max_d;
+                if (in_range) {
+                    const uint32_t x = val ^ ld_u32(src + qi);
+                    unit = x == 0 ? 4u : ((vn && (x & 0x00FFFFFFu) == 0) ? 3u : 0u);
+                }
+            }
+            const uint32_t oor = __ballot_sync(0xFFFFFFFFu, lane < 4 && !in_range);
+            const uint32_t live = oor ? ((1u << (__ffs(oor) - 1)) - 1u) : 0xFu;  // candidates before the first out-of-range one
+            Match inc = {0, 0, 0};
+            for (uint32_t c = 0; c < 4; c++) {
+                if (!((live >> c) & 1)) break;
+                const uint32_t u = __shfl_sync(0xFFFFFFFFu, unit, c);
+                if (u == 0) continue;
+                const uint32_t cand = __shfl_sync(0xFFFFFFFFu, qi, c);
+                const uint32_t l = u == 4 ? warp_match_inc(src, index, cand, 4, len - index, lane) : 3u;
+                if (l > inc.match_len) { inc.match_len = l; inc.match_idx = cand; }
+            }
+            if (inc.match_len != 0) {
+                inc.idx = index;
+                const uint32_t lit = index - literal_index;
+                const uint32_t dec = warp_match_dec(src, inc.idx, inc.match_idx, lit < inc.match_idx ? lit : inc.match_idx, lane);
+                inc.idx -= dec; inc.match_idx -= dec; inc.match_len += dec;
+            }
+            // Match::select (encode/match_object.rs:12-33)
+            bool have = false;
+            Match sel = {0, 0, 0};
+            if (inc.match_len == 0) {
+            } else if (inc.match_len >= kGoodMatchLen) { sel = inc; have = true; pending.match_len = 0; }
+            else if (pending.match_len == 0) { pending = inc; }
+            else if ((int32_t)(pending.idx + pending.match_len - inc.idx) <= 0) { sel = pending; have = true; pending = inc; }
+            else if (inc.match_len > pending.match_len) { sel = inc; have = true; pending.match_len = 0; }
+            else { sel = pending; have = true; pending.match_len = 0; }
+            if (have) {
+                push_match(literal_index, sel.idx - literal_index, sel.match_len, sel.idx - sel.match_idx);  // :287-302
+                literal_index = sel.idx + sel.match_len;
+                if (literal_index >= end) break;
+                index++;
+                // sync_history (:336-344): insert the skipped positions, 32 per step, buckets updated in position order
+                __syncwarp();
+                while (index < literal_index) {
+                    const uint32_t p = index + lane;
+                    const bool act = p < literal_index;
+                    const uint32_t h = act ? hash_u(ld_u32(src + p), vn) : 0xFFFFFFFFu;
+                    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, h);
+                    const bool leader = act && (peers & ~((2u << lane) - 1u)) == 0;  // newest position of its bucket
+                    if (leader) {
+                        uint32_t *bk = table + h * kHashWidth;
+                        const uint4 old = __ldcg(reinterpret_cast<const uint4 *>(bk));
+                        uint32_t slot[4], ns = 0, m = peers;
+                        while (m && ns < 4) { const int b = 31 - __clz(m); slot[ns++] = index + b; m &= ~(1u << b); }
+                        const uint32_t o[4] = {old.x, old.y, old.z, old.w};
+                        for (uint32_t k = 0; ns < 4; k++) slot[ns++] = o[k];
+                        __stcg(reinterpret_cast<uint4 *>(bk), make_uint4(slot[0], slot[1], slot[2], slot[3]));
+                    }
+                    __syncwarp();
+                    const uint32_t step = literal_index - index < 32 ? literal_index - index : 32;
+                    index += step;
+                }
+                if (index >= end) break;
+            } else {
+                index++;
+                if (index == end) break;
+            }
+        }
+        // flush_pending, flush_literals, backend.finalize (:121-131,271-317)
+        if (pending.match_len != 0) {
+            push_match(literal_index, pending.idx - literal_index, pending.match_len, pending.idx - pending.match_idx);
+            literal_index = pending.idx + pending.match_len;
+        }
+        if (!vn) {
+            if (len - literal_index != 0) sink_push_match(fs, src, literal_index, len - literal_index, 0, 1, lane);  // push_literals
+            sink_emit_block(fs, lane);  // finalize
+            if (lane == 0) streams[si].n_blocks = fs.n_blocks;
+        } else {
+            uint32_t from = literal_index, ll = len - literal_index;
+            if (ll != 0) { vs.n_literals += ll; vn_literal_runs(vs, src, from, ll, 0, lane); }
+            vn_put(vs, 0x06u, 4, src, 0, 0, lane);   // 8-byte EOS: 06 00 00 00 00 00 00 00
+            vn_put(vs, 0x00u, 4, src, 0, 0, lane);
+            if (lane == 0) {
+                uint8_t *h = vs.out;
+                const uint32_t f[3] = {kMagicVxn, vs.n_literals + vs.n_match_bytes, vs.pos - kVnHeaderSize};
+                for (int k = 0; k < 12; k++) h[k] = (uint8_t)(f[k >> 2] >> (8 * (k & 3)));
+                streams[si].vn_size = vs.pos;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// FSE block encode: lane per block.  Shared memory per lane: weights/histogram u16[360] and
+// encode-table entries u32[360], both laid out [symbol][lane].
+// ------------------------------------------------------------------------------------------------
+constexpr int kFseEncWarps = 3;
+constexpr size_t kFseEncSmemPerWarp = 360 * 32 * (2 + 4);
+
+__device__ __forceinline__ uint32_t l_sym(uint32_t v) { return v < 16 ? v : (v < 20 ? 16u : (v < 28 ? 17u : (v < 60 ? 18u : 19u))); }   // L_BASE_FROM_VALUE
+__device__ __forceinline__ uint32_t m_sym(uint32_t v) { return v < 16 ? v : (v < 24 ? 16u : (v < 56 ? 17u : (v < 312 ? 18u : 19u))); }  // M_BASE_FROM_VALUE
+__device__ __forceinline__ uint32_t d_sym(uint32_t v) {  // largest symbol with D_BASE_VALUE <= v (d_index + D_BASE_FROM_VALUE)
+    if (v < 4) return v;
+    const uint32_t e = 29 - __clz(v + 4);  // base(4e) = 2^(e+2) - 4 <= v
+    return 4 * e + (((v + 4) >> e) - 4);
+}
+__device__ __forceinline__ uint32_t d_base_e(uint32_t s) { return ((4u + (s & 3u)) << (s >> 2)) - 4u; }
+__device__ __forceinline__ uint32_t l_extra_e(uint32_t s) { return s < 16 ? 0u : (s == 16 ? 2u : (s == 17 ? 3u : (s == 18 ? 5u : 8u))); }
+__device__ __forceinline__ uint32_t m_extra_e(uint32_t s) { return s < 16 ? 0u : (s == 16 ? 3u : (s == 17 ? 5u : (s == 18 ? 8u : 11u))); }
+__device__ __forceinline__ uint32_t l_base_e(uint32_t s) { return s < 16 ? s : ((0x3C1C1410u >> ((s - 16) * 8)) & 0xFFu); }
+__device__ __forceinline__ uint32_t m_base_e(uint32_t s) { return s < 16 ? s : (uint32_t)((0x0138003800180010ull >> ((s - 16) * 16)) & 0xFFFFu); }
+
+// normalize_m1 (fse/weights.rs:218-278) on the lane's column of the histogram.
+__device__ void normalize_m1(uint16_t *w /* [sym*32] stride */, uint32_t n_sym, uint32_t in_total, uint32_t out_total) {
+    int32_t remaining = 0;
+    uint32_t max_index = 0;
+    if (in_total != 0) {
+        const uint32_t shift = __clz(out_total), multiply = (1u << 31) / in_total, round = 1u << (shift - 1);
+        uint32_t max_weight = 0;
+        remaining = (int32_t)out_total;
+        for (uint32_t i = 0; i < n_sym; i++) {
+            const uint32_t v = w[i * 32];
+            if (v == 0) continue;
+            uint32_t f = (v * multiply + round) >> shift;
+            if (f == 0) f = 1;
+            w[i * 32] = (uint16_t)f;
+            remaining -= (int32_t)f;
+            if (f > max_weight) { max_weight = f; max_index = i; }
+        }
+    }
+    if (-remaining < (int32_t)w[max_index * 32] / 4) {
+        w[max_index * 32] = (uint16_t)((int32_t)w[max_index * 32] + remaining);
+    } else {
+        uint32_t overflow = (uint32_t)(-remaining);
+        for (int shift = 3; shift >= 0; shift--)
+            for (uint32_t i = 0; i < n_sym; i++) {
+                if (overflow == 0) break;
+                const uint32_t v = w[i * 32];
+                if (v == 0) continue;
+                uint32_t k = (v - 1) >> shift;
+                if (k > overflow) k = overflow;
+                w[i * 32] = (uint16_t)(v - k);
+                overflow -= k;
+            }
+    }
+}
+// build_e_table (fse/encoder.rs:219-240): entry = t_k (low 16) | t_w (high 16), both i16
+__device__ void build_e_table(const uint16_t *w, uint32_t *e, uint32_t n_sym, uint32_t n_states) {
+    const uint32_t n_clz = __clz(n_states);
+    uint32_t total = 0;
+    for (uint32_t i = 0; i < n_sym; i++) {
+        const uint32_t v = w[i * 32];
+        int32_t t_k, t_w;
+        if (v == 0) { t_k = -(int32_t)n_states; t_w = 0; }
+        else {
+            const uint32_t k = __clz(v) - n_clz;
+            t_k = (int32_t)(1024 * k) - (int32_t)(v << k);
+            t_w = (int32_t)n_states + (int32_t)total - (int32_t)v;
+        }
+        e[i * 32] = ((uint32_t)t_k & 0xFFFFu) | ((uint32_t)t_w << 16);
+        total += v;
+    }
+}
+// Forward LSB-first bit writer with a 64-bit accumulator (bits/bit_writer.rs:16-57); bytes go out one by one.
+struct BitWriter {
+    uint8_t *p;
+    uint64_t accum;
+    uint32_t bits;
+    __device__ __forceinline__ void push(uint32_t v, uint32_t n) { accum |= (uint64_t)v << bits; bits += n; }
+    __device__ __forceinline__ void flush() {
+        while (bits >= 8) { *p++ = (uint8_t)accum; accum >>= 8; bits -= 8; }
+    }
+    __device__ __forceinline__ uint32_t finalize() {  // returns the unused bits of the last byte
+        flush();
+        if (bits == 0) return 0;
+        *p++ = (uint8_t)accum;
+        return 8 - bits;
+    }
+};
+// EEntry::encode (fse/encoder.rs:190-200)
+__device__ __forceinline__ void e_encode(uint32_t entry, BitWriter &bw, uint32_t &state) {
+    const int32_t t_k = (int16_t)(entry & 0xFFFF), t_w = (int16_t)(entry >> 16);
+    const uint32_t s = state;
+    const uint32_t nb = (uint32_t)(t_k + (int32_t)s) >> 10;
+    state = (uint32_t)(t_w + (int32_t)(s >> nb));
+    bw.push(s & ((1u << nb) - 1u), nb);
+}
+
+__global__ void __launch_bounds__(kFseEncWarps * 32, 1)
+k_enc_fse_blocks(EncBlock *blocks, const uint32_t *__restrict__ n_blocks_p, const uint2 *__restrict__ pack_scratch,
+                 const uint8_t *__restrict__ lit_scratch, uint8_t *out_scratch, uint32_t *work_counter) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+    uint16_t *W = reinterpret_cast<uint16_t *>(smem + warp * kFseEncSmemPerWarp) + lane;            // W[sym*32]
+    uint32_t *E = reinterpret_cast<uint32_t *>(smem + warp * kFseEncSmemPerWarp + 360 * 32 * 2) + lane;  // E[sym*32]
+    const uint32_t n_blocks = *n_blocks_p;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(work_counter, 32u);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (base >= n_blocks) break;
+        const uint32_t bi = base + lane;
+        if (bi < n_blocks) {
+            const EncBlock b = blocks[bi];
+            const uint2 *packs = pack_scratch + b.pack_off;
+            const uint8_t *lits = lit_scratch + b.lit_off;
+            uint8_t *out = out_scratch + b.out_off;
+            // Weights::load (fse/weights.rs:25-64): histograms of real packs / literals, then normalize
+            for (uint32_t i = 0; i < 360; i++) W[i * 32] = 0;
+            if (b.n_packs) {
+                for (uint32_t i = 0; i < b.n_packs; i++) {
+                    const uint2 p = packs[i];
+                    W[l_sym(p.x & 0xFFFF) * 32]++;
+                    W[(20 + m_sym(p.x >> 16)) * 32]++;
+                    W[(40 + d_sym(p.y)) * 32]++;
+                }
+                normalize_m1(W, 20, b.n_packs, kLStates);
+                normalize_m1(W + 20 * 32, 20, b.n_packs, kMStates);
+                normalize_m1(W + 40 * 32, 64, b.n_packs, kDStates);
+            }
+            if (b.n_lits) {
+                for (uint32_t i = 0; i < b.n_lits; i++) W[(104 + lits[i]) * 32]++;
+                normalize_m1(W + 104 * 32, 256, b.n_lits, kUStates);
+            }
+            // Weights::store_v2 (fse/weights.rs:139-163, fse/weight_encoder.rs:23-37) after the 32-byte header
+            BitWriter bw;
+            bw.p = out + kV2HeaderSize; bw.accum = 0; bw.bits = 0;
+            for (uint32_t i = 0; i < 360; i++) {
+                const uint32_t v = W[i * 32];
+                uint32_t u, ub;
+                if (v == 0) { u = 0; ub = 2; } else if (v == 1) { u = 2; ub = 2; } else if (v == 2) { u = 1; ub = 3; } else if (v == 3) { u = 5; ub = 3; }
+                else if (v < 8) { u = 3 + ((v - 4) << 3); ub = 5; } else if (v < 24) { u = ((v - 8) << 4) + 7; ub = 8; } else { u = ((v - 24) << 4) + 15; ub = 14; }
+                bw.push(u, ub);
+                bw.flush();
+            }
+            bw.finalize();
+            const uint32_t n_weight_bytes = (uint32_t)(bw.p - (out + kV2HeaderSize));
+            // Encoder::init
+            build_e_table(W, E, 20, kLStates);
+            build_e_table(W + 20 * 32, E + 20 * 32, 20, kMStates);
+            build_e_table(W + 40 * 32, E + 40 * 32, 64, kDStates);
+            build_e_table(W + 104 * 32, E + 104 * 32, 256, kUStates);
+            // Literals::store (fse/literals.rs:93-133): padded to x4 with literals[0], encoded last to first
+            const uint32_t n_lit_pad = (b.n_lits + 3) / 4 * 4;
+            uint8_t *lit_start = bw.p;
+            bw.accum = 0; bw.bits = 0;
+            uint32_t s0 = kUStates, s1 = kUStates, s2 = kUStates, s3 = kUStates;
+            const uint32_t pad = b.n_lits ? lits[0] : 0;
+            const uint32_t *EU = E + 104 * 32;
+            for (uint32_t i = n_lit_pad; i != 0; i -= 4) {
+                const uint32_t c3 = i - 1 < b.n_lits ? lits[i - 1] : pad, c2 = i - 2 < b.n_lits ? lits[i - 2] : pad;
+                const uint32_t c1 = i - 3 < b.n_lits ? lits[i - 3] : pad, c0 = lits[i - 4];
+                e_encode(EU[c3 * 32], bw, s3);
+                e_encode(EU[c2 * 32], bw, s2);
+                e_encode(EU[c1 * 32], bw, s1);
+                e_encode(EU[c0 * 32], bw, s0);
+                bw.flush();
+            }
+            const uint32_t lit_bits = bw.finalize();
+            const uint32_t n_lit_payload = (uint32_t)(bw.p - lit_start);
+            // Lmds::store (fse/lmds.rs:62-93): 8 zero bytes, then D, M, L of each pack from last to first
+            uint8_t *lmd_start = bw.p;
+            for (int k = 0; k < 8; k++) *bw.p++ = 0;
+            bw.accum = 0; bw.bits = 0;
+            uint32_t sl = kLStates, sm = kMStates, sd = kDStates;
+            for (uint32_t i = b.n_packs; i != 0; i--) {
+                const uint2 p = packs[i - 1];
+                const uint32_t l = p.x & 0xFFFF, m = p.x >> 16, d = p.y;
+                uint32_t sym = d_sym(d);
+                bw.push(d - d_base_e(sym), sym >> 2); e_encode(E[(40 + sym) * 32], bw, sd);
+                sym = m_sym(m);
+                bw.push(m - m_base_e(sym), m_extra_e(sym)); e_encode(E[(20 + sym) * 32], bw, sm);
+                sym = l_sym(l);
+                bw.push(l - l_base_e(sym), l_extra_e(sym)); e_encode(E[sym * 32], bw, sl);
+                bw.flush();
+            }
+            const uint32_t lmd_bits = bw.finalize();
+            const uint32_t n_lmd_payload = (uint32_t)(bw.p - lmd_start);
+            // FseBlock::store_v2 (fse/block.rs:168-196)
+            const uint32_t n_raw = b.n_lits + b.n_match_bytes;
+            uint64_t h[4];
+            h[0] = (uint64_t)kMagicVx2 | ((uint64_t)n_raw << 32);
+            h[1] = (uint64_t)n_lit_pad | ((uint64_t)n_lit_payload << 20) | ((uint64_t)b.n_packs << 40) | ((uint64_t)(7 - lit_bits) << 60);
+            h[2] = (uint64_t)(s0 - kUStates) | ((uint64_t)(s1 - kUStates) << 10) | ((uint64_t)(s2 - kUStates) << 20) | ((uint64_t)(s3 - kUStates) << 30) |
+                   ((uint64_t)n_lmd_payload << 40) | ((uint64_t)(7 - lmd_bits) << 60);
+            h[3] = (uint64_t)(kV2HeaderSize + n_weight_bytes) | ((uint64_t)(sl - kLStates) << 32) | ((uint64_t)(sm - kMStates) << 42) |
+                   ((uint64_t)(sd - kDStates) << 52);
+            for (int k = 0; k < 32; k++) out[k] = (uint8_t)(h[k >> 3] >> (8 * (k & 7)));
+            blocks[bi].out_size = (uint32_t)(bw.p - out);
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// assemble: warp per stream (frontend_bytes.rs:50-111: block selection, raw fallback, bvx$)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void warp_copy_bytes(uint8_t *dst, const uint8_t *src, uint64_t n, uint32_t lane) {
+    const uint64_t head = (16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15;
+    if (((reinterpret_cast<uintptr_t>(dst) ^ reinterpret_cast<uintptr_t>(src)) & 15) == 0 && n >= head + 16) {
+        if (lane < head) dst[lane] = src[lane];
+        const uint64_t nv = (n - head) / 16;
+        const uint4 *s4 = reinterpret_cast<const uint4 *>(src + head);
+        uint4 *d4 = reinterpret_cast<uint4 *>(dst + head);
+        for (uint64_t i = lane; i < nv; i += 32) d4[i] = s4[i];
+        for (uint64_t i = head + nv * 16 + lane; i < n; i += 32) dst[i] = src[i];
+    } else {
+        for (uint64_t i = lane; i < n; i += 32) dst[i] = src[i];
+    }
+}
+__device__ __forceinline__ void put_u32(uint8_t *p, uint32_t v) { for (int k = 0; k < 4; k++) p[k] = (uint8_t)(v >> (8 * k)); }
+
+constexpr int kAsmWarps = 8;
+__global__ void __launch_bounds__(kAsmWarps * 32)
+k_enc_assemble(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ src_off, const uint64_t *__restrict__ src_len,
+               uint8_t *__restrict__ dst_base, const uint64_t *__restrict__ dst_off, const uint64_t *__restrict__ dst_cap, size_t n_streams,
+               const EncStream *__restrict__ streams, const StreamCounts *__restrict__ bases, const uint32_t *__restrict__ block_ids,
+               const EncBlock *__restrict__ blocks, const uint8_t *__restrict__ out_scratch, uint64_t *out_len, int32_t *status) {
+    const uint32_t lane = lane_id();
+    const size_t si = (size_t)blockIdx.x * kAsmWarps + (threadIdx.x >> 5);
+    if (si >= n_streams) return;
+    if (status[si] != LZFSE_B200_OK) { if (lane == 0) out_len[si] = 0; return; }
+    const EncStream st = streams[si];
+    const uint8_t *src = src_base + src_off[si];
+    const uint64_t len = src_len[si], cap = dst_cap[si];
+    uint8_t *dst = dst_base + dst_off[si];
+    uint64_t total = 4;  // bvx$
+    bool raw = st.kind == SK_RAW;
+    if (st.kind == SK_VN) {
+        // frontend_bytes.rs:92-99: an LZVN block that is not smaller than a raw one is redone as raw
+        if (len < kRawLimit && len + 8 <= st.vn_size) raw = true;
+        else total += st.vn_size;
+    } else if (st.kind == SK_FSE) {
+        for (uint32_t k = 0; k < st.n_blocks; k++) total += blocks[block_ids[bases[si].n_literals + k]].out_size;
+    }
+    if (raw) total += 8 + len;
+    if (total > cap) {  // the reference would grow its Vec; a fixed buffer reports BufferOverflow
+        if (lane == 0) { status[si] = LZFSE_B200_BUFFER_OVERFLOW; out_len[si] = 0; }
+        return;
+    }
+    uint64_t pos = 0;
+    if (raw) {
+        if (lane == 0) { put_u32(dst, kMagicRaw); put_u32(dst + 4, (uint32_t)len); }
+        warp_copy_bytes(dst + 8, src, len, lane);
+        pos = 8 + len;
+    } else if (st.kind == SK_VN) {
+        warp_copy_bytes(dst, out_scratch + bases[si].n_lmds, st.vn_size, lane);
+        pos = st.vn_size;
+    } else {
+        for (uint32_t k = 0; k < st.n_blocks; k++) {
+            const EncBlock b = blocks[block_ids[bases[si].n_literals + k]];
+            warp_copy_bytes(dst + pos, out_scratch + b.out_off, b.out_size, lane);
+            pos += b.out_size;
+        }
+    }
+    if (lane == 0) { put_u32(dst + pos, kMagicEos); out_len[si] = total; }
+}
+
+}  // namespace lzb
+
 using namespace lzb;
 
 struct lzfse_b200_encoder {
     int device = 0;
+    int n_sms = 148;
+    cudaStream_t own_stream = nullptr;
     std::string last_error;
     uint64_t launches = 0;
+    DevBuf streams, counts, totals_dev, tables, packs, lits, block_ids, blocks, out, counters;
+    PinnedBuf totals_host;
+    HostStage stage;
 };
 
+namespace {
+
+constexpr int kParseWarpsPerSm = 16;  // resident history tables: 148 * 16 * 256 KiB = 592 MiB
+
+int encode_batch_device_impl(lzfse_b200_encoder *e, const uint8_t *src, const uint64_t *src_off, const uint64_t *src_len, uint8_t *dst,
+                             const uint64_t *dst_off, const uint64_t *dst_cap, uint64_t *out_len, int32_t *status, size_t n, cudaStream_t s) {
+    e->launches = 0;
+    if (n == 0) return LZFSE_B200_OK;
+    if (n > 0x7FFFFFFFull) { e->last_error = "too many streams in one batch"; return LZFSE_B200_INVALID_ARGUMENT; }
+    LZB_CK(e, e->streams.reserve(n * sizeof(EncStream)));
+    LZB_CK(e, e->counts.reserve((n + 1) * sizeof(StreamCounts)));
+    LZB_CK(e, e->totals_dev.reserve(sizeof(StreamCounts)));
+    LZB_CK(e, e->totals_host.reserve(sizeof(StreamCounts)));
+    LZB_CK(e, e->counters.reserve(4 * sizeof(uint32_t)));
+    const int tb = 128;
+    k_enc_prep<<<(unsigned)((n + tb - 1) / tb), tb, 0, s>>>(src_len, n, e->streams.as<EncStream>(), e->counts.as<StreamCounts>(), status);
+    k_exclusive_scan<<<1, 1024, 0, s>>>(e->counts.as<StreamCounts>(), n, e->totals_dev.as<StreamCounts>());
+    e->launches += 2;
+    LZB_CK(e, cudaMemcpyAsync(e->totals_host.p, e->totals_dev.p, sizeof(StreamCounts), cudaMemcpyDeviceToHost, s));
+    LZB_CK(e, cudaStreamSynchronize(s));
+    const StreamCounts tot = *e->totals_host.as<StreamCounts>();  // {packs, literal bytes, block slots, out bytes}
+    if (tot.n_literals > 0xFFFFFFF0ull) { e->last_error = "too many blocks in one batch"; return LZFSE_B200_INVALID_ARGUMENT; }
+    const unsigned parse_ctas = (unsigned)e->n_sms * kParseWarpsPerSm / kParseWarps;
+    const size_t n_slots = (size_t)parse_ctas * kParseWarps;
+    LZB_CK(e, e->tables.reserve(n_slots * kTableWords * sizeof(uint32_t)));
+    LZB_CK(e, e->packs.reserve((tot.n_blocks + 1) * sizeof(uint2)));
+    LZB_CK(e, e->lits.reserve(tot.n_fse + 64));
+    LZB_CK(e, e->block_ids.reserve((tot.n_literals + 1) * sizeof(uint32_t)));
+    LZB_CK(e, e->blocks.reserve((tot.n_literals + 1) * sizeof(EncBlock)));
+    LZB_CK(e, e->out.reserve(tot.n_lmds + 64));
+    LZB_CK(e, cudaMemsetAsync(e->counters.p, 0, 4 * sizeof(uint32_t), s));
+    uint32_t *ctr = e->counters.as<uint32_t>();  // [0] blocks produced, [1] parse stream cursor, [2] fse-encode cursor
+
+    k_enc_parse<<<parse_ctas, kParseWarps * 32, 0, s>>>(src, src_off, src_len, n, e->streams.as<EncStream>(), e->counts.as<StreamCounts>(),
+                                                       e->tables.as<uint32_t>(), e->packs.as<uint2>(), e->lits.as<uint8_t>(),
+                                                       e->block_ids.as<uint32_t>(), e->blocks.as<EncBlock>(), ctr, e->out.as<uint8_t>(), ctr + 1);
+    e->launches += 1;
+    if (tot.n_literals) {
+        unsigned g = (unsigned)((tot.n_literals + 32 * kFseEncWarps - 1) / (32 * kFseEncWarps));
+        if (g > (unsigned)e->n_sms) g = (unsigned)e->n_sms;
+        k_enc_fse_blocks<<<g, kFseEncWarps * 32, kFseEncWarps * kFseEncSmemPerWarp, s>>>(e->blocks.as<EncBlock>(), ctr, e->packs.as<uint2>(),
+                                                                                        e->lits.as<uint8_t>(), e->out.as<uint8_t>(), ctr + 2);
+        e->launches += 1;
+    }
+    k_enc_assemble<<<(unsigned)((n + kAsmWarps - 1) / kAsmWarps), kAsmWarps * 32, 0, s>>>(
+        src, src_off, src_len, dst, dst_off, dst_cap, n, e->streams.as<EncStream>(), e->counts.as<StreamCounts>(), e->block_ids.as<uint32_t>(),
+        e->blocks.as<EncBlock>(), e->out.as<uint8_t>(), out_len, status);
+    e->launches += 1;
+    LZB_CK(e, cudaGetLastError());
+    LZB_CK(e, cudaStreamSynchronize(s));
+    return LZFSE_B200_OK;
+}
+
+}  // namespace
+
 extern "C" {
-int lzfse_b200_encoder_create(int, lzfse_b200_encoder **out) { if (out) *out = nullptr; return LZFSE_B200_NO_DEVICE; }
-void lzfse_b200_encoder_destroy(lzfse_b200_encoder *e) { delete e; }
+
+int lzfse_b200_encoder_create(int device, lzfse_b200_encoder **out) {
+    if (!out) return LZFSE_B200_INVALID_ARGUMENT;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) { cudaGetLastError(); return LZFSE_B200_NO_DEVICE; }
+    DeviceGuard g(device);
+    if (!g.ok) return LZFSE_B200_NO_DEVICE;
+    lzfse_b200_encoder *e = new (std::nothrow) lzfse_b200_encoder();
+    if (!e) return LZFSE_B200_OUT_OF_MEMORY;
+    e->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete e; return LZFSE_B200_NO_DEVICE; }
+    e->n_sms = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete e; return LZFSE_B200_CUDA_ERROR; }
+    if (cudaFuncSetAttribute(k_enc_fse_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kFseEncWarps * kFseEncSmemPerWarp)) != cudaSuccess) {
+        cudaGetLastError();  // no sm_100a image for this device: there is no fallback path
+        cudaStreamDestroy(e->own_stream);
+        delete e;
+        return LZFSE_B200_NO_DEVICE;
+    }
+    *out = e;
+    return LZFSE_B200_OK;
+}
+
+void lzfse_b200_encoder_destroy(lzfse_b200_encoder *e) {
+    if (!e) return;
+    DeviceGuard g(e->device);
+    for (DevBuf *b : {&e->streams, &e->counts, &e->totals_dev, &e->tables, &e->packs, &e->lits, &e->block_ids, &e->blocks, &e->out, &e->counters}) b->release();
+    e->totals_host.release();
+    e->stage.release();
+    if (e->own_stream) cudaStreamDestroy(e->own_stream);
+    delete e;
+}
+
 const char *lzfse_b200_encoder_last_error(const lzfse_b200_encoder *e) { return e ? e->last_error.c_str() : ""; }
 uint64_t lzfse_b200_encoder_last_launches(const lzfse_b200_encoder *e) { return e ? e->launches : 0; }
 size_t lzfse_b200_encode_bound(size_t n) { return n + n / 4 + (n / 16384 + 2) * 768 + 64; }
-int lzfse_b200_encode_bytes(lzfse_b200_encoder *, const uint8_t *, size_t, uint8_t *, size_t, size_t *) { return LZFSE_B200_INVALID_ARGUMENT; }
-int lzfse_b200_encode_batch_device(lzfse_b200_encoder *, const uint8_t *, const uint64_t *, const uint64_t *, uint8_t *, const uint64_t *,
-                                   const uint64_t *, uint64_t *, int32_t *, size_t, void *) { return LZFSE_B200_INVALID_ARGUMENT; }
-int lzfse_b200_encode_batch_host(lzfse_b200_encoder *, const uint8_t *, const uint64_t *, const uint64_t *, uint8_t *, const uint64_t *,
-                                 const uint64_t *, uint64_t *, int32_t *, size_t) { return LZFSE_B200_INVALID_ARGUMENT; }
+
+int lzfse_b200_encode_batch_device(lzfse_b200_encoder *e, const uint8_t *src, const uint64_t *src_off, const uint64_t *src_len, uint8_t *dst,
+                                   const uint64_t *dst_off, const uint64_t *dst_cap, uint64_t *out_len, int32_t *status, size_t n, void *stream) {
+    if (!e || (n && (!src_off || !src_len || !dst_off || !dst_cap || !out_len || !status))) return LZFSE_B200_INVALID_ARGUMENT;
+    DeviceGuard g(e->device);
+    if (!g.ok) return LZFSE_B200_CUDA_ERROR;
+    cudaStream_t s = stream ? (cudaStream_t)stream : e->own_stream;
+    return encode_batch_device_impl(e, src, src_off, src_len, dst, dst_off, dst_cap, out_len, status, n, s);
 }
+
+int lzfse_b200_encode_batch_host(lzfse_b200_encoder *e, const uint8_t *src, const uint64_t *src_off, const uint64_t *src_len, uint8_t *dst,
+                                 const uint64_t *dst_off, const uint64_t *dst_cap, uint64_t *out_len, int32_t *status, size_t n) {
+    if (!e || (n && (!src || !src_off || !src_len || !dst_off || !dst_cap || !out_len || !status))) return LZFSE_B200_INVALID_ARGUMENT;
+    if (n == 0) return LZFSE_B200_OK;
+    DeviceGuard g(e->device);
+    if (!g.ok) return LZFSE_B200_CUDA_ERROR;
+    cudaStream_t s = e->own_stream;
+    HostStage &st = e->stage;
+    int rc = stage_sources(e, st, src, src_off, src_len, n, 4 * n, s);
+    if (rc) return rc;
+    rc = stage_outputs(e, st, dst_off, dst_cap, n);
+    if (rc) return rc;
+    LZB_CK(e, st.desc.reserve(4 * n * sizeof(uint64_t)));
+    LZB_CK(e, st.res.reserve(n * (sizeof(uint64_t) + sizeof(int32_t))));
+    LZB_CK(e, cudaMemcpyAsync(st.desc.p, st.pin.p, 4 * n * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    uint64_t *dd = st.desc.as<uint64_t>();
+    uint64_t *d_out_len = st.res.as<uint64_t>();
+    int32_t *d_status = reinterpret_cast<int32_t *>(d_out_len + n);
+    rc = encode_batch_device_impl(e, st.src.as<uint8_t>(), dd, dd + n, st.dst.as<uint8_t>(), dd + 2 * n, dd + 3 * n, d_out_len, d_status, n, s);
+    if (rc) return rc;
+    LZB_CK(e, cudaMemcpyAsync(out_len, d_out_len, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    LZB_CK(e, cudaMemcpyAsync(status, d_status, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    LZB_CK(e, cudaStreamSynchronize(s));
+    rc = fetch_outputs(e, st, dst, dst_off, out_len, status, n, s);
+    if (rc) return rc;
+    LZB_CK(e, cudaStreamSynchronize(s));
+    return LZFSE_B200_OK;
+}
+
+int lzfse_b200_encode_bytes(lzfse_b200_encoder *e, const uint8_t *src, size_t src_len, uint8_t *dst, size_t dst_cap, size_t *dst_len) {
+    if (!e || (!src && src_len) || (!dst && dst_cap)) return LZFSE_B200_INVALID_ARGUMENT;
+    uint64_t so = 0, sl = src_len, doff = 0, dc = dst_cap, ol = 0;
+    int32_t st = 0;
+    static const uint8_t empty = 0;
+    int rc = lzfse_b200_encode_batch_host(e, src ? src : &empty, &so, &sl, dst, &doff, &dc, &ol, &st, 1);
+    if (dst_len) *dst_len = (size_t)ol;
+    return rc ? rc : st;
+}
+
+}  // extern "C"
