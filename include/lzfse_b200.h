@@ -120,6 +120,13 @@ int lzfse_b200_decode_probe_batch_host(lzfse_b200_decoder *d, const uint8_t *src
 /* Kernel launches issued by the last batch call on this handle (bench.py's gpu_launches). */
 uint64_t lzfse_b200_decoder_last_launches(const lzfse_b200_decoder *d);
 
+/* Measurement aid (no reference counterpart): when enabled, the next *_batch_device calls bracket every
+ * pipeline stage with CUDA events on the launching stream.  stage_ms receives up to `cap` durations in
+ * milliseconds in pipeline order; the return value is the number of stages
+ * (decoder: scan, literals, lmds, expand, finish; encoder: prep, parse, fse_blocks, assemble). */
+void lzfse_b200_decoder_set_timing(lzfse_b200_decoder *d, int enabled);
+int lzfse_b200_decoder_last_stage_ms(const lzfse_b200_decoder *d, float *stage_ms, int cap);
+
 /* ---- encoder ---------------------------------------------------------------------------- */
 int lzfse_b200_encoder_create(int cuda_device, lzfse_b200_encoder **out);
 void lzfse_b200_encoder_destroy(lzfse_b200_encoder *e);
@@ -140,6 +147,8 @@ int lzfse_b200_encode_batch_host(lzfse_b200_encoder *e, const uint8_t *src_base,
                                  const uint64_t *src_len, uint8_t *dst_base, const uint64_t *dst_off,
                                  const uint64_t *dst_cap, uint64_t *out_len, int32_t *status, size_t n);
 uint64_t lzfse_b200_encoder_last_launches(const lzfse_b200_encoder *e);
+void lzfse_b200_encoder_set_timing(lzfse_b200_encoder *e, int enabled);
+int lzfse_b200_encoder_last_stage_ms(const lzfse_b200_encoder *e, float *stage_ms, int cap);
 
 #ifdef __cplusplus
 }

@@ -12,6 +12,7 @@ SYMBOLS = [
     "lzfse_b200_decode_batch_host", "lzfse_b200_decode_probe_batch_device", "lzfse_b200_decode_probe_batch_host",
     "lzfse_b200_decoder_last_launches", "lzfse_b200_encoder_create", "lzfse_b200_encoder_destroy", "lzfse_b200_encode_bound",
     "lzfse_b200_encode_bytes", "lzfse_b200_encode_batch_device", "lzfse_b200_encode_batch_host", "lzfse_b200_encoder_last_launches",
+    "lzfse_b200_decoder_set_timing", "lzfse_b200_decoder_last_stage_ms", "lzfse_b200_encoder_set_timing", "lzfse_b200_encoder_last_stage_ms",
 ]
 
 _lib = None
@@ -45,6 +46,9 @@ def load(build_if_missing=True):
         getattr(lib, "lzfse_b200_%s_destroy" % n).restype = None
         getattr(lib, "lzfse_b200_%s_last_launches" % n).argtypes = [vp]
         getattr(lib, "lzfse_b200_%s_last_launches" % n).restype = C.c_uint64
+        getattr(lib, "lzfse_b200_%s_set_timing" % n).argtypes = [vp, C.c_int]
+        getattr(lib, "lzfse_b200_%s_set_timing" % n).restype = None
+        getattr(lib, "lzfse_b200_%s_last_stage_ms" % n).argtypes = [vp, C.POINTER(C.c_float), C.c_int]
     lib.lzfse_b200_encode_bound.argtypes = [C.c_size_t]
     lib.lzfse_b200_encode_bound.restype = C.c_size_t
     for n in ("decode", "encode"):

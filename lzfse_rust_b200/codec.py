@@ -82,6 +82,17 @@ class _Handle:
     def last_launches(self):
         return int(getattr(self._lib, "lzfse_b200_%s_last_launches" % self._kind)(self._h))
 
+    def set_timing(self, enabled=True):
+        """Measurement aid: bracket every pipeline stage of *_batch_device calls with CUDA events."""
+        getattr(self._lib, "lzfse_b200_%s_set_timing" % self._kind)(self._h, int(bool(enabled)))
+
+    STAGES = ()
+
+    def last_stage_ms(self):
+        buf = (C.c_float * 8)()
+        n = getattr(self._lib, "lzfse_b200_%s_last_stage_ms" % self._kind)(self._h, buf, 8)
+        return dict(zip(self.STAGES, [float(buf[i]) for i in range(n)]))
+
     # ---- shared batch plumbing -------------------------------------------------------------
     def _batch_host(self, fn, src, src_off, src_len, dst, dst_off, dst_cap):
         n = len(src_off)
@@ -110,6 +121,7 @@ class LzfseDecoder(_Handle):
     """LZFSE decoder (lzfse_rust::LzfseDecoder).  Reusable; one call at a time per object."""
 
     _kind = "decoder"
+    STAGES = ("scan", "literals", "lmds", "expand", "finish")
 
     def decode_bytes(self, src, dst):
         """Decode the frame `src` and append it to the bytearray `dst`; returns the bytes appended."""
@@ -162,6 +174,7 @@ class LzfseEncoder(_Handle):
     """LZFSE encoder (lzfse_rust::LzfseEncoder).  Reusable; one call at a time per object."""
 
     _kind = "encoder"
+    STAGES = ("prep", "parse", "fse_blocks", "assemble")
 
     def encode_bound(self, n):
         return int(self._lib.lzfse_b200_encode_bound(int(n)))

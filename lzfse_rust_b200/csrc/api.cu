@@ -20,7 +20,7 @@ void launch_scan_fill(const uint8_t *, const uint64_t *, const uint64_t *, const
                       uint32_t *, cudaStream_t);
 int setup_decode_kernels();
 void launch_fse_stages(const uint8_t *, const uint64_t *, const uint64_t *, const uint64_t *, const uint64_t *, const BlockDesc *, FseDesc *, uint32_t, uint8_t *,
-                       LmdRec *, uint32_t *, uint32_t *, int, cudaStream_t);
+                       LmdRec *, uint32_t *, uint32_t *, int, cudaStream_t, cudaEvent_t);
 void launch_expand(const uint8_t *, const uint64_t *, const uint64_t *, uint8_t *, const uint64_t *, const uint64_t *, const StreamCounts *, const BlockDesc *,
                    const FseDesc *, const uint8_t *, const LmdRec *, uint32_t *, size_t, cudaStream_t);
 void launch_finish(const uint32_t *, const uint64_t *, uint64_t *, int32_t *, size_t, cudaStream_t);
@@ -39,6 +39,7 @@ struct lzfse_b200_decoder {
     PinnedBuf totals_host;
     // staging for the *_host entry points
     HostStage stage;
+    StageTimer timer;
 };
 
 namespace {
@@ -57,6 +58,7 @@ int decode_batch_device_impl(lzfse_b200_decoder *d, const uint8_t *src, const ui
     CK(d, d->totals_host.reserve(sizeof(StreamCounts)));
     CK(d, d->work.reserve(2 * sizeof(uint32_t)));
     uint64_t *raw_total = raw_len ? raw_len : d->raw_total.as<uint64_t>();
+    d->timer.begin(s);
 
     launch_scan_count(src, src_off, src_len, probe_only ? nullptr : dst_cap, n, d->counts.as<StreamCounts>(), d->err.as<uint32_t>(), raw_total,
                       n_blocks, d->totals_dev.as<StreamCounts>(), s);
@@ -82,17 +84,26 @@ int decode_batch_device_impl(lzfse_b200_decoder *d, const uint8_t *src, const ui
     launch_scan_fill(src, src_off, src_len, dst_off, dst_cap, n, d->counts.as<StreamCounts>(), d->blocks.as<BlockDesc>(), d->fse.as<FseDesc>(),
                      d->err.as<uint32_t>(), s);
     d->launches += 1;
+    d->timer.mark(s);  // scan (count + host round trip + fill)
     if (tot.n_fse) {
         launch_fse_stages(src, src_off, src_len, dst_off, dst_cap, d->blocks.as<BlockDesc>(), d->fse.as<FseDesc>(), (uint32_t)tot.n_fse,
-                          d->lits.as<uint8_t>(), d->lmds.as<LmdRec>(), d->err.as<uint32_t>(), d->work.as<uint32_t>(), d->n_sms, s);
+                          d->lits.as<uint8_t>(), d->lmds.as<LmdRec>(), d->err.as<uint32_t>(), d->work.as<uint32_t>(), d->n_sms, s,
+                          d->timer.enabled ? d->timer.ev[d->timer.n] : nullptr);
+        if (d->timer.enabled) d->timer.n++;  // literals
         d->launches += 2;
+    } else {
+        d->timer.mark(s);
     }
+    d->timer.mark(s);  // lmds
     launch_expand(src, src_off, src_len, dst, dst_off, dst_cap, d->counts.as<StreamCounts>(), d->blocks.as<BlockDesc>(), d->fse.as<FseDesc>(),
                   d->lits.as<uint8_t>(), d->lmds.as<LmdRec>(), d->err.as<uint32_t>(), n, s);
+    d->timer.mark(s);  // expand
     launch_finish(d->err.as<uint32_t>(), raw_total, out_len, status, n, s);
+    d->timer.mark(s);  // finish
     d->launches += 2;
     CK(d, cudaGetLastError());
     CK(d, cudaStreamSynchronize(s));
+    d->timer.finish();
     return LZFSE_B200_OK;
 }
 
@@ -169,11 +180,18 @@ void lzfse_b200_decoder_destroy(lzfse_b200_decoder *d) {
     for (DevBuf *b : {&d->counts, &d->err, &d->raw_total, &d->totals_dev, &d->blocks, &d->fse, &d->lits, &d->lmds, &d->work}) b->release();
     d->totals_host.release();
     d->stage.release();
+    d->timer.release();
     if (d->own_stream) cudaStreamDestroy(d->own_stream);
     delete d;
 }
 
 const char *lzfse_b200_decoder_last_error(const lzfse_b200_decoder *d) { return d ? d->last_error.c_str() : ""; }
+void lzfse_b200_decoder_set_timing(lzfse_b200_decoder *d, int enabled) { if (d) d->timer.enabled = enabled != 0; }
+int lzfse_b200_decoder_last_stage_ms(const lzfse_b200_decoder *d, float *ms, int cap) {
+    if (!d) return 0;
+    for (int i = 0; i < d->timer.n_done && i < cap; i++) ms[i] = d->timer.ms[i];
+    return d->timer.n_done;
+}
 uint64_t lzfse_b200_decoder_last_launches(const lzfse_b200_decoder *d) { return d ? d->launches : 0; }
 
 int lzfse_b200_decode_batch_device(lzfse_b200_decoder *d, const uint8_t *src, const uint64_t *src_off, const uint64_t *src_len, uint8_t *dst,

@@ -832,12 +832,13 @@ int setup_decode_kernels() {
 }
 void launch_fse_stages(const uint8_t *src, const uint64_t *src_off, const uint64_t *src_len, const uint64_t *dst_off, const uint64_t *dst_cap,
                        const BlockDesc *blocks, FseDesc *fse, uint32_t n_fse, uint8_t *lit_scratch, LmdRec *lmd_scratch, uint32_t *err,
-                       uint32_t *work_counters /* 2 zeroed u32 */, int n_sms, cudaStream_t s) {
+                       uint32_t *work_counters /* 2 zeroed u32 */, int n_sms, cudaStream_t s, cudaEvent_t between) {
     if (n_fse == 0) return;
     unsigned need_lit = (n_fse + 32 * kLitWarps - 1) / (32 * kLitWarps), need_lmd = (n_fse + 32 * kLmdWarps - 1) / (32 * kLmdWarps);
     unsigned g_lit = need_lit < (unsigned)n_sms ? need_lit : (unsigned)n_sms;
     unsigned g_lmd = need_lmd < (unsigned)n_sms ? need_lmd : (unsigned)n_sms;
     k_fse_literals<<<g_lit, kLitWarps * 32, kLitWarps * kLitSmemPerWarp, s>>>(src, blocks, fse, n_fse, lit_scratch, err, work_counters);
+    if (between) cudaEventRecord(between, s);
     k_fse_lmds<<<g_lmd, kLmdWarps * 32, kLmdWarps * kLmdSmemPerWarp, s>>>(src, dst_off, dst_cap, blocks, fse, n_fse, lmd_scratch, err, work_counters + 1);
 }
 void launch_expand(const uint8_t *src, const uint64_t *src_off, const uint64_t *src_len, uint8_t *dst, const uint64_t *dst_off,

@@ -681,6 +681,7 @@ struct lzfse_b200_encoder {
     DevBuf streams, counts, totals_dev, tables, packs, lits, block_ids, blocks, out, counters;
     PinnedBuf totals_host;
     HostStage stage;
+    StageTimer timer;
 };
 
 namespace {
@@ -698,6 +699,7 @@ int encode_batch_device_impl(lzfse_b200_encoder *e, const uint8_t *src, const ui
     LZB_CK(e, e->totals_host.reserve(sizeof(StreamCounts)));
     LZB_CK(e, e->counters.reserve(4 * sizeof(uint32_t)));
     const int tb = 128;
+    e->timer.begin(s);
     k_enc_prep<<<(unsigned)((n + tb - 1) / tb), tb, 0, s>>>(src_len, n, e->streams.as<EncStream>(), e->counts.as<StreamCounts>(), status);
     k_exclusive_scan<<<1, 1024, 0, s>>>(e->counts.as<StreamCounts>(), n, e->totals_dev.as<StreamCounts>());
     e->launches += 2;
@@ -715,11 +717,13 @@ int encode_batch_device_impl(lzfse_b200_encoder *e, const uint8_t *src, const ui
     LZB_CK(e, e->out.reserve(tot.n_lmds + 64));
     LZB_CK(e, cudaMemsetAsync(e->counters.p, 0, 4 * sizeof(uint32_t), s));
     uint32_t *ctr = e->counters.as<uint32_t>();  // [0] blocks produced, [1] parse stream cursor, [2] fse-encode cursor
+    e->timer.mark(s);  // prep
 
     k_enc_parse<<<parse_ctas, kParseWarps * 32, 0, s>>>(src, src_off, src_len, n, e->streams.as<EncStream>(), e->counts.as<StreamCounts>(),
                                                        e->tables.as<uint32_t>(), e->packs.as<uint2>(), e->lits.as<uint8_t>(),
                                                        e->block_ids.as<uint32_t>(), e->blocks.as<EncBlock>(), ctr, e->out.as<uint8_t>(), ctr + 1);
     e->launches += 1;
+    e->timer.mark(s);  // parse
     if (tot.n_literals) {
         unsigned g = (unsigned)((tot.n_literals + 32 * kFseEncWarps - 1) / (32 * kFseEncWarps));
         if (g > (unsigned)e->n_sms) g = (unsigned)e->n_sms;
@@ -727,12 +731,15 @@ int encode_batch_device_impl(lzfse_b200_encoder *e, const uint8_t *src, const ui
                                                                                         e->lits.as<uint8_t>(), e->out.as<uint8_t>(), ctr + 2);
         e->launches += 1;
     }
+    e->timer.mark(s);  // fse_blocks
     k_enc_assemble<<<(unsigned)((n + kAsmWarps - 1) / kAsmWarps), kAsmWarps * 32, 0, s>>>(
         src, src_off, src_len, dst, dst_off, dst_cap, n, e->streams.as<EncStream>(), e->counts.as<StreamCounts>(), e->block_ids.as<uint32_t>(),
         e->blocks.as<EncBlock>(), e->out.as<uint8_t>(), out_len, status);
     e->launches += 1;
+    e->timer.mark(s);  // assemble
     LZB_CK(e, cudaGetLastError());
     LZB_CK(e, cudaStreamSynchronize(s));
+    e->timer.finish();
     return LZFSE_B200_OK;
 }
 
@@ -770,12 +777,19 @@ void lzfse_b200_encoder_destroy(lzfse_b200_encoder *e) {
     for (DevBuf *b : {&e->streams, &e->counts, &e->totals_dev, &e->tables, &e->packs, &e->lits, &e->block_ids, &e->blocks, &e->out, &e->counters}) b->release();
     e->totals_host.release();
     e->stage.release();
+    e->timer.release();
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     delete e;
 }
 
 const char *lzfse_b200_encoder_last_error(const lzfse_b200_encoder *e) { return e ? e->last_error.c_str() : ""; }
 uint64_t lzfse_b200_encoder_last_launches(const lzfse_b200_encoder *e) { return e ? e->launches : 0; }
+void lzfse_b200_encoder_set_timing(lzfse_b200_encoder *e, int enabled) { if (e) e->timer.enabled = enabled != 0; }
+int lzfse_b200_encoder_last_stage_ms(const lzfse_b200_encoder *e, float *ms, int cap) {
+    if (!e) return 0;
+    for (int i = 0; i < e->timer.n_done && i < cap; i++) ms[i] = e->timer.ms[i];
+    return e->timer.n_done;
+}
 size_t lzfse_b200_encode_bound(size_t n) { return n + n / 4 + (n / 16384 + 2) * 768 + 64; }
 
 int lzfse_b200_encode_batch_device(lzfse_b200_encoder *e, const uint8_t *src, const uint64_t *src_off, const uint64_t *src_len, uint8_t *dst,

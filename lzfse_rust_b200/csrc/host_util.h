@@ -61,6 +61,30 @@ struct DeviceGuard {
         }                                                                                      \
     } while (0)
 
+// Optional per-stage CUDA-event timing on the launching stream (measurement aid for bench.py).
+struct StageTimer {
+    static constexpr int kMax = 8;
+    bool enabled = false;
+    cudaEvent_t ev[kMax + 1] = {};
+    int n = 0;          // events recorded in the current call
+    int n_done = 0;     // stages of the last finished call
+    float ms[kMax] = {};
+    void begin(cudaStream_t s) {
+        n = 0;
+        if (!enabled) return;
+        for (int i = 0; i <= kMax; i++)
+            if (!ev[i]) cudaEventCreate(&ev[i]);
+        cudaEventRecord(ev[0], s); n = 1;
+    }
+    void mark(cudaStream_t s) { if (enabled && n <= kMax) { cudaEventRecord(ev[n], s); n++; } }
+    void finish() {  // call after the stream was synchronised
+        if (!enabled) return;
+        n_done = n > 0 ? n - 1 : 0;
+        for (int i = 0; i < n_done; i++) cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]);
+    }
+    void release() { for (int i = 0; i <= kMax; i++) if (ev[i]) { cudaEventDestroy(ev[i]); ev[i] = nullptr; } }
+};
+
 // Host-buffer staging shared by both directions.  The device copy mirrors the host layout when the
 // streams cover their byte range densely (one H2D copy); sparse layouts are packed stream by stream.
 struct HostStage {

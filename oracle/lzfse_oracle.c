@@ -297,12 +297,24 @@ static inline int out_bytes(dctx *d, const uint8_t *p, size_t n) {
     memcpy(d->dst + d->out, p, n); d->out += n;
     return ORC_OK;
 }
+/* Same, for sources with >= 16 bytes of slack (the FSE literal buffer): over-copy like lz/writer.rs:115-128. */
+static inline int out_bytes_slack(dctx *d, const uint8_t *p, size_t n) {
+    if (n > d->dst_cap - d->out) return ORC_BUFFER_OVERFLOW;
+    uint8_t *q = d->dst + d->out;
+    if (n <= 16 && d->dst_cap - d->out >= 16) memcpy(q, p, 16); else memcpy(q, p, n);
+    d->out += n;
+    return ORC_OK;
+}
 /* lz/writer.rs:144-180: byte i of the match equals byte i-distance. */
 static inline int out_match(dctx *d, uint32_t len, uint32_t distance) {
     if ((size_t)distance > d->out || distance == 0) return ORC_BAD_D_VALUE;
     if (len > d->dst_cap - d->out) return ORC_BUFFER_OVERFLOW;
     uint8_t *q = d->dst + d->out; const uint8_t *s = q - distance;
-    for (uint32_t i = 0; i < len; i++) q[i] = s[i];
+    uint32_t i = 0;
+    if (distance >= 8) { /* 8-byte strides never read a byte this copy has not written yet (lz/object.rs:27-58) */
+        for (; i + 8 <= len; i += 8) memcpy(q + i, s + i, 8);
+    }
+    for (; i < len; i++) q[i] = s[i];
     d->out += len;
     return ORC_OK;
 }
@@ -347,7 +359,7 @@ static int fse_decode_internal(fse_core *c, dctx *d, const uint8_t *p, size_t le
         const uint8_t *lit = c->literals + literal_index;
         literal_index += literal_len;
         if (literal_index > LITERALS_PER_BLOCK) return ORC_FSE_BAD_LMD_PAYLOAD;
-        if ((e = out_bytes(d, lit, literal_len))) return e;
+        if ((e = out_bytes_slack(d, lit, literal_len))) return e;
         if (match_len != 0) {
             n_match_bytes += match_len;
             if ((e = out_match(d, match_len, match_distance))) return e;
@@ -885,6 +897,11 @@ static inline uint32_t match_inc(const uint8_t *b, size_t index, size_t match_in
 /* match_kit/match_fast.rs:61-89 */
 static inline uint32_t match_dec(const uint8_t *b, size_t index, size_t match_index, size_t max) {
     size_t len = 0;
+    while (len + 8 <= max) {
+        uint64_t x = le64(b + index - len - 8) ^ le64(b + match_index - len - 8);
+        if (x) return (uint32_t)(len + (size_t)(__builtin_clzll(x) / 8));
+        len += 8;
+    }
     while (len != max) { if (b[index - len - 1] != b[match_index - len - 1]) break; len++; }
     return (uint32_t)len;
 }
