@@ -256,8 +256,46 @@ __device__ void vn_push_match(VnSink &v, const uint8_t *src, uint32_t from, uint
 }
 
 constexpr int kParseWarps = 4;
+constexpr uint32_t kFwdCap = 64;  // per-lane forward extension stops here; longer matches are finished warp-wide
+constexpr uint32_t kBwdCap = 8;   // per-lane backward extension precomputed up to here
 
-__global__ void __launch_bounds__(kParseWarps * 32)
+__device__ __forceinline__ uint32_t ld4u(const uint8_t *p) {  // unaligned 4-byte load: two aligned words + funnel shift
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint32_t r = (uint32_t)a & 3u;
+    const uint32_t *q = reinterpret_cast<const uint32_t *>(a - r);
+    const uint32_t lo = q[0], hi = r ? q[1] : 0u;
+    return __funnelshift_r(lo, hi, r * 8);
+}
+
+// Ordered insert of positions [from, to) into the history table, 32 per step (HistoryTable::push x n,
+// encode/history.rs:24-31,119-131): the newest position of each bucket writes that bucket once.
+__device__ __forceinline__ void history_insert_range(uint32_t *table, const uint8_t *src, uint32_t from, uint32_t to, bool vn, uint32_t lane) {
+    while (from < to) {
+        const uint32_t p = from + lane;
+        const bool act = p < to;
+        const uint32_t h = act ? hash_u(ld4u(src + p), vn) : (0xFFFF0000u + lane);
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, h);
+        if (act && (peers & ~((2u << lane) - 1u)) == 0) {  // newest position of its bucket
+            uint32_t *bk = table + h * kHashWidth;
+            const uint4 old = __ldcg(reinterpret_cast<const uint4 *>(bk));
+            // new entries, newest first: this lane, then its lower peers
+            uint32_t m = peers & ~(1u << lane), n1 = 0, n2 = 0, n3 = 0, cnt = 1;
+            if (m) { const int b = 31 - __clz(m); n1 = from + b; m &= ~(1u << b); cnt = 2; }
+            if (m) { const int b = 31 - __clz(m); n2 = from + b; m &= ~(1u << b); cnt = 3; }
+            if (m) { const int b = 31 - __clz(m); n3 = from + b; cnt = 4; }
+            uint4 nw;
+            nw.x = p;
+            nw.y = cnt > 1 ? n1 : old.x;
+            nw.z = cnt > 2 ? n2 : (cnt == 2 ? old.x : old.y);
+            nw.w = cnt > 3 ? n3 : (cnt == 3 ? old.x : (cnt == 2 ? old.y : old.z));
+            __stcg(reinterpret_cast<uint4 *>(bk), nw);
+        }
+        __syncwarp();
+        from += 32;
+    }
+}
+
+__global__ void __launch_bounds__(kParseWarps * 32, 4)
 k_enc_parse(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ src_off, const uint64_t *__restrict__ src_len, size_t n_streams,
             EncStream *streams, const StreamCounts *__restrict__ bases, uint32_t *tables /* one per warp slot */, uint2 *pack_scratch,
             uint8_t *lit_scratch, uint32_t *block_ids, EncBlock *blocks, uint32_t *block_counter, uint8_t *out_scratch, uint32_t *stream_counter) {
@@ -297,85 +335,130 @@ k_enc_parse(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ s
             else sink_push_match(fs, src, lit_from, lit_len, match_len, d, lane);
         };
 
-        // FrontendBytes::match_any (encode/frontend_bytes.rs:160-211)
+        // FrontendBytes::match_any (encode/frontend_bytes.rs:160-211), 32 positions per step.
+        //
+        // Every position below the one being examined has been pushed into the history exactly once and in
+        // order (:185-207 visits, :336-344 sync_history), so what position p finds in its bucket does not
+        // depend on which matches were emitted.  Each lane therefore runs find_match (:214-244) for its own
+        // position -- candidates = same-bucket positions of lower lanes (newest first), then the table's
+        // bucket as of the step's start -- and the warp replays the sequential part (backward extension,
+        // Match::select, push) over those results.
         const uint32_t end = len - 3;
         uint32_t index = 0, literal_index = 0;
         Match pending = {0, 0, 0};
-        for (;;) {
-            const uint32_t val = ld_u32(src + index);
-            uint32_t *bucket = table + hash_u(val, vn) * kHashWidth;
-            const uint4 q = __ldcg(reinterpret_cast<const uint4 *>(bucket));  // History copy before the push
-            __syncwarp();
-            if (lane == 0) __stcg(reinterpret_cast<uint4 *>(bucket), make_uint4(index, q.x, q.y, q.z));  // HistoryTable::push
-            __syncwarp();  // orders the store before the next position's bucket read (shuffles/ballots do not)
-            // find_match (:214-244): newest first, stop at the first candidate out of range
-            const uint32_t qi = lane == 0 ? q.x : (lane == 1 ? q.y : (lane == 2 ? q.z : q.w));
-            uint32_t unit = 0;  // match_us: 4, 3 (LZVN only) or 0
-            bool in_range = false;
-            if (lane < 4) {
-                in_range = (index - qi) <= max_d;
-                if (in_range) {
-                    const uint32_t x = val ^ ld_u32(src + qi);
-                    unit = x == 0 ? 4u : ((vn && (x & 0x00FFFFFFu) == 0) ? 3u : 0u);
+        bool done = false;
+        while (!done) {
+            const uint32_t b0 = index;
+            const uint32_t nb = end - b0 < 32 ? end - b0 : 32;
+            const uint32_t p = b0 + lane;
+            const bool act = lane < nb;
+            // ---- phase 1: per-lane find_match ----
+            uint32_t val = 0, h = 0xFFFF0000u + lane;
+            uint4 tq = make_uint4(kEmptyIdx, kEmptyIdx, kEmptyIdx, kEmptyIdx);
+            if (act) {
+                val = ld4u(src + p);
+                h = hash_u(val, vn);
+                tq = __ldcg(reinterpret_cast<const uint4 *>(table + h * kHashWidth));
+            }
+            uint32_t earlier = __match_any_sync(0xFFFFFFFFu, h) & lanemask_lt();
+            uint32_t c[4];
+            {   // first the same-bucket positions of lower lanes (newest first), then the table's bucket
+                uint32_t n0 = 0, n1 = 0, n2 = 0, n3 = 0, e = 0;
+                if (earlier) { const int b = 31 - __clz(earlier); n0 = b0 + b; earlier &= ~(1u << b); e = 1; }
+                if (earlier) { const int b = 31 - __clz(earlier); n1 = b0 + b; earlier &= ~(1u << b); e = 2; }
+                if (earlier) { const int b = 31 - __clz(earlier); n2 = b0 + b; earlier &= ~(1u << b); e = 3; }
+                if (earlier) { const int b = 31 - __clz(earlier); n3 = b0 + b; e = 4; }
+                c[0] = e > 0 ? n0 : tq.x;
+                c[1] = e > 1 ? n1 : (e == 1 ? tq.x : tq.y);
+                c[2] = e > 2 ? n2 : (e == 2 ? tq.x : (e == 1 ? tq.y : tq.z));
+                c[3] = e > 3 ? n3 : (e == 3 ? tq.x : (e == 2 ? tq.y : (e == 1 ? tq.z : tq.w)));
+            }
+            uint32_t r_len = 0, r_idx = 0, r_bw = 0;
+            bool r_exact = false;  // best candidate hit the per-lane cap: lengths must be redone warp-wide
+            if (act) {
+                const uint32_t max = len - p;
+                bool stop = false;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    if (stop) continue;
+                    if (p - c[k] > max_d) { stop = true; continue; }  // also ends at the reset marker
+                    const uint32_t x = val ^ ld4u(src + c[k]);
+                    uint32_t l = 0;
+                    if (x == 0) {
+                        l = 4;
+                        while (l + 4 <= max && l < kFwdCap) {
+                            const uint32_t y = ld4u(src + p + l) ^ ld4u(src + c[k] + l);
+                            if (y) { l += (__ffs(y) - 1) >> 3; goto ext_done; }
+                            l += 4;
+                        }
+                        if (l < kFwdCap) while (l < max && src[p + l] == src[c[k] + l]) l++;
+                    ext_done:;
+                    } else if (vn && (x & 0x00FFFFFFu) == 0) l = 3;
+                    if (l >= kFwdCap && l < max) r_exact = true;
+                    if (l > r_len) { r_len = l; r_idx = c[k]; }
+                }
+                if (r_len && !r_exact) {
+                    const uint32_t lim = p < kBwdCap ? p : kBwdCap, lim2 = r_idx < lim ? r_idx : lim;
+                    while (r_bw < lim2 && src[p - r_bw - 1] == src[r_idx - r_bw - 1]) r_bw++;
                 }
             }
-            const uint32_t oor = __ballot_sync(0xFFFFFFFFu, lane < 4 && !in_range);
-            const uint32_t live = oor ? ((1u << (__ffs(oor) - 1)) - 1u) : 0xFu;  // candidates before the first out-of-range one
-            Match inc = {0, 0, 0};
-            for (uint32_t c = 0; c < 4; c++) {
-                if (!((live >> c) & 1)) break;
-                const uint32_t u = __shfl_sync(0xFFFFFFFFu, unit, c);
-                if (u == 0) continue;
-                const uint32_t cand = __shfl_sync(0xFFFFFFFFu, qi, c);
-                const uint32_t l = u == 4 ? warp_match_inc(src, index, cand, 4, len - index, lane) : 3u;
-                if (l > inc.match_len) { inc.match_len = l; inc.match_idx = cand; }
-            }
-            if (inc.match_len != 0) {
-                inc.idx = index;
-                const uint32_t lit = index - literal_index;
-                const uint32_t dec = warp_match_dec(src, inc.idx, inc.match_idx, lit < inc.match_idx ? lit : inc.match_idx, lane);
-                inc.idx -= dec; inc.match_idx -= dec; inc.match_len += dec;
-            }
-            // Match::select (encode/match_object.rs:12-33)
-            bool have = false;
-            Match sel = {0, 0, 0};
-            if (inc.match_len == 0) {
-            } else if (inc.match_len >= kGoodMatchLen) { sel = inc; have = true; pending.match_len = 0; }
-            else if (pending.match_len == 0) { pending = inc; }
-            else if ((int32_t)(pending.idx + pending.match_len - inc.idx) <= 0) { sel = pending; have = true; pending = inc; }
-            else if (inc.match_len > pending.match_len) { sel = inc; have = true; pending.match_len = 0; }
-            else { sel = pending; have = true; pending.match_len = 0; }
-            if (have) {
-                push_match(literal_index, sel.idx - literal_index, sel.match_len, sel.idx - sel.match_idx);  // :287-302
-                literal_index = sel.idx + sel.match_len;
-                if (literal_index >= end) break;
-                index++;
-                // sync_history (:336-344): insert the skipped positions, 32 per step, buckets updated in position order
-                __syncwarp();
-                while (index < literal_index) {
-                    const uint32_t p = index + lane;
-                    const bool act = p < literal_index;
-                    const uint32_t h = act ? hash_u(ld_u32(src + p), vn) : 0xFFFFFFFFu;
-                    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, h);
-                    const bool leader = act && (peers & ~((2u << lane) - 1u)) == 0;  // newest position of its bucket
-                    if (leader) {
-                        uint32_t *bk = table + h * kHashWidth;
-                        const uint4 old = __ldcg(reinterpret_cast<const uint4 *>(bk));
-                        uint32_t slot[4], ns = 0, m = peers;
-                        while (m && ns < 4) { const int b = 31 - __clz(m); slot[ns++] = index + b; m &= ~(1u << b); }
-                        const uint32_t o[4] = {old.x, old.y, old.z, old.w};
-                        for (uint32_t k = 0; ns < 4; k++) slot[ns++] = o[k];
-                        __stcg(reinterpret_cast<uint4 *>(bk), make_uint4(slot[0], slot[1], slot[2], slot[3]));
+            // ---- phase 2: the sequential front end over the step's positions ----
+            uint32_t cur = index;
+            while (cur < b0 + nb) {
+                const int l = (int)(cur - b0);
+                Match inc;
+                inc.match_len = __shfl_sync(0xFFFFFFFFu, r_len, l);
+                inc.match_idx = __shfl_sync(0xFFFFFFFFu, r_idx, l);
+                inc.idx = cur;
+                const bool exact = __shfl_sync(0xFFFFFFFFu, (int)r_exact, l) != 0;
+                if (exact) {  // redo find_match for this position with the whole warp (uncapped lengths)
+                    inc.match_len = 0; inc.match_idx = 0;
+                    const uint32_t v = __shfl_sync(0xFFFFFFFFu, val, l);
+                    for (int k = 0; k < 4; k++) {
+                        const uint32_t cand = __shfl_sync(0xFFFFFFFFu, c[k], l);
+                        if (cur - cand > max_d) break;
+                        const uint32_t x = v ^ ld4u(src + cand);
+                        uint32_t ml = 0;
+                        if (x == 0) ml = warp_match_inc(src, cur, cand, 4, len - cur, lane);
+                        else if (vn && (x & 0x00FFFFFFu) == 0) ml = 3;
+                        if (ml > inc.match_len) { inc.match_len = ml; inc.match_idx = cand; }
                     }
-                    __syncwarp();
-                    const uint32_t step = literal_index - index < 32 ? literal_index - index : 32;
-                    index += step;
                 }
-                if (index >= end) break;
-            } else {
-                index++;
-                if (index == end) break;
+                if (inc.match_len != 0) {  // match_dec (:261-268)
+                    const uint32_t lit = cur - literal_index;
+                    const uint32_t lim = lit < inc.match_idx ? lit : inc.match_idx;
+                    uint32_t dec;
+                    const uint32_t bw = __shfl_sync(0xFFFFFFFFu, r_bw, l);
+                    if (!exact && (bw < kBwdCap || lim <= kBwdCap)) dec = bw < lim ? bw : lim;
+                    else dec = warp_match_dec(src, inc.idx, inc.match_idx, lim, lane);
+                    inc.idx -= dec; inc.match_idx -= dec; inc.match_len += dec;
+                }
+                // Match::select (encode/match_object.rs:12-33)
+                bool have = false;
+                Match sel = {0, 0, 0};
+                if (inc.match_len == 0) {
+                } else if (inc.match_len >= kGoodMatchLen) { sel = inc; have = true; pending.match_len = 0; }
+                else if (pending.match_len == 0) { pending = inc; }
+                else if ((int32_t)(pending.idx + pending.match_len - inc.idx) <= 0) { sel = pending; have = true; pending = inc; }
+                else if (inc.match_len > pending.match_len) { sel = inc; have = true; pending.match_len = 0; }
+                else { sel = pending; have = true; pending.match_len = 0; }
+                if (have) {
+                    push_match(literal_index, sel.idx - literal_index, sel.match_len, sel.idx - sel.match_idx);  // :287-302
+                    literal_index = sel.idx + sel.match_len;
+                    if (literal_index >= end) { done = true; break; }
+                    cur = cur + 1 > literal_index ? cur + 1 : literal_index;  // index += 1; sync_history
+                    if (cur >= end) { done = true; break; }
+                } else {
+                    cur++;
+                    if (cur == end) { done = true; break; }
+                }
             }
+            // ---- phase 3: push every position this step passed into the history ----
+            if (!done) {
+                __syncwarp();
+                history_insert_range(table, src, b0, cur, vn, lane);
+            }
+            index = cur;
         }
         // flush_pending, flush_literals, backend.finalize (:121-131,271-317)
         if (pending.match_len != 0) {
