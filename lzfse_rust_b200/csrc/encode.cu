@@ -295,7 +295,7 @@ __device__ __forceinline__ void history_insert_range(uint32_t *table, const uint
     }
 }
 
-__global__ void __launch_bounds__(kParseWarps * 32, 4)
+__global__ void __launch_bounds__(kParseWarps * 32, 6)
 k_enc_parse(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ src_off, const uint64_t *__restrict__ src_len, size_t n_streams,
             EncStream *streams, const StreamCounts *__restrict__ bases, uint32_t *tables /* one per warp slot */, uint2 *pack_scratch,
             uint8_t *lit_scratch, uint32_t *block_ids, EncBlock *blocks, uint32_t *block_counter, uint8_t *out_scratch, uint32_t *stream_counter) {
@@ -403,14 +403,27 @@ k_enc_parse(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ s
                 }
             }
             // ---- phase 2: the sequential front end over the step's positions ----
+            // Positions whose find_match came back empty only advance the index (:203-209), so the replay
+            // jumps from one position with a candidate to the next.
+            const uint32_t has = __ballot_sync(0xFFFFFFFFu, act && r_len != 0);
+            const uint32_t packed = r_len | (r_bw << 8) | ((uint32_t)r_exact << 16);  // r_len < kFwdCap + 4
             uint32_t cur = index;
-            while (cur < b0 + nb) {
-                const int l = (int)(cur - b0);
+            for (;;) {
+                const uint32_t rel0 = cur - b0;
+                const uint32_t m = rel0 < 32 ? (has & (0xFFFFFFFFu << rel0)) : 0u;
+                if (m == 0) {  // nothing left in this step
+                    if (cur < b0 + nb) cur = b0 + nb;
+                    if (cur == end) done = true;
+                    break;
+                }
+                const int l = __ffs(m) - 1;
+                cur = b0 + l;
+                const uint32_t pk = __shfl_sync(0xFFFFFFFFu, packed, l);
                 Match inc;
-                inc.match_len = __shfl_sync(0xFFFFFFFFu, r_len, l);
+                inc.match_len = pk & 0xFF;
                 inc.match_idx = __shfl_sync(0xFFFFFFFFu, r_idx, l);
                 inc.idx = cur;
-                const bool exact = __shfl_sync(0xFFFFFFFFu, (int)r_exact, l) != 0;
+                const bool exact = (pk >> 16) & 1;
                 if (exact) {  // redo find_match for this position with the whole warp (uncapped lengths)
                     inc.match_len = 0; inc.match_idx = 0;
                     const uint32_t v = __shfl_sync(0xFFFFFFFFu, val, l);
@@ -424,24 +437,23 @@ k_enc_parse(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ s
                         if (ml > inc.match_len) { inc.match_len = ml; inc.match_idx = cand; }
                     }
                 }
-                if (inc.match_len != 0) {  // match_dec (:261-268)
+                {   // match_dec (:261-268)
                     const uint32_t lit = cur - literal_index;
                     const uint32_t lim = lit < inc.match_idx ? lit : inc.match_idx;
+                    const uint32_t bw = (pk >> 8) & 0xFF;
                     uint32_t dec;
-                    const uint32_t bw = __shfl_sync(0xFFFFFFFFu, r_bw, l);
                     if (!exact && (bw < kBwdCap || lim <= kBwdCap)) dec = bw < lim ? bw : lim;
                     else dec = warp_match_dec(src, inc.idx, inc.match_idx, lim, lane);
                     inc.idx -= dec; inc.match_idx -= dec; inc.match_len += dec;
                 }
-                // Match::select (encode/match_object.rs:12-33)
-                bool have = false;
-                Match sel = {0, 0, 0};
-                if (inc.match_len == 0) {
-                } else if (inc.match_len >= kGoodMatchLen) { sel = inc; have = true; pending.match_len = 0; }
-                else if (pending.match_len == 0) { pending = inc; }
-                else if ((int32_t)(pending.idx + pending.match_len - inc.idx) <= 0) { sel = pending; have = true; pending = inc; }
-                else if (inc.match_len > pending.match_len) { sel = inc; have = true; pending.match_len = 0; }
-                else { sel = pending; have = true; pending.match_len = 0; }
+                // Match::select (encode/match_object.rs:12-33), incoming.match_len != 0
+                bool have = true;
+                Match sel = pending;
+                if (inc.match_len >= kGoodMatchLen) { sel = inc; pending.match_len = 0; }
+                else if (pending.match_len == 0) { pending = inc; have = false; }
+                else if ((int32_t)(pending.idx + pending.match_len - inc.idx) <= 0) { pending = inc; }
+                else if (inc.match_len > pending.match_len) { sel = inc; pending.match_len = 0; }
+                else { pending.match_len = 0; }
                 if (have) {
                     push_match(literal_index, sel.idx - literal_index, sel.match_len, sel.idx - sel.match_idx);  // :287-302
                     literal_index = sel.idx + sel.match_len;
@@ -486,11 +498,23 @@ k_enc_parse(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ s
 }
 
 // ------------------------------------------------------------------------------------------------
-// FSE block encode: lane per block.  Shared memory per lane: weights/histogram u16[360] and
-// encode-table entries u32[360], both laid out [symbol][lane].
+// FSE block encode: warp per block.
+//
+// The seven FSE state machines of a block (4 literal states, L, M, D) are independent chains: each
+// only sees its own symbol sequence (fse/encoder.rs:190-200).  What couples them is the position of
+// their bits in the stream, and that is a prefix sum.  So per chunk (128 literals / 32 packs) a few
+// lanes run the chains and record (bits, count) per symbol, then all 32 lanes concatenate in the
+// reference's emission order (fse/literals.rs:109-121, fse/lmds.rs:74-87) with a warp scan and OR the
+// bits into a shared-memory bit buffer that is flushed to the block as whole bytes.
 // ------------------------------------------------------------------------------------------------
-constexpr int kFseEncWarps = 3;
-constexpr size_t kFseEncSmemPerWarp = 360 * 32 * (2 + 4);
+constexpr int kFseEncWarps = 8;
+struct FseEncSmem {
+    uint32_t W[360];       // histogram, then normalised weights
+    uint32_t E[360];       // encode table: t_k (low 16) | t_w (high 16)
+    uint32_t bitbuf[72];   // chunk bit buffer (<= 31 carried + 32 * 54 bits)
+    uint16_t chain[128];   // (count | bits << 4) per symbol, in emission order
+    uint8_t sym[128];      // chunk symbols for the chain lanes
+};
 
 __device__ __forceinline__ uint32_t l_sym(uint32_t v) { return v < 16 ? v : (v < 20 ? 16u : (v < 28 ? 17u : (v < 60 ? 18u : 19u))); }   // L_BASE_FROM_VALUE
 __device__ __forceinline__ uint32_t m_sym(uint32_t v) { return v < 16 ? v : (v < 24 ? 16u : (v < 56 ? 17u : (v < 312 ? 18u : 19u))); }  // M_BASE_FROM_VALUE
@@ -505,8 +529,8 @@ __device__ __forceinline__ uint32_t m_extra_e(uint32_t s) { return s < 16 ? 0u :
 __device__ __forceinline__ uint32_t l_base_e(uint32_t s) { return s < 16 ? s : ((0x3C1C1410u >> ((s - 16) * 8)) & 0xFFu); }
 __device__ __forceinline__ uint32_t m_base_e(uint32_t s) { return s < 16 ? s : (uint32_t)((0x0138003800180010ull >> ((s - 16) * 16)) & 0xFFFFu); }
 
-// normalize_m1 (fse/weights.rs:218-278) on the lane's column of the histogram.
-__device__ void normalize_m1(uint16_t *w /* [sym*32] stride */, uint32_t n_sym, uint32_t in_total, uint32_t out_total) {
+// normalize_m1 (fse/weights.rs:218-278), one thread.
+__device__ void normalize_m1(uint32_t *w, uint32_t n_sym, uint32_t in_total, uint32_t out_total) {
     int32_t remaining = 0;
     uint32_t max_index = 0;
     if (in_total != 0) {
@@ -514,37 +538,37 @@ __device__ void normalize_m1(uint16_t *w /* [sym*32] stride */, uint32_t n_sym, 
         uint32_t max_weight = 0;
         remaining = (int32_t)out_total;
         for (uint32_t i = 0; i < n_sym; i++) {
-            const uint32_t v = w[i * 32];
+            const uint32_t v = w[i];
             if (v == 0) continue;
             uint32_t f = (v * multiply + round) >> shift;
             if (f == 0) f = 1;
-            w[i * 32] = (uint16_t)f;
+            w[i] = f;
             remaining -= (int32_t)f;
             if (f > max_weight) { max_weight = f; max_index = i; }
         }
     }
-    if (-remaining < (int32_t)w[max_index * 32] / 4) {
-        w[max_index * 32] = (uint16_t)((int32_t)w[max_index * 32] + remaining);
+    if (-remaining < (int32_t)w[max_index] / 4) {
+        w[max_index] = (uint32_t)((int32_t)w[max_index] + remaining);
     } else {
         uint32_t overflow = (uint32_t)(-remaining);
         for (int shift = 3; shift >= 0; shift--)
             for (uint32_t i = 0; i < n_sym; i++) {
                 if (overflow == 0) break;
-                const uint32_t v = w[i * 32];
+                const uint32_t v = w[i];
                 if (v == 0) continue;
                 uint32_t k = (v - 1) >> shift;
                 if (k > overflow) k = overflow;
-                w[i * 32] = (uint16_t)(v - k);
+                w[i] = v - k;
                 overflow -= k;
             }
     }
 }
-// build_e_table (fse/encoder.rs:219-240): entry = t_k (low 16) | t_w (high 16), both i16
-__device__ void build_e_table(const uint16_t *w, uint32_t *e, uint32_t n_sym, uint32_t n_states) {
+// build_e_table (fse/encoder.rs:219-240), one thread
+__device__ void build_e_table(const uint32_t *w, uint32_t *e, uint32_t n_sym, uint32_t n_states) {
     const uint32_t n_clz = __clz(n_states);
     uint32_t total = 0;
     for (uint32_t i = 0; i < n_sym; i++) {
-        const uint32_t v = w[i * 32];
+        const uint32_t v = w[i];
         int32_t t_k, t_w;
         if (v == 0) { t_k = -(int32_t)n_states; t_w = 0; }
         else {
@@ -552,136 +576,185 @@ __device__ void build_e_table(const uint16_t *w, uint32_t *e, uint32_t n_sym, ui
             t_k = (int32_t)(1024 * k) - (int32_t)(v << k);
             t_w = (int32_t)n_states + (int32_t)total - (int32_t)v;
         }
-        e[i * 32] = ((uint32_t)t_k & 0xFFFFu) | ((uint32_t)t_w << 16);
+        e[i] = ((uint32_t)t_k & 0xFFFFu) | ((uint32_t)t_w << 16);
         total += v;
     }
 }
-// Forward LSB-first bit writer with a 64-bit accumulator (bits/bit_writer.rs:16-57); bytes go out one by one.
-struct BitWriter {
-    uint8_t *p;
-    uint64_t accum;
-    uint32_t bits;
-    __device__ __forceinline__ void push(uint32_t v, uint32_t n) { accum |= (uint64_t)v << bits; bits += n; }
-    __device__ __forceinline__ void flush() {
-        while (bits >= 8) { *p++ = (uint8_t)accum; accum >>= 8; bits -= 8; }
-    }
-    __device__ __forceinline__ uint32_t finalize() {  // returns the unused bits of the last byte
-        flush();
-        if (bits == 0) return 0;
-        *p++ = (uint8_t)accum;
-        return 8 - bits;
-    }
-};
-// EEntry::encode (fse/encoder.rs:190-200)
-__device__ __forceinline__ void e_encode(uint32_t entry, BitWriter &bw, uint32_t &state) {
+// EEntry::encode (fse/encoder.rs:190-200): returns count | bits << 4
+__device__ __forceinline__ uint32_t e_step(uint32_t entry, uint32_t &state) {
     const int32_t t_k = (int16_t)(entry & 0xFFFF), t_w = (int16_t)(entry >> 16);
     const uint32_t s = state;
     const uint32_t nb = (uint32_t)(t_k + (int32_t)s) >> 10;
     state = (uint32_t)(t_w + (int32_t)(s >> nb));
-    bw.push(s & ((1u << nb) - 1u), nb);
+    return nb | ((s & ((1u << nb) - 1u)) << 4);
+}
+// Warp-wide append of one value per lane (lane order = stream order) to the block's byte stream.
+// `carry` (< 8 bits, value in carry_val) is what the previous chunk left over.
+__device__ __forceinline__ void warp_emit(uint32_t *bitbuf, uint64_t v, uint32_t n, uint8_t *&out, uint32_t &carry, uint32_t &carry_val, uint32_t lane) {
+    for (uint32_t t = lane; t < 72; t += 32) bitbuf[t] = t == 0 ? carry_val : 0u;
+    uint32_t inc = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t x = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+        if (lane >= (uint32_t)o) inc += x;
+    }
+    const uint32_t total = carry + __shfl_sync(0xFFFFFFFFu, inc, 31);
+    __syncwarp();
+    if (n) {
+        const uint32_t pos = carry + inc - n, w = pos >> 5, sh = pos & 31;
+        const uint64_t lo = v << sh;
+        atomicOr(&bitbuf[w], (uint32_t)lo);
+        if (sh + n > 32) atomicOr(&bitbuf[w + 1], (uint32_t)(lo >> 32));
+        if (sh + n > 64) atomicOr(&bitbuf[w + 2], (uint32_t)(v >> (64 - sh)));
+    }
+    __syncwarp();
+    const uint32_t n_bytes = total >> 3;
+    const uint8_t *bb = reinterpret_cast<const uint8_t *>(bitbuf);
+    for (uint32_t t = lane; t < n_bytes; t += 32) out[t] = bb[t];
+    out += n_bytes;
+    carry = total & 7;
+    carry_val = carry ? (uint32_t)bb[n_bytes] & ((1u << carry) - 1u) : 0u;
+    __syncwarp();
 }
 
-__global__ void __launch_bounds__(kFseEncWarps * 32, 1)
+__global__ void __launch_bounds__(kFseEncWarps * 32)
 k_enc_fse_blocks(EncBlock *blocks, const uint32_t *__restrict__ n_blocks_p, const uint2 *__restrict__ pack_scratch,
                  const uint8_t *__restrict__ lit_scratch, uint8_t *out_scratch, uint32_t *work_counter) {
-    extern __shared__ __align__(16) uint8_t smem[];
-    const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
-    uint16_t *W = reinterpret_cast<uint16_t *>(smem + warp * kFseEncSmemPerWarp) + lane;            // W[sym*32]
-    uint32_t *E = reinterpret_cast<uint32_t *>(smem + warp * kFseEncSmemPerWarp + 360 * 32 * 2) + lane;  // E[sym*32]
+    __shared__ FseEncSmem sm_all[kFseEncWarps];
+    FseEncSmem &sm = sm_all[threadIdx.x >> 5];
+    const uint32_t lane = lane_id();
     const uint32_t n_blocks = *n_blocks_p;
     for (;;) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(work_counter, 32u);
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        if (base >= n_blocks) break;
-        const uint32_t bi = base + lane;
-        if (bi < n_blocks) {
-            const EncBlock b = blocks[bi];
-            const uint2 *packs = pack_scratch + b.pack_off;
-            const uint8_t *lits = lit_scratch + b.lit_off;
-            uint8_t *out = out_scratch + b.out_off;
-            // Weights::load (fse/weights.rs:25-64): histograms of real packs / literals, then normalize
-            for (uint32_t i = 0; i < 360; i++) W[i * 32] = 0;
-            if (b.n_packs) {
-                for (uint32_t i = 0; i < b.n_packs; i++) {
-                    const uint2 p = packs[i];
-                    W[l_sym(p.x & 0xFFFF) * 32]++;
-                    W[(20 + m_sym(p.x >> 16)) * 32]++;
-                    W[(40 + d_sym(p.y)) * 32]++;
-                }
-                normalize_m1(W, 20, b.n_packs, kLStates);
-                normalize_m1(W + 20 * 32, 20, b.n_packs, kMStates);
-                normalize_m1(W + 40 * 32, 64, b.n_packs, kDStates);
-            }
-            if (b.n_lits) {
-                for (uint32_t i = 0; i < b.n_lits; i++) W[(104 + lits[i]) * 32]++;
-                normalize_m1(W + 104 * 32, 256, b.n_lits, kUStates);
-            }
-            // Weights::store_v2 (fse/weights.rs:139-163, fse/weight_encoder.rs:23-37) after the 32-byte header
-            BitWriter bw;
-            bw.p = out + kV2HeaderSize; bw.accum = 0; bw.bits = 0;
-            for (uint32_t i = 0; i < 360; i++) {
-                const uint32_t v = W[i * 32];
-                uint32_t u, ub;
+        uint32_t bi = 0;
+        if (lane == 0) bi = atomicAdd(work_counter, 1u);
+        bi = __shfl_sync(0xFFFFFFFFu, bi, 0);
+        if (bi >= n_blocks) break;
+        const EncBlock b = blocks[bi];
+        const uint2 *packs = pack_scratch + b.pack_off;
+        const uint8_t *lits = lit_scratch + b.lit_off;
+        uint8_t *out = out_scratch + b.out_off;
+        // ---- Weights::load (fse/weights.rs:25-64): histograms of the real packs / literals ----
+        for (uint32_t t = lane; t < 360; t += 32) sm.W[t] = 0;
+        __syncwarp();
+        for (uint32_t i = lane; i < b.n_packs; i += 32) {
+            const uint2 p = packs[i];
+            atomicAdd(&sm.W[l_sym(p.x & 0xFFFF)], 1u);
+            atomicAdd(&sm.W[20 + m_sym(p.x >> 16)], 1u);
+            atomicAdd(&sm.W[40 + d_sym(p.y)], 1u);
+        }
+        for (uint32_t i = lane; i < b.n_lits; i += 32) atomicAdd(&sm.W[104 + lits[i]], 1u);
+        __syncwarp();
+        // ---- normalize_m1 x4, one table per lane ----
+        if (lane == 0 && b.n_packs) normalize_m1(sm.W, 20, b.n_packs, kLStates);
+        if (lane == 1 && b.n_packs) normalize_m1(sm.W + 20, 20, b.n_packs, kMStates);
+        if (lane == 2 && b.n_packs) normalize_m1(sm.W + 40, 64, b.n_packs, kDStates);
+        if (lane == 3 && b.n_lits) normalize_m1(sm.W + 104, 256, b.n_lits, kUStates);
+        __syncwarp();
+        // ---- Encoder::init: one table per lane ----
+        if (lane == 0) build_e_table(sm.W, sm.E, 20, kLStates);
+        if (lane == 1) build_e_table(sm.W + 20, sm.E + 20, 20, kMStates);
+        if (lane == 2) build_e_table(sm.W + 40, sm.E + 40, 64, kDStates);
+        if (lane == 3) build_e_table(sm.W + 104, sm.E + 104, 256, kUStates);
+        // ---- Weights::store_v2 (fse/weights.rs:139-163, fse/weight_encoder.rs:23-37), 32 weights per step ----
+        uint8_t *wp = out + kV2HeaderSize;
+        uint32_t carry = 0, carry_val = 0;
+        for (uint32_t base = 0; base < 360; base += 32) {
+            const uint32_t i = base + lane;
+            uint32_t u = 0, ub = 0;
+            if (i < 360) {
+                const uint32_t v = sm.W[i];
                 if (v == 0) { u = 0; ub = 2; } else if (v == 1) { u = 2; ub = 2; } else if (v == 2) { u = 1; ub = 3; } else if (v == 3) { u = 5; ub = 3; }
                 else if (v < 8) { u = 3 + ((v - 4) << 3); ub = 5; } else if (v < 24) { u = ((v - 8) << 4) + 7; ub = 8; } else { u = ((v - 24) << 4) + 15; ub = 14; }
-                bw.push(u, ub);
-                bw.flush();
             }
-            bw.finalize();
-            const uint32_t n_weight_bytes = (uint32_t)(bw.p - (out + kV2HeaderSize));
-            // Encoder::init
-            build_e_table(W, E, 20, kLStates);
-            build_e_table(W + 20 * 32, E + 20 * 32, 20, kMStates);
-            build_e_table(W + 40 * 32, E + 40 * 32, 64, kDStates);
-            build_e_table(W + 104 * 32, E + 104 * 32, 256, kUStates);
-            // Literals::store (fse/literals.rs:93-133): padded to x4 with literals[0], encoded last to first
-            const uint32_t n_lit_pad = (b.n_lits + 3) / 4 * 4;
-            uint8_t *lit_start = bw.p;
-            bw.accum = 0; bw.bits = 0;
-            uint32_t s0 = kUStates, s1 = kUStates, s2 = kUStates, s3 = kUStates;
-            const uint32_t pad = b.n_lits ? lits[0] : 0;
-            const uint32_t *EU = E + 104 * 32;
-            for (uint32_t i = n_lit_pad; i != 0; i -= 4) {
-                const uint32_t c3 = i - 1 < b.n_lits ? lits[i - 1] : pad, c2 = i - 2 < b.n_lits ? lits[i - 2] : pad;
-                const uint32_t c1 = i - 3 < b.n_lits ? lits[i - 3] : pad, c0 = lits[i - 4];
-                e_encode(EU[c3 * 32], bw, s3);
-                e_encode(EU[c2 * 32], bw, s2);
-                e_encode(EU[c1 * 32], bw, s1);
-                e_encode(EU[c0 * 32], bw, s0);
-                bw.flush();
+            warp_emit(sm.bitbuf, u, ub, wp, carry, carry_val, lane);
+        }
+        if (carry) { if (lane == 0) *wp = (uint8_t)carry_val; wp++; }
+        const uint32_t n_weight_bytes = (uint32_t)(wp - (out + kV2HeaderSize));
+        __syncwarp();
+        // ---- Literals::store (fse/literals.rs:93-133): padded to x4 with literals[0], last to first ----
+        const uint32_t n_lit_pad = (b.n_lits + 3) / 4 * 4;
+        uint8_t *lp = wp;
+        carry = 0; carry_val = 0;
+        uint32_t ust = kUStates;  // lanes 0..3 hold literal states 0..3
+        const uint32_t pad = b.n_lits ? lits[0] : 0;
+        for (uint32_t hi = n_lit_pad; hi != 0;) {
+            const uint32_t n = hi < 128 ? hi : 128;  // literals [hi - n, hi), emitted from hi - 1 downwards
+            for (uint32_t t = lane; t < n; t += 32) {  // emission slot t holds literal hi - 1 - t
+                const uint32_t idx = hi - 1 - t;
+                sm.sym[t] = (uint8_t)(idx < b.n_lits ? lits[idx] : pad);
             }
-            const uint32_t lit_bits = bw.finalize();
-            const uint32_t n_lit_payload = (uint32_t)(bw.p - lit_start);
-            // Lmds::store (fse/lmds.rs:62-93): 8 zero bytes, then D, M, L of each pack from last to first
-            uint8_t *lmd_start = bw.p;
-            for (int k = 0; k < 8; k++) *bw.p++ = 0;
-            bw.accum = 0; bw.bits = 0;
-            uint32_t sl = kLStates, sm = kMStates, sd = kDStates;
-            for (uint32_t i = b.n_packs; i != 0; i--) {
-                const uint2 p = packs[i - 1];
-                const uint32_t l = p.x & 0xFFFF, m = p.x >> 16, d = p.y;
-                uint32_t sym = d_sym(d);
-                bw.push(d - d_base_e(sym), sym >> 2); e_encode(E[(40 + sym) * 32], bw, sd);
-                sym = m_sym(m);
-                bw.push(m - m_base_e(sym), m_extra_e(sym)); e_encode(E[(20 + sym) * 32], bw, sm);
-                sym = l_sym(l);
-                bw.push(l - l_base_e(sym), l_extra_e(sym)); e_encode(E[sym * 32], bw, sl);
-                bw.flush();
+            __syncwarp();
+            if (lane < 4) {  // literal idx uses state idx & 3 (the loop encodes i-1 with state 3 ... i-4 with state 0)
+                const uint32_t first = 3 - lane;  // slots first, first + 4, ... belong to this state
+                for (uint32_t t = first; t < n; t += 4) sm.chain[t] = (uint16_t)e_step(sm.E[104 + sm.sym[t]], ust);
             }
-            const uint32_t lmd_bits = bw.finalize();
-            const uint32_t n_lmd_payload = (uint32_t)(bw.p - lmd_start);
-            // FseBlock::store_v2 (fse/block.rs:168-196)
+            __syncwarp();
+            {   // each lane packs four consecutive slots
+                uint64_t v = 0; uint32_t nb = 0;
+#pragma unroll
+                for (uint32_t k = 0; k < 4; k++) {
+                    const uint32_t t = lane * 4 + k;
+                    if (t < n) { const uint32_t c = sm.chain[t]; v |= (uint64_t)(c >> 4) << nb; nb += c & 15; }
+                }
+                warp_emit(sm.bitbuf, v, nb, lp, carry, carry_val, lane);
+            }
+            hi -= n;
+        }
+        uint32_t lit_bits = 0;
+        if (carry) { if (lane == 0) *lp = (uint8_t)carry_val; lp++; lit_bits = 8 - carry; }
+        const uint32_t n_lit_payload = (uint32_t)(lp - wp);
+        const uint32_t us0 = __shfl_sync(0xFFFFFFFFu, ust, 0), us1 = __shfl_sync(0xFFFFFFFFu, ust, 1), us2 = __shfl_sync(0xFFFFFFFFu, ust, 2),
+                       us3 = __shfl_sync(0xFFFFFFFFu, ust, 3);
+        // ---- Lmds::store (fse/lmds.rs:62-93): 8 zero bytes, then D, M, L of each pack, last pack first ----
+        uint8_t *mp = lp;
+        if (lane < 8) mp[lane] = 0;
+        mp += 8;
+        carry = 0; carry_val = 0;
+        uint32_t st = lane == 0 ? kLStates : (lane == 1 ? kMStates : kDStates);  // lanes 0,1,2 hold the L, M, D states
+        for (uint32_t hi = b.n_packs; hi != 0;) {
+            const uint32_t n = hi < 32 ? hi : 32;  // packs [hi - n, hi); slot t holds pack hi - 1 - t
+            uint32_t l = 0, m = 0, d = 0, sl = 0, smm = 0, sd = 0;
+            if (lane < n) {
+                const uint2 p = packs[hi - 1 - lane];
+                l = p.x & 0xFFFF; m = p.x >> 16; d = p.y;
+                sl = l_sym(l); smm = m_sym(m); sd = d_sym(d);
+                sm.sym[lane] = (uint8_t)sl; sm.sym[32 + lane] = (uint8_t)smm; sm.sym[64 + lane] = (uint8_t)sd;
+            }
+            __syncwarp();
+            if (lane < 3) {
+                const uint32_t off = lane == 0 ? 0u : (lane == 1 ? 20u : 40u);
+                for (uint32_t t = 0; t < n; t++) sm.chain[lane * 32 + t] = (uint16_t)e_step(sm.E[off + sm.sym[lane * 32 + t]], st);
+            }
+            __syncwarp();
+            uint64_t v = 0; uint32_t nb = 0;
+            if (lane < n) {  // D extra, D state, M extra, M state, L extra, L state
+                const uint32_t cl = sm.chain[lane], cm = sm.chain[32 + lane], cd = sm.chain[64 + lane];
+                v = d - d_base_e(sd); nb = sd >> 2;
+                v |= (uint64_t)(cd >> 4) << nb; nb += cd & 15;
+                v |= (uint64_t)(m - m_base_e(smm)) << nb; nb += m_extra_e(smm);
+                v |= (uint64_t)(cm >> 4) << nb; nb += cm & 15;
+                v |= (uint64_t)(l - l_base_e(sl)) << nb; nb += l_extra_e(sl);
+                v |= (uint64_t)(cl >> 4) << nb; nb += cl & 15;
+            }
+            warp_emit(sm.bitbuf, v, nb, mp, carry, carry_val, lane);
+            hi -= n;
+        }
+        uint32_t lmd_bits = 0;
+        if (carry) { if (lane == 0) *mp = (uint8_t)carry_val; mp++; lmd_bits = 8 - carry; }
+        const uint32_t n_lmd_payload = (uint32_t)(mp - lp);
+        const uint32_t fl = __shfl_sync(0xFFFFFFFFu, st, 0), fm = __shfl_sync(0xFFFFFFFFu, st, 1), fd = __shfl_sync(0xFFFFFFFFu, st, 2);
+        // ---- FseBlock::store_v2 (fse/block.rs:168-196) ----
+        if (lane == 0) {
             const uint32_t n_raw = b.n_lits + b.n_match_bytes;
             uint64_t h[4];
             h[0] = (uint64_t)kMagicVx2 | ((uint64_t)n_raw << 32);
             h[1] = (uint64_t)n_lit_pad | ((uint64_t)n_lit_payload << 20) | ((uint64_t)b.n_packs << 40) | ((uint64_t)(7 - lit_bits) << 60);
-            h[2] = (uint64_t)(s0 - kUStates) | ((uint64_t)(s1 - kUStates) << 10) | ((uint64_t)(s2 - kUStates) << 20) | ((uint64_t)(s3 - kUStates) << 30) |
+            h[2] = (uint64_t)(us0 - kUStates) | ((uint64_t)(us1 - kUStates) << 10) | ((uint64_t)(us2 - kUStates) << 20) | ((uint64_t)(us3 - kUStates) << 30) |
                    ((uint64_t)n_lmd_payload << 40) | ((uint64_t)(7 - lmd_bits) << 60);
-            h[3] = (uint64_t)(kV2HeaderSize + n_weight_bytes) | ((uint64_t)(sl - kLStates) << 32) | ((uint64_t)(sm - kMStates) << 42) |
-                   ((uint64_t)(sd - kDStates) << 52);
+            h[3] = (uint64_t)(kV2HeaderSize + n_weight_bytes) | ((uint64_t)(fl - kLStates) << 32) | ((uint64_t)(fm - kMStates) << 42) |
+                   ((uint64_t)(fd - kDStates) << 52);
             for (int k = 0; k < 32; k++) out[k] = (uint8_t)(h[k >> 3] >> (8 * (k & 7)));
-            blocks[bi].out_size = (uint32_t)(bw.p - out);
+            blocks[bi].out_size = (uint32_t)(mp - out);
         }
         __syncwarp();
     }
@@ -769,7 +842,7 @@ struct lzfse_b200_encoder {
 
 namespace {
 
-constexpr int kParseWarpsPerSm = 16;  // resident history tables: 148 * 16 * 256 KiB = 592 MiB
+constexpr int kParseWarpsPerSm = 24;  // resident history tables: 148 * 24 * 256 KiB = 888 MiB
 
 int encode_batch_device_impl(lzfse_b200_encoder *e, const uint8_t *src, const uint64_t *src_off, const uint64_t *src_len, uint8_t *dst,
                              const uint64_t *dst_off, const uint64_t *dst_cap, uint64_t *out_len, int32_t *status, size_t n, cudaStream_t s) {
@@ -808,9 +881,9 @@ int encode_batch_device_impl(lzfse_b200_encoder *e, const uint8_t *src, const ui
     e->launches += 1;
     e->timer.mark(s);  // parse
     if (tot.n_literals) {
-        unsigned g = (unsigned)((tot.n_literals + 32 * kFseEncWarps - 1) / (32 * kFseEncWarps));
-        if (g > (unsigned)e->n_sms) g = (unsigned)e->n_sms;
-        k_enc_fse_blocks<<<g, kFseEncWarps * 32, kFseEncWarps * kFseEncSmemPerWarp, s>>>(e->blocks.as<EncBlock>(), ctr, e->packs.as<uint2>(),
+        unsigned g = (unsigned)((tot.n_literals + kFseEncWarps - 1) / kFseEncWarps);
+        if (g > (unsigned)e->n_sms * 4) g = (unsigned)e->n_sms * 4;
+        k_enc_fse_blocks<<<g, kFseEncWarps * 32, 0, s>>>(e->blocks.as<EncBlock>(), ctr, e->packs.as<uint2>(),
                                                                                         e->lits.as<uint8_t>(), e->out.as<uint8_t>(), ctr + 2);
         e->launches += 1;
     }
@@ -844,7 +917,8 @@ int lzfse_b200_encoder_create(int device, lzfse_b200_encoder **out) {
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete e; return LZFSE_B200_NO_DEVICE; }
     e->n_sms = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete e; return LZFSE_B200_CUDA_ERROR; }
-    if (cudaFuncSetAttribute(k_enc_fse_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kFseEncWarps * kFseEncSmemPerWarp)) != cudaSuccess) {
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, k_enc_fse_blocks) != cudaSuccess) {
         cudaGetLastError();  // no sm_100a image for this device: there is no fallback path
         cudaStreamDestroy(e->own_stream);
         delete e;
