@@ -209,6 +209,13 @@ __device__ bool sink_buffer_push(FseSink &s, const uint8_t *src, uint32_t &lit_f
     return true;
 }
 __device__ void sink_push_match(FseSink &s, const uint8_t *src, uint32_t lit_from, uint32_t lit_len, uint32_t match_len, uint32_t d, uint32_t lane) {
+    // common case of Buffer::push: one pack, block has room
+    if (lit_len <= kMaxLValue && match_len <= kMaxMValue && s.n_packs_total - s.blk_pack0 < kLmdsPerBlock &&
+        s.n_lits_total - s.blk_lit0 + lit_len <= kLiteralsPerBlock) {
+        sink_copy_lits(s, src, lit_from, lit_len, lane);
+        sink_push_lmd(s, lit_len, match_len, d, lane);
+        return;
+    }
     while (!sink_buffer_push(s, src, lit_from, lit_len, match_len, d, lane)) sink_emit_block(s, lane);  // fse/backend.rs:76-90
 }
 
@@ -256,7 +263,7 @@ __device__ void vn_push_match(VnSink &v, const uint8_t *src, uint32_t from, uint
 }
 
 constexpr int kParseWarps = 4;
-constexpr uint32_t kFwdCap = 64;  // per-lane forward extension stops here; longer matches are finished warp-wide
+constexpr uint32_t kFwdCap = 44;  // per-lane forward extension stops here (>= GOOD_MATCH_LEN); longer matches are finished warp-wide
 constexpr uint32_t kBwdCap = 8;   // per-lane backward extension precomputed up to here
 
 __device__ __forceinline__ uint32_t ld4u(const uint8_t *p) {  // unaligned 4-byte load: two aligned words + funnel shift
@@ -265,6 +272,14 @@ __device__ __forceinline__ uint32_t ld4u(const uint8_t *p) {  // unaligned 4-byt
     const uint32_t *q = reinterpret_cast<const uint32_t *>(a - r);
     const uint32_t lo = q[0], hi = r ? q[1] : 0u;
     return __funnelshift_r(lo, hi, r * 8);
+}
+
+__device__ __forceinline__ uint64_t ld8u(const uint8_t *p) {  // unaligned 8-byte load: three aligned words + two funnel shifts
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint32_t r = (uint32_t)a & 3u;
+    const uint32_t *q = reinterpret_cast<const uint32_t *>(a - r);
+    const uint32_t w0 = q[0], w1 = q[1], w2 = r ? q[2] : 0u;
+    return (uint64_t)__funnelshift_r(w0, w1, r * 8) | ((uint64_t)__funnelshift_r(w1, w2, r * 8) << 32);
 }
 
 // Ordered insert of positions [from, to) into the history table, 32 per step (HistoryTable::push x n,
@@ -360,7 +375,22 @@ k_enc_parse(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ s
                 h = hash_u(val, vn);
                 tq = __ldcg(reinterpret_cast<const uint4 *>(table + h * kHashWidth));
             }
-            uint32_t earlier = __match_any_sync(0xFFFFFFFFu, h) & lanemask_lt();
+            const uint32_t peers = __match_any_sync(0xFFFFFFFFu, h);
+            uint32_t earlier = peers & lanemask_lt();
+            // Every position of the step ends up in the history (visited or skipped), so push them now: the
+            // newest position of each bucket writes it once (same merge as history_insert_range).
+            if (act && (peers & ~((2u << lane) - 1u)) == 0) {
+                uint32_t m = earlier, n1 = 0, n2 = 0, n3 = 0, cnt = 1;
+                if (m) { const int b = 31 - __clz(m); n1 = b0 + b; m &= ~(1u << b); cnt = 2; }
+                if (m) { const int b = 31 - __clz(m); n2 = b0 + b; m &= ~(1u << b); cnt = 3; }
+                if (m) { const int b = 31 - __clz(m); n3 = b0 + b; cnt = 4; }
+                uint4 nw;
+                nw.x = p;
+                nw.y = cnt > 1 ? n1 : tq.x;
+                nw.z = cnt > 2 ? n2 : (cnt == 2 ? tq.x : tq.y);
+                nw.w = cnt > 3 ? n3 : (cnt == 3 ? tq.x : (cnt == 2 ? tq.y : tq.z));
+                __stcg(reinterpret_cast<uint4 *>(table + h * kHashWidth), nw);
+            }
             uint32_t c[4];
             {   // first the same-bucket positions of lower lanes (newest first), then the table's bucket
                 uint32_t n0 = 0, n1 = 0, n2 = 0, n3 = 0, e = 0;
@@ -386,10 +416,10 @@ k_enc_parse(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ s
                     uint32_t l = 0;
                     if (x == 0) {
                         l = 4;
-                        while (l + 4 <= max && l < kFwdCap) {
-                            const uint32_t y = ld4u(src + p + l) ^ ld4u(src + c[k] + l);
-                            if (y) { l += (__ffs(y) - 1) >> 3; goto ext_done; }
-                            l += 4;
+                        while (l + 8 <= max && l < kFwdCap) {
+                            const uint64_t y = ld8u(src + p + l) ^ ld8u(src + c[k] + l);
+                            if (y) { l += (__ffsll((long long)y) - 1) >> 3; goto ext_done; }
+                            l += 8;
                         }
                         if (l < kFwdCap) while (l < max && src[p + l] == src[c[k] + l]) l++;
                     ext_done:;
@@ -402,6 +432,10 @@ k_enc_parse(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ s
                     while (r_bw < lim2 && src[p - r_bw - 1] == src[r_idx - r_bw - 1]) r_bw++;
                 }
             }
+            // While this step is replayed, pull the next step's buckets towards the SM (hint only: the
+            // history may still change before they are read).
+            if (b0 + 32 + lane < end)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(table + hash_u(ld4u(src + b0 + 32 + lane), vn) * kHashWidth));
             // ---- phase 2: the sequential front end over the step's positions ----
             // Positions whose find_match came back empty only advance the index (:203-209), so the replay
             // jumps from one position with a candidate to the next.
@@ -467,8 +501,8 @@ k_enc_parse(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ s
             }
             // ---- phase 3: push every position this step passed into the history ----
             if (!done) {
-                __syncwarp();
-                history_insert_range(table, src, b0, cur, vn, lane);
+                __syncwarp();  // the step's own positions were pushed in phase 1; a match may have run past them
+                if (cur > b0 + nb) history_insert_range(table, src, b0 + nb, cur, vn, lane);
             }
             index = cur;
         }
