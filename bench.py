@@ -40,13 +40,16 @@ def peaks():
 
 
 class ClockSampler:
+    """nvidia-smi clocks + throttle reasons, sampled in the background; stop(t0, t1) keeps the samples
+    taken while the timed region ran (the sampler is started before warm-up so it is up by then)."""
+
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
 
     def start(self):
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -55,18 +58,30 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
 
-    def stop(self):
+    def wait_first(self, timeout=10.0):
+        t = time.time()
+        while self.proc and not self.rows and time.time() - t < timeout:
+            time.sleep(0.02)
+
+    def stop(self, t0, t1):
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        time.sleep(0.05)
         self.proc.terminate()
         self.t.join(timeout=2)
-        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        inside = [r for ts, r in self.rows if t0 <= ts <= t1 + 0.03 and len(r) >= 6]
+        window = "timed region"
+        if not inside:
+            inside, window = [r for _, r in self.rows if len(r) >= 6], "whole run (timed region shorter than the sampling period)"
+        num = lambda x: x.replace(".", "", 1).isdigit()
+        sm = [float(r[0]) for r in inside if num(r[0])]
+        mx = [float(r[1]) for r in inside if num(r[1])]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+        reasons = sorted({names[i] for r in inside for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm), "window": window}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -217,15 +232,17 @@ def run_ours(a):
     # ---- decode, frames resident in HBM ----
     U, Cb = n * CHUNK, total_c
     dec.set_timing(True)
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(a.warmup):
         dec.decode_batch_device(packed_d, p_off, p_len, out_d, r_off, r_len)
+    sampler.wait_first()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local)
-    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stage_acc = {}
+    t_wall0 = time.time()
     e0.record()
     for _ in range(a.steps):
         dec.decode_batch_device(packed_d, p_off, p_len, out_d, r_off, r_len)
@@ -233,7 +250,7 @@ def run_ours(a):
             stage_acc[k] = stage_acc.get(k, 0.0) + v
     e1.record()
     torch.cuda.synchronize()
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_wall0, time.time())
     ms_total = e0.elapsed_time(e1)
     t = torch.tensor([ms_total], device=dev)
     if world > 1:
@@ -314,7 +331,7 @@ def run_ours(a):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--chunks", type=int, default=16384, help="64 KiB streams per GPU (16384 = 1 GiB)")

@@ -1,0 +1,13 @@
+# Round measurement pass: tests, smoke, bench (ours + reference), ncu launch list, full capture of the decode kernels.
+set -x
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err
+python bench.py > gpurun_out/bench_ours.json 2> gpurun_out/bench_ours.err; echo bench_rc=$?
+tail -3 gpurun_out/bench_ours.err
+python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/plain.log 2>&1 && \
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/ncu_launches.log 2>&1
+python bench.py --steps 1 --warmup 3 --no-cpu > gpurun_out/plain2.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:'k_fse_literals|k_fse_lmds|k_expand' -s 15 -c 3 -o gpurun_out/decode_full -f python bench.py --steps 1 --warmup 3 --no-cpu > gpurun_out/ncu_full.log 2>&1
+tail -2 gpurun_out/ncu_full.log
+cat gpurun_out/bench_ours.json
