@@ -132,36 +132,41 @@ __device__ __forceinline__ uint32_t warp_match_dec(const uint8_t *src, uint32_t 
 
 struct Match { uint32_t idx, match_idx, match_len; };
 
-// Per-stream back-end state, identical in every lane (the control flow is warp-uniform).
+// Per-stream back-end state, identical in every lane (the control flow is warp-uniform).  Kept small:
+// the parse kernel is occupancy-bound, so everything only needed when a block closes is re-read then.
 struct FseSink {   // fse/buffer.rs + fse/backend.rs:66-96
     uint2 *packs;            // stream's pack scratch
     uint8_t *lits;           // stream's literal scratch
-    EncBlock *blocks;        // compact block list
-    uint32_t *block_ids;     // stream's block slot list
-    uint32_t *block_counter;
-    uint64_t pack_base, lit_base, out_base;  // absolute offsets of the stream's scratch
     uint32_t n_packs_total, n_lits_total;    // appended so far (all blocks)
     uint32_t blk_pack0, blk_lit0;            // where the open block starts
     uint32_t n_match_bytes, match_distance;
     uint32_t n_blocks;
-    uint64_t out_used;
+    uint32_t out_used;
+};
+struct SinkEnv {  // what emit_block needs besides the sink (kernel parameters, re-read on use)
+    const StreamCounts *bases;
+    EncBlock *blocks;
+    uint32_t *block_ids;
+    uint32_t *block_counter;
+    uint32_t si;
 };
 
-__device__ __forceinline__ void sink_emit_block(FseSink &s, uint32_t lane) {  // emit_block_v2: close the open block
+__device__ __noinline__ void sink_emit_block(FseSink &s, const SinkEnv &env, uint32_t lane) {  // emit_block_v2: close the open block
     if (lane == 0) {
+        const StreamCounts base = env.bases[env.si];  // {packs, literal bytes, block slots, out bytes}
         EncBlock b;
-        b.pack_off = s.pack_base + s.blk_pack0;
-        b.lit_off = s.lit_base + s.blk_lit0;
-        b.out_off = s.out_base + s.out_used;
+        b.pack_off = base.n_blocks + s.blk_pack0;
+        b.lit_off = base.n_fse + s.blk_lit0;
+        b.out_off = base.n_lmds + s.out_used;
         b.n_packs = s.n_packs_total - s.blk_pack0;
         b.n_lits = s.n_lits_total - s.blk_lit0;
         b.n_match_bytes = s.n_match_bytes;
         b.out_size = 0;
-        const uint32_t id = atomicAdd(s.block_counter, 1u);
-        s.blocks[id] = b;
-        s.block_ids[s.n_blocks] = id;
+        const uint32_t id = atomicAdd(env.block_counter, 1u);
+        env.blocks[id] = b;
+        env.block_ids[base.n_literals + s.n_blocks] = id;
     }
-    s.out_used += (block_bound(s.n_lits_total - s.blk_lit0, s.n_packs_total - s.blk_pack0) + 15) & ~15ull;
+    s.out_used += (uint32_t)((block_bound(s.n_lits_total - s.blk_lit0, s.n_packs_total - s.blk_pack0) + 15) & ~15ull);
     s.n_blocks++;
     s.blk_pack0 = s.n_packs_total; s.blk_lit0 = s.n_lits_total;
     s.n_match_bytes = 0; s.match_distance = 0;  // Buffer::reset
@@ -208,7 +213,7 @@ __device__ bool sink_buffer_push(FseSink &s, const uint8_t *src, uint32_t &lit_f
     match_len = 0;
     return true;
 }
-__device__ void sink_push_match(FseSink &s, const uint8_t *src, uint32_t lit_from, uint32_t lit_len, uint32_t match_len, uint32_t d, uint32_t lane) {
+__device__ void sink_push_match(FseSink &s, const SinkEnv &env, const uint8_t *src, uint32_t lit_from, uint32_t lit_len, uint32_t match_len, uint32_t d, uint32_t lane) {
     // common case of Buffer::push: one pack, block has room
     if (lit_len <= kMaxLValue && match_len <= kMaxMValue && s.n_packs_total - s.blk_pack0 < kLmdsPerBlock &&
         s.n_lits_total - s.blk_lit0 + lit_len <= kLiteralsPerBlock) {
@@ -216,7 +221,7 @@ __device__ void sink_push_match(FseSink &s, const uint8_t *src, uint32_t lit_fro
         sink_push_lmd(s, lit_len, match_len, d, lane);
         return;
     }
-    while (!sink_buffer_push(s, src, lit_from, lit_len, match_len, d, lane)) sink_emit_block(s, lane);  // fse/backend.rs:76-90
+    while (!sink_buffer_push(s, src, lit_from, lit_len, match_len, d, lane)) sink_emit_block(s, env, lane);  // fse/backend.rs:76-90
 }
 
 // LZVN back end (vn/backend.rs:37-136 + vn/opc.rs).  Lane 0 writes the opcode bytes.
@@ -310,7 +315,7 @@ __device__ __forceinline__ void history_insert_range(uint32_t *table, const uint
     }
 }
 
-__global__ void __launch_bounds__(kParseWarps * 32, 6)
+__global__ void __launch_bounds__(kParseWarps * 32, 7)
 k_enc_parse(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ src_off, const uint64_t *__restrict__ src_len, size_t n_streams,
             EncStream *streams, const StreamCounts *__restrict__ bases, uint32_t *tables /* one per warp slot */, uint2 *pack_scratch,
             uint8_t *lit_scratch, uint32_t *block_ids, EncBlock *blocks, uint32_t *block_counter, uint8_t *out_scratch, uint32_t *stream_counter) {
@@ -333,21 +338,20 @@ k_enc_parse(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ s
         for (uint32_t t = lane; t < kTableWords / 4; t += 32) reinterpret_cast<uint4 *>(table)[t] = make_uint4(kEmptyIdx, kEmptyIdx, kEmptyIdx, kEmptyIdx);
         __syncwarp();
 
-        const StreamCounts base = bases[si];
         FseSink fs;
         VnSink vs;
-        if (!vn) {
-            fs.packs = pack_scratch + base.n_blocks; fs.lits = lit_scratch + base.n_fse; fs.blocks = blocks;
-            fs.block_ids = block_ids + base.n_literals; fs.block_counter = block_counter;
-            fs.pack_base = base.n_blocks; fs.lit_base = base.n_fse; fs.out_base = base.n_lmds;
+        SinkEnv env;
+        env.bases = bases; env.blocks = blocks; env.block_ids = block_ids; env.block_counter = block_counter; env.si = si;
+        {
+            const StreamCounts base = bases[si];
+            fs.packs = pack_scratch + base.n_blocks; fs.lits = lit_scratch + base.n_fse;
             fs.n_packs_total = 0; fs.n_lits_total = 0; fs.blk_pack0 = 0; fs.blk_lit0 = 0; fs.n_match_bytes = 0; fs.match_distance = 0;
             fs.n_blocks = 0; fs.out_used = 0;
-        } else {
             vs.out = out_scratch + base.n_lmds; vs.pos = kVnHeaderSize; vs.match_distance = 0; vs.n_literals = 0; vs.n_match_bytes = 0;
         }
         auto push_match = [&](uint32_t lit_from, uint32_t lit_len, uint32_t match_len, uint32_t d) {
             if (vn) vn_push_match(vs, src, lit_from, lit_len, match_len, d, lane);
-            else sink_push_match(fs, src, lit_from, lit_len, match_len, d, lane);
+            else sink_push_match(fs, env, src, lit_from, lit_len, match_len, d, lane);
         };
 
         // FrontendBytes::match_any (encode/frontend_bytes.rs:160-211), 32 positions per step.
@@ -512,8 +516,8 @@ k_enc_parse(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ s
             literal_index = pending.idx + pending.match_len;
         }
         if (!vn) {
-            if (len - literal_index != 0) sink_push_match(fs, src, literal_index, len - literal_index, 0, 1, lane);  // push_literals
-            sink_emit_block(fs, lane);  // finalize
+            if (len - literal_index != 0) sink_push_match(fs, env, src, literal_index, len - literal_index, 0, 1, lane);  // push_literals
+            sink_emit_block(fs, env, lane);  // finalize
             if (lane == 0) streams[si].n_blocks = fs.n_blocks;
         } else {
             uint32_t from = literal_index, ll = len - literal_index;
@@ -876,7 +880,7 @@ struct lzfse_b200_encoder {
 
 namespace {
 
-constexpr int kParseWarpsPerSm = 24;  // resident history tables: 148 * 24 * 256 KiB = 888 MiB
+constexpr int kParseWarpsPerSm = 28;  // resident history tables: 148 * 28 * 256 KiB = 1036 MiB
 
 int encode_batch_device_impl(lzfse_b200_encoder *e, const uint8_t *src, const uint64_t *src_off, const uint64_t *src_len, uint8_t *dst,
                              const uint64_t *dst_off, const uint64_t *dst_cap, uint64_t *out_len, int32_t *status, size_t n, cudaStream_t s) {
