@@ -77,7 +77,7 @@ int decode_batch_device_impl(lzfse_b200_decoder *d, const uint8_t *src, const ui
     if (tot.n_fse > 0xFFFFFFFFull) { d->last_error = "too many FSE blocks in one batch"; return LZFSE_B200_INVALID_ARGUMENT; }
     CK(d, d->blocks.reserve((tot.n_blocks + 1) * sizeof(BlockDesc)));
     CK(d, d->fse.reserve((tot.n_fse + 1) * sizeof(FseDesc)));
-    CK(d, d->lits.reserve(tot.n_literals + 64));
+    CK(d, d->lits.reserve(tot.n_literals + 512));  // slack: the expander prefetches up to 128 bytes past a block's run
     CK(d, d->lmds.reserve((tot.n_lmds + 1) * sizeof(LmdRec)));
     CK(d, cudaMemsetAsync(d->work.p, 0, 2 * sizeof(uint32_t), s));
 

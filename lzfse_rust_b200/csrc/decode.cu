@@ -685,12 +685,15 @@ __device__ void expand_fse_block(uint8_t *__restrict__ out /* block's first outp
                                  const uint8_t *__restrict__ lit, const LmdRec *__restrict__ lmds, uint32_t n_lmds, uint32_t lane) {
     uint32_t out_base = 0, lit_base = 0;  // running offsets inside the block
     (void)block_pos;
+    // The records of step b+1 are fetched while step b is being copied: one memory round trip less per step.
+    uint2 nxt = make_uint2(0, 0);
+    if (lane < n_lmds) nxt = __ldg(reinterpret_cast<const uint2 *>(lmds) + lane);
     for (uint32_t b = 0; b < n_lmds; b += 32) {
-        uint32_t L = 0, M = 0, D = 0;
-        if (b + lane < n_lmds) {
-            LmdRec r = lmds[b + lane];
-            L = r.l; M = r.m; D = r.d;
-        }
+        const uint2 rec = nxt;
+        nxt = make_uint2(0, 0);
+        if (b + 32 + lane < n_lmds) nxt = __ldg(reinterpret_cast<const uint2 *>(lmds) + b + 32 + lane);
+        const uint32_t L = rec.x & 0xFFFF, M = rec.x >> 16, D = rec.y;
+        if (lane == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(lit + lit_base + 128));  // scratch has slack past its end
         // inclusive scan of (sum L) << 17 | (sum L+M): 32*315 < 2^14, 32*(315+2359) < 2^17
         uint32_t v = (L << 17) + (L + M), inc = v;
 #pragma unroll
@@ -706,14 +709,19 @@ __device__ void expand_fse_block(uint8_t *__restrict__ out /* block's first outp
 
         // ---- literals ----
         const bool long_l = L > kShortCopy;
-        if (!long_l && L) {  // all loads first, then all stores: no per-byte round trip
-            uint8_t tmp[kShortCopy];
+        {   // short runs: every lane copies its own, in groups of 4 bytes (loads first, then stores), and the
+            // warp stops at the longest short run of the step instead of always issuing kShortCopy slots
+            const uint32_t sl = long_l ? 0u : L;
+            const uint32_t max_l = __reduce_max_sync(0xFFFFFFFFu, sl);
+            for (uint32_t t0 = 0; t0 < max_l; t0 += 4) {
+                uint8_t tmp[4];
 #pragma unroll
-            for (uint32_t t = 0; t < kShortCopy; t++)
-                if (t < L) tmp[t] = lit[my_lit + t];
+                for (uint32_t k = 0; k < 4; k++)
+                    if (t0 + k < sl) tmp[k] = lit[my_lit + t0 + k];
 #pragma unroll
-            for (uint32_t t = 0; t < kShortCopy; t++)
-                if (t < L) out[my_out + t] = tmp[t];
+                for (uint32_t k = 0; k < 4; k++)
+                    if (t0 + k < sl) out[my_out + t0 + k] = tmp[k];
+            }
         }
         uint32_t mask = __ballot_sync(0xFFFFFFFFu, long_l);
         while (mask) {
@@ -732,14 +740,18 @@ __device__ void expand_fse_block(uint8_t *__restrict__ out /* block's first outp
         const int64_t end_nonself = (src_rel + (int64_t)M < (int64_t)my_dst) ? src_rel + (int64_t)M : (int64_t)my_dst;
         const bool indep = end_nonself <= (int64_t)out_base;
         const bool solo = M != 0 && M <= kShortCopy && indep && D >= M;
-        if (solo) {
-            uint8_t tmp[kShortCopy];
+        {
+            const uint32_t sm_ = solo ? M : 0u;
+            const uint32_t max_m = __reduce_max_sync(0xFFFFFFFFu, sm_);
+            for (uint32_t t0 = 0; t0 < max_m; t0 += 4) {
+                uint8_t tmp[4];
 #pragma unroll
-            for (uint32_t t = 0; t < kShortCopy; t++)
-                if (t < M) tmp[t] = src[t];
+                for (uint32_t k = 0; k < 4; k++)
+                    if (t0 + k < sm_) tmp[k] = src[t0 + k];
 #pragma unroll
-            for (uint32_t t = 0; t < kShortCopy; t++)
-                if (t < M) out[my_dst + t] = tmp[t];
+                for (uint32_t k = 0; k < 4; k++)
+                    if (t0 + k < sm_) out[my_dst + t0 + k] = tmp[k];
+            }
         }
         mask = __ballot_sync(0xFFFFFFFFu, M != 0 && !solo);
         if (mask) __syncwarp();
