@@ -14,6 +14,8 @@
 // keeps all 32 lanes issuing, and the tables are laid out [state][lane] so a warp's 32 lookups hit
 // 32 different banks.  What the reference does in Literals::load / FseCore::decode_internal
 // (fse/literals.rs:49-91, fse/fse_core.rs:91-141) is restated below with every check it makes.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace lzb {
@@ -320,8 +322,29 @@ struct BitWindow {
         const uint32_t lo = __funnelshift_r(w0, w1, r * 8), hi = __funnelshift_r(w1, w2, r * 8);
         return ((uint64_t)hi << 32) | lo;
     }
+    // Same window without the dead-reader handling and the prefetch (callers guarantee P >= 57).
+    __device__ __forceinline__ uint64_t window_fast(int &cur) const {
+        const int byte = (P - 57) >> 3;
+        cur = P - byte * 8;
+        const uintptr_t a = reinterpret_cast<uintptr_t>(base) + (intptr_t)byte;
+        const uint32_t r = (uint32_t)a & 3u;
+        const uint32_t *a4 = reinterpret_cast<const uint32_t *>(a - r);
+        const uint32_t w0 = __ldg(a4), w1 = __ldg(a4 + 1);
+        const uint32_t w2 = r ? __ldg(a4 + 2) : 0u;
+        const uint32_t lo = __funnelshift_r(w0, w1, r * 8), hi = __funnelshift_r(w1, w2, r * 8);
+        return ((uint64_t)hi << 32) | lo;
+    }
+    __device__ __forceinline__ void prefetch() const {
+        const uintptr_t pf = reinterpret_cast<uintptr_t>(base) + (intptr_t)((P >> 3) - 256);
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(pf > pf_lo ? pf : pf_lo));
+    }
     __device__ __forceinline__ bool underflow() const { return P < 64; }  // BitReader::finalize
 };
+__device__ __forceinline__ uint32_t bfe(uint32_t v, uint32_t pos, uint32_t len) {
+    uint32_t r;
+    asm("bfe.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(v), "r"(pos), "r"(len));
+    return r;
+}
 __device__ __forceinline__ uint32_t bits_at(uint64_t win, int pos, uint32_t n) {  // n < 32
     uint32_t x = (uint32_t)(win >> pos), r;
     asm("bfe.u32 %0, %1, 0, %2;" : "=r"(r) : "r"(x), "r"(n));
@@ -395,9 +418,11 @@ k_fse_literals(const uint8_t *__restrict__ src_base, const BlockDesc *__restrict
                     uint32_t *out = reinterpret_cast<uint32_t *>(lit_scratch + fd.lit_off);  // 16-byte aligned
                     const uint32_t n_it = fd.n_literals >> 2;
                     // One step = the reference's loop body: 4 literals, states 0..3 in that order, one flush.
-                    auto step = [&]() -> uint32_t {
+                    // FAST = no dead-reader handling (the caller keeps P >= 57) and no per-step prefetch.
+                    auto step = [&](auto fast_tag) -> uint32_t {
+                        constexpr bool FAST = decltype(fast_tag)::value;
                         int cur;
-                        const uint64_t win = br.window(cur);
+                        const uint64_t win = FAST ? br.window_fast(cur) : br.window(cur);
                         const uint32_t e0 = kd[s0 * 32 + lane], e1 = kd[s1 * 32 + lane], e2 = kd[s2 * 32 + lane], e3 = kd[s3 * 32 + lane];
                         const uint32_t y0 = sy[s0 * 32 + lane], y1 = sy[s1 * 32 + lane], y2 = sy[s2 * 32 + lane], y3 = sy[s3 * 32 + lane];
                         const uint32_t k0 = e0 >> 12, k1 = e1 >> 12, k2 = e2 >> 12, k3 = e3 >> 12;
@@ -409,13 +434,21 @@ k_fse_literals(const uint8_t *__restrict__ src_base, const BlockDesc *__restrict
                         br.P -= cur - p3;
                         return y0 | (y1 << 8) | (y2 << 16) | (y3 << 24);
                     };
+                    const BitWindow br0 = br;
                     uint32_t it = 0;
-                    for (; it + 4 <= n_it; it += 4) {
+                    for (; it + 4 <= n_it && br.P >= 57 + 3 * 40; it += 4) {  // 16 literals, one 16-byte store
+                        br.prefetch();
                         uint4 v;
-                        v.x = step(); v.y = step(); v.z = step(); v.w = step();
+                        v.x = step(std::true_type{}); v.y = step(std::true_type{}); v.z = step(std::true_type{}); v.w = step(std::true_type{});
                         __stcg(reinterpret_cast<uint4 *>(out + it), v);
                     }
-                    for (; it < n_it; it++) out[it] = step();
+                    for (; it < n_it && br.P >= 57; it++) out[it] = step(std::true_type{});
+                    if (it != n_it) {  // the reader came within 57 bits of the pad: redo with the reference's exact flush semantics
+                        br = br0;
+                        s0 = fd.lit_state[0]; s1 = fd.lit_state[1]; s2 = fd.lit_state[2]; s3 = fd.lit_state[3];
+                        for (it = 0; it < n_it; it++) out[it] = step(std::false_type{});
+                    }
+                    { int cur; br.window(cur); }  // the final flush
                     if (br.underflow()) atomicMin(&err[bd.stream], err_key(kb, PH_LIT, LZFSE_B200_PAYLOAD_UNDERFLOW));
                     else if (s0 | s1 | s2 | s3) atomicMin(&err[bd.stream], err_key(kb, PH_LIT, LZFSE_B200_FSE_BAD_LMD_PAYLOAD));
                     else fse[f].ok_lit = 1;
@@ -428,8 +461,8 @@ k_fse_literals(const uint8_t *__restrict__ src_base, const BlockDesc *__restrict
 
 // ------------------------------------------------------------------------------------------------
 // LMD stage: lane per block.  L/M/D table [384][32] x u32 in shared memory (48 KiB per warp).
-// Entry bytes: [0] delta (relative to the symbol kind's first state)  [1] k  [2] k + v_bits  [3] symbol,
-// so every field is one byte-extract away.  v_base comes from the symbol in closed form.
+// Entry: delta[0:8] (relative to the symbol kind's first state) | k[8:12] | v_bits[12:16] | [16:32] = v_base for
+// L and M (<= 312), the symbol for D (v_base = ((4 + (s & 3)) << (s >> 2)) - 4 in closed form).
 // (fse/decoder.rs:244-292 build_v_table_block, fse/fse_core.rs:91-141 decode_internal)
 // ------------------------------------------------------------------------------------------------
 constexpr int kLmdWarps = 4;
@@ -453,12 +486,13 @@ __device__ __forceinline__ void build_v_block(WeightReader &r, uint32_t *tab, ui
         if (w == 0) continue;
         uint32_t k = __clz(w) - n_clz;
         uint32_t x = ((n_states << 1) >> k) - w;
-        uint32_t vb = KIND == 0 ? l_extra(sym) : (KIND == 1 ? m_extra(sym) : (sym >> 2));
+        const uint32_t vb = KIND == 0 ? l_extra(sym) : (KIND == 1 ? m_extra(sym) : (sym >> 2));
+        const uint32_t hi = KIND == 0 ? l_base(sym) : (KIND == 1 ? m_base(sym) : sym);
         for (uint32_t j = 0; j < w; j++) {
             uint32_t kk, delta;
             if (j < x) { kk = k; delta = ((w + j) << k) - n_states; }
             else { kk = k - 1; delta = (j - x) << (k - 1); }
-            tab[(offset + total + j) * 32 + lane] = delta | (kk << 8) | ((kk + vb) << 16) | (sym << 24);
+            tab[(offset + total + j) * 32 + lane] = delta | (kk << 8) | (vb << 12) | (hi << 16);
         }
         total += w;
     }
@@ -511,44 +545,83 @@ k_fse_lmds(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ ds
                     LmdRec *out = lmd_scratch + fd.lmd_off;
                     int fail = 0;
                     const uint32_t *tl = tab + lane, *tm = tab + 64 * 32 + lane, *td = tab + 128 * 32 + lane;
-                    // One step = one LMD (fse_core.rs:104-131).  Failures are latched, not branched on: the first
-                    // one wins, later (garbage) steps stay inside the tables and the scratch run.
-                    auto step = [&]() -> uint2 {
-                        int cur;
-                        const uint64_t win = br.window(cur);
-                        const uint32_t el = tl[sl * 32], em = tm[sm * 32], ed = td[sd * 32];
-                        const uint32_t kl = byte_of(el, 1), tlb = byte_of(el, 2);
-                        const uint32_t km = byte_of(em, 1), tmb = byte_of(em, 2);
-                        const uint32_t kd_ = byte_of(ed, 1), tdb = byte_of(ed, 2);
-                        const int pl = cur - (int)tlb, pm = pl - (int)tmb, pd = pm - (int)tdb;  // cursor after each symbol
-                        // state bits are pulled first, then the value bits (fse/decoder.rs:214-219)
-                        sl = bits_at(win, cur - (int)kl, kl) + byte_of(el, 0);
-                        const uint32_t L = l_base(el >> 24) + bits_at(win, pl, tlb - kl);
-                        sm = bits_at(win, pl - (int)km, km) + byte_of(em, 0);
-                        const uint32_t M = m_base(em >> 24) + bits_at(win, pm, tmb - km);
-                        sd = bits_at(win, pm - (int)kd_, kd_) + byte_of(ed, 0);
-                        const uint32_t dp = d_base(ed >> 24) + bits_at(win, pd, tdb - kd_);
-                        br.P -= cur - pd;
-                        D = dp ? dp : D;  // lmd/lmd_type.rs:155-159
-                        lit_index += L;
-                        rel += L;
-                        int f1 = lit_index > kLiteralsPerBlock ? LZFSE_B200_FSE_BAD_LMD_PAYLOAD
-                                 : (rel > room ? LZFSE_B200_BUFFER_OVERFLOW : 0);  // C-ABI: fixed-size Vec
-                        // lz/writer.rs:156-177: distance 0 or beyond what has been written
-                        const int f2 = (M != 0 && (D == 0 || D > before + rel)) ? LZFSE_B200_BAD_D_VALUE : 0;
-                        n_match += M;
-                        rel += M;
-                        const int f3 = rel > room ? LZFSE_B200_BUFFER_OVERFLOW : 0;
-                        f1 = f1 ? f1 : (f2 ? f2 : f3);
-                        fail = fail ? fail : f1;
-                        return make_uint2(L | (M << 16), D);
-                    };
-                    uint32_t i = 0;
-                    for (; i + 2 <= fd.n_lmds; i += 2) {  // two 8-byte records per 16-byte store (lmd_off is even)
-                        const uint2 r0 = step(), r1 = step();
-                        __stcg(reinterpret_cast<uint4 *>(out + i), make_uint4(r0.x, r0.y, r1.x, r1.y));
+                    const BitWindow br0 = br;
+                    // ---- fast path --------------------------------------------------------------------
+                    // literal_index and the bytes produced only grow, so "literal_index > 40000" and "does not
+                    // fit dst" are decided once at the end; per LMD only the distance is checked.  Anything
+                    // suspicious (or the reader getting within 57 bits of the pad) falls back to the exact loop
+                    // below, which reports what the reference reports first.
+                    bool suspicious = false;
+                    {
+                        auto fast = [&]() -> uint2 {
+                            int cur;
+                            const uint64_t win = br.window_fast(cur);
+                            const uint32_t el = tl[sl * 32], em = tm[sm * 32], ed = td[sd * 32];
+                            const uint32_t kl = bfe(el, 8, 4), vl = bfe(el, 12, 4), km = bfe(em, 8, 4), vm = bfe(em, 12, 4);
+                            const uint32_t kd_ = bfe(ed, 8, 4), vd = bfe(ed, 12, 4);
+                            const int a0 = cur - (int)kl, a1 = a0 - (int)vl, a2 = a1 - (int)km, a3 = a2 - (int)vm, a4 = a3 - (int)kd_,
+                                      a5 = a4 - (int)vd;
+                            sl = bits_at(win, a0, kl) + (el & 0xFF);
+                            const uint32_t L = (el >> 16) + bits_at(win, a1, vl);
+                            sm = bits_at(win, a2, km) + (em & 0xFF);
+                            const uint32_t M = (em >> 16) + bits_at(win, a3, vm);
+                            sd = bits_at(win, a4, kd_) + (ed & 0xFF);
+                            const uint32_t dp = d_base(ed >> 16) + bits_at(win, a5, vd);
+                            br.P -= cur - a5;
+                            D = dp ? dp : D;
+                            lit_index += L;
+                            rel += L;
+                            suspicious |= (M != 0) & (D - 1u >= before + rel);  // D == 0 or D beyond what exists
+                            rel += M;
+                            return make_uint2(L | (M << 16), D);
+                        };
+                        uint32_t i = 0;
+                        for (; i + 2 <= fd.n_lmds && br.P >= 57 + 54; i += 2) {  // two 8-byte records per 16-byte store
+                            br.prefetch();
+                            const uint2 r0 = fast(), r1 = fast();
+                            __stcg(reinterpret_cast<uint4 *>(out + i), make_uint4(r0.x, r0.y, r1.x, r1.y));
+                        }
+                        for (; i < fd.n_lmds && br.P >= 57; i++) *reinterpret_cast<uint2 *>(out + i) = fast();
+                        suspicious |= i != fd.n_lmds || lit_index > kLiteralsPerBlock || rel > room;
+                        n_match = rel - lit_index;
                     }
-                    if (i < fd.n_lmds) *reinterpret_cast<uint2 *>(out + i) = step();
+                    if (suspicious) {
+                        // ---- exact path: one step = one LMD (fse_core.rs:104-131), failures latched in order ----
+                        br = br0;
+                        sl = fd.lmd_state[0]; sm = fd.lmd_state[1]; sd = fd.lmd_state[2];
+                        lit_index = 0; n_match = 0; D = 0; rel = 0;
+                        auto step = [&]() -> uint2 {
+                            int cur;
+                            const uint64_t win = br.window(cur);
+                            const uint32_t el = tl[sl * 32], em = tm[sm * 32], ed = td[sd * 32];
+                            const uint32_t kl = bfe(el, 8, 4), vl = bfe(el, 12, 4), km = bfe(em, 8, 4), vm = bfe(em, 12, 4);
+                            const uint32_t kd_ = bfe(ed, 8, 4), vd = bfe(ed, 12, 4);
+                            const int a0 = cur - (int)kl, a1 = a0 - (int)vl, a2 = a1 - (int)km, a3 = a2 - (int)vm, a4 = a3 - (int)kd_,
+                                      a5 = a4 - (int)vd;
+                            // state bits are pulled first, then the value bits (fse/decoder.rs:214-219)
+                            sl = bits_at(win, a0, kl) + (el & 0xFF);
+                            const uint32_t L = (el >> 16) + bits_at(win, a1, vl);
+                            sm = bits_at(win, a2, km) + (em & 0xFF);
+                            const uint32_t M = (em >> 16) + bits_at(win, a3, vm);
+                            sd = bits_at(win, a4, kd_) + (ed & 0xFF);
+                            const uint32_t dp = d_base(ed >> 16) + bits_at(win, a5, vd);
+                            br.P -= cur - a5;
+                            D = dp ? dp : D;  // lmd/lmd_type.rs:155-159
+                            lit_index += L;
+                            rel += L;
+                            int f1 = lit_index > kLiteralsPerBlock ? LZFSE_B200_FSE_BAD_LMD_PAYLOAD
+                                     : (rel > room ? LZFSE_B200_BUFFER_OVERFLOW : 0);  // C-ABI: fixed-size Vec
+                            // lz/writer.rs:156-177: distance 0 or beyond what has been written
+                            const int f2 = (M != 0 && (D == 0 || D > before + rel)) ? LZFSE_B200_BAD_D_VALUE : 0;
+                            n_match += M;
+                            rel += M;
+                            const int f3 = rel > room ? LZFSE_B200_BUFFER_OVERFLOW : 0;
+                            f1 = f1 ? f1 : (f2 ? f2 : f3);
+                            fail = fail ? fail : f1;
+                            return make_uint2(L | (M << 16), D);
+                        };
+                        for (uint32_t i = 0; i < fd.n_lmds; i++) *reinterpret_cast<uint2 *>(out + i) = step();
+                    }
                     if (!fail) { int cur; br.window(cur); }  // the final flush (sets nothing, P unchanged)
                     if (!fail && br.underflow()) fail = LZFSE_B200_PAYLOAD_UNDERFLOW;
                     if (!fail && !(lit_index <= fd.n_literals && n_match + lit_index == fd.n_raw && sl == 0 && sm == 0 && sd == 0))
