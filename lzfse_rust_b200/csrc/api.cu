@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <new>
 #include <string>
 
@@ -60,8 +61,10 @@ int decode_batch_device_impl(lzfse_b200_decoder *d, const uint8_t *src, const ui
     uint64_t *raw_total = raw_len ? raw_len : d->raw_total.as<uint64_t>();
     d->timer.begin(s);
 
+    // Totals go straight into pinned host memory (UVA): no device-to-host copy that could queue behind a bulk
+    // download on the copy engine.
     launch_scan_count(src, src_off, src_len, probe_only ? nullptr : dst_cap, n, d->counts.as<StreamCounts>(), d->err.as<uint32_t>(), raw_total,
-                      n_blocks, d->totals_dev.as<StreamCounts>(), s);
+                      n_blocks, d->totals_host.as<StreamCounts>(), s);
     d->launches += 2;
     if (probe_only) {
         launch_finish(d->err.as<uint32_t>(), raw_total, nullptr, status, n, s);
@@ -71,7 +74,6 @@ int decode_batch_device_impl(lzfse_b200_decoder *d, const uint8_t *src, const ui
         return LZFSE_B200_OK;
     }
     // The one host round trip: scratch sizes depend on what the headers announce.
-    CK(d, cudaMemcpyAsync(d->totals_host.p, d->totals_dev.p, sizeof(StreamCounts), cudaMemcpyDeviceToHost, s));
     CK(d, cudaStreamSynchronize(s));
     const StreamCounts tot = *d->totals_host.as<StreamCounts>();
     if (tot.n_fse > 0xFFFFFFFFull) { d->last_error = "too many FSE blocks in one batch"; return LZFSE_B200_INVALID_ARGUMENT; }
@@ -213,6 +215,74 @@ int lzfse_b200_decode_probe_batch_device(lzfse_b200_decoder *d, const uint8_t *s
 }
 
 // Host-buffer variants: stage the bytes on the device (host_util.h), run the device path, copy back.
+//
+// Large dense batches are cut into a few consecutive slices so that the upload of slice k+1, the kernels
+// of slice k and the download of slice k-1 overlap (PCIe is full duplex).  Few slices only: the entropy
+// stages are bound by the serial latency of one block, so every extra slice costs that latency again.
+static int decode_batch_host_pipelined(lzfse_b200_decoder *d, const uint8_t *src, const uint64_t *src_off, const uint64_t *src_len, uint8_t *dst,
+                                       const uint64_t *dst_off, uint64_t *out_len, int32_t *status, size_t n, int n_slices) {
+    cudaStream_t s = d->own_stream;
+    HostStage &st = d->stage;
+    if (!st.copy_in) {
+        CK(d, cudaStreamCreateWithFlags(&st.copy_in, cudaStreamNonBlocking));
+        CK(d, cudaStreamCreateWithFlags(&st.copy_out, cudaStreamNonBlocking));
+        for (auto &e : st.ev_in) CK(d, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    const uint64_t *pin = st.pin.as<uint64_t>();
+    uint64_t *dd = st.desc.as<uint64_t>();
+    // per-stream results are written by k_finish directly into pinned host memory (after the 4n descriptor words)
+    uint64_t *d_out_len = st.pin.as<uint64_t>() + 4 * n;
+    int32_t *d_status = reinterpret_cast<int32_t *>(d_out_len + n);
+    // Slice boundaries by bytes crossing the bus.  The download engine is the bound, and it can only start
+    // once the first slice's kernels are done (a fixed latency), so the first slice is the smallest.
+    size_t cut[5] = {0, 0, 0, 0, n};
+    {
+        static const uint32_t share_pct[3][4] = {{100, 100, 100, 100}, {40, 100, 100, 100}, {20, 55, 100, 100}};
+        uint64_t total = 0, acc = 0;
+        for (size_t i = 0; i < n; i++) total += src_len[i] + pin[3 * n + i];
+        int k = 1;
+        for (size_t i = 0; i < n && k < n_slices; i++) {
+            acc += src_len[i] + pin[3 * n + i];
+            if (acc >= total / 100 * share_pct[n_slices - 1][k - 1]) cut[k++] = i + 1;
+        }
+        for (; k < n_slices; k++) cut[k] = n;
+        cut[n_slices] = n;
+    }
+    // uploads, in slice order, on their own stream
+    for (int k = 0; k < n_slices; k++) {
+        const size_t i0 = cut[k], i1 = cut[k + 1];
+        if (i1 > i0) {
+            const uint64_t lo = src_off[i0], hi = src_off[i1 - 1] + src_len[i1 - 1];
+            if (hi > lo) CK(d, cudaMemcpyAsync(st.src.as<uint8_t>() + (lo - st.src_lo), src + lo, hi - lo, cudaMemcpyHostToDevice, st.copy_in));
+        }
+        CK(d, cudaEventRecord(st.ev_in[k], st.copy_in));
+    }
+    uint64_t launches = 0;
+    const bool dbg = getenv("LZB_DEBUG") != nullptr;
+    auto now = []() { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec * 1e3 + t.tv_nsec * 1e-6; };
+    const double t_start = now();
+    for (int k = 0; k < n_slices; k++) {
+        const size_t i0 = cut[k], i1 = cut[k + 1], m = i1 - i0;
+        if (m == 0) continue;
+        if (dbg) fprintf(stderr, "[lzb] slice %d: streams [%zu,%zu) start %.2f ms\n", k, i0, i1, now() - t_start);
+        CK(d, cudaStreamWaitEvent(s, st.ev_in[k], 0));
+        int rc = decode_batch_device_impl(d, st.src.as<uint8_t>(), dd + i0, dd + n + i0, st.dst.as<uint8_t>(), dd + 2 * n + i0, dd + 3 * n + i0,
+                                          d_out_len + i0, d_status + i0, nullptr, nullptr, m, s, false);
+        if (rc) return rc;
+        launches += d->launches;
+        memcpy(out_len + i0, d_out_len + i0, m * sizeof(uint64_t));  // the call above synchronised the stream
+        memcpy(status + i0, d_status + i0, m * sizeof(int32_t));
+        if (dbg) fprintf(stderr, "[lzb] slice %d: kernels done %.2f ms\n", k, now() - t_start);
+        rc = fetch_outputs(d, st, dst, dst_off, out_len, status, n, st.copy_out, i0, i1);  // overlaps the next slice's kernels
+        if (rc) return rc;
+        if (dbg) fprintf(stderr, "[lzb] slice %d: download enqueued %.2f ms\n", k, now() - t_start);
+    }
+    d->launches = launches;
+    CK(d, cudaStreamSynchronize(st.copy_out));
+    if (dbg) fprintf(stderr, "[lzb] all downloads done %.2f ms\n", now() - t_start);
+    return LZFSE_B200_OK;
+}
+
 int lzfse_b200_decode_batch_host(lzfse_b200_decoder *d, const uint8_t *src, const uint64_t *src_off, const uint64_t *src_len, uint8_t *dst,
                                  const uint64_t *dst_off, const uint64_t *dst_cap, uint64_t *out_len, int32_t *status, size_t n) {
     if (!d || (n && (!src || !src_off || !src_len || !dst_off || !dst_cap || !out_len || !status))) return LZFSE_B200_INVALID_ARGUMENT;
@@ -221,13 +291,27 @@ int lzfse_b200_decode_batch_host(lzfse_b200_decoder *d, const uint8_t *src, cons
     if (!g.ok) return LZFSE_B200_CUDA_ERROR;
     cudaStream_t s = d->own_stream;
     HostStage &st = d->stage;
-    int rc = stage_sources(d, st, src, src_off, src_len, n, 4 * n, s);
+    // pipelining needs streams laid out in order on both sides (the usual packed batch) and enough bytes to matter
+    uint64_t bytes = 0;
+    bool ordered = n >= 64;
+    for (size_t i = 0; i < n; i++) {
+        bytes += src_len[i] + dst_cap[i];
+        if (i && (src_off[i] < src_off[i - 1] + src_len[i - 1] || dst_off[i] < dst_off[i - 1] + dst_cap[i - 1])) ordered = false;
+    }
+    const bool want_pipeline = ordered && bytes >= (256ull << 20);
+    int rc = stage_sources(d, st, src, src_off, src_len, n, 6 * n + 8, s, want_pipeline);
     if (rc) return rc;
     rc = stage_outputs(d, st, dst_off, dst_cap, n);
     if (rc) return rc;
     CK(d, st.desc.reserve(4 * n * sizeof(uint64_t)));
     CK(d, st.res.reserve(n * (sizeof(uint64_t) + sizeof(int32_t))));
     CK(d, cudaMemcpyAsync(st.desc.p, st.pin.p, 4 * n * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    if (want_pipeline && st.src_mirrored && st.dst_mirrored) return decode_batch_host_pipelined(d, src, src_off, src_len, dst, dst_off, out_len, status, n, 3);
+    if (want_pipeline && st.src_mirrored) {  // upload was deferred but the output side cannot be sliced: do it now
+        uint64_t lo = ~0ull, hi = 0;
+        for (size_t i = 0; i < n; i++) { if (src_off[i] < lo) lo = src_off[i]; if (src_off[i] + src_len[i] > hi) hi = src_off[i] + src_len[i]; }
+        if (hi > lo) CK(d, cudaMemcpyAsync(st.src.p, src + lo, hi - lo, cudaMemcpyHostToDevice, s));
+    }
     uint64_t *dd = st.desc.as<uint64_t>();
     uint64_t *d_out_len = st.res.as<uint64_t>();
     int32_t *d_status = reinterpret_cast<int32_t *>(d_out_len + n);

@@ -895,9 +895,8 @@ int encode_batch_device_impl(lzfse_b200_encoder *e, const uint8_t *src, const ui
     const int tb = 128;
     e->timer.begin(s);
     k_enc_prep<<<(unsigned)((n + tb - 1) / tb), tb, 0, s>>>(src_len, n, e->streams.as<EncStream>(), e->counts.as<StreamCounts>(), status);
-    k_exclusive_scan<<<1, 1024, 0, s>>>(e->counts.as<StreamCounts>(), n, e->totals_dev.as<StreamCounts>());
+    k_exclusive_scan<<<1, 1024, 0, s>>>(e->counts.as<StreamCounts>(), n, e->totals_host.as<StreamCounts>());  // pinned host memory (UVA)
     e->launches += 2;
-    LZB_CK(e, cudaMemcpyAsync(e->totals_host.p, e->totals_dev.p, sizeof(StreamCounts), cudaMemcpyDeviceToHost, s));
     LZB_CK(e, cudaStreamSynchronize(s));
     const StreamCounts tot = *e->totals_host.as<StreamCounts>();  // {packs, literal bytes, block slots, out bytes}
     if (tot.n_literals > 0xFFFFFFF0ull) { e->last_error = "too many blocks in one batch"; return LZFSE_B200_INVALID_ARGUMENT; }

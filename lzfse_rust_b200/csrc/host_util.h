@@ -91,14 +91,23 @@ struct HostStage {
     DevBuf src, dst, desc, res;
     PinnedBuf pin;
     uint64_t src_lo = 0, dst_lo = 0;
-    bool dst_mirrored = false;
-    void release() { src.release(); dst.release(); desc.release(); res.release(); pin.release(); }
+    bool src_mirrored = false, dst_mirrored = false;
+    size_t pin_n = 0;  // batch size the pin[] layout was built for
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;  // side streams of the pipelined host path
+    cudaEvent_t ev_in[4] = {};
+    void release() {
+        src.release(); dst.release(); desc.release(); res.release(); pin.release();
+        if (copy_in) cudaStreamDestroy(copy_in);
+        if (copy_out) cudaStreamDestroy(copy_out);
+        for (auto &e : ev_in) if (e) cudaEventDestroy(e);
+        copy_in = copy_out = nullptr;
+    }
 };
 
 // Fills pin[0..n) = device src offsets, pin[n..2n) = src_len and uploads the source bytes.
 template <class H>
 int stage_sources(H *h, HostStage &st, const uint8_t *src, const uint64_t *src_off, const uint64_t *src_len, size_t n, size_t pin_words,
-                  cudaStream_t s) {
+                  cudaStream_t s, bool defer_dense_upload = false) {
     uint64_t lo = ~0ull, hi = 0, sum = 0;
     for (size_t i = 0; i < n; i++) {
         if (src_off[i] < lo) lo = src_off[i];
@@ -107,11 +116,13 @@ int stage_sources(H *h, HostStage &st, const uint8_t *src, const uint64_t *src_o
     }
     if (n == 0) { lo = 0; hi = 0; }
     LZB_CK(h, st.pin.reserve(pin_words * sizeof(uint64_t)));
+    st.pin_n = n;
     uint64_t *pin = st.pin.as<uint64_t>();
     const bool dense = (hi - lo) <= 2 * sum + 4096;
+    st.src_mirrored = dense;
     if (dense) {
         LZB_CK(h, st.src.reserve(hi - lo + 64));
-        if (hi > lo) LZB_CK(h, cudaMemcpyAsync(st.src.p, src + lo, hi - lo, cudaMemcpyHostToDevice, s));
+        if (hi > lo && !defer_dense_upload) LZB_CK(h, cudaMemcpyAsync(st.src.p, src + lo, hi - lo, cudaMemcpyHostToDevice, s));
         for (size_t i = 0; i < n; i++) { pin[i] = src_off[i] - lo; pin[n + i] = src_len[i]; }
     } else {
         uint64_t off = 0;
@@ -151,14 +162,16 @@ int stage_outputs(H *h, HostStage &st, const uint64_t *dst_off, const uint64_t *
 // Copies every successful stream's bytes back; neighbours that are adjacent on both sides share a copy.
 template <class H>
 int fetch_outputs(H *h, HostStage &st, uint8_t *dst, const uint64_t *dst_off, const uint64_t *out_len, const int32_t *status, size_t n,
-                  cudaStream_t s) {
+                  cudaStream_t s, size_t i0 = 0, size_t i1 = ~(size_t)0) {
     const uint64_t *pin = st.pin.as<uint64_t>();
-    size_t i = 0;
+    size_t i = i0;
+    if (i1 < n) n = i1;  // only streams [i0, i1); pin[] is still indexed with the full batch size
+    const size_t full = st.pin_n;
     while (i < n) {
         if (status[i] != 0 || out_len[i] == 0) { i++; continue; }
-        uint64_t h0 = dst_off[i], d0 = pin[2 * n + i], run = out_len[i];
+        uint64_t h0 = dst_off[i], d0 = pin[2 * full + i], run = out_len[i];
         size_t j = i + 1;
-        while (j < n && status[j] == 0 && dst_off[j] == h0 + run && pin[2 * n + j] == d0 + run) { run += out_len[j]; j++; }
+        while (j < n && status[j] == 0 && dst_off[j] == h0 + run && pin[2 * full + j] == d0 + run) { run += out_len[j]; j++; }
         LZB_CK(h, cudaMemcpyAsync(dst + h0, st.dst.template as<uint8_t>() + d0, run, cudaMemcpyDeviceToHost, s));
         i = j;
     }

@@ -176,3 +176,33 @@ def test_frame_level_errors(dec):
     outs, status = dec.decode_batch([comp], caps=[999])
     assert status[0] == 5
     assert dec.decode_batch([], caps=[])[0] == []
+
+
+def test_large_host_batch_pipelined(dec):
+    """>= 256 MiB crossing the bus: the host entry point slices the batch and overlaps copies with kernels.
+    Size-independent property: decode(encode(x)) == x for every stream; one corrupted stream in the
+    middle must fail alone."""
+    import lzfse_rust_b200 as L
+    from bench_support import workload as W
+
+    enc = L.LzfseEncoder(0)
+    pool, woff = W.word_pool(dec)
+    n, cl = 3200, 65536
+    raw = W.text_chunks(pool, woff, n, cl, seed0=0x0BAD5EED)
+    bound = enc.encode_bound(cl)
+    comp = np.empty(n * bound, np.uint8)
+    c_len, st = enc.encode_batch_into(raw, np.arange(n) * cl, np.full(n, cl), comp, np.arange(n) * bound, np.full(n, bound))
+    assert not st.any()
+    offs = np.concatenate([[0], np.cumsum(c_len)[:-1]]).astype(np.uint64)
+    packed = np.concatenate([comp[i * bound:i * bound + int(c_len[i])] for i in range(n)])
+    bad = n // 2
+    packed[int(offs[bad]) + 40] ^= 0xFF  # inside the weight table / payload of one frame
+    out = np.zeros(n * cl, np.uint8)
+    o_len, status = dec.decode_batch_into(packed, offs, c_len, out, np.arange(n) * cl, np.full(n, cl))
+    frame = packed[int(offs[bad]):int(offs[bad]) + int(c_len[bad])].tobytes()
+    assert status[bad] == ob.decode(frame, cap=cl)[0] != 0
+    ok = np.ones(n, bool); ok[bad] = False
+    assert not status[ok].any() and (o_len[ok] == cl).all()
+    got, want = out.reshape(n, cl), raw.reshape(n, cl)
+    assert np.array_equal(got[ok], want[ok])
+    enc.close()
