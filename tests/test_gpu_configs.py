@@ -1,0 +1,70 @@
+"""Parity on the other BASELINE.json workloads at reduced scale: large multi-block streams with
+cross-block match distances (configs[3]) and the mixed corpus (configs[4]: incompressible, LZVN-sized
+and raw-sized chunks, highly repetitive data, text).  Both directions, checked against the oracle."""
+import numpy as np
+import pytest
+
+import oracle_binding as ob
+import testkit as tk
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def codec():
+    import lzfse_rust_b200 as L
+
+    e, d = L.LzfseEncoder(0), L.LzfseDecoder(0)
+    yield e, d
+    e.close(); d.close()
+
+
+def test_large_streams(codec):
+    """One 16 MiB stream (~250 bvx2 blocks, matches reaching up to 262139 bytes back across blocks) plus 4 MiB ones."""
+    from bench_support import workload as W
+
+    enc, dec = codec
+    pool, woff = W.word_pool(dec)
+    big = W.text_chunks(pool, woff, 1, 16 << 20, seed0=0x16000000).tobytes()
+    mids = [W.text_chunks(pool, woff, 1, 4 << 20, seed0=0x16000001 + i).tobytes() for i in range(2)]
+    rep = (tk.rng_gen_vec(5, 300000) * 14)[: 4 << 20]  # period 300000 > max distance: long far matches fail, near ones hit
+    streams = [big] + mids + [rep]
+    frames, st = enc.encode_batch(streams)
+    assert not st.any()
+    oenc = ob.Encoder()
+    for s, f in zip(streams, frames):
+        assert f == oenc.encode(s)[1]                      # bit-exact with the reference encoder
+    raw, nb, pst = dec.probe_batch(np.frombuffer(b"".join(frames), np.uint8), np.cumsum([0] + [len(f) for f in frames[:-1]]), [len(f) for f in frames])
+    assert not pst.any() and list(raw) == [len(s) for s in streams] and nb[0] > 200
+    outs, dst = dec.decode_batch(frames)
+    assert not dst.any() and outs == streams
+
+
+def test_mixed_corpus(codec):
+    enc, dec = codec
+    rng = np.random.default_rng(2024)
+    chunks = []
+    for i in range(48):                                                     # (i) incompressible 64 KiB
+        chunks.append(tk.rng_gen_vec(i, 65536))
+    x = 12345
+    for i in range(400):                                                    # (ii) LZVN-sized + a sprinkle of raw-sized
+        x = (x * 1103515245 + 12345) & 0xFFFFFFFF
+        n = 21 + (x % 4076) if i % 10 else x % 21
+        chunks.append(tk.synth_text(7000 + i, n) if i % 3 else tk.seq_bytes(i, n, 0x07070707))
+    for p in list(range(1, 17)) + [32, 64]:                                  # (iii) period-p repeats + the huge-test stream
+        chunks.append((tk.rng_gen_vec(p, p) * (65536 // p + 1))[:65536])
+    chunks.append(tk.seq_bytes(0, 65536, 0x03030000))
+    for i in range(48):                                                     # (iv) text
+        chunks.append(tk.synth_text(0x5EED0000 + i, 65536))
+    order = rng.permutation(len(chunks))
+    chunks = [chunks[i] for i in order]
+    frames, st = enc.encode_batch(chunks)
+    assert not st.any()
+    oenc = ob.Encoder()
+    kinds = set()
+    for c, f in zip(chunks, frames):
+        assert f == oenc.encode(c)[1]
+        kinds.add(f[:4])
+    assert kinds >= {b"bvx-", b"bvxn", b"bvx2"}
+    outs, dst = dec.decode_batch(frames)
+    assert not dst.any() and outs == chunks
