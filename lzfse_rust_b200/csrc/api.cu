@@ -299,6 +299,8 @@ int lzfse_b200_decode_batch_host(lzfse_b200_decoder *d, const uint8_t *src, cons
         if (i && (src_off[i] < src_off[i - 1] + src_len[i - 1] || dst_off[i] < dst_off[i - 1] + dst_cap[i - 1])) ordered = false;
     }
     const bool want_pipeline = ordered && bytes >= (256ull << 20);
+    // Stage timing is a device-API measurement aid; its timestamp events would serialise the copy/compute overlap here.
+    struct TimerOff { StageTimer &t; bool was; explicit TimerOff(StageTimer &x) : t(x), was(x.enabled) { t.enabled = false; } ~TimerOff() { t.enabled = was; } } timer_off(d->timer);
     int rc = stage_sources(d, st, src, src_off, src_len, n, 6 * n + 8, s, want_pipeline);
     if (rc) return rc;
     rc = stage_outputs(d, st, dst_off, dst_cap, n);

@@ -760,11 +760,11 @@ __device__ void expand_fse_block(uint8_t *__restrict__ out /* block's first outp
     (void)block_pos;
     // The records of step b+1 are fetched while step b is being copied: one memory round trip less per step.
     uint2 nxt = make_uint2(0, 0);
-    if (lane < n_lmds) nxt = __ldg(reinterpret_cast<const uint2 *>(lmds) + lane);
+    if (lane < n_lmds) nxt = __ldcs(reinterpret_cast<const uint2 *>(lmds) + lane);  // read once: do not displace output lines in L2
     for (uint32_t b = 0; b < n_lmds; b += 32) {
         const uint2 rec = nxt;
         nxt = make_uint2(0, 0);
-        if (b + 32 + lane < n_lmds) nxt = __ldg(reinterpret_cast<const uint2 *>(lmds) + b + 32 + lane);
+        if (b + 32 + lane < n_lmds) nxt = __ldcs(reinterpret_cast<const uint2 *>(lmds) + b + 32 + lane);
         const uint32_t L = rec.x & 0xFFFF, M = rec.x >> 16, D = rec.y;
         if (lane == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(lit + lit_base + 128));  // scratch has slack past its end
         // inclusive scan of (sum L) << 17 | (sum L+M): 32*315 < 2^14, 32*(315+2359) < 2^17
@@ -782,18 +782,24 @@ __device__ void expand_fse_block(uint8_t *__restrict__ out /* block's first outp
 
         // ---- literals ----
         const bool long_l = L > kShortCopy;
-        {   // short runs: every lane copies its own, in groups of 4 bytes (loads first, then stores), and the
-            // warp stops at the longest short run of the step instead of always issuing kShortCopy slots
+        {   // short runs: every lane copies its own.  Pointers are hoisted and the byte offsets are immediates,
+            // so a group of 4 bytes is 4 predicates + 4 loads + 4 stores; groups beyond the longest short run
+            // of the step are skipped for the whole warp.
             const uint32_t sl = long_l ? 0u : L;
             const uint32_t max_l = __reduce_max_sync(0xFFFFFFFFu, sl);
-            for (uint32_t t0 = 0; t0 < max_l; t0 += 4) {
-                uint8_t tmp[4];
+            const uint8_t *ps = lit + my_lit;
+            uint8_t *pd = out + my_out;
 #pragma unroll
-                for (uint32_t k = 0; k < 4; k++)
-                    if (t0 + k < sl) tmp[k] = lit[my_lit + t0 + k];
+            for (uint32_t g = 0; g < kShortCopy; g += 4) {
+                if (g < max_l) {
+                    uint8_t tmp[4];
 #pragma unroll
-                for (uint32_t k = 0; k < 4; k++)
-                    if (t0 + k < sl) out[my_out + t0 + k] = tmp[k];
+                    for (uint32_t k = 0; k < 4; k++)
+                        if (g + k < sl) tmp[k] = __ldcs(ps + g + k);
+#pragma unroll
+                    for (uint32_t k = 0; k < 4; k++)
+                        if (g + k < sl) pd[g + k] = tmp[k];
+                }
             }
         }
         uint32_t mask = __ballot_sync(0xFFFFFFFFu, long_l);
@@ -816,14 +822,18 @@ __device__ void expand_fse_block(uint8_t *__restrict__ out /* block's first outp
         {
             const uint32_t sm_ = solo ? M : 0u;
             const uint32_t max_m = __reduce_max_sync(0xFFFFFFFFu, sm_);
-            for (uint32_t t0 = 0; t0 < max_m; t0 += 4) {
-                uint8_t tmp[4];
+            uint8_t *pd = out + my_dst;
 #pragma unroll
-                for (uint32_t k = 0; k < 4; k++)
-                    if (t0 + k < sm_) tmp[k] = src[t0 + k];
+            for (uint32_t g = 0; g < kShortCopy; g += 4) {
+                if (g < max_m) {
+                    uint8_t tmp[4];
 #pragma unroll
-                for (uint32_t k = 0; k < 4; k++)
-                    if (t0 + k < sm_) out[my_dst + t0 + k] = tmp[k];
+                    for (uint32_t k = 0; k < 4; k++)
+                        if (g + k < sm_) tmp[k] = src[g + k];
+#pragma unroll
+                    for (uint32_t k = 0; k < 4; k++)
+                        if (g + k < sm_) pd[g + k] = tmp[k];
+                }
             }
         }
         mask = __ballot_sync(0xFFFFFFFFu, M != 0 && !solo);

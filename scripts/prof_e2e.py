@@ -6,6 +6,7 @@ sys.path.insert(0, ROOT)
 import lzfse_rust_b200 as L
 from bench_support import workload as W
 dec, enc = L.LzfseDecoder(0), L.LzfseEncoder(0)
+if os.environ.get("LZB_TIMING"): dec.set_timing(True)
 pool, woff = W.word_pool(dec)
 n, cl = 16384, 65536
 raw_h = torch.empty(n * cl, dtype=torch.uint8).pin_memory()
