@@ -760,11 +760,11 @@ __device__ void expand_fse_block(uint8_t *__restrict__ out /* block's first outp
     (void)block_pos;
     // The records of step b+1 are fetched while step b is being copied: one memory round trip less per step.
     uint2 nxt = make_uint2(0, 0);
-    if (lane < n_lmds) nxt = __ldcs(reinterpret_cast<const uint2 *>(lmds) + lane);  // read once: do not displace output lines in L2
+    if (lane < n_lmds) nxt = __ldg(reinterpret_cast<const uint2 *>(lmds) + lane);
     for (uint32_t b = 0; b < n_lmds; b += 32) {
         const uint2 rec = nxt;
         nxt = make_uint2(0, 0);
-        if (b + 32 + lane < n_lmds) nxt = __ldcs(reinterpret_cast<const uint2 *>(lmds) + b + 32 + lane);
+        if (b + 32 + lane < n_lmds) nxt = __ldg(reinterpret_cast<const uint2 *>(lmds) + b + 32 + lane);
         const uint32_t L = rec.x & 0xFFFF, M = rec.x >> 16, D = rec.y;
         if (lane == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(lit + lit_base + 128));  // scratch has slack past its end
         // inclusive scan of (sum L) << 17 | (sum L+M): 32*315 < 2^14, 32*(315+2359) < 2^17
@@ -795,7 +795,7 @@ __device__ void expand_fse_block(uint8_t *__restrict__ out /* block's first outp
                     uint8_t tmp[4];
 #pragma unroll
                     for (uint32_t k = 0; k < 4; k++)
-                        if (g + k < sl) tmp[k] = __ldcs(ps + g + k);
+                        if (g + k < sl) tmp[k] = ps[g + k];
 #pragma unroll
                     for (uint32_t k = 0; k < 4; k++)
                         if (g + k < sl) pd[g + k] = tmp[k];
