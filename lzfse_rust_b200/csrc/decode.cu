@@ -345,6 +345,81 @@ __device__ __forceinline__ uint32_t bfe(uint32_t v, uint32_t pos, uint32_t len) 
     asm("bfe.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(v), "r"(pos), "r"(len));
     return r;
 }
+
+// ------------------------------------------------------------------------------------------------
+// The same reader, fed from shared memory.
+//
+// A divergent global load (32 lanes, 32 different lines) costs one L1 wavefront per lane, and three of
+// them per symbol were more than half of the entropy kernels' time.  Each lane therefore owns a
+// 128-byte ring in shared memory that mirrors the 128 stream bytes around its cursor (ring offset =
+// global address mod 128); `cp.async` refills one 16-byte chunk at a time about 100 bytes ahead of the
+// cursor, so the window is three shared-memory loads and the global traffic is asynchronous.
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t kRing = 128;                 // bytes mirrored per lane
+constexpr uint32_t kRingStride = kRing + 16;    // per-lane stride (keeps 16-byte alignment, skews banks)
+constexpr uint32_t kRingBytesPerWarp = 32 * kRingStride;
+
+struct RingWindow {
+    const uint8_t *base;     // slice start
+    uintptr_t lo16, hi;      // chunks below lo16 are never needed (zero-filled); bytes at or above hi are not read
+    uintptr_t next_chunk;    // global address of the next (lower) 16-byte chunk to fetch
+    uint32_t ring;           // shared-memory address of this lane's ring
+    int P;                   // bit cursor, relative to the slice start
+    bool dead;
+
+    __device__ __forceinline__ void fetch_chunk(uintptr_t c) const {
+        uint32_t n = 16;
+        if (c < lo16) n = 0;
+        else if (c + 16 > hi) n = c < hi ? (uint32_t)(hi - c) : 0u;
+        const uintptr_t src = n ? c : lo16;  // any valid address when nothing is read
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(ring + ((uint32_t)c & (kRing - 1))), "l"(src), "r"(n) : "memory");
+    }
+    // slice = [start, start+len), len >= 8; `off` = unused high bits of the last byte; [rlo, rhi) = the stream's bytes.
+    __device__ __forceinline__ int init(const uint8_t *start, uint32_t len, uint32_t off, const uint8_t *rlo, const uint8_t *rhi,
+                                        uint32_t ring_addr) {
+        base = start; dead = false; ring = ring_addr;
+        lo16 = (reinterpret_cast<uintptr_t>(rlo) + 15) & ~(uintptr_t)15;
+        hi = reinterpret_cast<uintptr_t>(rhi);
+        P = (int)len * 8 - (int)off;
+        const uint32_t last = start[len - 1];  // BitReader::new: the `off` bits above the cursor must be zero
+        if (off != 0 && (last >> (8 - off)) != 0) return LZFSE_B200_BAD_BITSTREAM;
+        // first window: word-aligned address a4 .. a4 + 12; fill the 8 chunks ending with the one that holds a4 + 11
+        const uintptr_t a = reinterpret_cast<uintptr_t>(base) + (intptr_t)((P - 57) >> 3);
+        const uintptr_t top = (((a & ~(uintptr_t)3) + 11) & ~(uintptr_t)15);
+        for (uint32_t k = 0; k < kRing / 16; k++) fetch_chunk(top - 16 * k);
+        next_chunk = top - kRing;
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        return LZFSE_B200_OK;
+    }
+    // Window for the current cursor (callers guarantee P >= 57).  Also keeps the ring topped up.
+    __device__ __forceinline__ uint64_t window_fast(int &cur) {
+        const int byte = (P - 57) >> 3;
+        cur = P - byte * 8;
+        const uintptr_t a = reinterpret_cast<uintptr_t>(base) + (intptr_t)byte;
+        const uint32_t r = (uint32_t)a & 3u;
+        const uintptr_t a4 = a - r;
+        // the chunk slot above the window is free once the window's 12 bytes lie below it
+        if (a4 + 12 <= next_chunk + kRing) { fetch_chunk(next_chunk); next_chunk -= 16; }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 4;" ::: "memory");  // a chunk is needed dozens of steps after it was requested
+        const uint32_t o = (uint32_t)a4 & (kRing - 1);
+        uint32_t w0, w1, w2;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(ring + o));
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w1) : "r"(ring + ((o + 4) & (kRing - 1))));
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w2) : "r"(ring + ((o + 8) & (kRing - 1))));
+        const uint32_t lo = __funnelshift_r(w0, w1, r * 8), hi32 = __funnelshift_r(w1, w2, r * 8);
+        return ((uint64_t)hi32 << 32) | lo;
+    }
+    // Flush point with the reference's dead-reader semantics (reads below index 0 yield 0).
+    __device__ __forceinline__ uint64_t window(int &cur) {
+        if (P < 57) dead = true;
+        if (dead) { cur = P - ((P - 57) >> 3) * 8; return 0; }
+        return window_fast(cur);
+    }
+    __device__ __forceinline__ void prefetch() const {}
+    __device__ __forceinline__ bool underflow() const { return P < 64; }  // BitReader::finalize
+};
 __device__ __forceinline__ uint32_t bits_at(uint64_t win, int pos, uint32_t n) {  // n < 32
     uint32_t x = (uint32_t)(win >> pos), r;
     asm("bfe.u32 %0, %1, 0, %2;" : "=r"(r) : "r"(x), "r"(n));
@@ -360,15 +435,17 @@ __device__ __forceinline__ uint32_t byte_of(uint32_t v, int i) {  // one PRMT
 // (fse/decoder.rs:299-335 build_u_table, fse/literals.rs:49-91 Literals::load)
 // ------------------------------------------------------------------------------------------------
 constexpr int kLitWarps = 2;
-constexpr size_t kLitSmemPerWarp = 1024 * 32 * 3;
+constexpr size_t kLitSmemPerWarp = 1024 * 32 * 3 + kRingBytesPerWarp;
 
 __global__ void __launch_bounds__(kLitWarps * 32, 1)
-k_fse_literals(const uint8_t *__restrict__ src_base, const BlockDesc *__restrict__ blocks, FseDesc *__restrict__ fse, uint32_t n_fse, uint8_t *__restrict__ lit_scratch,
+k_fse_literals(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ src_off, const uint64_t *__restrict__ src_len,
+               const BlockDesc *__restrict__ blocks, FseDesc *__restrict__ fse, uint32_t n_fse, uint8_t *__restrict__ lit_scratch,
                uint32_t *err, uint32_t *work_counter) {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
     uint16_t *kd = reinterpret_cast<uint16_t *>(smem + warp * kLitSmemPerWarp);
     uint8_t *sy = smem + warp * kLitSmemPerWarp + 1024 * 32 * 2;
+    const uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(smem + warp * kLitSmemPerWarp + 1024 * 32 * 3) + lane * kRingStride;
     for (;;) {
         uint32_t base = 0;
         if (lane == 0) base = atomicAdd(work_counter, 32u);
@@ -409,8 +486,9 @@ k_fse_literals(const uint8_t *__restrict__ src_base, const BlockDesc *__restrict
 
                 // Literals::load.  The slice borrows the 8 bytes before the payload as the BitSrc pad
                 // (fse_core.rs:30-33): it is never consumed by a well-formed stream.
-                BitWindow br;
-                int st = br.init(blk + fd.header_size - 8, fd.n_lit_payload + 8, fd.lit_bits);
+                const uint8_t *s_lo = src_base + src_off[bd.stream], *s_hi = s_lo + src_len[bd.stream];
+                RingWindow br;
+                int st = br.init(blk + fd.header_size - 8, fd.n_lit_payload + 8, fd.lit_bits, s_lo, s_hi, ring_addr);
                 if (st) {
                     atomicMin(&err[bd.stream], err_key(kb, PH_LIT, st));
                 } else {
@@ -434,7 +512,6 @@ k_fse_literals(const uint8_t *__restrict__ src_base, const BlockDesc *__restrict
                         br.P -= cur - p3;
                         return y0 | (y1 << 8) | (y2 << 16) | (y3 << 24);
                     };
-                    const BitWindow br0 = br;
                     uint32_t it = 0;
                     for (; it + 4 <= n_it && br.P >= 57 + 3 * 40; it += 4) {  // 16 literals, one 16-byte store
                         br.prefetch();
@@ -444,7 +521,7 @@ k_fse_literals(const uint8_t *__restrict__ src_base, const BlockDesc *__restrict
                     }
                     for (; it < n_it && br.P >= 57; it++) out[it] = step(std::true_type{});
                     if (it != n_it) {  // the reader came within 57 bits of the pad: redo with the reference's exact flush semantics
-                        br = br0;
+                        br.init(blk + fd.header_size - 8, fd.n_lit_payload + 8, fd.lit_bits, s_lo, s_hi, ring_addr);
                         s0 = fd.lit_state[0]; s1 = fd.lit_state[1]; s2 = fd.lit_state[2]; s3 = fd.lit_state[3];
                         for (it = 0; it < n_it; it++) out[it] = step(std::false_type{});
                     }
@@ -466,7 +543,7 @@ k_fse_literals(const uint8_t *__restrict__ src_base, const BlockDesc *__restrict
 // (fse/decoder.rs:244-292 build_v_table_block, fse/fse_core.rs:91-141 decode_internal)
 // ------------------------------------------------------------------------------------------------
 constexpr int kLmdWarps = 4;
-constexpr size_t kLmdSmemPerWarp = 384 * 32 * 4;
+constexpr size_t kLmdSmemPerWarp = 384 * 32 * 4 + kRingBytesPerWarp;
 
 __device__ __forceinline__ uint32_t l_extra(uint32_t s) { return s < 16 ? 0u : (s == 16 ? 2u : (s == 17 ? 3u : (s == 18 ? 5u : 8u))); }
 __device__ __forceinline__ uint32_t m_extra(uint32_t s) { return s < 16 ? 0u : (s == 16 ? 3u : (s == 17 ? 5u : (s == 18 ? 8u : 11u))); }
@@ -500,12 +577,14 @@ __device__ __forceinline__ void build_v_block(WeightReader &r, uint32_t *tab, ui
 }
 
 __global__ void __launch_bounds__(kLmdWarps * 32, 1)
-k_fse_lmds(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ dst_off, const uint64_t *__restrict__ dst_cap,
+k_fse_lmds(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ src_off, const uint64_t *__restrict__ src_len,
+           const uint64_t *__restrict__ dst_off, const uint64_t *__restrict__ dst_cap,
            const BlockDesc *__restrict__ blocks, FseDesc *__restrict__ fse, uint32_t n_fse, LmdRec *__restrict__ lmd_scratch, uint32_t *err,
            uint32_t *work_counter) {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
     uint32_t *tab = reinterpret_cast<uint32_t *>(smem + warp * kLmdSmemPerWarp);
+    const uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(smem + warp * kLmdSmemPerWarp + 384 * 32 * 4) + lane * kRingStride;
     for (;;) {
         uint32_t base = 0;
         if (lane == 0) base = atomicAdd(work_counter, 32u);
@@ -527,8 +606,9 @@ k_fse_lmds(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ ds
                 build_v_block<1>(r, tab, lane, kMSymbols, kMStates, 64);
                 build_v_block<2>(r, tab, lane, kDSymbols, kDStates, 128);
 
-                BitWindow br;
-                int st = br.init(blk + fd.header_size + fd.n_lit_payload, fd.n_lmd_payload, fd.lmd_bits);
+                const uint8_t *s_lo = src_base + src_off[bd.stream], *s_hi = s_lo + src_len[bd.stream];
+                RingWindow br;
+                int st = br.init(blk + fd.header_size + fd.n_lit_payload, fd.n_lmd_payload, fd.lmd_bits, s_lo, s_hi, ring_addr);
                 if (st) {
                     atomicMin(&err[bd.stream], err_key(kb, PH_LMD, st));
                 } else {
@@ -545,7 +625,6 @@ k_fse_lmds(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ ds
                     LmdRec *out = lmd_scratch + fd.lmd_off;
                     int fail = 0;
                     const uint32_t *tl = tab + lane, *tm = tab + 64 * 32 + lane, *td = tab + 128 * 32 + lane;
-                    const BitWindow br0 = br;
                     // ---- fast path --------------------------------------------------------------------
                     // literal_index and the bytes produced only grow, so "literal_index > 40000" and "does not
                     // fit dst" are decided once at the end; per LMD only the distance is checked.  Anything
@@ -587,7 +666,7 @@ k_fse_lmds(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ ds
                     }
                     if (suspicious) {
                         // ---- exact path: one step = one LMD (fse_core.rs:104-131), failures latched in order ----
-                        br = br0;
+                        br.init(blk + fd.header_size + fd.n_lit_payload, fd.n_lmd_payload, fd.lmd_bits, s_lo, s_hi, ring_addr);
                         sl = fd.lmd_state[0]; sm = fd.lmd_state[1]; sd = fd.lmd_state[2];
                         lit_index = 0; n_match = 0; D = 0; rel = 0;
                         auto step = [&]() -> uint2 {
@@ -932,9 +1011,9 @@ void launch_fse_stages(const uint8_t *src, const uint64_t *src_off, const uint64
     unsigned need_lit = (n_fse + 32 * kLitWarps - 1) / (32 * kLitWarps), need_lmd = (n_fse + 32 * kLmdWarps - 1) / (32 * kLmdWarps);
     unsigned g_lit = need_lit < (unsigned)n_sms ? need_lit : (unsigned)n_sms;
     unsigned g_lmd = need_lmd < (unsigned)n_sms ? need_lmd : (unsigned)n_sms;
-    k_fse_literals<<<g_lit, kLitWarps * 32, kLitWarps * kLitSmemPerWarp, s>>>(src, blocks, fse, n_fse, lit_scratch, err, work_counters);
+    k_fse_literals<<<g_lit, kLitWarps * 32, kLitWarps * kLitSmemPerWarp, s>>>(src, src_off, src_len, blocks, fse, n_fse, lit_scratch, err, work_counters);
     if (between) cudaEventRecord(between, s);
-    k_fse_lmds<<<g_lmd, kLmdWarps * 32, kLmdWarps * kLmdSmemPerWarp, s>>>(src, dst_off, dst_cap, blocks, fse, n_fse, lmd_scratch, err, work_counters + 1);
+    k_fse_lmds<<<g_lmd, kLmdWarps * 32, kLmdWarps * kLmdSmemPerWarp, s>>>(src, src_off, src_len, dst_off, dst_cap, blocks, fse, n_fse, lmd_scratch, err, work_counters + 1);
 }
 void launch_expand(const uint8_t *src, const uint64_t *src_off, const uint64_t *src_len, uint8_t *dst, const uint64_t *dst_off,
                    const uint64_t *dst_cap, const StreamCounts *bases, const BlockDesc *blocks, const FseDesc *fse, const uint8_t *lit_scratch,
