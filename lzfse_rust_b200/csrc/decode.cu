@@ -345,6 +345,11 @@ __device__ __forceinline__ uint32_t bfe(uint32_t v, uint32_t pos, uint32_t len) 
     asm("bfe.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(v), "r"(pos), "r"(len));
     return r;
 }
+__device__ __forceinline__ uint32_t bits_at(uint64_t win, int pos, uint32_t n) {  // n < 32
+    uint32_t x = (uint32_t)(win >> pos), r;
+    asm("bfe.u32 %0, %1, 0, %2;" : "=r"(r) : "r"(x), "r"(n));
+    return r;
+}
 
 // ------------------------------------------------------------------------------------------------
 // The same reader, fed from shared memory.
@@ -360,50 +365,62 @@ constexpr uint32_t kRingStride = kRing + 16;    // per-lane stride (keeps 16-byt
 constexpr uint32_t kRingBytesPerWarp = 32 * kRingStride;
 
 struct RingWindow {
-    const uint8_t *base;     // slice start
-    uintptr_t lo16, hi;      // chunks below lo16 are never needed (zero-filled); bytes at or above hi are not read
-    uintptr_t next_chunk;    // global address of the next (lower) 16-byte chunk to fetch
+    // All positions are 32-bit byte offsets from g0, a 16-byte aligned address 256 bytes below the stream's
+    // first chunk (never dereferenced below lo16), so the upkeep is 32-bit arithmetic.
+    uintptr_t g0;
+    uint32_t a_base;         // offset of the slice start
+    uint32_t lo16, hi;       // chunks below lo16 are never needed (zero-filled); bytes at or above hi are not read
+    uint32_t next_chunk;     // offset of the next (lower) 16-byte chunk to fetch
     uint32_t ring;           // shared-memory address of this lane's ring
     int P;                   // bit cursor, relative to the slice start
     bool dead;
 
-    __device__ __forceinline__ void fetch_chunk(uintptr_t c) const {
-        uint32_t n = 16;
-        if (c < lo16) n = 0;
-        else if (c + 16 > hi) n = c < hi ? (uint32_t)(hi - c) : 0u;
-        const uintptr_t src = n ? c : lo16;  // any valid address when nothing is read
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(ring + ((uint32_t)c & (kRing - 1))), "l"(src), "r"(n) : "memory");
+    __device__ __forceinline__ void fetch_chunk(uint32_t c) const {
+        uint32_t n = 16, from = c;
+        if (c - lo16 > hi - 16 - lo16) {  // not entirely inside [lo16, hi): partial or nothing (unsigned range check)
+            n = c < lo16 ? 0u : (c < hi ? hi - c : 0u);
+            if (n == 0) from = lo16;      // any valid address when nothing is read
+        }
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(ring + (c & (kRing - 1))), "l"(g0 + from), "r"(n) : "memory");
     }
     // slice = [start, start+len), len >= 8; `off` = unused high bits of the last byte; [rlo, rhi) = the stream's bytes.
     __device__ __forceinline__ int init(const uint8_t *start, uint32_t len, uint32_t off, const uint8_t *rlo, const uint8_t *rhi,
                                         uint32_t ring_addr) {
-        base = start; dead = false; ring = ring_addr;
-        lo16 = (reinterpret_cast<uintptr_t>(rlo) + 15) & ~(uintptr_t)15;
-        hi = reinterpret_cast<uintptr_t>(rhi);
+        dead = false; ring = ring_addr;
+        g0 = (reinterpret_cast<uintptr_t>(rlo) & ~(uintptr_t)15) - 256;
+        lo16 = (uint32_t)(((reinterpret_cast<uintptr_t>(rlo) + 15) & ~(uintptr_t)15) - g0);
+        hi = (uint32_t)(reinterpret_cast<uintptr_t>(rhi) - g0);
+        a_base = (uint32_t)(reinterpret_cast<uintptr_t>(start) - g0);
         P = (int)len * 8 - (int)off;
         const uint32_t last = start[len - 1];  // BitReader::new: the `off` bits above the cursor must be zero
         if (off != 0 && (last >> (8 - off)) != 0) return LZFSE_B200_BAD_BITSTREAM;
-        // first window: word-aligned address a4 .. a4 + 12; fill the 8 chunks ending with the one that holds a4 + 11
-        const uintptr_t a = reinterpret_cast<uintptr_t>(base) + (intptr_t)((P - 57) >> 3);
-        const uintptr_t top = (((a & ~(uintptr_t)3) + 11) & ~(uintptr_t)15);
+        // first window: word-aligned offset a4 .. a4 + 12; fill the 8 chunks ending with the one that holds a4 + 11
+        const uint32_t a = a_base + (uint32_t)((P - 57) >> 3);
+        const uint32_t top = ((a & ~3u) + 11) & ~15u;
         for (uint32_t k = 0; k < kRing / 16; k++) fetch_chunk(top - 16 * k);
         next_chunk = top - kRing;
         asm volatile("cp.async.commit_group;" ::: "memory");
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         return LZFSE_B200_OK;
     }
-    // Window for the current cursor (callers guarantee P >= 57).  Also keeps the ring topped up.
-    __device__ __forceinline__ uint64_t window_fast(int &cur) {
+    // Keeps the ring topped up: at most one chunk per call, so call it at least once per 16 bytes consumed.
+    // A chunk is requested ~100 bytes (dozens of steps) before the window reaches it; waiting for the
+    // previous request when issuing a new one is therefore free and always sufficient.
+    __device__ __forceinline__ void refill() {
+        const uint32_t a4 = (a_base + (uint32_t)((P - 57) >> 3)) & ~3u;
+        if (a4 + 12 <= next_chunk + kRing) {  // the chunk slot above the window is free
+            fetch_chunk(next_chunk);
+            next_chunk -= 16;
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        }
+    }
+    // Window for the current cursor (callers guarantee P >= 57 and call refill() often enough).
+    __device__ __forceinline__ uint64_t window_fast(int &cur) const {
         const int byte = (P - 57) >> 3;
         cur = P - byte * 8;
-        const uintptr_t a = reinterpret_cast<uintptr_t>(base) + (intptr_t)byte;
-        const uint32_t r = (uint32_t)a & 3u;
-        const uintptr_t a4 = a - r;
-        // the chunk slot above the window is free once the window's 12 bytes lie below it
-        if (a4 + 12 <= next_chunk + kRing) { fetch_chunk(next_chunk); next_chunk -= 16; }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 4;" ::: "memory");  // a chunk is needed dozens of steps after it was requested
-        const uint32_t o = (uint32_t)a4 & (kRing - 1);
+        const uint32_t a = a_base + (uint32_t)byte;
+        const uint32_t r = a & 3u, o = (a - r) & (kRing - 1);
         uint32_t w0, w1, w2;
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(ring + o));
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w1) : "r"(ring + ((o + 4) & (kRing - 1))));
@@ -415,19 +432,11 @@ struct RingWindow {
     __device__ __forceinline__ uint64_t window(int &cur) {
         if (P < 57) dead = true;
         if (dead) { cur = P - ((P - 57) >> 3) * 8; return 0; }
+        refill();
         return window_fast(cur);
     }
-    __device__ __forceinline__ void prefetch() const {}
     __device__ __forceinline__ bool underflow() const { return P < 64; }  // BitReader::finalize
 };
-__device__ __forceinline__ uint32_t bits_at(uint64_t win, int pos, uint32_t n) {  // n < 32
-    uint32_t x = (uint32_t)(win >> pos), r;
-    asm("bfe.u32 %0, %1, 0, %2;" : "=r"(r) : "r"(x), "r"(n));
-    return r;
-}
-__device__ __forceinline__ uint32_t byte_of(uint32_t v, int i) {  // one PRMT
-    return __byte_perm(v, 0, 0x4440 | i);
-}
 
 // ------------------------------------------------------------------------------------------------
 // Literal stage: lane per block.  U table [1024][32] in shared memory, split into a 16-bit
@@ -514,12 +523,14 @@ k_fse_literals(const uint8_t *__restrict__ src_base, const uint64_t *__restrict_
                     };
                     uint32_t it = 0;
                     for (; it + 4 <= n_it && br.P >= 57 + 3 * 40; it += 4) {  // 16 literals, one 16-byte store
-                        br.prefetch();
                         uint4 v;
-                        v.x = step(std::true_type{}); v.y = step(std::true_type{}); v.z = step(std::true_type{}); v.w = step(std::true_type{});
+                        br.refill();  // two steps consume at most 10 bytes
+                        v.x = step(std::true_type{}); v.y = step(std::true_type{});
+                        br.refill();
+                        v.z = step(std::true_type{}); v.w = step(std::true_type{});
                         __stcg(reinterpret_cast<uint4 *>(out + it), v);
                     }
-                    for (; it < n_it && br.P >= 57; it++) out[it] = step(std::true_type{});
+                    for (; it < n_it && br.P >= 57; it++) { br.refill(); out[it] = step(std::true_type{}); }
                     if (it != n_it) {  // the reader came within 57 bits of the pad: redo with the reference's exact flush semantics
                         br.init(blk + fd.header_size - 8, fd.n_lit_payload + 8, fd.lit_bits, s_lo, s_hi, ring_addr);
                         s0 = fd.lit_state[0]; s1 = fd.lit_state[1]; s2 = fd.lit_state[2]; s3 = fd.lit_state[3];
@@ -656,11 +667,11 @@ k_fse_lmds(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ sr
                         };
                         uint32_t i = 0;
                         for (; i + 2 <= fd.n_lmds && br.P >= 57 + 54; i += 2) {  // two 8-byte records per 16-byte store
-                            br.prefetch();
+                            br.refill();  // two steps consume at most 13.5 bytes
                             const uint2 r0 = fast(), r1 = fast();
                             __stcg(reinterpret_cast<uint4 *>(out + i), make_uint4(r0.x, r0.y, r1.x, r1.y));
                         }
-                        for (; i < fd.n_lmds && br.P >= 57; i++) *reinterpret_cast<uint2 *>(out + i) = fast();
+                        for (; i < fd.n_lmds && br.P >= 57; i++) { br.refill(); *reinterpret_cast<uint2 *>(out + i) = fast(); }
                         suspicious |= i != fd.n_lmds || lit_index > kLiteralsPerBlock || rel > room;
                         n_match = rel - lit_index;
                     }
