@@ -3,7 +3,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "liblzfse_b200.so")
+SO_PATH = os.environ.get("LZB_SO") or os.path.join(_HERE, "liblzfse_b200.so")  # LZB_SO: tuning builds only
 
 # Every symbol include/lzfse_b200.h declares (tests check the library exports all of them).
 SYMBOLS = [
@@ -23,7 +23,7 @@ def load(build_if_missing=True):
     global _lib
     if _lib is not None:
         return _lib
-    if build_if_missing:
+    if build_if_missing and not os.environ.get("LZB_SO"):
         from . import build as _build
 
         try:

@@ -25,6 +25,11 @@ void launch_fse_stages(const uint8_t *, const uint64_t *, const uint64_t *, cons
 void launch_expand(const uint8_t *, const uint64_t *, const uint64_t *, uint8_t *, const uint64_t *, const uint64_t *, const StreamCounts *, const BlockDesc *,
                    const FseDesc *, const uint8_t *, const LmdRec *, uint32_t *, size_t, cudaStream_t);
 void launch_finish(const uint32_t *, const uint64_t *, uint64_t *, int32_t *, size_t, cudaStream_t);
+// expand.cu
+int setup_expand_kernel();
+void launch_expand_cta(const uint8_t *, const uint64_t *, const uint64_t *, uint8_t *, const uint64_t *, const uint64_t *, const StreamCounts *,
+                       const BlockDesc *, const FseDesc *, const uint8_t *, const LmdRec *, const uint64_t *, uint32_t *, size_t, uint32_t *, int,
+                       cudaStream_t);
 }  // namespace lzb
 
 using namespace lzb;
@@ -35,6 +40,7 @@ struct lzfse_b200_decoder {
     cudaStream_t own_stream = nullptr;
     std::string last_error;
     uint64_t launches = 0;
+    int expand_mode = 0;  // 0 = choose per batch, 1 = warp per stream, 2 = CTA per stream (LZB_EXPAND=warp|cta: measurements only)
     // scratch
     DevBuf counts, err, raw_total, totals_dev, blocks, fse, lits, lmds, work;
     PinnedBuf totals_host;
@@ -57,7 +63,7 @@ int decode_batch_device_impl(lzfse_b200_decoder *d, const uint8_t *src, const ui
     CK(d, d->raw_total.reserve(n * sizeof(uint64_t)));
     CK(d, d->totals_dev.reserve(sizeof(StreamCounts)));
     CK(d, d->totals_host.reserve(sizeof(StreamCounts)));
-    CK(d, d->work.reserve(2 * sizeof(uint32_t)));
+    CK(d, d->work.reserve(4 * sizeof(uint32_t)));
     uint64_t *raw_total = raw_len ? raw_len : d->raw_total.as<uint64_t>();
     d->timer.begin(s);
 
@@ -81,7 +87,7 @@ int decode_batch_device_impl(lzfse_b200_decoder *d, const uint8_t *src, const ui
     CK(d, d->fse.reserve((tot.n_fse + 1) * sizeof(FseDesc)));
     CK(d, d->lits.reserve(tot.n_literals + 512));  // slack: the expander prefetches up to 128 bytes past a block's run
     CK(d, d->lmds.reserve((tot.n_lmds + 1) * sizeof(LmdRec)));
-    CK(d, cudaMemsetAsync(d->work.p, 0, 2 * sizeof(uint32_t), s));
+    CK(d, cudaMemsetAsync(d->work.p, 0, 4 * sizeof(uint32_t), s));
 
     launch_scan_fill(src, src_off, src_len, dst_off, dst_cap, n, d->counts.as<StreamCounts>(), d->blocks.as<BlockDesc>(), d->fse.as<FseDesc>(),
                      d->err.as<uint32_t>(), s);
@@ -97,8 +103,16 @@ int decode_batch_device_impl(lzfse_b200_decoder *d, const uint8_t *src, const ui
         d->timer.mark(s);
     }
     d->timer.mark(s);  // lmds
-    launch_expand(src, src_off, src_len, dst, dst_off, dst_cap, d->counts.as<StreamCounts>(), d->blocks.as<BlockDesc>(), d->fse.as<FseDesc>(),
-                  d->lits.as<uint8_t>(), d->lmds.as<LmdRec>(), d->err.as<uint32_t>(), n, s);
+    // Expansion: a warp per stream when there are enough streams to fill the machine that way (64 warps x 148 SMs);
+    // otherwise a CTA per stream, whose 7 worker warps share one stream through a shared-memory window.
+    const bool use_cta = d->expand_mode == 2 || (d->expand_mode == 0 && n < (size_t)d->n_sms * 16);
+    if (!use_cta)
+        launch_expand(src, src_off, src_len, dst, dst_off, dst_cap, d->counts.as<StreamCounts>(), d->blocks.as<BlockDesc>(), d->fse.as<FseDesc>(),
+                      d->lits.as<uint8_t>(), d->lmds.as<LmdRec>(), d->err.as<uint32_t>(), n, s);
+    else
+        launch_expand_cta(src, src_off, src_len, dst, dst_off, dst_cap, d->counts.as<StreamCounts>(), d->blocks.as<BlockDesc>(),
+                          d->fse.as<FseDesc>(), d->lits.as<uint8_t>(), d->lmds.as<LmdRec>(), raw_total, d->err.as<uint32_t>(), n, d->work.as<uint32_t>() + 2,
+                          d->n_sms, s);
     d->timer.mark(s);  // expand
     launch_finish(d->err.as<uint32_t>(), raw_total, out_len, status, n, s);
     d->timer.mark(s);  // finish
@@ -165,7 +179,9 @@ int lzfse_b200_decoder_create(int device, lzfse_b200_decoder **out) {
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete d; return LZFSE_B200_NO_DEVICE; }
     d->n_sms = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&d->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete d; return LZFSE_B200_CUDA_ERROR; }
-    if (setup_decode_kernels() != 0) {
+    const char *xe = getenv("LZB_EXPAND");
+    d->expand_mode = xe && strcmp(xe, "warp") == 0 ? 1 : (xe && strcmp(xe, "cta") == 0 ? 2 : 0);
+    if (setup_decode_kernels() != 0 || setup_expand_kernel() != 0) {
         // no sm_100a image for this device, or not enough shared memory: there is no fallback path
         cudaStreamDestroy(d->own_stream);
         delete d;

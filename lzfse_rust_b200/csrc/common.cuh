@@ -26,6 +26,8 @@ constexpr uint32_t kMagicEos = 0x24787662u, kMagicRaw = 0x2D787662u, kMagicVx1 =
                    kMagicVx2 = 0x32787662u, kMagicVxn = 0x6E787662u;
 constexpr uint32_t kVnHeaderSize = 12, kVnPayloadLimit = 0x2000, kVnMaxD = 65535;
 
+constexpr uint64_t kMaxStreamRaw = 0xF0000000ull;  // decoded bytes per stream (32-bit positions in expand.cu)
+
 constexpr uint32_t kGoodMatchLen = 40, kRawCutoff = 20, kRawLimit = 0x4000, kVnCutoff = 4096;
 constexpr uint32_t kHashBits = 14, kHashWidth = 4;
 

@@ -17,6 +17,7 @@
 #include <type_traits>
 
 #include "common.cuh"
+#include "lz_blocks.cuh"
 
 namespace lzb {
 
@@ -182,6 +183,8 @@ __global__ void k_scan(const uint8_t *__restrict__ src_base, const uint64_t *__r
             key = err_key(kb, PH_HEADER, LZFSE_B200_BAD_BLOCK);
             break;
         }
+        // C-ABI limit: the expansion stage keeps stream positions in 32 bits
+        if (raw + bd.n_raw > kMaxStreamRaw) { key = err_key(kb, PH_HEADER, LZFSE_B200_BUFFER_OVERFLOW); break; }
         if (FILL) blocks[base.n_blocks + blk] = bd;
         raw += bd.n_raw;
         blk++;
@@ -346,9 +349,8 @@ __device__ __forceinline__ uint32_t bfe(uint32_t v, uint32_t pos, uint32_t len) 
     return r;
 }
 __device__ __forceinline__ uint32_t bits_at(uint64_t win, int pos, uint32_t n) {  // n < 32
-    uint32_t x = (uint32_t)(win >> pos), r;
-    asm("bfe.u32 %0, %1, 0, %2;" : "=r"(r) : "r"(x), "r"(n));
-    return r;
+    // one 64-bit funnel shift, then shl + and-not: bfe.u32 with a register length costs five instructions on sm_100
+    return (uint32_t)(win >> pos) & ~(0xFFFFFFFFu << n);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -550,7 +552,7 @@ k_fse_literals(const uint8_t *__restrict__ src_base, const uint64_t *__restrict_
 // ------------------------------------------------------------------------------------------------
 // LMD stage: lane per block.  L/M/D table [384][32] x u32 in shared memory (48 KiB per warp).
 // Entry: delta[0:8] (relative to the symbol kind's first state) | k[8:12] | v_bits[12:16] | [16:32] = v_base for
-// L and M (<= 312), the symbol for D (v_base = ((4 + (s & 3)) << (s >> 2)) - 4 in closed form).
+// L and M (<= 312), and 4 + (s & 3) for D, whose v_base = ((4 + (s & 3)) << (s >> 2)) - 4 = (field << v_bits) - 4.
 // (fse/decoder.rs:244-292 build_v_table_block, fse/fse_core.rs:91-141 decode_internal)
 // ------------------------------------------------------------------------------------------------
 constexpr int kLmdWarps = 4;
@@ -561,8 +563,7 @@ __device__ __forceinline__ uint32_t m_extra(uint32_t s) { return s < 16 ? 0u : (
 // L_BASE_VALUE = 0..15,16,20,28,60; M_BASE_VALUE = 0..15,16,24,56,312 (fse/constants.rs:132-134,164-166)
 __device__ __forceinline__ uint32_t l_base(uint32_t s) { return s < 16 ? s : ((0x3C1C1410u >> ((s - 16) * 8)) & 0xFFu); }
 __device__ __forceinline__ uint32_t m_base(uint32_t s) { return s < 16 ? s : (uint32_t)((0x0138003800180010ull >> ((s - 16) * 16)) & 0xFFFFu); }
-// D_BASE_VALUE[s] = ((4 + (s & 3)) << (s >> 2)) - 4, D_EXTRA_BITS[s] = s >> 2 (fse/constants.rs:305-321)
-__device__ __forceinline__ uint32_t d_base(uint32_t s) { return ((4u + (s & 3u)) << (s >> 2)) - 4u; }
+// D_BASE_VALUE[s] = ((4 + (s & 3)) << (s >> 2)) - 4, D_EXTRA_BITS[s] = s >> 2 (fse/constants.rs:305-321): computed from the entry
 
 template <int KIND>  // 0 = L, 1 = M, 2 = D
 __device__ __forceinline__ void build_v_block(WeightReader &r, uint32_t *tab, uint32_t lane, uint32_t n_sym, uint32_t n_states,
@@ -575,7 +576,7 @@ __device__ __forceinline__ void build_v_block(WeightReader &r, uint32_t *tab, ui
         uint32_t k = __clz(w) - n_clz;
         uint32_t x = ((n_states << 1) >> k) - w;
         const uint32_t vb = KIND == 0 ? l_extra(sym) : (KIND == 1 ? m_extra(sym) : (sym >> 2));
-        const uint32_t hi = KIND == 0 ? l_base(sym) : (KIND == 1 ? m_base(sym) : sym);
+        const uint32_t hi = KIND == 0 ? l_base(sym) : (KIND == 1 ? m_base(sym) : 4u + (sym & 3u));  // D: v_base = (hi << v_bits) - 4
         for (uint32_t j = 0; j < w; j++) {
             uint32_t kk, delta;
             if (j < x) { kk = k; delta = ((w + j) << k) - n_states; }
@@ -656,7 +657,7 @@ k_fse_lmds(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ sr
                             sm = bits_at(win, a2, km) + (em & 0xFF);
                             const uint32_t M = (em >> 16) + bits_at(win, a3, vm);
                             sd = bits_at(win, a4, kd_) + (ed & 0xFF);
-                            const uint32_t dp = d_base(ed >> 16) + bits_at(win, a5, vd);
+                            const uint32_t dp = ((ed >> 16) << vd) - 4u + bits_at(win, a5, vd);
                             br.P -= cur - a5;
                             D = dp ? dp : D;
                             lit_index += L;
@@ -694,7 +695,7 @@ k_fse_lmds(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ sr
                             sm = bits_at(win, a2, km) + (em & 0xFF);
                             const uint32_t M = (em >> 16) + bits_at(win, a3, vm);
                             sd = bits_at(win, a4, kd_) + (ed & 0xFF);
-                            const uint32_t dp = d_base(ed >> 16) + bits_at(win, a5, vd);
+                            const uint32_t dp = ((ed >> 16) << vd) - 4u + bits_at(win, a5, vd);
                             br.P -= cur - a5;
                             D = dp ? dp : D;  // lmd/lmd_type.rs:155-159
                             lit_index += L;
@@ -726,121 +727,8 @@ k_fse_lmds(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ sr
 }
 
 // ------------------------------------------------------------------------------------------------
-// Expansion stage: one warp per stream walks its blocks in order.
+// Expansion stage (legacy): one warp per stream walks its blocks in order.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void warp_copy(uint8_t *dst, const uint8_t *src, uint64_t n, uint32_t lane) {
-    // head: align dst to 16
-    uint64_t head = (16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15;
-    if (head > n) head = n;
-    if (lane < head) dst[lane] = src[lane];
-    dst += head; src += head; n -= head;
-    uint64_t nv = n / 16;
-    if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
-        const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
-        uint4 *d4 = reinterpret_cast<uint4 *>(dst);
-        for (uint64_t i = lane; i < nv; i += 32) d4[i] = __ldg(s4 + i);
-    } else {
-        uint4 *d4 = reinterpret_cast<uint4 *>(dst);
-        for (uint64_t i = lane; i < nv; i += 32) {
-            const uint8_t *p = src + i * 16;
-            uint4 v;
-            v.x = ld_u32(p); v.y = ld_u32(p + 4); v.z = ld_u32(p + 8); v.w = ld_u32(p + 12);
-            d4[i] = v;
-        }
-    }
-    uint64_t done = nv * 16;
-    for (uint64_t i = done + lane; i < n; i += 32) dst[i] = src[i];
-}
-
-// LZVN opcode classes (vn/constants.rs:24-72) in closed form.
-enum { OP_SML_L, OP_LRG_L, OP_SML_M, OP_LRG_M, OP_PRE_D, OP_SML_D, OP_MED_D, OP_LRG_D, OP_EOS, OP_UDEF, OP_NOP };
-__device__ __forceinline__ int vn_op(uint32_t b) {
-    uint32_t hi = b >> 4, lo3 = b & 7;
-    if (hi == 0xE) return b == 0xE0 ? OP_LRG_L : OP_SML_L;
-    if (hi == 0xF) return b == 0xF0 ? OP_LRG_M : OP_SML_M;
-    if (hi == 0x7 || hi == 0xD) return OP_UDEF;
-    if (hi == 0xA || hi == 0xB) return OP_MED_D;
-    if (lo3 == 7) return OP_LRG_D;
-    if (lo3 == 6) {
-        if (b == 0x06) return OP_EOS;
-        if (b == 0x0E || b == 0x16) return OP_NOP;
-        if (b < 0x40) return OP_UDEF;
-        return OP_PRE_D;
-    }
-    return OP_SML_D;
-}
-
-// LZVN block, interpreted by one lane (vn/vn_core.rs:51-286).  `stream_out` = first output byte of the
-// stream, `out_pos` = bytes of the stream already produced, `cap_end` = the stream's dst capacity: a write
-// past it is the C-ABI's BufferOverflow (the reference's Vec would grow).  A block that produces more
-// than its header announces can only overwrite later output of its own stream, which then fails.
-__device__ int vn_decode_block(const uint8_t *src, uint64_t src_rest /* bytes from block start to stream end */,
-                               uint8_t *stream_out, uint64_t out_pos, uint64_t cap_end) {
-    uint32_t n_raw = ld_u32(src + 4), n_payload = ld_u32(src + 8), match_distance = 0;
-    uint64_t p = kVnHeaderSize;  // offset inside src
-    for (;;) {
-        const uint64_t src_len = src_rest - p;
-        const uint64_t vlen = src_len < kVnPayloadLimit ? src_len : kVnPayloadLimit;
-        const uint64_t out0 = out_pos;
-        uint64_t used = 0;
-        int res = LZFSE_B200_OK;
-        bool eos = false;
-        if (vlen < 8) res = LZFSE_B200_PAYLOAD_UNDERFLOW;
-        while (res == LZFSE_B200_OK && !eos) {
-            const uint8_t *s = src + p + used;
-            const uint64_t rem = vlen - used;
-            const uint32_t opu = ld_u32(s);
-            uint32_t L = 0, M = 0, D = 0, oplen = 0;
-            const int op = vn_op(opu & 0xFF);
-            switch (op) {
-            case OP_SML_L: L = opu & 0xF; oplen = 1; break;
-            case OP_LRG_L: L = ((opu >> 8) & 0xFF) + 16; oplen = 2; break;
-            case OP_SML_M: M = opu & 0xF; oplen = 1; break;
-            case OP_LRG_M: M = ((opu >> 8) & 0xFF) + 16; oplen = 2; break;
-            case OP_PRE_D: M = ((opu >> 3) & 7) + 3; L = (opu >> 6) & 3; oplen = 1; break;
-            case OP_SML_D: D = ((opu & 7) << 8) | ((opu >> 8) & 0xFF); M = ((opu >> 3) & 7) + 3; L = (opu >> 6) & 3; oplen = 2; break;
-            case OP_MED_D: M = (((opu & 7) << 2) | ((opu >> 8) & 3)) + 3; L = (opu >> 3) & 3; D = (opu >> 10) & 0x3FFF; oplen = 3; break;
-            case OP_LRG_D: M = ((opu >> 3) & 7) + 3; L = (opu >> 6) & 3; D = (opu >> 8) & 0xFFFF; oplen = 3; break;
-            case OP_NOP: oplen = 1; break;
-            case OP_EOS:
-                if (ld_u64(s) != 0x06ull) res = LZFSE_B200_VN_BAD_PAYLOAD;
-                else { used += 8; eos = true; }
-                continue;
-            default: res = LZFSE_B200_VN_BAD_OPCODE; continue;
-            }
-            if (rem - oplen < (uint64_t)L + 8) { res = LZFSE_B200_PAYLOAD_UNDERFLOW; continue; }
-            if (op == OP_SML_D || op == OP_MED_D || op == OP_LRG_D) match_distance = D;
-            if (L) {
-                if (out_pos + L > cap_end) { res = LZFSE_B200_BUFFER_OVERFLOW; continue; }
-                for (uint32_t t = 0; t < L; t++) stream_out[out_pos + t] = s[oplen + t];
-                out_pos += L;
-            }
-            if (M) {
-                if (match_distance == 0 || match_distance > out_pos) { res = LZFSE_B200_BAD_D_VALUE; continue; }
-                if (out_pos + M > cap_end) { res = LZFSE_B200_BUFFER_OVERFLOW; continue; }
-                uint8_t *q = stream_out + out_pos;
-                for (uint32_t t = 0; t < M; t++) q[t] = q[(int64_t)t - (int64_t)match_distance];
-                out_pos += M;
-            }
-            used += oplen + L;
-        }
-        const uint64_t produced = out_pos - out0;
-        if (used > n_payload) return LZFSE_B200_PAYLOAD_UNDERFLOW;
-        if (produced > n_raw) return LZFSE_B200_VN_BAD_PAYLOAD;
-        n_payload -= (uint32_t)used;
-        n_raw -= (uint32_t)produced;
-        const bool cycle = src_len > kVnPayloadLimit;
-        p += used;
-        if (res == LZFSE_B200_OK) {
-            if (n_payload != 0) return LZFSE_B200_PAYLOAD_OVERFLOW;
-            if (n_raw != 0) return LZFSE_B200_VN_BAD_PAYLOAD;
-            return LZFSE_B200_OK;
-        }
-        if (res == LZFSE_B200_PAYLOAD_UNDERFLOW && cycle) continue;
-        return res;
-    }
-}
-
 constexpr uint32_t kShortCopy = 16;  // per-lane copies up to this many bytes; longer ones go warp-wide
 
 // One bvx1/bvx2 block: 32 LMDs per step, one per lane.  (fse_core.rs:108-129, lz/writer.rs:115-180)

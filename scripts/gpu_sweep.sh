@@ -1,0 +1,6 @@
+# Times the 1 GiB text decode with every tuning variant under scratch/variants/, then profiles one of them.
+for so in scratch/variants/*.so; do
+  echo "== $so"
+  LZB_SO=$PWD/$so timeout 200 python scripts/prof_decode.py --chunks 16384 --iters 3 2>&1 | grep -E "iter 2|parity|rror" 
+done
+LZB_SO=$PWD/scratch/variants/r16w7c3.so bash scripts/gpu_prof_expand.sh

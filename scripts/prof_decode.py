@@ -23,6 +23,7 @@ ap.add_argument("--iters", type=int, default=5)
 a = ap.parse_args()
 
 dec = L.LzfseDecoder(0)
+dec.set_timing(True)
 pool, woff = W.word_pool(dec)
 n, cl = a.chunks, a.chunk_len
 raw = W.text_chunks(pool, woff, n, cl)
@@ -53,7 +54,7 @@ for it in range(a.iters):
     out_len, status = dec.decode_batch_device(d_src, d_soff, d_slen, d_dst, d_doff, d_dcap)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
-    print("iter %d: %.3f ms  %.1f GB/s uncompressed, %.1f GB/s (U+C)" % (it, ms, n * cl / ms / 1e6, (n * cl + int(c_len.sum())) / ms / 1e6))
+    print("iter %d: %.3f ms  %.1f GB/s uncompressed, %.1f GB/s (U+C)  stages %s" % (it, ms, n * cl / ms / 1e6, (n * cl + int(c_len.sum())) / ms / 1e6, {k: round(v, 3) for k, v in dec.last_stage_ms().items()}))
 assert int((status != 0).sum()) == 0
 assert bytes(d_dst.cpu().numpy()) == raw.tobytes()
 print("parity ok; launches", dec.last_launches)
