@@ -24,7 +24,12 @@ namespace lzb {
 __global__ void k_exclusive_scan(StreamCounts *counts, size_t n, StreamCounts *totals);  // decode.cu
 
 constexpr uint32_t kEmptyIdx = 0xC0C0C0C0u;  // history reset marker (encode/history.rs:72-83: any idx whose distance is out of range)
-constexpr uint32_t kTableWords = (1u << kHashBits) * kHashWidth;
+// A bucket is one 32-byte sector: 4 positions (newest first) followed by the 4 source bytes found at each of them --
+// the reference's Item {val, idx} (encode/history.rs:144-154).  Keeping the values next to the positions means a
+// candidate is accepted or rejected without touching the source: four random 32-byte source sectors per position
+// were most of the parse kernel's HBM traffic.
+constexpr uint32_t kBucketWords = 2 * kHashWidth;
+constexpr uint32_t kTableWords = (1u << kHashBits) * kBucketWords;
 
 enum StreamKind : uint32_t { SK_RAW = 0, SK_VN = 1, SK_FSE = 2 };
 
@@ -267,6 +272,68 @@ __device__ void vn_push_match(VnSink &v, const uint8_t *src, uint32_t from, uint
     if (match_len > 0) vn_put(v, 0xF0u | match_len, 1, src, from, 0, lane);
 }
 
+// A history table is private to one warp, hence to one SM: its buckets can live in that SM's L1 (default loads and
+// stores, prefetch into L1) instead of being fetched from L2 at every step.  LZB_PARSE_L1=0 restores the L2-only path.
+#ifndef LZB_PARSE_CTAS
+#define LZB_PARSE_CTAS 7   // resident 4-warp CTAs per SM (register bound: 72 registers -> 7)
+#endif
+#ifndef LZB_PARSE_SINK_SMEM
+#define LZB_PARSE_SINK_SMEM 1
+#endif
+#ifndef LZB_PARSE_L1
+#define LZB_PARSE_L1 1
+#endif
+struct Bucket { uint4 idx, val; };
+__device__ __forceinline__ Bucket bucket_load(const uint32_t *bk) {
+    Bucket b;
+#if LZB_PARSE_L1
+    b.idx = *reinterpret_cast<const uint4 *>(bk);
+    b.val = *reinterpret_cast<const uint4 *>(bk + 4);
+#else
+    b.idx = __ldcg(reinterpret_cast<const uint4 *>(bk));
+    b.val = __ldcg(reinterpret_cast<const uint4 *>(bk + 4));
+#endif
+    return b;
+}
+__device__ __forceinline__ void bucket_store(uint32_t *bk, const Bucket &b) {
+#if LZB_PARSE_L1
+    *reinterpret_cast<uint4 *>(bk) = b.idx;
+    *reinterpret_cast<uint4 *>(bk + 4) = b.val;
+#else
+    __stcg(reinterpret_cast<uint4 *>(bk), b.idx);
+    __stcg(reinterpret_cast<uint4 *>(bk + 4), b.val);
+#endif
+}
+__device__ __forceinline__ void bucket_prefetch(const uint32_t *bk) {
+#if LZB_PARSE_L1
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(bk));
+#else
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(bk));
+#endif
+}
+// Bucket after pushing this step's same-bucket positions: `me` = the newest one (this lane), `lower` = its lower
+// peer lanes, `old` = the bucket before the step (HistoryTable::push x n, newest first, encode/history.rs:119-131).
+// Every lane of the warp must call (shuffles).
+// Positions are stored biased by the stream's epoch `vb` (see k_enc_parse); base_pos and me_idx are already biased.
+__device__ __forceinline__ Bucket bucket_merge(const Bucket &old, uint32_t me_idx, uint32_t me_val, uint32_t lower, uint32_t base_pos, uint32_t val) {
+    uint32_t m = lower, cnt = 1;
+    int b1 = 0, b2 = 0, b3 = 0;
+    if (m) { b1 = 31 - __clz(m); m &= ~(1u << b1); cnt = 2; }
+    if (m) { b2 = 31 - __clz(m); m &= ~(1u << b2); cnt = 3; }
+    if (m) { b3 = 31 - __clz(m); cnt = 4; }
+    const uint32_t v1 = __shfl_sync(0xFFFFFFFFu, val, b1), v2 = __shfl_sync(0xFFFFFFFFu, val, b2), v3 = __shfl_sync(0xFFFFFFFFu, val, b3);
+    Bucket nw;
+    nw.idx.x = me_idx;
+    nw.idx.y = cnt > 1 ? base_pos + b1 : old.idx.x;
+    nw.idx.z = cnt > 2 ? base_pos + b2 : (cnt == 2 ? old.idx.x : old.idx.y);
+    nw.idx.w = cnt > 3 ? base_pos + b3 : (cnt == 3 ? old.idx.x : (cnt == 2 ? old.idx.y : old.idx.z));
+    nw.val.x = me_val;
+    nw.val.y = cnt > 1 ? v1 : old.val.x;
+    nw.val.z = cnt > 2 ? v2 : (cnt == 2 ? old.val.x : old.val.y);
+    nw.val.w = cnt > 3 ? v3 : (cnt == 3 ? old.val.x : (cnt == 2 ? old.val.y : old.val.z));
+    return nw;
+}
+
 constexpr int kParseWarps = 4;
 constexpr uint32_t kFwdCap = 44;  // per-lane forward extension stops here (>= GOOD_MATCH_LEN); longer matches are finished warp-wide
 constexpr uint32_t kBwdCap = 8;   // per-lane backward extension precomputed up to here
@@ -289,39 +356,39 @@ __device__ __forceinline__ uint64_t ld8u(const uint8_t *p) {  // unaligned 8-byt
 
 // Ordered insert of positions [from, to) into the history table, 32 per step (HistoryTable::push x n,
 // encode/history.rs:24-31,119-131): the newest position of each bucket writes that bucket once.
-__device__ __forceinline__ void history_insert_range(uint32_t *table, const uint8_t *src, uint32_t from, uint32_t to, bool vn, uint32_t lane) {
+__device__ __forceinline__ void history_insert_range(uint32_t *table, const uint8_t *src, uint32_t from, uint32_t to, bool vn, uint32_t lane, uint32_t vb) {
     while (from < to) {
         const uint32_t p = from + lane;
         const bool act = p < to;
-        const uint32_t h = act ? hash_u(ld4u(src + p), vn) : (0xFFFF0000u + lane);
+        const uint32_t val = act ? ld4u(src + p) : 0u;
+        const uint32_t h = act ? hash_u(val, vn) : (0xFFFF0000u + lane);
         const uint32_t peers = __match_any_sync(0xFFFFFFFFu, h);
-        if (act && (peers & ~((2u << lane) - 1u)) == 0) {  // newest position of its bucket
-            uint32_t *bk = table + h * kHashWidth;
-            const uint4 old = __ldcg(reinterpret_cast<const uint4 *>(bk));
-            // new entries, newest first: this lane, then its lower peers
-            uint32_t m = peers & ~(1u << lane), n1 = 0, n2 = 0, n3 = 0, cnt = 1;
-            if (m) { const int b = 31 - __clz(m); n1 = from + b; m &= ~(1u << b); cnt = 2; }
-            if (m) { const int b = 31 - __clz(m); n2 = from + b; m &= ~(1u << b); cnt = 3; }
-            if (m) { const int b = 31 - __clz(m); n3 = from + b; cnt = 4; }
-            uint4 nw;
-            nw.x = p;
-            nw.y = cnt > 1 ? n1 : old.x;
-            nw.z = cnt > 2 ? n2 : (cnt == 2 ? old.x : old.y);
-            nw.w = cnt > 3 ? n3 : (cnt == 3 ? old.x : (cnt == 2 ? old.y : old.z));
-            __stcg(reinterpret_cast<uint4 *>(bk), nw);
-        }
+        const bool writer = act && (peers & ~((2u << lane) - 1u)) == 0;  // newest position of its bucket
+        uint32_t *bk = table + (writer ? h : 0u) * kBucketWords;
+        Bucket old;
+        old.idx = old.val = make_uint4(0, 0, 0, 0);
+        if (writer) old = bucket_load(bk);
+        const Bucket nw = bucket_merge(old, p + vb, val, peers & lanemask_lt(), from + vb, val);
+        if (writer) bucket_store(bk, nw);
         __syncwarp();
         from += 32;
     }
 }
 
-__global__ void __launch_bounds__(kParseWarps * 32, 7)
+__global__ void __launch_bounds__(kParseWarps * 32, LZB_PARSE_CTAS)
 k_enc_parse(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ src_off, const uint64_t *__restrict__ src_len, size_t n_streams,
-            EncStream *streams, const StreamCounts *__restrict__ bases, uint32_t *tables /* one per warp slot */, uint2 *pack_scratch,
+            EncStream *streams, const StreamCounts *__restrict__ bases, uint32_t *tables /* one per warp slot */, uint32_t *epochs, uint2 *pack_scratch,
             uint8_t *lit_scratch, uint32_t *block_ids, EncBlock *blocks, uint32_t *block_counter, uint8_t *out_scratch, uint32_t *stream_counter) {
     const uint32_t lane = lane_id();
     const uint32_t warp_slot = blockIdx.x * kParseWarps + (threadIdx.x >> 5);
     uint32_t *table = tables + (size_t)warp_slot * kTableWords;
+    // HistoryTable::reset (encode/history.rs:72-83) makes every entry fail the distance test.  Instead of rewriting
+    // 256 KiB per stream, positions are stored biased by an epoch that grows by more than (stream length + maximum
+    // distance) from one stream to the next: whatever an earlier stream left behind is then too far away by
+    // construction, exactly like a reset entry.  The epoch survives across launches next to the table; a table
+    // fresh from cudaMemset (all zero) is covered by starting at kMaxDValue + 1.
+    uint32_t epoch = epochs[warp_slot];
+    if (epoch < kMaxDValue + 1) epoch = kMaxDValue + 1;
     for (;;) {
         // persistent warps pull streams from a counter; each owns one history table
         uint32_t si = 0;
@@ -334,12 +401,26 @@ k_enc_parse(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ s
         const uint8_t *src = src_base + src_off[si];
         const uint32_t len = (uint32_t)src_len[si];
         const uint32_t max_d = vn ? kVnMaxD : kMaxDValue;
-        // HistoryTable::reset
-        for (uint32_t t = lane; t < kTableWords / 4; t += 32) reinterpret_cast<uint4 *>(table)[t] = make_uint4(kEmptyIdx, kEmptyIdx, kEmptyIdx, kEmptyIdx);
-        __syncwarp();
+        if (epoch > 0xFFFFFFFFu - len - (kMaxDValue + 1)) {  // 32-bit positions would wrap inside this stream: really reset
+            for (uint32_t t = lane; t < (1u << kHashBits); t += 32) *reinterpret_cast<uint4 *>(table + t * kBucketWords) = make_uint4(0, 0, 0, 0);
+            epoch = kMaxDValue + 1;
+            __syncwarp();
+        }
+        const uint32_t vb = epoch;
+        epoch += len + kMaxDValue + 1;
 
+        // The back-end state is warp-uniform and only touched in the sequential part.  It lives in shared memory: on
+        // the stack (its address goes to the out-of-line block emitter) it competed for L1 with the history buckets
+        // and the source, and every push waited for local-memory loads that had been evicted.
+#if LZB_PARSE_SINK_SMEM
+        __shared__ FseSink s_fs[kParseWarps];
+        __shared__ VnSink s_vs[kParseWarps];
+        FseSink &fs = s_fs[threadIdx.x >> 5];
+        VnSink &vs = s_vs[threadIdx.x >> 5];
+#else
         FseSink fs;
         VnSink vs;
+#endif
         SinkEnv env;
         env.bases = bases; env.blocks = blocks; env.block_ids = block_ids; env.block_counter = block_counter; env.si = si;
         {
@@ -373,50 +454,55 @@ k_enc_parse(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ s
             const bool act = lane < nb;
             // ---- phase 1: per-lane find_match ----
             uint32_t val = 0, h = 0xFFFF0000u + lane;
-            uint4 tq = make_uint4(kEmptyIdx, kEmptyIdx, kEmptyIdx, kEmptyIdx);
+            Bucket tq;
+            tq.idx = make_uint4(kEmptyIdx, kEmptyIdx, kEmptyIdx, kEmptyIdx);
+            tq.val = make_uint4(0, 0, 0, 0);
             if (act) {
                 val = ld4u(src + p);
                 h = hash_u(val, vn);
-                tq = __ldcg(reinterpret_cast<const uint4 *>(table + h * kHashWidth));
+                tq = bucket_load(table + h * kBucketWords);
             }
             const uint32_t peers = __match_any_sync(0xFFFFFFFFu, h);
             uint32_t earlier = peers & lanemask_lt();
             // Every position of the step ends up in the history (visited or skipped), so push them now: the
             // newest position of each bucket writes it once (same merge as history_insert_range).
-            if (act && (peers & ~((2u << lane) - 1u)) == 0) {
-                uint32_t m = earlier, n1 = 0, n2 = 0, n3 = 0, cnt = 1;
-                if (m) { const int b = 31 - __clz(m); n1 = b0 + b; m &= ~(1u << b); cnt = 2; }
-                if (m) { const int b = 31 - __clz(m); n2 = b0 + b; m &= ~(1u << b); cnt = 3; }
-                if (m) { const int b = 31 - __clz(m); n3 = b0 + b; cnt = 4; }
-                uint4 nw;
-                nw.x = p;
-                nw.y = cnt > 1 ? n1 : tq.x;
-                nw.z = cnt > 2 ? n2 : (cnt == 2 ? tq.x : tq.y);
-                nw.w = cnt > 3 ? n3 : (cnt == 3 ? tq.x : (cnt == 2 ? tq.y : tq.z));
-                __stcg(reinterpret_cast<uint4 *>(table + h * kHashWidth), nw);
+            {
+                const bool writer = act && (peers & ~((2u << lane) - 1u)) == 0;
+                const Bucket nw = bucket_merge(tq, p + vb, val, earlier, b0 + vb, val);
+                if (writer) bucket_store(table + h * kBucketWords, nw);
             }
-            uint32_t c[4];
+            uint32_t c[4], cv[4];
             {   // first the same-bucket positions of lower lanes (newest first), then the table's bucket
-                uint32_t n0 = 0, n1 = 0, n2 = 0, n3 = 0, e = 0;
-                if (earlier) { const int b = 31 - __clz(earlier); n0 = b0 + b; earlier &= ~(1u << b); e = 1; }
-                if (earlier) { const int b = 31 - __clz(earlier); n1 = b0 + b; earlier &= ~(1u << b); e = 2; }
-                if (earlier) { const int b = 31 - __clz(earlier); n2 = b0 + b; earlier &= ~(1u << b); e = 3; }
-                if (earlier) { const int b = 31 - __clz(earlier); n3 = b0 + b; e = 4; }
-                c[0] = e > 0 ? n0 : tq.x;
-                c[1] = e > 1 ? n1 : (e == 1 ? tq.x : tq.y);
-                c[2] = e > 2 ? n2 : (e == 2 ? tq.x : (e == 1 ? tq.y : tq.z));
-                c[3] = e > 3 ? n3 : (e == 3 ? tq.x : (e == 2 ? tq.y : (e == 1 ? tq.z : tq.w)));
+                int e0 = 0, e1 = 0, e2 = 0, e3 = 0;
+                uint32_t e = 0;
+                if (earlier) { e0 = 31 - __clz(earlier); earlier &= ~(1u << e0); e = 1; }
+                if (earlier) { e1 = 31 - __clz(earlier); earlier &= ~(1u << e1); e = 2; }
+                if (earlier) { e2 = 31 - __clz(earlier); earlier &= ~(1u << e2); e = 3; }
+                if (earlier) { e3 = 31 - __clz(earlier); e = 4; }
+                const uint32_t w0 = __shfl_sync(0xFFFFFFFFu, val, e0), w1 = __shfl_sync(0xFFFFFFFFu, val, e1), w2 = __shfl_sync(0xFFFFFFFFu, val, e2),
+                               w3 = __shfl_sync(0xFFFFFFFFu, val, e3);
+                const uint32_t t0 = tq.idx.x - vb, t1 = tq.idx.y - vb, t2 = tq.idx.z - vb, t3 = tq.idx.w - vb;  // un-bias (stale entries stay out of range)
+                c[0] = e > 0 ? b0 + e0 : t0;
+                c[1] = e > 1 ? b0 + e1 : (e == 1 ? t0 : t1);
+                c[2] = e > 2 ? b0 + e2 : (e == 2 ? t0 : (e == 1 ? t1 : t2));
+                c[3] = e > 3 ? b0 + e3 : (e == 3 ? t0 : (e == 2 ? t1 : (e == 1 ? t2 : t3)));
+                cv[0] = e > 0 ? w0 : tq.val.x;
+                cv[1] = e > 1 ? w1 : (e == 1 ? tq.val.x : tq.val.y);
+                cv[2] = e > 2 ? w2 : (e == 2 ? tq.val.x : (e == 1 ? tq.val.y : tq.val.z));
+                cv[3] = e > 3 ? w3 : (e == 3 ? tq.val.x : (e == 2 ? tq.val.y : (e == 1 ? tq.val.z : tq.val.w)));
             }
             uint32_t r_len = 0, r_idx = 0, r_bw = 0;
             bool r_exact = false;  // best candidate hit the per-lane cap: lengths must be redone warp-wide
             if (act) {
                 const uint32_t max = len - p;
-                bool stop = false;
+                // Candidates are examined newest first up to the first one out of range (that also ends at the reset
+                // marker); their first four bytes come with the bucket.
+                const bool ok0 = p - c[0] <= max_d, ok1 = ok0 && p - c[1] <= max_d, ok2 = ok1 && p - c[2] <= max_d, ok3 = ok2 && p - c[3] <= max_d;
+                const bool ok[4] = {ok0, ok1, ok2, ok3};
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
-                    if (stop) continue;
-                    if (p - c[k] > max_d) { stop = true; continue; }  // also ends at the reset marker
-                    const uint32_t x = val ^ ld4u(src + c[k]);
+                    if (!ok[k]) continue;
+                    const uint32_t x = val ^ cv[k];
                     uint32_t l = 0;
                     if (x == 0) {
                         l = 4;
@@ -439,7 +525,7 @@ k_enc_parse(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ s
             // While this step is replayed, pull the next step's buckets towards the SM (hint only: the
             // history may still change before they are read).
             if (b0 + 32 + lane < end)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(table + hash_u(ld4u(src + b0 + 32 + lane), vn) * kHashWidth));
+                bucket_prefetch(table + hash_u(ld4u(src + b0 + 32 + lane), vn) * kBucketWords);
             // ---- phase 2: the sequential front end over the step's positions ----
             // Positions whose find_match came back empty only advance the index (:203-209), so the replay
             // jumps from one position with a candidate to the next.
@@ -506,7 +592,7 @@ k_enc_parse(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ s
             // ---- phase 3: push every position this step passed into the history ----
             if (!done) {
                 __syncwarp();  // the step's own positions were pushed in phase 1; a match may have run past them
-                if (cur > b0 + nb) history_insert_range(table, src, b0 + nb, cur, vn, lane);
+                if (cur > b0 + nb) history_insert_range(table, src, b0 + nb, cur, vn, lane, vb);
             }
             index = cur;
         }
@@ -533,6 +619,7 @@ k_enc_parse(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ s
         }
         __syncwarp();
     }
+    if (lane == 0) epochs[warp_slot] = epoch;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -880,7 +967,7 @@ struct lzfse_b200_encoder {
 
 namespace {
 
-constexpr int kParseWarpsPerSm = 28;  // resident history tables: 148 * 28 * 256 KiB = 1036 MiB
+constexpr int kParseWarpsPerSm = LZB_PARSE_CTAS * 4;  // resident history tables: 148 * 28 * 512 KiB = 2072 MiB
 
 int encode_batch_device_impl(lzfse_b200_encoder *e, const uint8_t *src, const uint64_t *src_off, const uint64_t *src_len, uint8_t *dst,
                              const uint64_t *dst_off, const uint64_t *dst_cap, uint64_t *out_len, int32_t *status, size_t n, cudaStream_t s) {
@@ -902,7 +989,11 @@ int encode_batch_device_impl(lzfse_b200_encoder *e, const uint8_t *src, const ui
     if (tot.n_literals > 0xFFFFFFF0ull) { e->last_error = "too many blocks in one batch"; return LZFSE_B200_INVALID_ARGUMENT; }
     const unsigned parse_ctas = (unsigned)e->n_sms * kParseWarpsPerSm / kParseWarps;
     const size_t n_slots = (size_t)parse_ctas * kParseWarps;
-    LZB_CK(e, e->tables.reserve(n_slots * kTableWords * sizeof(uint32_t)));
+    {   // history tables + one epoch word per table; zeroed when (re)allocated, never again (see k_enc_parse)
+        const void *before = e->tables.p;
+        LZB_CK(e, e->tables.reserve(n_slots * (kTableWords + 1) * sizeof(uint32_t)));
+        if (e->tables.p != before) LZB_CK(e, cudaMemsetAsync(e->tables.p, 0, e->tables.cap, s));
+    }
     LZB_CK(e, e->packs.reserve((tot.n_blocks + 1) * sizeof(uint2)));
     LZB_CK(e, e->lits.reserve(tot.n_fse + 64));
     LZB_CK(e, e->block_ids.reserve((tot.n_literals + 1) * sizeof(uint32_t)));
@@ -913,7 +1004,8 @@ int encode_batch_device_impl(lzfse_b200_encoder *e, const uint8_t *src, const ui
     e->timer.mark(s);  // prep
 
     k_enc_parse<<<parse_ctas, kParseWarps * 32, 0, s>>>(src, src_off, src_len, n, e->streams.as<EncStream>(), e->counts.as<StreamCounts>(),
-                                                       e->tables.as<uint32_t>(), e->packs.as<uint2>(), e->lits.as<uint8_t>(),
+                                                       e->tables.as<uint32_t>(), e->tables.as<uint32_t>() + n_slots * kTableWords, e->packs.as<uint2>(),
+                                                       e->lits.as<uint8_t>(),
                                                        e->block_ids.as<uint32_t>(), e->blocks.as<EncBlock>(), ctr, e->out.as<uint8_t>(), ctr + 1);
     e->launches += 1;
     e->timer.mark(s);  // parse

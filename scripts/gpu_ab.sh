@@ -1,6 +1,4 @@
-# GPU tests, then decode timing of the 1 GiB text workload and of the 16 MiB streams with both expansion kernels.
+# Encode: parity tests, then timing of the 1 GiB text workload.
 set -x
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
-timeout 300 python scripts/prof_decode.py --chunks 16384 --iters 4 2>&1 | tail -3
-LZB_EXPAND=warp timeout 300 python scripts/prof_large.py 2>&1 | tail -4
-LZB_EXPAND=cta timeout 300 python scripts/prof_large.py 2>&1 | tail -3
+timeout 900 python -m pytest tests/test_gpu_encode.py tests/test_gpu_configs.py -m gpu -x -q 2>&1 | tail -3
+timeout 300 python scripts/prof_encode.py --chunks 16384 --iters 3 2>&1 | tail -2
