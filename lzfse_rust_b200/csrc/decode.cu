@@ -731,11 +731,145 @@ k_fse_lmds(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ sr
 // ------------------------------------------------------------------------------------------------
 constexpr uint32_t kShortCopy = 16;  // per-lane copies up to this many bytes; longer ones go warp-wide
 
-// One bvx1/bvx2 block: 32 LMDs per step, one per lane.  (fse_core.rs:108-129, lz/writer.rs:115-180)
-__device__ void expand_fse_block(uint8_t *__restrict__ out /* block's first output byte */, uint64_t block_pos /* stream bytes before it */,
-                                 const uint8_t *__restrict__ lit, const LmdRec *__restrict__ lmds, uint32_t n_lmds, uint32_t lane) {
+constexpr uint32_t kStageBytes = 512;              // a step producing at most this much is assembled in shared memory first
+constexpr uint32_t kStageStride = kStageBytes + 32;  // + up to 15 bytes of alignment in front, 16-byte multiple
+
+__device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+
+// One step of a bvx1/bvx2 block: 32 LMDs, one per lane (fse_core.rs:108-129, lz/writer.rs:115-180).
+//
+// STAGED: the step's literals and independent matches are first written into a per-warp shared-memory buffer laid out
+// like the output (same address modulo 16) and then flushed with 16-byte stores.  Byte stores straight to the output
+// cost an L1 sector lookup per touched sector and instruction -- after the source side was fixed they were the larger
+// half of the L1 traffic that bounds this kernel.
+template <bool STAGED>
+__device__ __forceinline__ void expand_step(uint8_t *__restrict__ out, const uint8_t *__restrict__ lit, uint32_t L, uint32_t M, uint32_t D,
+                                            uint32_t my_out, uint32_t my_lit, uint32_t out_base, uint32_t tot_o, uint32_t stage_s, uint32_t lane) {
+    const uint32_t my_dst = my_out + L;  // where my match goes
+    const uint32_t align = STAGED ? (uint32_t)(reinterpret_cast<uintptr_t>(out + out_base) & 15u) : 0u;
+    const uint32_t sbase = stage_s + align - out_base;  // shared address of block offset 0 (only offsets of this step are used)
+    // ---- literals ----
+    const bool long_l = L > kShortCopy;
+    {   // short runs: every lane copies its own; groups beyond the longest short run of the step are skipped warp-wide
+        const uint32_t sl = long_l ? 0u : L;
+        const uint32_t max_l = __reduce_max_sync(0xFFFFFFFFu, sl);
+        const uint8_t *ps = lit + my_lit;
+        uint8_t *pd = out + my_out;
+#pragma unroll
+        for (uint32_t g = 0; g < kShortCopy; g += 4) {
+            if (g < max_l) {
+                uint8_t tmp[4];
+#pragma unroll
+                for (uint32_t k = 0; k < 4; k++)
+                    if (g + k < sl) tmp[k] = ps[g + k];
+#pragma unroll
+                for (uint32_t k = 0; k < 4; k++)
+                    if (g + k < sl) {
+                        if (STAGED) sts_u8(sbase + my_out + g + k, tmp[k]);
+                        else pd[g + k] = tmp[k];
+                    }
+            }
+        }
+    }
+    uint32_t mask = __ballot_sync(0xFFFFFFFFu, long_l);
+    while (mask) {
+        int j = __ffs(mask) - 1;
+        mask &= mask - 1;
+        uint32_t o = __shfl_sync(0xFFFFFFFFu, my_out, j), li = __shfl_sync(0xFFFFFFFFu, my_lit, j), n = __shfl_sync(0xFFFFFFFFu, L, j);
+        for (uint32_t t = lane; t < n; t += 32) {
+            if (STAGED) sts_u8(sbase + o + t, lit[li + t]);
+            else out[o + t] = lit[li + t];
+        }
+    }
+    if (!STAGED) __syncwarp();
+
+    // ---- matches ----
+    // A lane may copy on its own when everything it reads was final before this step started
+    // (or is its own output); the rest go one at a time, in order, with the whole warp copying.
+    const uint8_t *src = out + my_dst - D;  // may point before `out` (earlier blocks of the stream)
+    const int64_t src_rel = (int64_t)my_dst - (int64_t)D;
+    const int64_t end_nonself = (src_rel + (int64_t)M < (int64_t)my_dst) ? src_rel + (int64_t)M : (int64_t)my_dst;
+    const bool indep = end_nonself <= (int64_t)out_base;
+    const bool solo = M != 0 && M <= kShortCopy && indep && D >= M;
+    {
+        // The source is fetched as aligned 32-bit words (at most five cover 16 bytes at any alignment) and
+        // realigned with funnel shifts: a byte load per source byte made every byte its own L1 sector lookup,
+        // and the L1 pipe, not HBM, was this kernel's bound (65 % of its peak, 10 sectors per request).
+        const uint32_t sm_ = solo ? M : 0u;
+        const uint32_t max_m = __reduce_max_sync(0xFFFFFFFFu, sm_);
+        if (max_m != 0) {
+            const uintptr_t sa = reinterpret_cast<uintptr_t>(src);
+            const uint32_t r = (uint32_t)sa & 3u;
+            const uint32_t *a4 = reinterpret_cast<const uint32_t *>(sa - r);
+            const uint32_t nw = sm_ ? (r + sm_ + 3) >> 2 : 0u;
+            uint32_t w[5];
+#pragma unroll
+            for (uint32_t j = 0; j < 5; j++) {
+                w[j] = 0;
+                if (j * 4 < max_m + 6 && j < nw) w[j] = a4[j];
+            }
+            uint32_t v[4];
+#pragma unroll
+            for (uint32_t j = 0; j < 4; j++) v[j] = __funnelshift_r(w[j], w[j + 1], r * 8);
+            uint8_t *pd = out + my_dst;
+#pragma unroll
+            for (uint32_t g = 0; g < kShortCopy; g += 4) {
+                if (g < max_m) {
+#pragma unroll
+                    for (uint32_t k = 0; k < 4; k++)
+                        if (g + k < sm_) {
+                            if (STAGED) sts_u8(sbase + my_dst + g + k, v[g >> 2] >> (8 * k));
+                            else pd[g + k] = (uint8_t)(v[g >> 2] >> (8 * k));
+                        }
+                }
+            }
+        }
+    }
+    if (STAGED) {
+        // flush [out_base, out_base + tot_o): bytes up to the first 16-byte boundary, whole 16-byte units, the rest.
+        // (Positions of the matches still to come carry garbage; they are written next.)
+        __syncwarp();
+        uint8_t *g0 = out + out_base;
+        const uint32_t end = align + tot_o;
+        const uint32_t body_lo = (align + 15) & ~15u, body_hi = end & ~15u;
+        if (body_lo <= body_hi) {
+            if (lane < body_lo - align) g0[lane] = (uint8_t)lds_u8(stage_s + align + lane);
+            for (uint32_t c = body_lo + lane * 16; c < body_hi; c += 512) {
+                uint4 q;
+                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(stage_s + c) : "memory");
+                *reinterpret_cast<uint4 *>(g0 + (c - align)) = q;
+            }
+            if (lane < end - body_hi) g0[body_hi - align + lane] = (uint8_t)lds_u8(stage_s + body_hi + lane);
+        } else if (lane < tot_o) {
+            g0[lane] = (uint8_t)lds_u8(stage_s + align + lane);
+        }
+    }
+    mask = __ballot_sync(0xFFFFFFFFu, M != 0 && !solo);
+    if (mask || STAGED) __syncwarp();
+    while (mask) {
+        int j = __ffs(mask) - 1;
+        mask &= mask - 1;
+        uint32_t o = __shfl_sync(0xFFFFFFFFu, my_dst, j), d = __shfl_sync(0xFFFFFFFFu, D, j), n = __shfl_sync(0xFFFFFFFFu, M, j);
+        const uint8_t *s = out + o - d;
+        if (d >= n) {
+            for (uint32_t t = lane; t < n; t += 32) out[o + t] = s[t];
+        } else {
+            for (uint32_t t = lane; t < n; t += 32) out[o + t] = s[t % d];  // byte i == byte i mod D of the seed
+        }
+        __syncwarp();
+    }
+    __syncwarp();
+}
+
+// One bvx1/bvx2 block, 32 LMDs per step.
+__device__ void expand_fse_block(uint8_t *__restrict__ out /* block's first output byte */, const uint8_t *__restrict__ lit,
+                                 const LmdRec *__restrict__ lmds, uint32_t n_lmds, uint32_t stage_s, uint32_t lane) {
     uint32_t out_base = 0, lit_base = 0;  // running offsets inside the block
-    (void)block_pos;
     // The records of step b+1 are fetched while step b is being copied: one memory round trip less per step.
     uint2 nxt = make_uint2(0, 0);
     if (lane < n_lmds) nxt = __ldg(reinterpret_cast<const uint2 *>(lmds) + lane);
@@ -756,93 +890,25 @@ __device__ void expand_fse_block(uint8_t *__restrict__ out /* block's first outp
         const uint32_t tot = __shfl_sync(0xFFFFFFFFu, inc, 31);
         const uint32_t my_out = out_base + (exc & 0x1FFFF);  // where my literals go
         const uint32_t my_lit = lit_base + (exc >> 17);
-        const uint32_t my_dst = my_out + L;                  // where my match goes
-
-        // ---- literals ----
-        const bool long_l = L > kShortCopy;
-        {   // short runs: every lane copies its own.  Pointers are hoisted and the byte offsets are immediates,
-            // so a group of 4 bytes is 4 predicates + 4 loads + 4 stores; groups beyond the longest short run
-            // of the step are skipped for the whole warp.
-            const uint32_t sl = long_l ? 0u : L;
-            const uint32_t max_l = __reduce_max_sync(0xFFFFFFFFu, sl);
-            const uint8_t *ps = lit + my_lit;
-            uint8_t *pd = out + my_out;
-#pragma unroll
-            for (uint32_t g = 0; g < kShortCopy; g += 4) {
-                if (g < max_l) {
-                    uint8_t tmp[4];
-#pragma unroll
-                    for (uint32_t k = 0; k < 4; k++)
-                        if (g + k < sl) tmp[k] = ps[g + k];
-#pragma unroll
-                    for (uint32_t k = 0; k < 4; k++)
-                        if (g + k < sl) pd[g + k] = tmp[k];
-                }
-            }
-        }
-        uint32_t mask = __ballot_sync(0xFFFFFFFFu, long_l);
-        while (mask) {
-            int j = __ffs(mask) - 1;
-            mask &= mask - 1;
-            uint32_t o = __shfl_sync(0xFFFFFFFFu, my_out, j), li = __shfl_sync(0xFFFFFFFFu, my_lit, j), n = __shfl_sync(0xFFFFFFFFu, L, j);
-            for (uint32_t t = lane; t < n; t += 32) out[o + t] = lit[li + t];
-        }
-        __syncwarp();
-
-        // ---- matches ----
-        // A lane may copy on its own when everything it reads was final before this step started
-        // (or is its own output); the rest go one at a time, in order, with the whole warp copying.
-        const uint8_t *src = out + my_dst - D;  // may point before `out` (earlier blocks of the stream)
-        const int64_t src_rel = (int64_t)my_dst - (int64_t)D;
-        const int64_t end_nonself = (src_rel + (int64_t)M < (int64_t)my_dst) ? src_rel + (int64_t)M : (int64_t)my_dst;
-        const bool indep = end_nonself <= (int64_t)out_base;
-        const bool solo = M != 0 && M <= kShortCopy && indep && D >= M;
-        {
-            const uint32_t sm_ = solo ? M : 0u;
-            const uint32_t max_m = __reduce_max_sync(0xFFFFFFFFu, sm_);
-            uint8_t *pd = out + my_dst;
-#pragma unroll
-            for (uint32_t g = 0; g < kShortCopy; g += 4) {
-                if (g < max_m) {
-                    uint8_t tmp[4];
-#pragma unroll
-                    for (uint32_t k = 0; k < 4; k++)
-                        if (g + k < sm_) tmp[k] = src[g + k];
-#pragma unroll
-                    for (uint32_t k = 0; k < 4; k++)
-                        if (g + k < sm_) pd[g + k] = tmp[k];
-                }
-            }
-        }
-        mask = __ballot_sync(0xFFFFFFFFu, M != 0 && !solo);
-        if (mask) __syncwarp();
-        while (mask) {
-            int j = __ffs(mask) - 1;
-            mask &= mask - 1;
-            uint32_t o = __shfl_sync(0xFFFFFFFFu, my_dst, j), d = __shfl_sync(0xFFFFFFFFu, D, j), n = __shfl_sync(0xFFFFFFFFu, M, j);
-            const uint8_t *s = out + o - d;
-            if (d >= n) {
-                for (uint32_t t = lane; t < n; t += 32) out[o + t] = s[t];
-            } else {
-                for (uint32_t t = lane; t < n; t += 32) out[o + t] = s[t % d];  // byte i == byte i mod D of the seed
-            }
-            __syncwarp();
-        }
-        __syncwarp();
-        out_base += tot & 0x1FFFF;
+        const uint32_t tot_o = tot & 0x1FFFF;
+        if (tot_o <= kStageBytes) expand_step<true>(out, lit, L, M, D, my_out, my_lit, out_base, tot_o, stage_s, lane);
+        else expand_step<false>(out, lit, L, M, D, my_out, my_lit, out_base, tot_o, stage_s, lane);
+        out_base += tot_o;
         lit_base += tot >> 17;
     }
 }
 
 constexpr int kExpandWarps = 8;
 
-__global__ void __launch_bounds__(kExpandWarps * 32)
+__global__ void __launch_bounds__(kExpandWarps * 32, 4)
 k_expand(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ src_off, const uint64_t *__restrict__ src_len,
          uint8_t *__restrict__ dst_base, const uint64_t *__restrict__ dst_off, const uint64_t *__restrict__ dst_cap,
          const StreamCounts *__restrict__ bases,
          const BlockDesc *__restrict__ blocks, const FseDesc *__restrict__ fse, const uint8_t *__restrict__ lit_scratch,
          const LmdRec *__restrict__ lmd_scratch, uint32_t *err, size_t n_streams) {
+    __shared__ __align__(16) uint8_t stage[kExpandWarps][kStageStride];
     const uint32_t lane = lane_id();
+    const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage[threadIdx.x >> 5]);
     const size_t stream = (size_t)blockIdx.x * kExpandWarps + (threadIdx.x >> 5);
     if (stream >= n_streams) return;
     const uint64_t b0 = bases[stream].n_blocks, b1 = bases[stream + 1].n_blocks;
@@ -866,7 +932,7 @@ k_expand(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ src_
         } else {
             const FseDesc &fd = fse[bd.fse_idx];
             if (!(fd.ok_lit && fd.ok_lmd)) return;  // the entropy stages already recorded why
-            expand_fse_block(out, bd.dst_off - dst_off[stream], lit_scratch + fd.lit_off, lmd_scratch + fd.lmd_off, fd.n_lmds, lane);
+            expand_fse_block(out, lit_scratch + fd.lit_off, lmd_scratch + fd.lmd_off, fd.n_lmds, stage_s, lane);
         }
         __syncwarp();
     }

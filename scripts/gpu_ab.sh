@@ -1,4 +1,4 @@
-# Encode: parity tests, then timing of the 1 GiB text workload.
+# Decode: parity tests, then timing of the 1 GiB text workload.
 set -x
-timeout 900 python -m pytest tests/test_gpu_encode.py tests/test_gpu_configs.py -m gpu -x -q 2>&1 | tail -3
-timeout 300 python scripts/prof_encode.py --chunks 16384 --iters 3 2>&1 | tail -2
+timeout 900 python -m pytest tests/test_gpu_decode.py tests/test_gpu_configs.py -m gpu -x -q 2>&1 | tail -3
+timeout 300 python scripts/prof_decode.py --chunks 16384 --iters 4 2>&1 | tail -3
