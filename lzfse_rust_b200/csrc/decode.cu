@@ -898,9 +898,12 @@ __device__ void expand_fse_block(uint8_t *__restrict__ out /* block's first outp
     }
 }
 
+#ifndef LZB_EXPAND_CTAS
+#define LZB_EXPAND_CTAS 4   // resident 8-warp CTAs per SM the register budget is set for
+#endif
 constexpr int kExpandWarps = 8;
 
-__global__ void __launch_bounds__(kExpandWarps * 32, 4)
+__global__ void __launch_bounds__(kExpandWarps * 32, LZB_EXPAND_CTAS)
 k_expand(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ src_off, const uint64_t *__restrict__ src_len,
          uint8_t *__restrict__ dst_base, const uint64_t *__restrict__ dst_off, const uint64_t *__restrict__ dst_cap,
          const StreamCounts *__restrict__ bases,

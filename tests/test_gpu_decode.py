@@ -14,11 +14,23 @@ import testkit as tk
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def dec():
+@pytest.fixture(scope="module", params=["warp", "cta"])
+def dec(request):
+    """Every test runs once per expansion kernel (warp per stream / CTA per stream); left alone the library picks by
+    batch size.  LZB_EXPAND is read when the decoder is created."""
+    import os
+
     import lzfse_rust_b200 as L
 
-    d = L.LzfseDecoder(0)
+    old = os.environ.get("LZB_EXPAND")
+    os.environ["LZB_EXPAND"] = request.param
+    try:
+        d = L.LzfseDecoder(0)
+    finally:
+        if old is None:
+            del os.environ["LZB_EXPAND"]
+        else:
+            os.environ["LZB_EXPAND"] = old
     yield d
     d.close()
 
