@@ -406,15 +406,17 @@ struct RingWindow {
         return LZFSE_B200_OK;
     }
     // Keeps the ring topped up: at most one chunk per call, so call it at least once per 16 bytes consumed.
-    // A chunk is requested ~100 bytes (dozens of steps) before the window reaches it; waiting for the
-    // previous request when issuing a new one is therefore free and always sufficient.
+    // A chunk is requested at least 100 bytes before the window reaches it, and the window cannot move 16 bytes
+    // without another request being issued: by the time a chunk is read, six younger requests exist.  Waiting
+    // until at most five requests are pending is therefore sufficient -- and it matters: waiting for all but the
+    // newest one (wait_group 1) was a third of the entropy kernels' time in the profile (profiles/, r1b).
     __device__ __forceinline__ void refill() {
         const uint32_t a4 = (a_base + (uint32_t)((P - 57) >> 3)) & ~3u;
         if (a4 + 12 <= next_chunk + kRing) {  // the chunk slot above the window is free
             fetch_chunk(next_chunk);
             next_chunk -= 16;
             asm volatile("cp.async.commit_group;" ::: "memory");
-            asm volatile("cp.async.wait_group 1;" ::: "memory");
+            asm volatile("cp.async.wait_group 5;" ::: "memory");
         }
     }
     // Window for the current cursor (callers guarantee P >= 57 and call refill() often enough).
