@@ -99,7 +99,9 @@ int lzfse_b200_decode_bytes(lzfse_b200_decoder *d, const uint8_t *src, size_t sr
  * its output region's contents are unspecified (as in the reference, src/lz/writer.rs:18,28).
  * _device: every pointer is device memory on the handle's GPU; `cuda_stream` is a cudaStream_t (or NULL).
  * _host:   every pointer is host memory; H2D/D2H copies happen inside the call.
- * Return value: call-level status (LZFSE_B200_OK even if individual streams failed). */
+ * Return value: call-level status (LZFSE_B200_OK even if individual streams failed).
+ * Limit (no reference counterpart): a frame that decodes to more than 0xF0000000 bytes fails with
+ * LZFSE_B200_BUFFER_OVERFLOW at the block that crosses the limit (32-bit stream positions on the device). */
 int lzfse_b200_decode_batch_device(lzfse_b200_decoder *d, const uint8_t *src_base, const uint64_t *src_off,
                                    const uint64_t *src_len, uint8_t *dst_base, const uint64_t *dst_off,
                                    const uint64_t *dst_cap, uint64_t *out_len, int32_t *status, size_t n,

@@ -34,6 +34,21 @@ void launch_expand_cta(const uint8_t *, const uint64_t *, const uint64_t *, uint
 
 using namespace lzb;
 
+// Device scratch of one kernel chain.  The host entry point runs several chains (one per slice of the batch) at the
+// same time, each with its own scratch and stream; everything else uses chain 0.
+struct DecodeScratch {
+    DevBuf counts, err, raw_total, totals_dev, blocks, fse, lits, lmds, work;
+    PinnedBuf totals_host;
+    cudaStream_t stream = nullptr;  // chains 1.. only
+    void release() {
+        for (DevBuf *b : {&counts, &err, &raw_total, &totals_dev, &blocks, &fse, &lits, &lmds, &work}) b->release();
+        totals_host.release();
+        if (stream) cudaStreamDestroy(stream);
+        stream = nullptr;
+    }
+};
+constexpr int kMaxChains = 6;
+
 struct lzfse_b200_decoder {
     int device = 0;
     int n_sms = 148;
@@ -41,9 +56,7 @@ struct lzfse_b200_decoder {
     std::string last_error;
     uint64_t launches = 0;
     int expand_mode = 0;  // 0 = choose per batch, 1 = warp per stream, 2 = CTA per stream (LZB_EXPAND=warp|cta: measurements only)
-    // scratch
-    DevBuf counts, err, raw_total, totals_dev, blocks, fse, lits, lmds, work;
-    PinnedBuf totals_host;
+    DecodeScratch chain[kMaxChains];
     // staging for the *_host entry points
     HostStage stage;
     StageTimer timer;
@@ -53,71 +66,89 @@ namespace {
 
 #define CK LZB_CK
 
+// Phase A of a chain: header scan (counts only).  Asynchronous.
+int decode_launch_scan(lzfse_b200_decoder *d, DecodeScratch &c, const uint8_t *src, const uint64_t *src_off, const uint64_t *src_len,
+                       const uint64_t *dst_cap, uint64_t *raw_len, uint32_t *n_blocks, size_t n, cudaStream_t s, bool probe_only) {
+    CK(d, c.counts.reserve((n + 1) * sizeof(StreamCounts)));
+    CK(d, c.err.reserve(n * sizeof(uint32_t)));
+    CK(d, c.raw_total.reserve(n * sizeof(uint64_t)));
+    CK(d, c.totals_dev.reserve(sizeof(StreamCounts)));
+    CK(d, c.totals_host.reserve(sizeof(StreamCounts)));
+    CK(d, c.work.reserve(4 * sizeof(uint32_t)));
+    uint64_t *raw_total = raw_len ? raw_len : c.raw_total.as<uint64_t>();
+    // Totals go straight into pinned host memory (UVA): no device-to-host copy that could queue behind a bulk
+    // download on the copy engine.
+    launch_scan_count(src, src_off, src_len, probe_only ? nullptr : dst_cap, n, c.counts.as<StreamCounts>(), c.err.as<uint32_t>(), raw_total,
+                      n_blocks, c.totals_host.as<StreamCounts>(), s);
+    d->launches += 2;
+    return LZFSE_B200_OK;
+}
+
+// Phase B: waits for the scan (the one host round trip: scratch sizes depend on what the headers announce), then
+// launches the rest of the chain.  Asynchronous after that; the caller synchronises `s`.
+int decode_launch_rest(lzfse_b200_decoder *d, DecodeScratch &c, const uint8_t *src, const uint64_t *src_off, const uint64_t *src_len, uint8_t *dst,
+                       const uint64_t *dst_off, const uint64_t *dst_cap, uint64_t *out_len, int32_t *status, size_t n, cudaStream_t s,
+                       StageTimer *timer) {
+    uint64_t *raw_total = c.raw_total.as<uint64_t>();
+    CK(d, cudaStreamSynchronize(s));
+    const StreamCounts tot = *c.totals_host.as<StreamCounts>();
+    if (tot.n_fse > 0xFFFFFFFFull) { d->last_error = "too many FSE blocks in one batch"; return LZFSE_B200_INVALID_ARGUMENT; }
+    CK(d, c.blocks.reserve((tot.n_blocks + 1) * sizeof(BlockDesc)));
+    CK(d, c.fse.reserve((tot.n_fse + 1) * sizeof(FseDesc)));
+    CK(d, c.lits.reserve(tot.n_literals + 512));  // slack: the expander prefetches up to 128 bytes past a block's run
+    CK(d, c.lmds.reserve((tot.n_lmds + 1) * sizeof(LmdRec)));
+    CK(d, cudaMemsetAsync(c.work.p, 0, 4 * sizeof(uint32_t), s));
+
+    launch_scan_fill(src, src_off, src_len, dst_off, dst_cap, n, c.counts.as<StreamCounts>(), c.blocks.as<BlockDesc>(), c.fse.as<FseDesc>(),
+                     c.err.as<uint32_t>(), s);
+    d->launches += 1;
+    if (timer) timer->mark(s);  // scan (count + host round trip + fill)
+    if (tot.n_fse) {
+        launch_fse_stages(src, src_off, src_len, dst_off, dst_cap, c.blocks.as<BlockDesc>(), c.fse.as<FseDesc>(), (uint32_t)tot.n_fse,
+                          c.lits.as<uint8_t>(), c.lmds.as<LmdRec>(), c.err.as<uint32_t>(), c.work.as<uint32_t>(), d->n_sms, s,
+                          timer && timer->enabled ? timer->ev[timer->n] : nullptr);
+        if (timer && timer->enabled) timer->n++;  // literals
+        d->launches += 2;
+    } else if (timer) {
+        timer->mark(s);
+    }
+    if (timer) timer->mark(s);  // lmds
+    // Expansion: a warp per stream when there are enough streams to fill the machine that way (64 warps x 148 SMs);
+    // otherwise a CTA per stream, whose 7 worker warps share one stream through a shared-memory window.
+    const bool use_cta = d->expand_mode == 2 || (d->expand_mode == 0 && n < (size_t)d->n_sms * 16);
+    if (!use_cta)
+        launch_expand(src, src_off, src_len, dst, dst_off, dst_cap, c.counts.as<StreamCounts>(), c.blocks.as<BlockDesc>(), c.fse.as<FseDesc>(),
+                      c.lits.as<uint8_t>(), c.lmds.as<LmdRec>(), c.err.as<uint32_t>(), n, s);
+    else
+        launch_expand_cta(src, src_off, src_len, dst, dst_off, dst_cap, c.counts.as<StreamCounts>(), c.blocks.as<BlockDesc>(),
+                          c.fse.as<FseDesc>(), c.lits.as<uint8_t>(), c.lmds.as<LmdRec>(), raw_total, c.err.as<uint32_t>(), n, c.work.as<uint32_t>() + 2,
+                          d->n_sms, s);
+    if (timer) timer->mark(s);  // expand
+    launch_finish(c.err.as<uint32_t>(), raw_total, out_len, status, n, s);
+    if (timer) timer->mark(s);  // finish
+    d->launches += 2;
+    CK(d, cudaGetLastError());
+    return LZFSE_B200_OK;
+}
+
 int decode_batch_device_impl(lzfse_b200_decoder *d, const uint8_t *src, const uint64_t *src_off, const uint64_t *src_len, uint8_t *dst,
                              const uint64_t *dst_off, const uint64_t *dst_cap, uint64_t *out_len, int32_t *status, uint64_t *raw_len,
                              uint32_t *n_blocks, size_t n, cudaStream_t s, bool probe_only) {
     d->launches = 0;
     if (n == 0) return LZFSE_B200_OK;
-    CK(d, d->counts.reserve((n + 1) * sizeof(StreamCounts)));
-    CK(d, d->err.reserve(n * sizeof(uint32_t)));
-    CK(d, d->raw_total.reserve(n * sizeof(uint64_t)));
-    CK(d, d->totals_dev.reserve(sizeof(StreamCounts)));
-    CK(d, d->totals_host.reserve(sizeof(StreamCounts)));
-    CK(d, d->work.reserve(4 * sizeof(uint32_t)));
-    uint64_t *raw_total = raw_len ? raw_len : d->raw_total.as<uint64_t>();
+    DecodeScratch &c = d->chain[0];
     d->timer.begin(s);
-
-    // Totals go straight into pinned host memory (UVA): no device-to-host copy that could queue behind a bulk
-    // download on the copy engine.
-    launch_scan_count(src, src_off, src_len, probe_only ? nullptr : dst_cap, n, d->counts.as<StreamCounts>(), d->err.as<uint32_t>(), raw_total,
-                      n_blocks, d->totals_host.as<StreamCounts>(), s);
-    d->launches += 2;
+    int rc = decode_launch_scan(d, c, src, src_off, src_len, dst_cap, raw_len, n_blocks, n, s, probe_only);
+    if (rc) return rc;
     if (probe_only) {
-        launch_finish(d->err.as<uint32_t>(), raw_total, nullptr, status, n, s);
+        launch_finish(c.err.as<uint32_t>(), raw_len ? raw_len : c.raw_total.as<uint64_t>(), nullptr, status, n, s);
         d->launches += 1;
         CK(d, cudaStreamSynchronize(s));
         CK(d, cudaGetLastError());
         return LZFSE_B200_OK;
     }
-    // The one host round trip: scratch sizes depend on what the headers announce.
-    CK(d, cudaStreamSynchronize(s));
-    const StreamCounts tot = *d->totals_host.as<StreamCounts>();
-    if (tot.n_fse > 0xFFFFFFFFull) { d->last_error = "too many FSE blocks in one batch"; return LZFSE_B200_INVALID_ARGUMENT; }
-    CK(d, d->blocks.reserve((tot.n_blocks + 1) * sizeof(BlockDesc)));
-    CK(d, d->fse.reserve((tot.n_fse + 1) * sizeof(FseDesc)));
-    CK(d, d->lits.reserve(tot.n_literals + 512));  // slack: the expander prefetches up to 128 bytes past a block's run
-    CK(d, d->lmds.reserve((tot.n_lmds + 1) * sizeof(LmdRec)));
-    CK(d, cudaMemsetAsync(d->work.p, 0, 4 * sizeof(uint32_t), s));
-
-    launch_scan_fill(src, src_off, src_len, dst_off, dst_cap, n, d->counts.as<StreamCounts>(), d->blocks.as<BlockDesc>(), d->fse.as<FseDesc>(),
-                     d->err.as<uint32_t>(), s);
-    d->launches += 1;
-    d->timer.mark(s);  // scan (count + host round trip + fill)
-    if (tot.n_fse) {
-        launch_fse_stages(src, src_off, src_len, dst_off, dst_cap, d->blocks.as<BlockDesc>(), d->fse.as<FseDesc>(), (uint32_t)tot.n_fse,
-                          d->lits.as<uint8_t>(), d->lmds.as<LmdRec>(), d->err.as<uint32_t>(), d->work.as<uint32_t>(), d->n_sms, s,
-                          d->timer.enabled ? d->timer.ev[d->timer.n] : nullptr);
-        if (d->timer.enabled) d->timer.n++;  // literals
-        d->launches += 2;
-    } else {
-        d->timer.mark(s);
-    }
-    d->timer.mark(s);  // lmds
-    // Expansion: a warp per stream when there are enough streams to fill the machine that way (64 warps x 148 SMs);
-    // otherwise a CTA per stream, whose 7 worker warps share one stream through a shared-memory window.
-    const bool use_cta = d->expand_mode == 2 || (d->expand_mode == 0 && n < (size_t)d->n_sms * 16);
-    if (!use_cta)
-        launch_expand(src, src_off, src_len, dst, dst_off, dst_cap, d->counts.as<StreamCounts>(), d->blocks.as<BlockDesc>(), d->fse.as<FseDesc>(),
-                      d->lits.as<uint8_t>(), d->lmds.as<LmdRec>(), d->err.as<uint32_t>(), n, s);
-    else
-        launch_expand_cta(src, src_off, src_len, dst, dst_off, dst_cap, d->counts.as<StreamCounts>(), d->blocks.as<BlockDesc>(),
-                          d->fse.as<FseDesc>(), d->lits.as<uint8_t>(), d->lmds.as<LmdRec>(), raw_total, d->err.as<uint32_t>(), n, d->work.as<uint32_t>() + 2,
-                          d->n_sms, s);
-    d->timer.mark(s);  // expand
-    launch_finish(d->err.as<uint32_t>(), raw_total, out_len, status, n, s);
-    d->timer.mark(s);  // finish
-    d->launches += 2;
-    CK(d, cudaGetLastError());
+    rc = decode_launch_rest(d, c, src, src_off, src_len, dst, dst_off, dst_cap, out_len, status, n, s, &d->timer);
+    if (rc) return rc;
     CK(d, cudaStreamSynchronize(s));
     d->timer.finish();
     return LZFSE_B200_OK;
@@ -195,8 +226,7 @@ int lzfse_b200_decoder_create(int device, lzfse_b200_decoder **out) {
 void lzfse_b200_decoder_destroy(lzfse_b200_decoder *d) {
     if (!d) return;
     DeviceGuard g(d->device);
-    for (DevBuf *b : {&d->counts, &d->err, &d->raw_total, &d->totals_dev, &d->blocks, &d->fse, &d->lits, &d->lmds, &d->work}) b->release();
-    d->totals_host.release();
+    for (auto &c : d->chain) c.release();
     d->stage.release();
     d->timer.release();
     if (d->own_stream) cudaStreamDestroy(d->own_stream);
@@ -232,38 +262,58 @@ int lzfse_b200_decode_probe_batch_device(lzfse_b200_decoder *d, const uint8_t *s
 
 // Host-buffer variants: stage the bytes on the device (host_util.h), run the device path, copy back.
 //
-// Large dense batches are cut into a few consecutive slices so that the upload of slice k+1, the kernels
-// of slice k and the download of slice k-1 overlap (PCIe is full duplex).  Few slices only: the entropy
-// stages are bound by the serial latency of one block, so every extra slice costs that latency again.
+// Large dense batches are cut into consecutive slices, each with its own kernel chain (stream + scratch), so that
+// the upload of later slices, the kernels and the download of earlier slices overlap (PCIe is full duplex) -- and so
+// that the chains themselves overlap: the entropy stages are bound by the serial latency of one block, not by the
+// machine, hence a chain takes ~2.5 ms however small its slice is, and running the chains one after the other would
+// leave the download engine idle between slices.  The download (the bound: ~56 GB/s) starts as soon as the first,
+// small slice is done; by then the other chains have been running next to it.
 static int decode_batch_host_pipelined(lzfse_b200_decoder *d, const uint8_t *src, const uint64_t *src_off, const uint64_t *src_len, uint8_t *dst,
-                                       const uint64_t *dst_off, uint64_t *out_len, int32_t *status, size_t n, int n_slices) {
-    cudaStream_t s = d->own_stream;
+                                       const uint64_t *dst_off, uint64_t *out_len, int32_t *status, size_t n) {
+    uint32_t share_pct[kMaxChains] = {4, 12, 28, 52, 76, 100};  // cumulative share of the bytes crossing the bus
+    int n_slices = kMaxChains;
+    if (const char *ov = getenv("LZB_SLICES")) {  // tuning aid: comma-separated cumulative percentages
+        int k = 0;
+        for (const char *p = ov; *p && k < kMaxChains; k++) {
+            share_pct[k] = (uint32_t)strtoul(p, const_cast<char **>(&p), 10);
+            if (*p == ',') p++;
+        }
+        if (k > 0) { n_slices = k; share_pct[k - 1] = 100; }
+    }
     HostStage &st = d->stage;
     if (!st.copy_in) {
         CK(d, cudaStreamCreateWithFlags(&st.copy_in, cudaStreamNonBlocking));
         CK(d, cudaStreamCreateWithFlags(&st.copy_out, cudaStreamNonBlocking));
         for (auto &e : st.ev_in) CK(d, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (auto &e : st.ev_scan) CK(d, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        CK(d, cudaEventCreateWithFlags(&st.ev_desc, cudaEventDisableTiming));
+        int lo = 0, hi = 0;  // earlier slices get the higher priority: their output is needed first
+        CK(d, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        for (int k = 0; k < kMaxChains; k++) {
+            const int prio = hi + k < lo ? hi + k : lo;
+            CK(d, cudaStreamCreateWithPriority(&d->chain[k].stream, cudaStreamNonBlocking, prio));
+        }
     }
     const uint64_t *pin = st.pin.as<uint64_t>();
     uint64_t *dd = st.desc.as<uint64_t>();
     // per-stream results are written by k_finish directly into pinned host memory (after the 4n descriptor words)
     uint64_t *d_out_len = st.pin.as<uint64_t>() + 4 * n;
     int32_t *d_status = reinterpret_cast<int32_t *>(d_out_len + n);
-    // Slice boundaries by bytes crossing the bus.  The download engine is the bound, and it can only start
-    // once the first slice's kernels are done (a fixed latency), so the first slice is the smallest.
-    size_t cut[5] = {0, 0, 0, 0, n};
+    size_t cut[kMaxChains + 1];
     {
-        static const uint32_t share_pct[3][4] = {{100, 100, 100, 100}, {40, 100, 100, 100}, {20, 55, 100, 100}};
         uint64_t total = 0, acc = 0;
         for (size_t i = 0; i < n; i++) total += src_len[i] + pin[3 * n + i];
         int k = 1;
+        cut[0] = 0;
         for (size_t i = 0; i < n && k < n_slices; i++) {
             acc += src_len[i] + pin[3 * n + i];
-            if (acc >= total / 100 * share_pct[n_slices - 1][k - 1]) cut[k++] = i + 1;
+            while (k < n_slices && acc >= total / 100 * share_pct[k - 1]) cut[k++] = i + 1;
         }
         for (; k < n_slices; k++) cut[k] = n;
         cut[n_slices] = n;
     }
+    // the descriptor upload was enqueued on the caller-facing stream: every chain waits for it
+    CK(d, cudaEventRecord(st.ev_desc, d->own_stream));
     // uploads, in slice order, on their own stream
     for (int k = 0; k < n_slices; k++) {
         const size_t i0 = cut[k], i1 = cut[k + 1];
@@ -273,29 +323,57 @@ static int decode_batch_host_pipelined(lzfse_b200_decoder *d, const uint8_t *src
         }
         CK(d, cudaEventRecord(st.ev_in[k], st.copy_in));
     }
-    uint64_t launches = 0;
-    const bool dbg = getenv("LZB_DEBUG") != nullptr;
-    auto now = []() { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec * 1e3 + t.tv_nsec * 1e-6; };
-    const double t_start = now();
+    d->launches = 0;
+    // Phase A of every chain (asynchronous: each chain's stream waits for its own upload).
     for (int k = 0; k < n_slices; k++) {
-        const size_t i0 = cut[k], i1 = cut[k + 1], m = i1 - i0;
+        const size_t i0 = cut[k], m = cut[k + 1] - i0;
         if (m == 0) continue;
-        if (dbg) fprintf(stderr, "[lzb] slice %d: streams [%zu,%zu) start %.2f ms\n", k, i0, i1, now() - t_start);
-        CK(d, cudaStreamWaitEvent(s, st.ev_in[k], 0));
-        int rc = decode_batch_device_impl(d, st.src.as<uint8_t>(), dd + i0, dd + n + i0, st.dst.as<uint8_t>(), dd + 2 * n + i0, dd + 3 * n + i0,
-                                          d_out_len + i0, d_status + i0, nullptr, nullptr, m, s, false);
+        DecodeScratch &c = d->chain[k];
+        CK(d, cudaStreamWaitEvent(c.stream, st.ev_desc, 0));
+        CK(d, cudaStreamWaitEvent(c.stream, st.ev_in[k], 0));
+        int rc = decode_launch_scan(d, c, st.src.as<uint8_t>(), dd + i0, dd + n + i0, dd + 3 * n + i0, nullptr, nullptr, m, c.stream, false);
         if (rc) return rc;
-        launches += d->launches;
-        memcpy(out_len + i0, d_out_len + i0, m * sizeof(uint64_t));  // the call above synchronised the stream
-        memcpy(status + i0, d_status + i0, m * sizeof(int32_t));
-        if (dbg) fprintf(stderr, "[lzb] slice %d: kernels done %.2f ms\n", k, now() - t_start);
-        rc = fetch_outputs(d, st, dst, dst_off, out_len, status, n, st.copy_out, i0, i1);  // overlaps the next slice's kernels
-        if (rc) return rc;
-        if (dbg) fprintf(stderr, "[lzb] slice %d: download enqueued %.2f ms\n", k, now() - t_start);
+        CK(d, cudaEventRecord(st.ev_scan[k], c.stream));
     }
+    // Phase B of every chain in order, each as soon as its scan is through (i.e. its upload has arrived); while the
+    // host waits for that it enqueues, in slice order, the downloads of the chains that have finished meanwhile.
+    int next_dl = 0, launched = 0;
+    auto service_downloads = [&](bool block) -> int {
+        while (next_dl < launched) {
+            const size_t i0 = cut[next_dl], i1 = cut[next_dl + 1], m = i1 - i0;
+            if (m != 0) {
+                if (block) CK(d, cudaStreamSynchronize(d->chain[next_dl].stream));
+                else if (cudaStreamQuery(d->chain[next_dl].stream) != cudaSuccess) { cudaGetLastError(); return LZFSE_B200_OK; }
+                memcpy(out_len + i0, d_out_len + i0, m * sizeof(uint64_t));
+                memcpy(status + i0, d_status + i0, m * sizeof(int32_t));
+                int rc = fetch_outputs(d, st, dst, dst_off, out_len, status, n, st.copy_out, i0, i1);
+                if (rc) return rc;
+            }
+            next_dl++;
+        }
+        return LZFSE_B200_OK;
+    };
+    for (int k = 0; k < n_slices; k++) {
+        const size_t i0 = cut[k], m = cut[k + 1] - i0;
+        if (m != 0) {
+            while (cudaEventQuery(st.ev_scan[k]) == cudaErrorNotReady) {
+                int rc = service_downloads(false);
+                if (rc) return rc;
+            }
+            DecodeScratch &c = d->chain[k];
+            int rc = decode_launch_rest(d, c, st.src.as<uint8_t>(), dd + i0, dd + n + i0, st.dst.as<uint8_t>(), dd + 2 * n + i0, dd + 3 * n + i0,
+                                        d_out_len + i0, d_status + i0, m, c.stream, nullptr);
+            if (rc) return rc;
+        }
+        launched = k + 1;
+    }
+    {
+        int rc = service_downloads(true);
+        if (rc) return rc;
+    }
+    const uint64_t launches = d->launches;
     d->launches = launches;
     CK(d, cudaStreamSynchronize(st.copy_out));
-    if (dbg) fprintf(stderr, "[lzb] all downloads done %.2f ms\n", now() - t_start);
     return LZFSE_B200_OK;
 }
 
@@ -324,7 +402,7 @@ int lzfse_b200_decode_batch_host(lzfse_b200_decoder *d, const uint8_t *src, cons
     CK(d, st.desc.reserve(4 * n * sizeof(uint64_t)));
     CK(d, st.res.reserve(n * (sizeof(uint64_t) + sizeof(int32_t))));
     CK(d, cudaMemcpyAsync(st.desc.p, st.pin.p, 4 * n * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
-    if (want_pipeline && st.src_mirrored && st.dst_mirrored) return decode_batch_host_pipelined(d, src, src_off, src_len, dst, dst_off, out_len, status, n, 3);
+    if (want_pipeline && st.src_mirrored && st.dst_mirrored) return decode_batch_host_pipelined(d, src, src_off, src_len, dst, dst_off, out_len, status, n);
     if (want_pipeline && st.src_mirrored) {  // upload was deferred but the output side cannot be sliced: do it now
         uint64_t lo = ~0ull, hi = 0;
         for (size_t i = 0; i < n; i++) { if (src_off[i] < lo) lo = src_off[i]; if (src_off[i] + src_len[i] > hi) hi = src_off[i] + src_len[i]; }

@@ -832,7 +832,7 @@ __device__ __forceinline__ void expand_step(uint8_t *__restrict__ out, const uin
             }
         }
     }
-    if (STAGED) {
+    if constexpr (STAGED) {
         // flush [out_base, out_base + tot_o): bytes up to the first 16-byte boundary, whole 16-byte units, the rest.
         // (Positions of the matches still to come carry garbage; they are written next.)
         __syncwarp();

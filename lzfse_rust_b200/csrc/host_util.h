@@ -94,12 +94,19 @@ struct HostStage {
     bool src_mirrored = false, dst_mirrored = false;
     size_t pin_n = 0;  // batch size the pin[] layout was built for
     cudaStream_t copy_in = nullptr, copy_out = nullptr;  // side streams of the pipelined host path
-    cudaEvent_t ev_in[4] = {};
+    cudaEvent_t ev_in[8] = {};
+    cudaEvent_t ev_scan[8] = {};
+    cudaEvent_t ev_desc = nullptr;
     void release() {
         src.release(); dst.release(); desc.release(); res.release(); pin.release();
         if (copy_in) cudaStreamDestroy(copy_in);
         if (copy_out) cudaStreamDestroy(copy_out);
         for (auto &e : ev_in) if (e) cudaEventDestroy(e);
+        if (ev_desc) cudaEventDestroy(ev_desc);
+        for (auto &e : ev_scan) if (e) cudaEventDestroy(e);
+        for (auto &e : ev_in) e = nullptr;
+        for (auto &e : ev_scan) e = nullptr;
+        ev_desc = nullptr;
         copy_in = copy_out = nullptr;
     }
 };
