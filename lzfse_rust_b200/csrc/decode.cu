@@ -14,6 +14,7 @@
 // keeps all 32 lanes issuing, and the tables are laid out [state][lane] so a warp's 32 lookups hit
 // 32 different banks.  What the reference does in Literals::load / FseCore::decode_internal
 // (fse/literals.rs:49-91, fse/fse_core.rs:91-141) is restated below with every check it makes.
+#include <cstdlib>
 #include <type_traits>
 
 #include "common.cuh"
@@ -918,6 +919,7 @@ k_expand(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ src_
     if (stream >= n_streams) return;
     const uint64_t b0 = bases[stream].n_blocks, b1 = bases[stream + 1].n_blocks;
     uint8_t *stream_out = dst_base + dst_off[stream];
+    if (b1 - b0 == 1 && vn_fast_eligible(1, blocks[b0], src_off[stream] + src_len[stream] - blocks[b0].src_off, dst_cap[stream])) return;  // k_expand_vn
     for (uint64_t b = b0; b < b1; b++) {
         const BlockDesc bd = blocks[b];
         uint8_t *out = dst_base + bd.dst_off;
@@ -940,6 +942,99 @@ k_expand(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ src_
             expand_fse_block(out, lit_scratch + fd.lit_off, lmd_scratch + fd.lmd_off, fd.n_lmds, stage_s, lane);
         }
         __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Single-LZVN-block streams (vn_fast_eligible): a warp per stream.
+//
+// The opcode stream is a serial chain (an opcode's position depends on the length of the one before), so every lane
+// decodes the same opcode -- one broadcast load, uniform control flow, no shuffles -- and the lanes share the copies:
+// literal bytes go from the payload to a shared-memory image of the output, match bytes from the image to the
+// image (LZ77 overlap: byte i = byte i mod D of the D bytes before the match), and the finished image is written to
+// HBM once in 16-byte stores.  One lane interpreting the block against HBM, as the in-order kernels do, waits for a
+// store-to-load round trip per match byte: 20.8 ms for 512 MiB of 21..4096-byte inputs.
+// Any irregularity (bad opcode, short payload, distance before the start, counts that do not add up) abandons the
+// image and re-runs the exact interpreter, which reports what the reference reports (vn/vn_core.rs:51-140).
+// ------------------------------------------------------------------------------------------------
+constexpr int kVnWarps = 8;
+constexpr uint32_t kVnImage = kVnFastRaw + 16;  // + up to 15 bytes in front so that image and output agree modulo 16
+
+__global__ void __launch_bounds__(kVnWarps * 32)
+k_expand_vn(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ src_off, const uint64_t *__restrict__ src_len,
+            uint8_t *__restrict__ dst_base, const uint64_t *__restrict__ dst_off, const uint64_t *__restrict__ dst_cap,
+            const StreamCounts *__restrict__ bases, const BlockDesc *__restrict__ blocks, uint32_t *err, size_t n_streams) {
+    __shared__ __align__(16) uint8_t image[kVnWarps][kVnImage];
+    const uint32_t lane = lane_id();
+    const size_t stream = (size_t)blockIdx.x * kVnWarps + (threadIdx.x >> 5);
+    if (stream >= n_streams) return;
+    const uint64_t b0 = bases[stream].n_blocks, nb = bases[stream + 1].n_blocks - b0;
+    if (nb != 1) return;
+    const BlockDesc bd = blocks[b0];
+    const uint64_t src_rest = src_off[stream] + src_len[stream] - bd.src_off, cap = dst_cap[stream];
+    if (!vn_fast_eligible(nb, bd, src_rest, cap)) return;
+    const uint8_t *src = src_base + bd.src_off;
+    uint8_t *out = dst_base + dst_off[stream];
+    const uint32_t n_raw = bd.n_raw, n_payload = ld_u32(src + 8);
+    const uint32_t vlen = (uint32_t)src_rest - kVnHeaderSize;
+    const uint32_t bias = (uint32_t)(reinterpret_cast<uintptr_t>(out) & 15u);
+    const uint32_t img = (uint32_t)__cvta_generic_to_shared(image[threadIdx.x >> 5]) + bias;  // shared address of output byte 0
+    uint32_t used = 0, out_pos = 0, D = 0;
+    bool ok = true, eos = false;
+    while (ok && !eos) {
+        const uint8_t *s = src + kVnHeaderSize + used;
+        const uint32_t rem = vlen - used;  // >= 8 (loop invariant, vn_core.rs:155-160)
+        const uint32_t opu = ldg4u(s);
+        uint32_t L = 0, M = 0, oplen = 0;
+        switch (vn_op(opu & 0xFF)) {
+        case OP_SML_L: L = opu & 0xF; oplen = 1; break;
+        case OP_LRG_L: L = ((opu >> 8) & 0xFF) + 16; oplen = 2; break;
+        case OP_SML_M: M = opu & 0xF; oplen = 1; break;
+        case OP_LRG_M: M = ((opu >> 8) & 0xFF) + 16; oplen = 2; break;
+        case OP_PRE_D: M = ((opu >> 3) & 7) + 3; L = (opu >> 6) & 3; oplen = 1; break;
+        case OP_SML_D: D = ((opu & 7) << 8) | ((opu >> 8) & 0xFF); M = ((opu >> 3) & 7) + 3; L = (opu >> 6) & 3; oplen = 2; break;
+        case OP_MED_D: M = (((opu & 7) << 2) | ((opu >> 8) & 3)) + 3; L = (opu >> 3) & 3; D = (opu >> 10) & 0x3FFF; oplen = 3; break;
+        case OP_LRG_D: M = ((opu >> 3) & 7) + 3; L = (opu >> 6) & 3; D = (opu >> 8) & 0xFFFF; oplen = 3; break;
+        case OP_NOP: oplen = 1; break;
+        case OP_EOS:
+            if (opu != 0x06u || ldg4u(s + 4) != 0u) ok = false;
+            else { used += 8; eos = true; }
+            continue;
+        default: ok = false; continue;
+        }
+        if (rem - oplen < L + 8 || out_pos + L + M > n_raw || (M != 0 && (D == 0 || D > out_pos + L))) { ok = false; continue; }
+        if (L) {
+            for (uint32_t t = lane; t < L; t += 32) sts_u8(img + out_pos + t, s[oplen + t]);
+            out_pos += L;
+        }
+        if (M) {
+            __syncwarp();  // the literals above (and every earlier byte) are visible to all lanes
+            const uint32_t from = img + out_pos - D;
+            if (D >= M) for (uint32_t t = lane; t < M; t += 32) sts_u8(img + out_pos + t, lds_u8(from + t));
+            else for (uint32_t t = lane; t < M; t += 32) sts_u8(img + out_pos + t, lds_u8(from + t % D));
+            out_pos += M;
+        }
+        used += oplen + L;
+        __syncwarp();
+    }
+    if (ok && used == n_payload && out_pos == n_raw) {  // VnCore::decode's final accounting (vn_core.rs:96-111)
+        __syncwarp();
+        // head up to the first 16-byte boundary of the output, 16-byte units, tail
+        uint32_t head = (16u - bias) & 15u;
+        if (head > n_raw) head = n_raw;
+        if (lane < head) out[lane] = (uint8_t)lds_u8(img + lane);
+        const uint32_t nv = (n_raw - head) >> 4;
+        for (uint32_t i = lane; i < nv; i += 32) {
+            uint4 q;
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(img + head + i * 16) : "memory");
+            *reinterpret_cast<uint4 *>(out + head + i * 16) = q;
+        }
+        const uint32_t done = head + nv * 16;
+        if (done + lane < n_raw) out[done + lane] = (uint8_t)lds_u8(img + done + lane);
+    } else if (lane == 0) {
+        const int st = vn_decode_block(src, src_rest, out, 0, cap);
+        const uint32_t kb = bd.index < 0x1FFFFFu ? bd.index : 0x1FFFFFu;
+        if (st) atomicMin(&err[stream], err_key(kb, PH_LMD, st));
     }
 }
 
@@ -989,7 +1084,15 @@ void launch_expand(const uint8_t *src, const uint64_t *src_off, const uint64_t *
                    const uint64_t *dst_cap, const StreamCounts *bases, const BlockDesc *blocks, const FseDesc *fse, const uint8_t *lit_scratch,
                    const LmdRec *lmd_scratch, uint32_t *err, size_t n, cudaStream_t s) {
     if (n == 0) return;
-    k_expand<<<(unsigned)((n + kExpandWarps - 1) / kExpandWarps), kExpandWarps * 32, 0, s>>>(src, src_off, src_len, dst, dst_off, dst_cap, bases, blocks, fse, lit_scratch, lmd_scratch, err, n);
+    // Tuning aid: LZB_EXPAND_PAD_KB adds unused dynamic shared memory per CTA and so caps the resident CTAs per SM.
+    static const int pad_kb = [] { const char *e = getenv("LZB_EXPAND_PAD_KB"); return e ? atoi(e) : 0; }();
+    if (pad_kb > 48) cudaFuncSetAttribute(k_expand, cudaFuncAttributeMaxDynamicSharedMemorySize, pad_kb * 1024);
+    k_expand<<<(unsigned)((n + kExpandWarps - 1) / kExpandWarps), kExpandWarps * 32, (size_t)pad_kb * 1024, s>>>(src, src_off, src_len, dst, dst_off, dst_cap, bases, blocks, fse, lit_scratch, lmd_scratch, err, n);
+}
+void launch_expand_vn(const uint8_t *src, const uint64_t *src_off, const uint64_t *src_len, uint8_t *dst, const uint64_t *dst_off,
+                      const uint64_t *dst_cap, const StreamCounts *bases, const BlockDesc *blocks, uint32_t *err, size_t n, cudaStream_t s) {
+    if (n == 0) return;
+    k_expand_vn<<<(unsigned)((n + kVnWarps - 1) / kVnWarps), kVnWarps * 32, 0, s>>>(src, src_off, src_len, dst, dst_off, dst_cap, bases, blocks, err, n);
 }
 void launch_finish(const uint32_t *err, const uint64_t *raw_total, uint64_t *out_len, int32_t *status, size_t n, cudaStream_t s) {
     if (n == 0) return;

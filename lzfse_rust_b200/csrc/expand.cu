@@ -330,7 +330,9 @@ k_expand_cta(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ 
         e.out_g = dst_base + dst_off[stream];
         e.bias = (uint32_t)(reinterpret_cast<uintptr_t>(e.out_g) & 15u);
         e.total = (uint32_t)raw_total[stream];
-        const uint64_t b0 = bases[stream].n_blocks, b1 = bases[stream + 1].n_blocks;
+        const uint64_t b0 = bases[stream].n_blocks;
+        uint64_t b1 = bases[stream + 1].n_blocks;
+        if (b1 - b0 == 1 && vn_fast_eligible(1, blocks[b0], src_off[stream] + src_len[stream] - blocks[b0].src_off, dst_cap[stream])) b1 = b0;  // k_expand_vn
         uint32_t fl = 0;   // flusher's copy of ctl->flushed
         for (uint64_t b = b0; b < b1; b++) {
             const BlockDesc bd = blocks[b];

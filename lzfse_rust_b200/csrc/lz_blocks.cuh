@@ -117,5 +117,27 @@ __device__ inline int vn_decode_block(const uint8_t *src, uint64_t src_rest /* b
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Streams that consist of ONE small LZVN block -- what the reference's encoder emits for every input of 21..4096
+// bytes (encode/frontend_bytes.rs:63-77) -- are expanded by k_expand_vn (decode.cu), a warp per stream with the
+// output assembled in shared memory; the in-order expansion kernels skip them.  Everything else (LZVN blocks inside
+// longer frames, payloads beyond the interpreter's 0x2000-byte window, too small a destination) takes the one-lane
+// interpreter above, which is also the fast kernel's fallback whenever a stream is not well-formed.
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t kVnFastRaw = 4096;
+__device__ __forceinline__ bool vn_fast_eligible(uint64_t n_stream_blocks, const BlockDesc &bd, uint64_t src_rest, uint64_t cap) {
+    return n_stream_blocks == 1 && bd.type == BT_VXN && bd.n_raw <= kVnFastRaw && src_rest >= kVnHeaderSize + 8 &&
+           src_rest - kVnHeaderSize <= kVnPayloadLimit && cap >= bd.n_raw;
+}
+
+// Unaligned little-endian loads through aligned words (the bytes up to the next word boundary may lie past `p + n`;
+// callers guarantee that word still belongs to the buffer).
+__device__ __forceinline__ uint32_t ldg4u(const uint8_t *p) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint32_t r = (uint32_t)a & 3u;
+    const uint32_t *q = reinterpret_cast<const uint32_t *>(a - r);
+    const uint32_t lo = __ldg(q), hi = r ? __ldg(q + 1) : 0u;
+    return __funnelshift_r(lo, hi, r * 8);
+}
 
 }  // namespace lzb

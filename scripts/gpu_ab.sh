@@ -1,6 +1,4 @@
-# Host-path slice tuning: e2e of the bench workload for a few slice layouts.
-for sl in "4,12,28,52,76,100" "2,8,20,44,72,100" "3,10,25,50,75,100" "5,15,35,65,100" "8,24,48,74,100" "6,18,40,70,100"; do
-  echo "== $sl"
-  LZB_SLICES=$sl timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu 2>/dev/null | python -c "
-import json,sys; d=json.loads(sys.stdin.read()); print('e2e', d['e2e']['value'], d['e2e']['ms_per_step'])"
-done
+# ncu capture of the single-LZVN-block expansion kernel on the small-chunk class.
+timeout 600 python scripts/prof_mixed.py --mib 256 --kinds small 2>&1 | tail -2
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_expand_vn -s 1 -c 1 -o gpurun_out/vn_full -f python scripts/prof_mixed.py --mib 256 --kinds small > gpurun_out/vn_full.log 2>&1
+tail -2 gpurun_out/vn_full.log
