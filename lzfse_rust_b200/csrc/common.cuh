@@ -50,7 +50,7 @@ struct BlockDesc {
     uint32_t type;     // BlockType
     uint32_t index;    // block index inside its stream
     uint32_t fse_idx;  // index into FseDesc[] for bvx1/bvx2
-    uint32_t pad;
+    uint32_t pad;      // 1: LZVN block whose n_raw was clamped to the destination by the scan (see k_scan)
 };
 
 // Parsed bvx1/bvx2 header plus scratch placement (fse/block.rs:80-136).

@@ -139,6 +139,16 @@ __global__ void k_scan(const uint8_t *__restrict__ src_base, const uint64_t *__r
             bd.type = BT_VXN;
             blen = (uint64_t)kVnHeaderSize + ld_u32(s + pos + 8);
             if (rest < blen) stop = true;  // the opcode interpreter decides which error this is
+            // An LZVN header can announce any n_raw_bytes; the reference only compares it with what the opcodes
+            // produced (vn_core.rs:96-111).  When the announcement would cross the 32-bit position limit below but the
+            // destination is smaller than that anyway, the block cannot succeed: let the interpreter find the error
+            // the reference finds (bad opcode, BufferOverflow at the write that does not fit, VnBadPayload at the
+            // end) and keep the positions of the descriptors inside the destination.
+            if (raw + bd.n_raw > kMaxStreamRaw && dst_cap != nullptr && dst_cap[i] < raw + bd.n_raw) {
+                stop = true;
+                bd.n_raw = (uint32_t)(dst_cap[i] > raw ? dst_cap[i] - raw : 0);
+                bd.pad = 1;  // n_raw is not the header's: one-lane interpreter only (vn_fast_eligible)
+            }
         } else if (magic == kMagicVx2 || magic == kMagicVx1) {
             const bool v1 = magic == kMagicVx1;
             const uint32_t hs = v1 ? kV1HeaderSize : kV2HeaderSize;
@@ -588,7 +598,8 @@ __device__ __forceinline__ void build_v_block(WeightReader &r, uint32_t *tab, ui
         }
         total += w;
     }
-    for (uint32_t t = total; t < n_states; t++) tab[(offset + t) * 32 + lane] = t;  // latch: k = 0, no value bits, symbol 0
+    // latch (fse/decoder.rs:288-291): k = 0, no value bits, v_base = 0 -- which for D is the field value 4: (4 << 0) - 4
+    for (uint32_t t = total; t < n_states; t++) tab[(offset + t) * 32 + lane] = t | (KIND == 2 ? (4u << 16) : 0u);
 }
 
 __global__ void __launch_bounds__(kLmdWarps * 32, 1)
@@ -953,7 +964,10 @@ k_expand(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ src_
 // literal bytes go from the payload to a shared-memory image of the output, match bytes from the image to the
 // image (LZ77 overlap: byte i = byte i mod D of the D bytes before the match), and the finished image is written to
 // HBM once in 16-byte stores.  One lane interpreting the block against HBM, as the in-order kernels do, waits for a
-// store-to-load round trip per match byte: 20.8 ms for 512 MiB of 21..4096-byte inputs.
+// store-to-load round trip per match byte: 20.8 ms for 512 MiB of 21..4096-byte inputs; this kernel takes 11.9 ms and
+// is bound by instruction issue (~100 instructions per opcode, repeated by every lane).  Measured and dropped: eight
+// lanes per stream, four streams per warp -- the groups diverge on the opcode class, 167 instructions per step for
+// 2.4 opcodes, 12 resident warps instead of 48: 15.8 ms.
 // Any irregularity (bad opcode, short payload, distance before the start, counts that do not add up) abandons the
 // image and re-runs the exact interpreter, which reports what the reference reports (vn/vn_core.rs:51-140).
 // ------------------------------------------------------------------------------------------------

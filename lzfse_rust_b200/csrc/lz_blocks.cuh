@@ -126,7 +126,7 @@ __device__ inline int vn_decode_block(const uint8_t *src, uint64_t src_rest /* b
 // ------------------------------------------------------------------------------------------------
 constexpr uint32_t kVnFastRaw = 4096;
 __device__ __forceinline__ bool vn_fast_eligible(uint64_t n_stream_blocks, const BlockDesc &bd, uint64_t src_rest, uint64_t cap) {
-    return n_stream_blocks == 1 && bd.type == BT_VXN && bd.n_raw <= kVnFastRaw && src_rest >= kVnHeaderSize + 8 &&
+    return n_stream_blocks == 1 && bd.type == BT_VXN && bd.pad == 0 && bd.n_raw <= kVnFastRaw && src_rest >= kVnHeaderSize + 8 &&
            src_rest - kVnHeaderSize <= kVnPayloadLimit && cap >= bd.n_raw;
 }
 
