@@ -774,10 +774,13 @@ __device__ __forceinline__ void expand_step(uint8_t *__restrict__ out, const uin
         const uint32_t max_l = __reduce_max_sync(0xFFFFFFFFu, sl);
         const uint8_t *ps = lit + my_lit;
         uint8_t *pd = out + my_out;
+        // keep the two addresses in registers: left alone, the compiler rebuilds them from the kernel parameters for
+        // every predicated byte (three extra instructions per literal byte in the r1b profile)
+        asm volatile("" : "+l"(ps), "+l"(pd));
 #pragma unroll
         for (uint32_t g = 0; g < kShortCopy; g += 4) {
             if (g < max_l) {
-                uint8_t tmp[4];
+                uint32_t tmp[4];
 #pragma unroll
                 for (uint32_t k = 0; k < 4; k++)
                     if (g + k < sl) tmp[k] = ps[g + k];
@@ -849,6 +852,7 @@ __device__ __forceinline__ void expand_step(uint8_t *__restrict__ out, const uin
         // (Positions of the matches still to come carry garbage; they are written next.)
         __syncwarp();
         uint8_t *g0 = out + out_base;
+        asm volatile("" : "+l"(g0));  // as above: one address, not one per store
         const uint32_t end = align + tot_o;
         const uint32_t body_lo = (align + 15) & ~15u, body_hi = end & ~15u;
         if (body_lo <= body_hi) {
@@ -925,7 +929,8 @@ k_expand(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ src_
          const LmdRec *__restrict__ lmd_scratch, uint32_t *err, size_t n_streams) {
     __shared__ __align__(16) uint8_t stage[kExpandWarps][kStageStride];
     const uint32_t lane = lane_id();
-    const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage[threadIdx.x >> 5]);
+    uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage[threadIdx.x >> 5]);
+    asm volatile("" : "+r"(stage_s));  // or the compiler re-derives it from %tid and the shared window base in every step
     const size_t stream = (size_t)blockIdx.x * kExpandWarps + (threadIdx.x >> 5);
     if (stream >= n_streams) return;
     const uint64_t b0 = bases[stream].n_blocks, b1 = bases[stream + 1].n_blocks;

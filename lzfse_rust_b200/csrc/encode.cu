@@ -399,6 +399,7 @@ k_enc_parse(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ s
         if (kind == SK_RAW) continue;
         const bool vn = kind == SK_VN;
         const uint8_t *src = src_base + src_off[si];
+        asm volatile("" : "+l"(src));  // one pointer in registers; otherwise every access re-adds the kernel parameter and the offset
         const uint32_t len = (uint32_t)src_len[si];
         const uint32_t max_d = vn ? kVnMaxD : kMaxDValue;
         if (epoch > 0xFFFFFFFFu - len - (kMaxDValue + 1)) {  // 32-bit positions would wrap inside this stream: really reset
