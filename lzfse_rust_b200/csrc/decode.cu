@@ -214,33 +214,56 @@ __global__ void k_scan(const uint8_t *__restrict__ src_base, const uint64_t *__r
 
 // Exclusive scan of StreamCounts in place with one CTA; totals[0] receives the grand totals and
 // counts[n] too (so stream i's range is [counts[i], counts[i+1])).
+__device__ __forceinline__ StreamCounts sc_add(StreamCounts a, const StreamCounts &b) {
+    a.n_blocks += b.n_blocks; a.n_fse += b.n_fse; a.n_literals += b.n_literals; a.n_lmds += b.n_lmds;
+    return a;
+}
+__device__ __forceinline__ StreamCounts sc_shfl_up(const StreamCounts &v, int o) {
+    StreamCounts r;
+    r.n_blocks = __shfl_up_sync(0xFFFFFFFFu, v.n_blocks, o); r.n_fse = __shfl_up_sync(0xFFFFFFFFu, v.n_fse, o);
+    r.n_literals = __shfl_up_sync(0xFFFFFFFFu, v.n_literals, o); r.n_lmds = __shfl_up_sync(0xFFFFFFFFu, v.n_lmds, o);
+    return r;
+}
+__device__ __forceinline__ StreamCounts sc_warp_inclusive(StreamCounts v, uint32_t lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const StreamCounts t = sc_shfl_up(v, o);
+        if (lane >= (uint32_t)o) v = sc_add(v, t);
+    }
+    return v;
+}
 __global__ void __launch_bounds__(1024) k_exclusive_scan(StreamCounts *counts, size_t n, StreamCounts *totals) {
-    __shared__ StreamCounts part[1024];
+    __shared__ StreamCounts warp_tot[32];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t per = (n + blockDim.x - 1) / blockDim.x;
     const size_t lo = (size_t)threadIdx.x * per, hi = lo + per < n ? lo + per : n;
+    const uint4 *c4 = reinterpret_cast<const uint4 *>(counts);
     StreamCounts acc = {0, 0, 0, 0};
-    for (size_t i = lo; i < hi; i++) {
-        acc.n_blocks += counts[i].n_blocks; acc.n_fse += counts[i].n_fse;
-        acc.n_literals += counts[i].n_literals; acc.n_lmds += counts[i].n_lmds;
+#pragma unroll 4
+    for (size_t i = lo; i < hi; i++) {  // independent 16-byte loads: the unrolled body keeps eight of them in flight
+        const uint4 a = c4[2 * i], b = c4[2 * i + 1];
+        acc.n_blocks += a.x | ((uint64_t)a.y << 32); acc.n_fse += a.z | ((uint64_t)a.w << 32);
+        acc.n_literals += b.x | ((uint64_t)b.y << 32); acc.n_lmds += b.z | ((uint64_t)b.w << 32);
     }
-    part[threadIdx.x] = acc;
+    // block-wide exclusive scan of the 1024 partial sums: warp scans through shuffles, then the 32 warp totals
+    const StreamCounts inc = sc_warp_inclusive(acc, lane);
+    if (lane == 31) warp_tot[warp] = inc;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        StreamCounts run = {0, 0, 0, 0};
-        for (unsigned t = 0; t < blockDim.x; t++) {
-            StreamCounts v = part[t];
-            part[t] = run;
-            run.n_blocks += v.n_blocks; run.n_fse += v.n_fse; run.n_literals += v.n_literals; run.n_lmds += v.n_lmds;
-        }
-        *totals = run;
-        counts[n] = run;
+    if (warp == 0) {
+        const StreamCounts w = sc_warp_inclusive(warp_tot[lane], lane);
+        if (lane == 31) { *totals = w; counts[n] = w; }
+        StreamCounts ex = sc_shfl_up(w, 1);
+        if (lane == 0) ex = StreamCounts{0, 0, 0, 0};
+        warp_tot[lane] = ex;
     }
     __syncthreads();
-    StreamCounts run = part[threadIdx.x];
+    StreamCounts run = sc_add(warp_tot[warp], inc);
+    run.n_blocks -= acc.n_blocks; run.n_fse -= acc.n_fse; run.n_literals -= acc.n_literals; run.n_lmds -= acc.n_lmds;  // exclusive
+#pragma unroll 4
     for (size_t i = lo; i < hi; i++) {
-        StreamCounts v = counts[i];
+        const StreamCounts v = counts[i];
         counts[i] = run;
-        run.n_blocks += v.n_blocks; run.n_fse += v.n_fse; run.n_literals += v.n_literals; run.n_lmds += v.n_lmds;
+        run = sc_add(run, v);
     }
 }
 
@@ -360,8 +383,11 @@ __device__ __forceinline__ uint32_t bfe(uint32_t v, uint32_t pos, uint32_t len) 
     return r;
 }
 __device__ __forceinline__ uint32_t bits_at(uint64_t win, int pos, uint32_t n) {  // n < 32
-    // one 64-bit funnel shift, then shl + and-not: bfe.u32 with a register length costs five instructions on sm_100
-    return (uint32_t)(win >> pos) & ~(0xFFFFFFFFu << n);
+    // one 64-bit funnel shift + one SGXT.W (szext: keep the low n bits, 0 for n == 0); bfe.u32 with a register length
+    // costs five instructions on sm_100, shl + and-not two
+    uint32_t r;
+    asm("szext.wrap.u32 %0, %1, %2;" : "=r"(r) : "r"((uint32_t)(win >> pos)), "r"(n));
+    return r;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -783,7 +809,7 @@ __device__ __forceinline__ void expand_step(uint8_t *__restrict__ out, const uin
                 uint32_t tmp[4];
 #pragma unroll
                 for (uint32_t k = 0; k < 4; k++)
-                    if (g + k < sl) tmp[k] = ps[g + k];
+                    if (g + k < sl) tmp[k] = __ldg(ps + g + k);
 #pragma unroll
                 for (uint32_t k = 0; k < 4; k++)
                     if (g + k < sl) {
@@ -888,6 +914,7 @@ __device__ __forceinline__ void expand_step(uint8_t *__restrict__ out, const uin
 __device__ void expand_fse_block(uint8_t *__restrict__ out /* block's first output byte */, const uint8_t *__restrict__ lit,
                                  const LmdRec *__restrict__ lmds, uint32_t n_lmds, uint32_t stage_s, uint32_t lane) {
     uint32_t out_base = 0, lit_base = 0;  // running offsets inside the block
+    asm volatile("" : "+l"(out), "+l"(lit), "+l"(lmds));  // plain register pointers (see expand_step)
     // The records of step b+1 are fetched while step b is being copied: one memory round trip less per step.
     uint2 nxt = make_uint2(0, 0);
     if (lane < n_lmds) nxt = __ldg(reinterpret_cast<const uint2 *>(lmds) + lane);
