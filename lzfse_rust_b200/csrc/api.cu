@@ -71,7 +71,7 @@ namespace {
 // Phase A of a chain: header scan (counts only).  Asynchronous.
 int decode_launch_scan(lzfse_b200_decoder *d, DecodeScratch &c, const uint8_t *src, const uint64_t *src_off, const uint64_t *src_len,
                        const uint64_t *dst_cap, uint64_t *raw_len, uint32_t *n_blocks, size_t n, cudaStream_t s, bool probe_only) {
-    CK(d, c.counts.reserve((n + 1) * sizeof(StreamCounts)));
+    CK(d, c.counts.reserve((n + 1 + n / 1024 + 2) * sizeof(StreamCounts)));  // + tile sums of the scan
     CK(d, c.err.reserve(n * sizeof(uint32_t)));
     CK(d, c.raw_total.reserve(n * sizeof(uint64_t)));
     CK(d, c.totals_dev.reserve(sizeof(StreamCounts)));
@@ -82,7 +82,7 @@ int decode_launch_scan(lzfse_b200_decoder *d, DecodeScratch &c, const uint8_t *s
     // download on the copy engine.
     launch_scan_count(src, src_off, src_len, probe_only ? nullptr : dst_cap, n, c.counts.as<StreamCounts>(), c.err.as<uint32_t>(), raw_total,
                       n_blocks, c.totals_host.as<StreamCounts>(), s);
-    d->launches += 2;
+    d->launches += n > 8192 ? 4 : 2;  // k_scan + the exclusive scan (three launches for large batches)
     return LZFSE_B200_OK;
 }
 

@@ -267,6 +267,57 @@ __global__ void __launch_bounds__(1024) k_exclusive_scan(StreamCounts *counts, s
     }
 }
 
+// Batches of many streams: the same scan in three short launches over 1024-element tiles (tile sums, scan of the tile
+// sums with the kernel above, tile-local scans + offsets).  One CTA walking 512 Ki stream records on its own took
+// longer than the header scan it serves.
+__global__ void __launch_bounds__(1024) k_scan_tile_sums(const StreamCounts *__restrict__ counts, size_t n, StreamCounts *tile_sums) {
+    __shared__ StreamCounts warp_tot[32];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t i = (size_t)blockIdx.x * 1024 + threadIdx.x;
+    StreamCounts v = {0, 0, 0, 0};
+    if (i < n) v = counts[i];
+    const StreamCounts inc = sc_warp_inclusive(v, lane);
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        const StreamCounts w = sc_warp_inclusive(warp_tot[lane], lane);
+        if (lane == 31) tile_sums[blockIdx.x] = w;
+    }
+}
+__global__ void __launch_bounds__(1024) k_scan_tile_apply(StreamCounts *counts, size_t n, const StreamCounts *__restrict__ tile_offsets, size_t n_tiles) {
+    __shared__ StreamCounts warp_tot[32];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t i = (size_t)blockIdx.x * 1024 + threadIdx.x;
+    StreamCounts v = {0, 0, 0, 0};
+    if (i < n) v = counts[i];
+    const StreamCounts inc = sc_warp_inclusive(v, lane);
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        const StreamCounts w = sc_warp_inclusive(warp_tot[lane], lane);
+        StreamCounts ex = sc_shfl_up(w, 1);
+        if (lane == 0) ex = StreamCounts{0, 0, 0, 0};
+        warp_tot[lane] = ex;
+    }
+    __syncthreads();
+    StreamCounts run = sc_add(sc_add(tile_offsets[blockIdx.x], warp_tot[warp]), inc);
+    run.n_blocks -= v.n_blocks; run.n_fse -= v.n_fse; run.n_literals -= v.n_literals; run.n_lmds -= v.n_lmds;  // exclusive
+    if (i < n) counts[i] = run;
+    if (i == n) counts[n] = tile_offsets[n_tiles];  // grand totals (the tile holding index n exists: see the launcher)
+}
+// counts must have room for n + 1 + (n / 1024 + 2) elements.
+void launch_exclusive_scan(StreamCounts *counts, size_t n, StreamCounts *totals, cudaStream_t s) {
+    if (n <= 8192) {
+        k_exclusive_scan<<<1, 1024, 0, s>>>(counts, n, totals);
+        return;
+    }
+    const size_t n_tiles = (n + 1 + 1023) / 1024;  // covers index n as well
+    StreamCounts *tiles = counts + n + 1;
+    k_scan_tile_sums<<<(unsigned)n_tiles, 1024, 0, s>>>(counts, n, tiles);
+    k_exclusive_scan<<<1, 1024, 0, s>>>(tiles, n_tiles, totals);
+    k_scan_tile_apply<<<(unsigned)n_tiles, 1024, 0, s>>>(counts, n, tiles, n_tiles);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Weight payload reader (fse/weights.rs:66-105, fse/weight_encoder.rs:10-20)
 // ------------------------------------------------------------------------------------------------
@@ -1101,7 +1152,7 @@ void launch_scan_count(const uint8_t *src, const uint64_t *src_off, const uint64
     if (n == 0) return;
     const int tb = 128;
     k_scan<false><<<(unsigned)((n + tb - 1) / tb), tb, 0, s>>>(src, src_off, src_len, nullptr, dst_cap, n, counts, nullptr, nullptr, err, raw_total, n_blocks_out);
-    k_exclusive_scan<<<1, 1024, 0, s>>>(counts, n, totals);
+    launch_exclusive_scan(counts, n, totals, s);
 }
 void launch_scan_fill(const uint8_t *src, const uint64_t *src_off, const uint64_t *src_len, const uint64_t *dst_off, const uint64_t *dst_cap, size_t n,
                       StreamCounts *bases, BlockDesc *blocks, FseDesc *fse, uint32_t *err, cudaStream_t s) {

@@ -21,7 +21,7 @@
 
 namespace lzb {
 
-__global__ void k_exclusive_scan(StreamCounts *counts, size_t n, StreamCounts *totals);  // decode.cu
+void launch_exclusive_scan(StreamCounts *counts, size_t n, StreamCounts *totals, cudaStream_t s);  // decode.cu
 
 constexpr uint32_t kEmptyIdx = 0xC0C0C0C0u;  // history reset marker (encode/history.rs:72-83: any idx whose distance is out of range)
 // A bucket is one 32-byte sector: 4 positions (newest first) followed by the 4 source bytes found at each of them --
@@ -976,15 +976,15 @@ int encode_batch_device_impl(lzfse_b200_encoder *e, const uint8_t *src, const ui
     if (n == 0) return LZFSE_B200_OK;
     if (n > 0x7FFFFFFFull) { e->last_error = "too many streams in one batch"; return LZFSE_B200_INVALID_ARGUMENT; }
     LZB_CK(e, e->streams.reserve(n * sizeof(EncStream)));
-    LZB_CK(e, e->counts.reserve((n + 1) * sizeof(StreamCounts)));
+    LZB_CK(e, e->counts.reserve((n + 1 + n / 1024 + 2) * sizeof(StreamCounts)));  // + tile sums of the scan
     LZB_CK(e, e->totals_dev.reserve(sizeof(StreamCounts)));
     LZB_CK(e, e->totals_host.reserve(sizeof(StreamCounts)));
     LZB_CK(e, e->counters.reserve(4 * sizeof(uint32_t)));
     const int tb = 128;
     e->timer.begin(s);
     k_enc_prep<<<(unsigned)((n + tb - 1) / tb), tb, 0, s>>>(src_len, n, e->streams.as<EncStream>(), e->counts.as<StreamCounts>(), status);
-    k_exclusive_scan<<<1, 1024, 0, s>>>(e->counts.as<StreamCounts>(), n, e->totals_host.as<StreamCounts>());  // pinned host memory (UVA)
-    e->launches += 2;
+    launch_exclusive_scan(e->counts.as<StreamCounts>(), n, e->totals_host.as<StreamCounts>(), s);  // pinned host memory (UVA)
+    e->launches += n > 8192 ? 4 : 2;  // prep + the exclusive scan (three launches for large batches)
     LZB_CK(e, cudaStreamSynchronize(s));
     const StreamCounts tot = *e->totals_host.as<StreamCounts>();  // {packs, literal bytes, block slots, out bytes}
     if (tot.n_literals > 0xFFFFFFF0ull) { e->last_error = "too many blocks in one batch"; return LZFSE_B200_INVALID_ARGUMENT; }
