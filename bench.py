@@ -153,8 +153,8 @@ def run_reference(a):
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": round(v, 4), "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": round(n * CHUNK / v / 1e6, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
-        "data": "synthetic", "config": {"workload": "batched decode of synthetic text in 64 KiB independent LZFSE streams", "chunk_bytes": CHUNK,
-                                         "streams_sampled": n, "streams_full": a.chunks},
+        "data": "synthetic", "config": {"workload": "batched decode of 1 GiB synthetic text split into 64 KiB independent LZFSE streams per GPU (BASELINE.json configs[1])",
+                                         "chunk_bytes": CHUNK, "streams_per_gpu": a.chunks, "streams_sampled_per_step": n},
         "cpu_baseline": {"value": round(v, 4), "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": "%d of %d streams (%d MiB), oracle/lzfse_oracle.c -O3, %d threads" % (n, a.chunks, n * CHUNK >> 20, threads)},
         "encode": {"value": round(float(np.median(encs)), 4), "unit": UNIT, "ratio": round(ratio, 4)},

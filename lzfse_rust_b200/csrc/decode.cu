@@ -1040,28 +1040,55 @@ k_expand(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ src_
 }
 
 // ------------------------------------------------------------------------------------------------
-// Single-LZVN-block streams (vn_fast_eligible): a warp per stream.
+// Single-LZVN-block streams (vn_fast_eligible): a warp per stream, 32 payload bytes per step.
 //
-// The opcode stream is a serial chain (an opcode's position depends on the length of the one before), so every lane
-// decodes the same opcode -- one broadcast load, uniform control flow, no shuffles -- and the lanes share the copies:
-// literal bytes go from the payload to a shared-memory image of the output, match bytes from the image to the
-// image (LZ77 overlap: byte i = byte i mod D of the D bytes before the match), and the finished image is written to
-// HBM once in 16-byte stores.  One lane interpreting the block against HBM, as the in-order kernels do, waits for a
-// store-to-load round trip per match byte: 20.8 ms for 512 MiB of 21..4096-byte inputs; this kernel takes 11.9 ms and
-// is bound by instruction issue (~100 instructions per opcode, repeated by every lane).  Measured and dropped: eight
-// lanes per stream, four streams per warp -- the groups diverge on the opcode class, 167 instructions per step for
-// 2.4 opcodes, 12 resident warps instead of 48: 15.8 ms.
-// Any irregularity (bad opcode, short payload, distance before the start, counts that do not add up) abandons the
+// The opcode stream is a serial chain -- an opcode's position depends on the length of the one before -- but the
+// chain is cheap to resolve in parallel: every lane decodes "the opcode that would start at payload byte p + lane"
+// (class, lengths, distance: one table lookup and a few selects), the lanes that really are opcode starts are found
+// by pointer doubling over next = lane + opcode length (five rounds), distances inherited from the previous opcode
+// come from a ballot, output positions from a warp scan.  The real opcodes of the window (about eight on text) then
+// copy side by side: literals from the payload to a shared-memory image of the output, matches inside the image
+// (independent short ones per lane; long, overlapping or in-window-dependent ones in order, warp-wide), and the
+// finished image goes to HBM once in 16-byte stores.
+// History (512 MiB of 21..4096-byte inputs): one lane interpreting the block against HBM, what the in-order kernels
+// do, 20.8 ms; a warp per stream with every lane decoding the same opcode 11.9 ms (bound by instruction issue, ~100
+// per opcode); eight lanes per stream, four streams per warp 15.8 ms (the groups diverge on the opcode class).
+// Anything irregular (bad opcode, short payload, distance before the start, counts that do not add up) abandons the
 // image and re-runs the exact interpreter, which reports what the reference reports (vn/vn_core.rs:51-140).
 // ------------------------------------------------------------------------------------------------
 constexpr int kVnWarps = 8;
 constexpr uint32_t kVnImage = kVnFastRaw + 16;  // + up to 15 bytes in front so that image and output agree modulo 16
+constexpr uint32_t kVnSolo = 16;                // per-lane copies up to this many bytes
+
+// Opcode table entry: oplen[0:2] | inline L[2:6] | inline M[6:12] | L += byte1 + 16 [12] | M += byte1 + 16 [13] |
+// distance kind [14:16] (0 none, 1 SmlD, 2 MedD, 3 LrgD) | Eos [16] | undefined [17]   (vn/opc.rs:18-228)
+__device__ uint32_t vn_table_entry(uint32_t b) {
+    switch (vn_op(b)) {
+    case OP_SML_L: return 1u | ((b & 0xF) << 2);
+    case OP_LRG_L: return 2u | (1u << 12);
+    case OP_SML_M: return 1u | ((b & 0xF) << 6);
+    case OP_LRG_M: return 2u | (1u << 13);
+    case OP_PRE_D: return 1u | (((b >> 6) & 3) << 2) | ((((b >> 3) & 7) + 3) << 6);
+    case OP_SML_D: return 2u | (((b >> 6) & 3) << 2) | ((((b >> 3) & 7) + 3) << 6) | (1u << 14);
+    case OP_MED_D: return 3u | (((b >> 3) & 3) << 2) | ((((b & 7) << 2) + 3) << 6) | (2u << 14);
+    case OP_LRG_D: return 3u | (((b >> 6) & 3) << 2) | ((((b >> 3) & 7) + 3) << 6) | (3u << 14);
+    case OP_NOP: return 1u;
+    case OP_EOS: return 1u << 16;
+    default: return 1u << 17;
+    }
+}
+__device__ __forceinline__ uint32_t lanemask_le() { uint32_t m; asm("mov.u32 %0, %%lanemask_le;" : "=r"(m)); return m; }
 
 __global__ void __launch_bounds__(kVnWarps * 32)
 k_expand_vn(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ src_off, const uint64_t *__restrict__ src_len,
             uint8_t *__restrict__ dst_base, const uint64_t *__restrict__ dst_off, const uint64_t *__restrict__ dst_cap,
             const StreamCounts *__restrict__ bases, const BlockDesc *__restrict__ blocks, uint32_t *err, size_t n_streams) {
     __shared__ __align__(16) uint8_t image[kVnWarps][kVnImage];
+    __shared__ uint32_t optab[256];
+    static_assert(kVnWarps * 32 == 256, "one table entry per thread");
+    optab[threadIdx.x] = vn_table_entry(threadIdx.x);
+    __syncthreads();
+    constexpr uint32_t kFull = 0xFFFFFFFFu;
     const uint32_t lane = lane_id();
     const size_t stream = (size_t)blockIdx.x * kVnWarps + (threadIdx.x >> 5);
     if (stream >= n_streams) return;
@@ -1079,42 +1106,117 @@ k_expand_vn(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ s
     uint32_t used = 0, out_pos = 0, D = 0;
     bool ok = true, eos = false;
     while (ok && !eos) {
-        const uint8_t *s = src + kVnHeaderSize + used;
-        const uint32_t rem = vlen - used;  // >= 8 (loop invariant, vn_core.rs:155-160)
-        const uint32_t opu = ldg4u(s);
-        uint32_t L = 0, M = 0, oplen = 0;
-        switch (vn_op(opu & 0xFF)) {
-        case OP_SML_L: L = opu & 0xF; oplen = 1; break;
-        case OP_LRG_L: L = ((opu >> 8) & 0xFF) + 16; oplen = 2; break;
-        case OP_SML_M: M = opu & 0xF; oplen = 1; break;
-        case OP_LRG_M: M = ((opu >> 8) & 0xFF) + 16; oplen = 2; break;
-        case OP_PRE_D: M = ((opu >> 3) & 7) + 3; L = (opu >> 6) & 3; oplen = 1; break;
-        case OP_SML_D: D = ((opu & 7) << 8) | ((opu >> 8) & 0xFF); M = ((opu >> 3) & 7) + 3; L = (opu >> 6) & 3; oplen = 2; break;
-        case OP_MED_D: M = (((opu & 7) << 2) | ((opu >> 8) & 3)) + 3; L = (opu >> 3) & 3; D = (opu >> 10) & 0x3FFF; oplen = 3; break;
-        case OP_LRG_D: M = ((opu >> 3) & 7) + 3; L = (opu >> 6) & 3; D = (opu >> 8) & 0xFFFF; oplen = 3; break;
-        case OP_NOP: oplen = 1; break;
-        case OP_EOS:
-            if (opu != 0x06u || ldg4u(s + 4) != 0u) ok = false;
-            else { used += 8; eos = true; }
-            continue;
-        default: ok = false; continue;
+        // ---- what would an opcode starting at payload byte used + lane be? ----
+        const uint8_t *s = src + kVnHeaderSize + used + lane;
+        const uint32_t rem = vlen - used - lane;  // wraps for lanes past the end: caught by `alive`
+        const bool alive = used + lane + 8 <= vlen;  // an opcode may only start where at least 8 bytes are left (vn_core.rs:155-160)
+        const uint32_t w = alive ? ldg4u(s) : 0u;
+        const uint32_t e = optab[w & 0xFF], b1 = (w >> 8) & 0xFF, dk = (e >> 14) & 3;
+        const uint32_t oplen = e & 3;
+        const uint32_t L = ((e >> 2) & 15) + ((e >> 12) & 1) * (b1 + 16);
+        const uint32_t M = ((e >> 6) & 63) + ((e >> 13) & 1) * (b1 + 16) + (dk == 2 ? (b1 & 3) : 0u);
+        const uint32_t d_new = dk == 1 ? (((w & 7) << 8) | b1) : (dk == 2 ? ((w >> 10) & 0x3FFF) : ((w >> 8) & 0xFFFF));
+        const bool is_eos = alive && ((e >> 16) & 1);
+        const bool bad = !alive || ((e >> 17) & 1) || (!is_eos && rem - oplen < L + 8);
+        // ---- which lanes are opcode starts: the orbit of lane 0 under next = lane + length ----
+        uint32_t jump = (bad || is_eos) ? 64u : lane + oplen + L;  // the chain stops at an Eos or a bad opcode
+        const uint32_t next = jump;
+        uint32_t reach = 1u;
+#pragma unroll
+        for (int r = 0; r < 5; r++) {
+            const uint32_t c = (((reach >> lane) & 1u) && jump < 32u) ? (1u << jump) : 0u;
+            reach |= __reduce_or_sync(kFull, c);
+            const uint32_t j2 = __shfl_sync(kFull, jump, jump & 31u);
+            jump = jump < 32u ? j2 : jump;
         }
-        if (rem - oplen < L + 8 || out_pos + L + M > n_raw || (M != 0 && (D == 0 || D > out_pos + L))) { ok = false; continue; }
-        if (L) {
-            for (uint32_t t = lane; t < L; t += 32) sts_u8(img + out_pos + t, s[oplen + t]);
-            out_pos += L;
+        const bool real = (reach >> lane) & 1u;
+        if (__any_sync(kFull, real && bad)) { ok = false; break; }
+        const uint32_t real_m = reach;
+        const int last = 31 - __clz(real_m);                       // the window's last opcode
+        const uint32_t eos_m = __ballot_sync(kFull, real && is_eos);  // at most the last one
+        // ---- distances: an opcode without one inherits the previous opcode's ----
+        const uint32_t d_m = __ballot_sync(kFull, real && dk != 0);
+        const uint32_t below = d_m & lanemask_le();
+        const uint32_t d_src = __shfl_sync(kFull, d_new, below ? 31 - __clz(below) : 0);
+        const uint32_t my_d = below ? d_src : D;
+        // ---- output positions ----
+        const uint32_t n_out = (real && !is_eos) ? L + M : 0u;
+        uint32_t inc = n_out;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(kFull, inc, o);
+            if (lane >= (uint32_t)o) inc += t;
         }
-        if (M) {
-            __syncwarp();  // the literals above (and every earlier byte) are visible to all lanes
-            const uint32_t from = img + out_pos - D;
-            if (D >= M) for (uint32_t t = lane; t < M; t += 32) sts_u8(img + out_pos + t, lds_u8(from + t));
-            else for (uint32_t t = lane; t < M; t += 32) sts_u8(img + out_pos + t, lds_u8(from + t % D));
-            out_pos += M;
+        const uint32_t total = __shfl_sync(kFull, inc, 31);
+        const uint32_t my_out = out_pos + inc - n_out, my_dst = my_out + L;
+        const bool has_l = real && !is_eos && L != 0, has_m = real && !is_eos && M != 0;
+        if (out_pos + total > n_raw || __any_sync(kFull, has_m && (my_d == 0 || my_d > my_dst))) { ok = false; break; }
+        // ---- literals: payload -> image ----
+        {
+            const uint8_t *ls = s + oplen;
+            const uint32_t sl = (has_l && L <= kVnSolo) ? L : 0u;
+            const uint32_t max_l = __reduce_max_sync(kFull, sl);
+            for (uint32_t g = 0; g < max_l; g += 4) {
+                uint32_t t[4];
+#pragma unroll
+                for (uint32_t k = 0; k < 4; k++)
+                    if (g + k < sl) t[k] = __ldg(ls + g + k);
+#pragma unroll
+                for (uint32_t k = 0; k < 4; k++)
+                    if (g + k < sl) sts_u8(img + my_out + g + k, t[k]);
+            }
+            uint32_t lm = __ballot_sync(kFull, has_l && L > kVnSolo);
+            while (lm) {
+                const int j = __ffs(lm) - 1;
+                lm &= lm - 1;
+                const uint32_t o = __shfl_sync(kFull, my_out, j), n = __shfl_sync(kFull, L, j), ol = __shfl_sync(kFull, oplen, j);
+                const uint8_t *p = src + kVnHeaderSize + used + j + ol;
+                for (uint32_t t = lane; t < n; t += 32) sts_u8(img + o + t, __ldg(p + t));
+            }
         }
-        used += oplen + L;
         __syncwarp();
+        // ---- matches: image -> image (lz/writer.rs:144-180) ----
+        {
+            const uint32_t from = my_dst - my_d;
+            const uint32_t end_nonself = from + M < my_dst ? from + M : my_dst;
+            const bool solo = has_m && M <= kVnSolo && my_d >= M && end_nonself <= out_pos;  // everything it reads was final before this window
+            const uint32_t sm = solo ? M : 0u;
+            const uint32_t max_m = __reduce_max_sync(kFull, sm);
+            for (uint32_t g = 0; g < max_m; g += 4) {
+                uint32_t t[4];
+#pragma unroll
+                for (uint32_t k = 0; k < 4; k++)
+                    if (g + k < sm) t[k] = lds_u8(img + from + g + k);
+#pragma unroll
+                for (uint32_t k = 0; k < 4; k++)
+                    if (g + k < sm) sts_u8(img + my_dst + g + k, t[k]);
+            }
+            uint32_t mm = __ballot_sync(kFull, has_m && !solo);
+            if (mm) __syncwarp();
+            while (mm) {  // in order, the whole warp on one match
+                const int j = __ffs(mm) - 1;
+                mm &= mm - 1;
+                const uint32_t o = __shfl_sync(kFull, my_dst, j), d = __shfl_sync(kFull, my_d, j), n = __shfl_sync(kFull, M, j);
+                if (d >= n) for (uint32_t t = lane; t < n; t += 32) sts_u8(img + o + t, lds_u8(img + o - d + t));
+                else for (uint32_t t = lane; t < n; t += 32) sts_u8(img + o + t, lds_u8(img + o - d + t % d));
+                __syncwarp();
+            }
+        }
+        __syncwarp();
+        // ---- advance ----
+        out_pos += total;
+        if (d_m) D = __shfl_sync(kFull, d_new, 31 - __clz(d_m));
+        if (eos_m) {  // Eos must be 06 00 00 00 00 00 00 00 (vn_core.rs:179-187)
+            const int j = __ffs(eos_m) - 1;
+            const uint8_t *p = src + kVnHeaderSize + used + j;
+            if (ldg4u(p) != 0x06u || ldg4u(p + 4) != 0u) { ok = false; break; }
+            used += j + 8;
+            eos = true;
+        } else {
+            used += __shfl_sync(kFull, next, last);
+        }
     }
-    if (ok && used == n_payload && out_pos == n_raw) {  // VnCore::decode's final accounting (vn_core.rs:96-111)
+    if (ok && eos && used == n_payload && out_pos == n_raw) {  // VnCore::decode's final accounting (vn_core.rs:96-111)
         __syncwarp();
         // head up to the first 16-byte boundary of the output, 16-byte units, tail
         uint32_t head = (16u - bias) & 15u;
