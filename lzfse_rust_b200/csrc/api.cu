@@ -25,7 +25,7 @@ void launch_fse_stages(const uint8_t *, const uint64_t *, const uint64_t *, cons
 void launch_expand(const uint8_t *, const uint64_t *, const uint64_t *, uint8_t *, const uint64_t *, const uint64_t *, const StreamCounts *, const BlockDesc *,
                    const FseDesc *, const uint8_t *, const LmdRec *, uint32_t *, size_t, cudaStream_t);
 void launch_expand_vn(const uint8_t *, const uint64_t *, const uint64_t *, uint8_t *, const uint64_t *, const uint64_t *, const StreamCounts *,
-                      const BlockDesc *, uint32_t *, size_t, cudaStream_t);
+                      const BlockDesc *, uint32_t *, size_t, uint32_t *, int, cudaStream_t);
 void launch_finish(const uint32_t *, const uint64_t *, uint64_t *, int32_t *, size_t, cudaStream_t);
 // expand.cu
 int setup_expand_kernel();
@@ -118,7 +118,8 @@ int decode_launch_rest(lzfse_b200_decoder *d, DecodeScratch &c, const uint8_t *s
     // Expansion: a warp per stream when there are enough streams to fill the machine that way (64 warps x 148 SMs);
     // otherwise a CTA per stream, whose 7 worker warps share one stream through a shared-memory window.
     if (tot.n_blocks > tot.n_fse) {  // raw or LZVN blocks present: single-LZVN-block streams have their own kernel
-        launch_expand_vn(src, src_off, src_len, dst, dst_off, dst_cap, c.counts.as<StreamCounts>(), c.blocks.as<BlockDesc>(), c.err.as<uint32_t>(), n, s);
+        launch_expand_vn(src, src_off, src_len, dst, dst_off, dst_cap, c.counts.as<StreamCounts>(), c.blocks.as<BlockDesc>(), c.err.as<uint32_t>(), n,
+                         c.work.as<uint32_t>() + 3, d->n_sms, s);
         d->launches += 1;
     }
     const bool use_cta = d->expand_mode == 2 || (d->expand_mode == 0 && n < (size_t)d->n_sms * 16);

@@ -1079,10 +1079,14 @@ __device__ uint32_t vn_table_entry(uint32_t b) {
 }
 __device__ __forceinline__ uint32_t lanemask_le() { uint32_t m; asm("mov.u32 %0, %%lanemask_le;" : "=r"(m)); return m; }
 
-__global__ void __launch_bounds__(kVnWarps * 32)
+#ifndef LZB_VN_CTAS
+#define LZB_VN_CTAS 4
+#endif
+__global__ void __launch_bounds__(kVnWarps * 32, LZB_VN_CTAS)
 k_expand_vn(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ src_off, const uint64_t *__restrict__ src_len,
             uint8_t *__restrict__ dst_base, const uint64_t *__restrict__ dst_off, const uint64_t *__restrict__ dst_cap,
-            const StreamCounts *__restrict__ bases, const BlockDesc *__restrict__ blocks, uint32_t *err, size_t n_streams) {
+            const StreamCounts *__restrict__ bases, const BlockDesc *__restrict__ blocks, uint32_t *err, size_t n_streams,
+            uint32_t *work_counter) {
     __shared__ __align__(16) uint8_t image[kVnWarps][kVnImage];
     __shared__ uint32_t optab[256];
     static_assert(kVnWarps * 32 == 256, "one table entry per thread");
@@ -1090,13 +1094,18 @@ k_expand_vn(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ s
     __syncthreads();
     constexpr uint32_t kFull = 0xFFFFFFFFu;
     const uint32_t lane = lane_id();
-    const size_t stream = (size_t)blockIdx.x * kVnWarps + (threadIdx.x >> 5);
+  // Persistent warps pull streams from a counter: inputs of 21..4096 bytes take very different times, and a CTA that
+  // waits for its longest stream left a third of the resident warps idle.
+  for (;;) {
+    size_t stream = 0;
+    if (lane == 0) stream = atomicAdd(work_counter, 1u);
+    stream = __shfl_sync(kFull, (uint32_t)stream, 0);
     if (stream >= n_streams) return;
     const uint64_t b0 = bases[stream].n_blocks, nb = bases[stream + 1].n_blocks - b0;
-    if (nb != 1) return;
+    if (nb != 1) continue;
     const BlockDesc bd = blocks[b0];
     const uint64_t src_rest = src_off[stream] + src_len[stream] - bd.src_off, cap = dst_cap[stream];
-    if (!vn_fast_eligible(nb, bd, src_rest, cap)) return;
+    if (!vn_fast_eligible(nb, bd, src_rest, cap)) continue;
     const uint8_t *src = src_base + bd.src_off;
     uint8_t *out = dst_base + dst_off[stream];
     const uint32_t n_raw = bd.n_raw, n_payload = ld_u32(src + 8);
@@ -1235,6 +1244,8 @@ k_expand_vn(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ s
         const uint32_t kb = bd.index < 0x1FFFFFu ? bd.index : 0x1FFFFFu;
         if (st) atomicMin(&err[stream], err_key(kb, PH_LMD, st));
     }
+    __syncwarp();  // the image is reused by the next stream
+  }
 }
 
 __global__ void k_finish(const uint32_t *__restrict__ err, const uint64_t *__restrict__ raw_total, uint64_t *out_len, int32_t *status, size_t n) {
@@ -1289,9 +1300,12 @@ void launch_expand(const uint8_t *src, const uint64_t *src_off, const uint64_t *
     k_expand<<<(unsigned)((n + kExpandWarps - 1) / kExpandWarps), kExpandWarps * 32, (size_t)pad_kb * 1024, s>>>(src, src_off, src_len, dst, dst_off, dst_cap, bases, blocks, fse, lit_scratch, lmd_scratch, err, n);
 }
 void launch_expand_vn(const uint8_t *src, const uint64_t *src_off, const uint64_t *src_len, uint8_t *dst, const uint64_t *dst_off,
-                      const uint64_t *dst_cap, const StreamCounts *bases, const BlockDesc *blocks, uint32_t *err, size_t n, cudaStream_t s) {
+                      const uint64_t *dst_cap, const StreamCounts *bases, const BlockDesc *blocks, uint32_t *err, size_t n,
+                      uint32_t *work_counter /* zeroed */, int n_sms, cudaStream_t s) {
     if (n == 0) return;
-    k_expand_vn<<<(unsigned)((n + kVnWarps - 1) / kVnWarps), kVnWarps * 32, 0, s>>>(src, src_off, src_len, dst, dst_off, dst_cap, bases, blocks, err, n);
+    const size_t need = (n + kVnWarps - 1) / kVnWarps, resident = (size_t)n_sms * LZB_VN_CTAS;
+    k_expand_vn<<<(unsigned)(need < resident ? need : resident), kVnWarps * 32, 0, s>>>(src, src_off, src_len, dst, dst_off, dst_cap, bases, blocks, err, n,
+                                                                                           work_counter);
 }
 void launch_finish(const uint32_t *err, const uint64_t *raw_total, uint64_t *out_len, int32_t *status, size_t n, cudaStream_t s) {
     if (n == 0) return;

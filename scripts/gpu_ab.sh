@@ -1,2 +1,3 @@
-python -m pytest tests -m gpu -x -q 2>&1 | grep -E "mismatch|passed|failed|^FAILED|Error" | head -20
-timeout 600 python scripts/prof_mixed.py --mib 512 --kinds small 2>&1 | tail -1
+for so in scratch/variants/vn_c2.so scratch/variants/vn_c3.so; do
+  echo "== $so"; LZB_SO=$PWD/$so timeout 600 python scripts/prof_mixed.py --mib 512 --kinds small 2>&1 | tail -1 | grep -o "decode.*"
+done
