@@ -23,7 +23,7 @@ int setup_decode_kernels();
 void launch_fse_stages(const uint8_t *, const uint64_t *, const uint64_t *, const uint64_t *, const uint64_t *, const BlockDesc *, FseDesc *, uint32_t, uint8_t *,
                        LmdRec *, uint32_t *, uint32_t *, int, cudaStream_t, cudaEvent_t);
 void launch_expand(const uint8_t *, const uint64_t *, const uint64_t *, uint8_t *, const uint64_t *, const uint64_t *, const StreamCounts *, const BlockDesc *,
-                   const FseDesc *, const uint8_t *, const LmdRec *, uint32_t *, size_t, cudaStream_t);
+                   const FseDesc *, const uint8_t *, const LmdRec *, uint32_t *, size_t, uint32_t *, int, cudaStream_t);
 void launch_expand_vn(const uint8_t *, const uint64_t *, const uint64_t *, uint8_t *, const uint64_t *, const uint64_t *, const StreamCounts *,
                       const BlockDesc *, uint32_t *, size_t, uint32_t *, int, cudaStream_t);
 void launch_finish(const uint32_t *, const uint64_t *, uint64_t *, int32_t *, size_t, cudaStream_t);
@@ -125,7 +125,7 @@ int decode_launch_rest(lzfse_b200_decoder *d, DecodeScratch &c, const uint8_t *s
     const bool use_cta = d->expand_mode == 2 || (d->expand_mode == 0 && n < (size_t)d->n_sms * 16);
     if (!use_cta)
         launch_expand(src, src_off, src_len, dst, dst_off, dst_cap, c.counts.as<StreamCounts>(), c.blocks.as<BlockDesc>(), c.fse.as<FseDesc>(),
-                      c.lits.as<uint8_t>(), c.lmds.as<LmdRec>(), c.err.as<uint32_t>(), n, s);
+                      c.lits.as<uint8_t>(), c.lmds.as<LmdRec>(), c.err.as<uint32_t>(), n, c.work.as<uint32_t>() + 2, d->n_sms, s);
     else
         launch_expand_cta(src, src_off, src_len, dst, dst_off, dst_cap, c.counts.as<StreamCounts>(), c.blocks.as<BlockDesc>(),
                           c.fse.as<FseDesc>(), c.lits.as<uint8_t>(), c.lmds.as<LmdRec>(), raw_total, c.err.as<uint32_t>(), n, c.work.as<uint32_t>() + 2,

@@ -1004,16 +1004,21 @@ k_expand(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ src_
          uint8_t *__restrict__ dst_base, const uint64_t *__restrict__ dst_off, const uint64_t *__restrict__ dst_cap,
          const StreamCounts *__restrict__ bases,
          const BlockDesc *__restrict__ blocks, const FseDesc *__restrict__ fse, const uint8_t *__restrict__ lit_scratch,
-         const LmdRec *__restrict__ lmd_scratch, uint32_t *err, size_t n_streams) {
+         const LmdRec *__restrict__ lmd_scratch, uint32_t *err, size_t n_streams, uint32_t *work_counter) {
     __shared__ __align__(16) uint8_t stage[kExpandWarps][kStageStride];
     const uint32_t lane = lane_id();
     uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage[threadIdx.x >> 5]);
     asm volatile("" : "+r"(stage_s));  // or the compiler re-derives it from %tid and the shared window base in every step
-    const size_t stream = (size_t)blockIdx.x * kExpandWarps + (threadIdx.x >> 5);
+  // Persistent warps pull streams from a counter: with a fixed stream per warp a CTA's eight slots stay occupied until
+  // its slowest stream is done.
+  for (;;) {
+    size_t stream = 0;
+    if (lane == 0) stream = atomicAdd(work_counter, 1u);
+    stream = __shfl_sync(0xFFFFFFFFu, (uint32_t)stream, 0);
     if (stream >= n_streams) return;
     const uint64_t b0 = bases[stream].n_blocks, b1 = bases[stream + 1].n_blocks;
     uint8_t *stream_out = dst_base + dst_off[stream];
-    if (b1 - b0 == 1 && vn_fast_eligible(1, blocks[b0], src_off[stream] + src_len[stream] - blocks[b0].src_off, dst_cap[stream])) return;  // k_expand_vn
+    if (b1 - b0 == 1 && vn_fast_eligible(1, blocks[b0], src_off[stream] + src_len[stream] - blocks[b0].src_off, dst_cap[stream])) continue;  // k_expand_vn
     for (uint64_t b = b0; b < b1; b++) {
         const BlockDesc bd = blocks[b];
         uint8_t *out = dst_base + bd.dst_off;
@@ -1029,14 +1034,16 @@ k_expand(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ src_
                 if (st) atomicMin(&err[stream], err_key(kb, PH_LMD, st));
             }
             st = __shfl_sync(0xFFFFFFFFu, st, 0);
-            if (st) return;
+            if (st) break;
         } else {
             const FseDesc &fd = fse[bd.fse_idx];
-            if (!(fd.ok_lit && fd.ok_lmd)) return;  // the entropy stages already recorded why
+            if (!(fd.ok_lit && fd.ok_lmd)) break;  // the entropy stages already recorded why
             expand_fse_block(out, lit_scratch + fd.lit_off, lmd_scratch + fd.lmd_off, fd.n_lmds, stage_s, lane);
         }
         __syncwarp();
     }
+    __syncwarp();
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1292,12 +1299,14 @@ void launch_fse_stages(const uint8_t *src, const uint64_t *src_off, const uint64
 }
 void launch_expand(const uint8_t *src, const uint64_t *src_off, const uint64_t *src_len, uint8_t *dst, const uint64_t *dst_off,
                    const uint64_t *dst_cap, const StreamCounts *bases, const BlockDesc *blocks, const FseDesc *fse, const uint8_t *lit_scratch,
-                   const LmdRec *lmd_scratch, uint32_t *err, size_t n, cudaStream_t s) {
+                   const LmdRec *lmd_scratch, uint32_t *err, size_t n, uint32_t *work_counter /* zeroed */, int n_sms, cudaStream_t s) {
     if (n == 0) return;
     // Tuning aid: LZB_EXPAND_PAD_KB adds unused dynamic shared memory per CTA and so caps the resident CTAs per SM.
     static const int pad_kb = [] { const char *e = getenv("LZB_EXPAND_PAD_KB"); return e ? atoi(e) : 0; }();
     if (pad_kb > 48) cudaFuncSetAttribute(k_expand, cudaFuncAttributeMaxDynamicSharedMemorySize, pad_kb * 1024);
-    k_expand<<<(unsigned)((n + kExpandWarps - 1) / kExpandWarps), kExpandWarps * 32, (size_t)pad_kb * 1024, s>>>(src, src_off, src_len, dst, dst_off, dst_cap, bases, blocks, fse, lit_scratch, lmd_scratch, err, n);
+    const size_t need = (n + kExpandWarps - 1) / kExpandWarps, resident = (size_t)n_sms * LZB_EXPAND_CTAS;
+    k_expand<<<(unsigned)(need < resident ? need : resident), kExpandWarps * 32, (size_t)pad_kb * 1024, s>>>(src, src_off, src_len, dst, dst_off, dst_cap, bases, blocks, fse,
+                                                                                                        lit_scratch, lmd_scratch, err, n, work_counter);
 }
 void launch_expand_vn(const uint8_t *src, const uint64_t *src_off, const uint64_t *src_len, uint8_t *dst, const uint64_t *dst_off,
                       const uint64_t *dst_cap, const StreamCounts *bases, const BlockDesc *blocks, uint32_t *err, size_t n,
