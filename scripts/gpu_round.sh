@@ -11,3 +11,8 @@ python bench.py --steps 1 --warmup 3 --no-cpu > gpurun_out/plain2.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:'k_fse_literals|k_fse_lmds|^k_expand$' -s 11 -c 3 -o gpurun_out/decode_full -f python bench.py --steps 1 --warmup 3 --no-cpu > gpurun_out/ncu_full.log 2>&1
 tail -2 gpurun_out/ncu_full.log
 cat gpurun_out/bench_ours.json
+# mixed corpus (BASELINE configs[4]) on one GPU, oracle port timed on a 64 MiB sample per class
+timeout 1200 python scripts/bench_mixed.py --mib-per-class 1024 --waves 1 --cpu-mib 64 > gpurun_out/bench_mixed_1gpu.json 2> gpurun_out/bench_mixed_1gpu.err; echo mixed_rc=$?
+cut -c1-300 gpurun_out/bench_mixed_1gpu.json
+# BASELINE configs[3]: 8 streams of 16 MiB
+timeout 300 python scripts/prof_large.py 2>&1 | tail -5 > gpurun_out/prof_large.log; cat gpurun_out/prof_large.log
