@@ -1,2 +1,3 @@
-python -m pytest tests/test_gpu_encode.py tests/test_gpu_configs.py -m gpu -x -q 2>&1 | tail -2
-timeout 300 python scripts/prof_encode.py --chunks 16384 --iters 3 2>&1 | tail -1
+for so in scratch/variants/exp_c5.so scratch/variants/exp_c6.so; do
+  echo "== $so"; LZB_SO=$PWD/$so timeout 300 python scripts/prof_decode.py --chunks 16384 --iters 4 2>&1 | grep -E "iter 3|rror"
+done
