@@ -68,3 +68,33 @@ def test_mixed_corpus(codec):
     assert kinds >= {b"bvx-", b"bvxn", b"bvx2"}
     outs, dst = dec.decode_batch(frames)
     assert not dst.any() and outs == chunks
+
+
+def test_many_small_streams(codec):
+    """5 000 inputs of 0..4200 bytes in one batch: the LZVN window kernel, raw blocks and (above 4096 bytes) small bvx2
+    frames side by side, with enough streams for the warp-per-stream expansion kernel.  Frames must equal the oracle
+    encoder's (sampled) and decode back on both sides."""
+    enc, dec = codec
+    x, chunks = 99, []
+    for i in range(5000):
+        x = (x * 1103515245 + 12345) & 0xFFFFFFFF
+        n = (x >> 8) % 4201
+        kind = i % 4
+        if kind == 0:
+            c = tk.synth_text(90000 + i, n)
+        elif kind == 1:
+            c = tk.seq_bytes(i, n, 0x0F0F0F0F)
+        elif kind == 2:
+            c = (tk.rng_gen_vec(i, 1 + i % 37) * (n // (1 + i % 37) + 1))[:n]
+        else:
+            c = tk.rng_gen_vec(i, n)
+        chunks.append(c)
+    frames, st = enc.encode_batch(chunks)
+    assert not st.any()
+    oenc = ob.Encoder()
+    for i in range(0, len(chunks), 41):
+        assert frames[i] == oenc.encode(chunks[i])[1], i
+        assert ob.decode(frames[i]) == (0, chunks[i]), i
+    outs, dst = dec.decode_batch(frames)
+    assert not dst.any() and outs == chunks
+    assert {f[:4] for f in frames} >= {b"bvx-", b"bvxn", b"bvx2", b"bvx$"}
