@@ -1,3 +1,1 @@
-for so in scratch/variants/exp_c5.so scratch/variants/exp_c6.so; do
-  echo "== $so"; LZB_SO=$PWD/$so timeout 300 python scripts/prof_decode.py --chunks 16384 --iters 4 2>&1 | grep -E "iter 3|rror"
-done
+python -m pytest tests/test_gpu_configs.py -m gpu -x -q -k many_small 2>&1 | grep -E "^E|assert|Error" | head -20

@@ -89,6 +89,7 @@ def test_many_small_streams(codec):
         else:
             c = tk.rng_gen_vec(i, n)
         chunks.append(c)
+    chunks[0], chunks[1] = b"", b"x" * 4097   # the empty frame and the smallest bvx2 input
     frames, st = enc.encode_batch(chunks)
     assert not st.any()
     oenc = ob.Encoder()
@@ -97,4 +98,4 @@ def test_many_small_streams(codec):
         assert ob.decode(frames[i]) == (0, chunks[i]), i
     outs, dst = dec.decode_batch(frames)
     assert not dst.any() and outs == chunks
-    assert {f[:4] for f in frames} >= {b"bvx-", b"bvxn", b"bvx2", b"bvx$"}
+    assert {f[:4] for f in frames} >= {b"bvx-", b"bvxn", b"bvx2"}
