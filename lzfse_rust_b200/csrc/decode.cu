@@ -844,6 +844,31 @@ __device__ __forceinline__ void expand_step(uint8_t *__restrict__ out, const uin
     const uint32_t my_dst = my_out + L;  // where my match goes
     const uint32_t align = STAGED ? (uint32_t)(reinterpret_cast<uintptr_t>(out + out_base) & 15u) : 0u;
     const uint32_t sbase = stage_s + align - out_base;  // shared address of block offset 0 (only offsets of this step are used)
+    // ---- match sources, requested first ----
+    // A lane may copy its match on its own when everything it reads was final before this step started (or is its own
+    // output); the rest go one at a time, in order, with the whole warp copying.  The independent ones' source words
+    // are requested before the literals are copied so that the two round trips overlap (the kernel waits on memory).
+    // The source is fetched as aligned 32-bit words (at most five cover 16 bytes at any alignment) and realigned with
+    // funnel shifts: a byte load per source byte made every byte its own L1 sector lookup, and the L1 pipe, not HBM,
+    // was this kernel's bound (65 % of its peak, 10 sectors per request).
+    const uint8_t *src = out + my_dst - D;  // may point before `out` (earlier blocks of the stream)
+    const int64_t src_rel = (int64_t)my_dst - (int64_t)D;
+    const int64_t end_nonself = (src_rel + (int64_t)M < (int64_t)my_dst) ? src_rel + (int64_t)M : (int64_t)my_dst;
+    const bool indep = end_nonself <= (int64_t)out_base;
+    const bool solo = M != 0 && M <= kShortCopy && indep && D >= M;
+    const uint32_t sm_ = solo ? M : 0u;
+    const uint32_t max_m = __reduce_max_sync(0xFFFFFFFFu, sm_);
+    const uint32_t src_r = (uint32_t)reinterpret_cast<uintptr_t>(src) & 3u;
+    uint32_t w[5];
+    {
+        const uint32_t *a4 = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(src) - src_r);
+        const uint32_t nw = sm_ ? (src_r + sm_ + 3) >> 2 : 0u;
+#pragma unroll
+        for (uint32_t j = 0; j < 5; j++) {
+            w[j] = 0;
+            if (j * 4 < max_m + 6 && j < nw) w[j] = a4[j];
+        }
+    }
     // ---- literals ----
     const bool long_l = L > kShortCopy;
     {   // short runs: every lane copies its own; groups beyond the longest short run of the step are skipped warp-wide
@@ -883,33 +908,11 @@ __device__ __forceinline__ void expand_step(uint8_t *__restrict__ out, const uin
     if (!STAGED) __syncwarp();
 
     // ---- matches ----
-    // A lane may copy on its own when everything it reads was final before this step started
-    // (or is its own output); the rest go one at a time, in order, with the whole warp copying.
-    const uint8_t *src = out + my_dst - D;  // may point before `out` (earlier blocks of the stream)
-    const int64_t src_rel = (int64_t)my_dst - (int64_t)D;
-    const int64_t end_nonself = (src_rel + (int64_t)M < (int64_t)my_dst) ? src_rel + (int64_t)M : (int64_t)my_dst;
-    const bool indep = end_nonself <= (int64_t)out_base;
-    const bool solo = M != 0 && M <= kShortCopy && indep && D >= M;
     {
-        // The source is fetched as aligned 32-bit words (at most five cover 16 bytes at any alignment) and
-        // realigned with funnel shifts: a byte load per source byte made every byte its own L1 sector lookup,
-        // and the L1 pipe, not HBM, was this kernel's bound (65 % of its peak, 10 sectors per request).
-        const uint32_t sm_ = solo ? M : 0u;
-        const uint32_t max_m = __reduce_max_sync(0xFFFFFFFFu, sm_);
         if (max_m != 0) {
-            const uintptr_t sa = reinterpret_cast<uintptr_t>(src);
-            const uint32_t r = (uint32_t)sa & 3u;
-            const uint32_t *a4 = reinterpret_cast<const uint32_t *>(sa - r);
-            const uint32_t nw = sm_ ? (r + sm_ + 3) >> 2 : 0u;
-            uint32_t w[5];
-#pragma unroll
-            for (uint32_t j = 0; j < 5; j++) {
-                w[j] = 0;
-                if (j * 4 < max_m + 6 && j < nw) w[j] = a4[j];
-            }
             uint32_t v[4];
 #pragma unroll
-            for (uint32_t j = 0; j < 4; j++) v[j] = __funnelshift_r(w[j], w[j + 1], r * 8);
+            for (uint32_t j = 0; j < 4; j++) v[j] = __funnelshift_r(w[j], w[j + 1], src_r * 8);
             uint8_t *pd = out + my_dst;
 #pragma unroll
             for (uint32_t g = 0; g < kShortCopy; g += 4) {
