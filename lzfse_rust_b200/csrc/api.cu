@@ -115,13 +115,15 @@ int decode_launch_rest(lzfse_b200_decoder *d, DecodeScratch &c, const uint8_t *s
         timer->mark(s);
     }
     if (timer) timer->mark(s);  // lmds
-    // Expansion: a warp per stream when there are enough streams to fill the machine that way (64 warps x 148 SMs);
-    // otherwise a CTA per stream, whose 7 worker warps share one stream through a shared-memory window.
-    if (tot.n_blocks > tot.n_fse) {  // raw or LZVN blocks present: single-LZVN-block streams have their own kernel
+    // Expansion.  Streams that consist of one small LZVN block have their own kernel (the in-order kernels below skip
+    // them); it is only launched when the batch has raw or LZVN blocks at all.
+    if (tot.n_blocks > tot.n_fse) {
         launch_expand_vn(src, src_off, src_len, dst, dst_off, dst_cap, c.counts.as<StreamCounts>(), c.blocks.as<BlockDesc>(), c.err.as<uint32_t>(), n,
                          c.work.as<uint32_t>() + 3, d->n_sms, s);
         d->launches += 1;
     }
+    // Everything else: a warp per stream when there are enough streams to fill the machine that way (32 warps x 148
+    // SMs); otherwise a CTA per stream, whose 7 worker warps share one stream through a shared-memory window.
     const bool use_cta = d->expand_mode == 2 || (d->expand_mode == 0 && n < (size_t)d->n_sms * 16);
     if (!use_cta)
         launch_expand(src, src_off, src_len, dst, dst_off, dst_cap, c.counts.as<StreamCounts>(), c.blocks.as<BlockDesc>(), c.fse.as<FseDesc>(),

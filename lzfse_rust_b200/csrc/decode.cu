@@ -2,11 +2,14 @@
 //
 // Pipeline (all launches on one CUDA stream, see api.cu):
 //   k_scan<false>   thread / stream   walk block headers, count blocks / literals / LMDs, validate
-//   k_exclusive_scan                   per-stream bases
+//   k_exclusive_scan                   per-stream bases (k_scan_tile_sums / k_scan_tile_apply around it for > 8 Ki streams)
 //   k_scan<true>    thread / stream   fill BlockDesc[] / FseDesc[]
 //   k_fse_literals  lane / FSE block  weights -> U table in shared memory -> 4-state literal decode
 //   k_fse_lmds      lane / FSE block  weights -> L/M/D table in shared memory -> LMD decode + validation
-//   k_expand        warp / stream     literal placement + match copies, raw and LZVN blocks
+//   k_expand_vn     warp / stream     streams that are one small LZVN block: 32 payload bytes per step (only launched
+//                                     when the batch has raw or LZVN blocks)
+//   k_expand        warp / stream     literal placement + match copies, raw blocks, LZVN blocks inside longer frames
+//                                     (or k_expand_cta, expand.cu, for batches of few large streams)
 //   k_finish        thread / stream   error key -> status, out_len
 //
 // The entropy stages map one LANE to one block: an FSE stream is a serial chain (the bit position of

@@ -1,4 +1,3 @@
-for pad in 0 56; do
-  echo "== pad_kb $pad"
-  LZB_EXPAND_PAD_KB=$pad timeout 300 python scripts/prof_decode.py --chunks 16384 --iters 4 2>&1 | grep -E "iter 3|rror"
+for so in scratch/variants/pf256.so scratch/variants/pf384.so; do
+  echo "== $so"; LZB_SO=$PWD/$so timeout 300 python scripts/prof_decode.py --chunks 16384 --iters 4 2>&1 | grep -E "iter 3|rror"
 done
