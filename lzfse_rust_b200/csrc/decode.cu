@@ -601,12 +601,14 @@ k_fse_literals(const uint8_t *__restrict__ src_base, const uint64_t *__restrict_
                     const uint32_t n_it = fd.n_literals >> 2;
                     // One step = the reference's loop body: 4 literals, states 0..3 in that order, one flush.
                     // FAST = no dead-reader handling (the caller keeps P >= 57) and no per-step prefetch.
+                    const uint16_t *kdl = kd + lane;  // this lane's column of the two table planes: one multiply-add per lookup
+                    const uint8_t *syl = sy + lane;
                     auto step = [&](auto fast_tag) -> uint32_t {
                         constexpr bool FAST = decltype(fast_tag)::value;
                         int cur;
                         const uint64_t win = FAST ? br.window_fast(cur) : br.window(cur);
-                        const uint32_t e0 = kd[s0 * 32 + lane], e1 = kd[s1 * 32 + lane], e2 = kd[s2 * 32 + lane], e3 = kd[s3 * 32 + lane];
-                        const uint32_t y0 = sy[s0 * 32 + lane], y1 = sy[s1 * 32 + lane], y2 = sy[s2 * 32 + lane], y3 = sy[s3 * 32 + lane];
+                        const uint32_t e0 = kdl[s0 * 32], e1 = kdl[s1 * 32], e2 = kdl[s2 * 32], e3 = kdl[s3 * 32];
+                        const uint32_t y0 = syl[s0 * 32], y1 = syl[s1 * 32], y2 = syl[s2 * 32], y3 = syl[s3 * 32];
                         const uint32_t k0 = e0 >> 12, k1 = e1 >> 12, k2 = e2 >> 12, k3 = e3 >> 12;
                         const int p0 = cur - (int)k0, p1 = p0 - (int)k1, p2 = p1 - (int)k2, p3 = p2 - (int)k3;
                         s0 = bits_at(win, p0, k0) + (e0 & 0xFFF);
