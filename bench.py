@@ -312,7 +312,10 @@ def run_ours(a):
         "roofline": {"bound": "hbm", "kernel": {"literals": "k_fse_literals", "lmds": "k_fse_lmds", "expand": "k_expand"}[dom],
                      "achieved": round(achieved, 2), "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": round(achieved / peak, 5),
                      "traffic": traffic, "algorithmic_bytes": U + Cb, "kernel_ms": round(stage_ms[dom], 4),
-                     "whole_step_frac": round((U + Cb) / (ms_step * 1e-3) / 1e9 / peak, 5), "frac_of_8TBps_nominal": round(achieved / 8000.0, 5)},
+                     "whole_step_frac": round((U + Cb) / (ms_step * 1e-3) / 1e9 / peak, 5), "frac_of_8TBps_nominal": round(achieved / 8000.0, 5),
+                     # what the kernel really moves (ncu dram bytes of profiles/roofline_traffic.json over the live kernel time):
+                     # mostly random 32-byte sectors of match sources that miss L2, see DESIGN.md section 3
+                     "traffic_frac_of_peak": round(traffic / (stage_ms[dom] * 1e-3) / 1e9 / peak, 5) if traffic else None},
         "stage_ms": {k: round(v, 4) for k, v in stage_ms.items()},
         "e2e": {"value": round(world * U / e2e_s / 1e9, 3), "unit": UNIT, "h2d_bytes_per_step": Cb + 4 * 8 * n, "d2h_bytes_per_step": U + 12 * n,
                 "ms_per_step": round(e2e_s * 1e3, 3), "api": "lzfse_b200_decode_batch_host (pinned host buffers)"},
