@@ -731,6 +731,7 @@ k_fse_lmds(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ sr
                     const uint32_t room = (uint32_t)(room64 < 0x40000000ull ? room64 : 0x40000000ull);
                     uint32_t rel = 0;  // bytes this block has produced
                     LmdRec *out = lmd_scratch + fd.lmd_off;
+                    asm volatile("" : "+l"(out));  // one register pair, not scratch base + offset at every store
                     int fail = 0;
                     const uint32_t *tl = tab + lane, *tm = tab + 64 * 32 + lane, *td = tab + 128 * 32 + lane;
                     // ---- fast path --------------------------------------------------------------------
