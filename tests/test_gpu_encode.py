@@ -127,3 +127,41 @@ def test_capacity_too_small(enc):
     out_len, status = enc.encode_batch_into(src, [0], [len(data)], dst, [0], [n])
     assert status[0] == 0 and out_len[0] == n and dst.tobytes() == ob.encode(data)[1]
     assert enc.encode_batch([])[0] == []
+
+
+def _patchwork(seed, n):
+    """Random patchwork in the spirit of test/src/patchwork_*.rs: literal runs of several kinds interleaved with copies of
+    earlier output at random distances (short, medium, beyond 64 KiB, beyond the 262 139-byte window) and random lengths
+    (below GOOD_MATCH_LEN, above it, above MAX_M_VALUE), plus byte runs."""
+    rng = np.random.default_rng(seed)
+    out = bytearray()
+    while len(out) < n:
+        kind = rng.integers(0, 6)
+        if kind == 0:
+            out += rng.integers(0, 256, int(rng.integers(1, 400)), dtype=np.uint8).tobytes()
+        elif kind == 1:
+            out += tk.synth_text(int(rng.integers(0, 1 << 20)), int(rng.integers(1, 600)))
+        elif kind == 2:
+            out += bytes([int(rng.integers(0, 256))]) * int(rng.integers(1, 300))
+        elif len(out) > 8:
+            d = int(rng.choice([rng.integers(1, 17), rng.integers(1, 1024), rng.integers(1, 70000), rng.integers(1, 300000)]))
+            d = min(d, len(out))
+            m = int(rng.choice([rng.integers(3, 12), rng.integers(12, 60), rng.integers(60, 5000)]))
+            start = len(out) - d
+            for k in range(m):  # LZ77 semantics, overlaps included
+                out.append(out[start + k])
+    return bytes(out[:n])
+
+
+def test_patchwork_frames_equal(enc, dec):
+    """120 random patchworks of 1 B .. 400 KB (LZVN, single- and multi-block bvx2, far and out-of-window copies)."""
+    rng = np.random.default_rng(4242)
+    sizes = [int(x) for x in np.concatenate([rng.integers(1, 4097, 40), rng.integers(4097, 70000, 50), rng.integers(70000, 400000, 30)])]
+    datas = [_patchwork(1000 + i, n) for i, n in enumerate(sizes)]
+    frames, status = enc.encode_batch(datas)
+    assert (status == 0).all()
+    oenc = ob.Encoder()
+    for i, (d, f) in enumerate(zip(datas, frames)):
+        assert f == oenc.encode(d)[1], (i, len(d))
+    outs, dst = dec.decode_batch(list(frames))
+    assert (dst == 0).all() and list(outs) == datas
