@@ -174,7 +174,7 @@ class LzfseEncoder(_Handle):
     """LZFSE encoder (lzfse_rust::LzfseEncoder).  Reusable; one call at a time per object."""
 
     _kind = "encoder"
-    STAGES = ("prep", "parse", "fse_blocks", "assemble")
+    STAGES = ("prep", "find", "replay", "parse", "fse_blocks", "assemble")
 
     def encode_bound(self, n):
         return int(self._lib.lzfse_b200_encode_bound(int(n)))

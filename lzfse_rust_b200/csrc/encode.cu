@@ -13,6 +13,7 @@
 //   k_enc_fse_blocks  lane / block      histogram, normalize_m1, weight varints, encode tables, 4-state
 //                                       literal stream, L/M/D stream, bvx2 header
 //   k_enc_assemble    warp / stream     compaction of the blocks into the caller's frame + bvx$
+#include <cstdlib>
 #include <new>
 #include <string>
 
@@ -30,6 +31,7 @@ constexpr uint32_t kEmptyIdx = 0xC0C0C0C0u;  // history reset marker (encode/his
 // were most of the parse kernel's HBM traffic.
 constexpr uint32_t kBucketWords = 2 * kHashWidth;
 constexpr uint32_t kTableWords = (1u << kHashBits) * kBucketWords;
+constexpr uint32_t kFastMaxLen = 65536;  // streams up to this long take the shared-memory path (positions fit 16 bits)
 
 enum StreamKind : uint32_t { SK_RAW = 0, SK_VN = 1, SK_FSE = 2 };
 
@@ -49,26 +51,30 @@ struct EncStream {       // per stream, written by prep / parse, read by assembl
     uint32_t kind;       // StreamKind
     uint32_t n_blocks;   // FSE blocks produced
     uint32_t vn_size;    // LZVN: bytes of the finished block (header included) in the out scratch
-    uint32_t pad;
+    uint32_t fast;       // 1: parsed by k_enc_find + k_enc_replay (bvx2 streams of <= kFastMaxLen bytes), 0: by k_enc_parse
 };
 
 struct EncBlock {        // one bvx2 block to encode (compact list, any order)
     uint64_t pack_off;   // element offset into the pack scratch
     uint64_t lit_off;    // byte offset into the literal scratch
     uint64_t out_off;    // byte offset into the out scratch
+    uint64_t src_pos;    // gather != 0: absolute offset inside src_base of the first byte the block covers
     uint32_t n_packs, n_lits, n_match_bytes;
     uint32_t out_size;   // filled by k_enc_fse_blocks
+    uint32_t gather;     // 1: the literal bytes are not in the literal scratch yet (k_enc_fse_blocks collects them from the source)
+    uint32_t pad;
 };
 
 // ------------------------------------------------------------------------------------------------
 // prep: policy + sizing.  counts[i] = {packs, literal bytes, block slots, out bytes}
 // ------------------------------------------------------------------------------------------------
-__global__ void k_enc_prep(const uint64_t *__restrict__ src_len, size_t n, EncStream *streams, StreamCounts *counts, int32_t *status) {
+__global__ void k_enc_prep(const uint64_t *__restrict__ src_len, size_t n, EncStream *streams, StreamCounts *counts, int32_t *status,
+                           uint32_t *path_counts /* [0] fast streams, [1] streams for k_enc_parse */, int allow_fast) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint64_t len = src_len[i];
     EncStream st;
-    st.n_blocks = 0; st.vn_size = 0; st.pad = 0;
+    st.n_blocks = 0; st.vn_size = 0; st.fast = 0;
     StreamCounts c = {0, 0, 0, 0};
     status[i] = LZFSE_B200_OK;
     if (len > 0x7FFFFFFFull) {  // BLOCK_GUIDE repositioning (frontend_bytes.rs:348-375) is out of scope
@@ -76,6 +82,7 @@ __global__ void k_enc_prep(const uint64_t *__restrict__ src_len, size_t n, EncSt
         status[i] = LZFSE_B200_INVALID_ARGUMENT;
     } else if (len > kVnCutoff) {
         st.kind = SK_FSE;
+        st.fast = allow_fast && len <= kFastMaxLen;
         c.n_blocks = pack_cap(len);                  // packs
         c.n_fse = (len + 31) & ~15ull;               // literal bytes
         c.n_literals = block_cap(len);               // block slots
@@ -88,7 +95,9 @@ __global__ void k_enc_prep(const uint64_t *__restrict__ src_len, size_t n, EncSt
     }
     streams[i] = st;
     counts[i] = c;
+    if (st.kind != SK_RAW) atomicAdd(&path_counts[st.fast ? 0 : 1], 1u);
 }
+__global__ void k_enc_publish_counts(const uint32_t *path_counts, uint32_t *host_out) { host_out[0] = path_counts[0]; host_out[1] = path_counts[1]; }
 
 // ------------------------------------------------------------------------------------------------
 // parse: warp per stream
@@ -167,6 +176,7 @@ __device__ __noinline__ void sink_emit_block(FseSink &s, const SinkEnv &env, uin
         b.n_lits = s.n_lits_total - s.blk_lit0;
         b.n_match_bytes = s.n_match_bytes;
         b.out_size = 0;
+        b.src_pos = 0; b.gather = 0; b.pad = 0;
         const uint32_t id = atomicAdd(env.block_counter, 1u);
         env.blocks[id] = b;
         env.block_ids[base.n_literals + s.n_blocks] = id;
@@ -396,7 +406,7 @@ k_enc_parse(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ s
         si = __shfl_sync(0xFFFFFFFFu, si, 0);
         if (si >= n_streams) break;
         const uint32_t kind = streams[si].kind;
-        if (kind == SK_RAW) continue;
+        if (kind == SK_RAW || streams[si].fast) continue;
         const bool vn = kind == SK_VN;
         const uint8_t *src = src_base + src_off[si];
         asm volatile("" : "+l"(src));  // one pointer in registers; otherwise every access re-adds the kernel parameter and the offset
@@ -631,6 +641,383 @@ k_enc_parse(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ s
 }
 
 // ------------------------------------------------------------------------------------------------
+// Fast parse for bvx2 streams of <= kFastMaxLen bytes: k_enc_find (CTA per stream) + k_enc_replay (thread per stream).
+//
+// What a position finds in the history does not depend on the parse (see the top of this file), so find_match
+// (encode/frontend_bytes.rs:214-244) can be evaluated for EVERY position of a stream in parallel, before the sequential
+// front end runs.  The reference's HistoryTable (encode/history.rs:24-31,101-131: 2^14 buckets x the 4 newest positions)
+// is replaced by the equivalent hash chain: prev[p] = the newest position q < p in p's bucket; the bucket as position p
+// sees it is prev[p], prev[prev[p]], ... (4 hops).  With 16-bit positions the chain (128 KiB), the bucket heads
+// (32 KiB) and the stream itself (64 KiB) fit one SM's shared memory, so every probe, compare and extension is a
+// shared-memory access instead of a random HBM sector into a 512 KiB table per warp (r1: 242 GB of DRAM traffic per GiB).
+//
+//   k_enc_find    CTA (32 warps) per stream.  The stream is staged with one bulk async copy (cp.async.bulk + mbarrier).
+//                 Warp 0 builds the chain in order, 32 positions per step (__match_any_sync resolves the step's own
+//                 bucket collisions); warps 1..31 follow it unit by unit and compute, per position, the best candidate
+//                 (strictly longest, newest first), its exact forward length and its backward length, packed into one
+//                 32-bit word per position in HBM: distance[0:18] | min(len, 1023)[18:28] | min(bw, 15)[28:32].
+//   k_enc_replay  thread per stream: the sequential front end (backward extension limit, Match::select, Buffer::push
+//                 with splits and block closing) over those words; emits packs and block records only -- the literal
+//                 bytes are collected by k_enc_fse_blocks from the packs.
+// ------------------------------------------------------------------------------------------------
+constexpr int kFindThreads = 1024;
+constexpr uint32_t kFindUnit = 256;       // positions a find warp takes at a time
+constexpr uint32_t kNone = 0xFFFFu;       // chain end (positions are < kFastMaxLen - 3)
+constexpr uint32_t kLaneCap = 1024;       // per-lane forward extension stops here; longer ones are finished warp-wide
+constexpr uint32_t kWordLenSat = 1023, kWordBwSat = 15;
+constexpr uint32_t kRunSlots = 64;        // (distance, start, end) of long runs already measured, per stream
+constexpr uint32_t kFsSrc = 0, kFsSrcBytes = kFastMaxLen + 48;  // up to 15 bytes of alignment in front, over-read slack behind
+constexpr uint32_t kFsHead = kFsSrc + kFsSrcBytes, kFsPrev = kFsHead + (1u << kHashBits) * 2, kFsCtrl = kFsPrev + kFastMaxLen * 2;
+struct FindCtrl {
+    unsigned long long mbar;
+    uint32_t chain_done, next_unit, stream, pad;
+    unsigned long long runs[kRunSlots];
+};
+constexpr uint32_t kFindSmemBytes = kFsCtrl + sizeof(FindCtrl);
+static_assert(kFindSmemBytes <= 232448, "k_enc_find shared memory");
+
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds_b8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+// unaligned reads from shared memory: aligned words + funnel shifts
+__device__ __forceinline__ uint32_t lds4u(uint32_t a) {
+    const uint32_t r = a & 3u, q = a - r;
+    return __funnelshift_r(lds_u32(q), lds_u32(q + 4), r * 8);
+}
+__device__ __forceinline__ uint64_t lds8u(uint32_t a) {
+    const uint32_t r = a & 3u, q = a - r;
+    const uint32_t w0 = lds_u32(q), w1 = lds_u32(q + 4), w2 = lds_u32(q + 8);
+    return (uint64_t)__funnelshift_r(w0, w1, r * 8) | ((uint64_t)__funnelshift_r(w1, w2, r * 8) << 32);
+}
+// Forward match length of s[a..] against s[b..] starting from `l` known equal bytes, at most `lim` (match_kit/match_fast.rs:22-49).
+__device__ __forceinline__ uint32_t smem_match_inc(uint32_t s, uint32_t a, uint32_t b, uint32_t l, uint32_t lim) {
+    while (l + 8 <= lim) {
+        const uint64_t y = lds8u(s + a + l) ^ lds8u(s + b + l);
+        if (y) return l + ((__ffsll((long long)y) - 1) >> 3);
+        l += 8;
+    }
+    while (l < lim && lds_b8(s + a + l) == lds_b8(s + b + l)) l++;
+    return l;
+}
+// The same, whole warp, 8 bytes per lane and step (for runs longer than kLaneCap).
+__device__ __forceinline__ uint32_t smem_warp_match_inc(uint32_t s, uint32_t a, uint32_t b, uint32_t l, uint32_t lim, uint32_t lane) {
+    while (l < lim) {
+        const uint32_t off = l + lane * 8;
+        uint64_t y = 0;
+        if (off + 8 <= lim) y = lds8u(s + a + off) ^ lds8u(s + b + off);
+        else for (uint32_t k = 0; off + k < lim; k++) y |= (uint64_t)(lds_b8(s + a + off + k) ^ lds_b8(s + b + off + k)) << (8 * k);
+        const uint32_t diff = __ballot_sync(0xFFFFFFFFu, y != 0);
+        if (diff) {
+            const int j = __ffs(diff) - 1;
+            const uint64_t yj = __shfl_sync(0xFFFFFFFFu, y, j);
+            return l + j * 8 + ((__ffsll((long long)yj) - 1) >> 3);
+        }
+        l += 256;
+    }
+    return lim;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t phase) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(mbar), "r"(phase) : "memory");
+}
+
+__global__ void __launch_bounds__(kFindThreads, 1)
+k_enc_find(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ src_off, const uint64_t *__restrict__ src_len, size_t n_streams,
+           const EncStream *__restrict__ streams, const StreamCounts *__restrict__ bases, uint32_t *__restrict__ words, uint32_t *stream_counter) {
+    extern __shared__ __align__(128) uint8_t fsm[];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t sm0 = (uint32_t)__cvta_generic_to_shared(fsm);
+    FindCtrl *ctrl = reinterpret_cast<FindCtrl *>(fsm + kFsCtrl);
+    const uint32_t mbar = sm0 + kFsCtrl;
+    const uint32_t s_head = sm0 + kFsHead, s_prev = sm0 + kFsPrev;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    uint32_t phase = 0;
+    for (;;) {
+        if (tid == 0) ctrl->stream = atomicAdd(stream_counter, 1u);
+        __syncthreads();
+        const uint32_t si = ctrl->stream;
+        if (si >= n_streams) break;
+        if (!streams[si].fast) { __syncthreads(); continue; }
+        const uint32_t len = (uint32_t)src_len[si], end = len - 3;
+        const uint8_t *g = src_base + src_off[si];
+        const uint32_t mis = (uint32_t)reinterpret_cast<uintptr_t>(g) & 15u;
+        const uint32_t s = sm0 + kFsSrc + mis;  // shared address of stream byte 0
+        if (tid == 0) {
+            // One bulk async copy stages the whole stream: 16-byte aligned on both sides, the stream's misalignment kept.
+            // (The last 16-byte unit may reach past the stream's end; it lies inside the same 16-byte aligned granule as
+            // the last stream byte, hence inside the caller's allocation.)
+            const uint32_t bytes = (mis + len + 15u) & ~15u;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sm0 + kFsSrc),
+                         "l"(g - mis), "r"(bytes), "r"(mbar)
+                         : "memory");
+            ctrl->chain_done = 0; ctrl->next_unit = 0;
+        }
+        // meanwhile: empty bucket heads and run cache
+        for (uint32_t t = tid; t < (1u << kHashBits) * 2 / 16; t += kFindThreads)
+            *reinterpret_cast<uint4 *>(fsm + kFsHead + t * 16) = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+        if (tid < kRunSlots) ctrl->runs[tid] = 0;
+        mbar_wait(mbar, phase);
+        phase ^= 1;
+        __syncthreads();
+        uint32_t *wout = words + bases[si].n_fse;
+        if (warp == 0) {
+            // ---- the chain: HistoryTable::push for every position, in order, 32 per step ----
+            uint32_t val_n = lds4u(s + lane);  // end >= 4094
+            for (uint32_t b0 = 0; b0 < end; b0 += 32) {
+                const uint32_t p = b0 + lane;
+                const bool act = p < end;
+                const uint32_t val = val_n;
+                if (b0 + 32 < end) val_n = lds4u(s + (p + 32 < end ? p + 32 : end - 1));
+                const uint32_t h = act ? hash_u(val, false) : (0xFFFF0000u + lane);
+                const uint32_t peers = __match_any_sync(0xFFFFFFFFu, h);
+                const uint32_t lower = peers & lanemask_lt();
+                if (act) {
+                    const uint32_t old = lds_u16(s_head + h * 2);
+                    sts_u16(s_prev + p * 2, lower ? b0 + (31 - __clz(lower)) : old);
+                    if ((peers >> lane) == 1u) sts_u16(s_head + h * 2, p);  // newest position of its bucket in this step
+                }
+                __syncwarp();
+                if (((b0 + 32) & (kFindUnit - 1)) == 0 || b0 + 32 >= end) {
+                    __threadfence_block();
+                    if (lane == 0) *reinterpret_cast<volatile uint32_t *>(&ctrl->chain_done) = b0 + 32 < end ? b0 + 32 : end;
+                }
+            }
+        } else {
+            // ---- find_match for every position, unit by unit behind the chain ----
+            for (;;) {
+                uint32_t u = 0;
+                if (lane == 0) u = atomicAdd(&ctrl->next_unit, 1u);
+                u = __shfl_sync(0xFFFFFFFFu, u, 0);
+                const uint32_t p0 = u * kFindUnit;
+                if (p0 >= end) break;
+                const uint32_t p1 = p0 + kFindUnit < end ? p0 + kFindUnit : end;
+                while (*reinterpret_cast<volatile uint32_t *>(&ctrl->chain_done) < p1) __nanosleep(200);
+                __threadfence_block();
+                for (uint32_t b0 = p0; b0 < p1; b0 += 32) {
+                    const uint32_t p = b0 + lane;
+                    const bool act = p < p1;
+                    uint32_t best_len = 0, best_c = 0;
+                    uint32_t cs[4], ls[4];  // candidates whose length reached kLaneCap
+                    uint32_t n_sat = 0;
+                    const uint32_t maxl = len - p;
+                    if (act) {
+                        const uint32_t val = lds4u(s + p);
+                        uint32_t c = lds_u16(s_prev + p * 2);
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            if (c == kNone) break;  // (the distance limit 262 139 cannot be exceeded inside 64 KiB)
+                            if (lds4u(s + c) == val) {
+                                const uint32_t lim = maxl < kLaneCap ? maxl : kLaneCap;
+                                const uint32_t l = smem_match_inc(s, p, c, 4, lim);
+                                if (l == kLaneCap && l < maxl) { cs[n_sat] = c; ls[n_sat] = 0; n_sat++; }
+                                if (l > best_len) { best_len = l; best_c = c; }
+                            }
+                            c = lds_u16(s_prev + c * 2);
+                        }
+                    }
+                    // Two or more candidates beyond the per-lane cap: their exact lengths decide (strictly longest, newest
+                    // first).  Runs are measured once per (distance, start) with the whole warp and remembered: inside a
+                    // run every later position inherits end - p, which keeps periodic data linear.
+                    bool need = n_sat >= 2;
+                    while (__any_sync(0xFFFFFFFFu, need)) {
+                        if (need) {
+                            bool open = false;
+                            for (uint32_t k = 0; k < n_sat; k++) {
+                                if (ls[k]) continue;
+                                const uint32_t d = p - cs[k];
+                                const unsigned long long e = *reinterpret_cast<volatile unsigned long long *>(&ctrl->runs[(d * 0x9E3779B1u) >> 26]);
+                                const uint32_t ed = (uint32_t)(e & 0x3FFFF), es = (uint32_t)(e >> 18) & 0x1FFFFF, ee = (uint32_t)(e >> 39);
+                                if (ed == d && es <= p && p + kLaneCap <= ee) ls[k] = ee - p;
+                                else open = true;
+                            }
+                            need = open;
+                        }
+                        const uint32_t todo = __ballot_sync(0xFFFFFFFFu, need);
+                        if (!todo) break;
+                        const int j = __ffs(todo) - 1;
+                        uint32_t k0 = 0;
+                        while (k0 < 3 && !(k0 < n_sat && ls[k0] == 0)) k0++;
+                        const uint32_t pj = __shfl_sync(0xFFFFFFFFu, p, j), cj = __shfl_sync(0xFFFFFFFFu, cs[k0 & 3], j);
+                        const uint32_t ej = pj + smem_warp_match_inc(s, pj, cj, kLaneCap, len - pj, lane);
+                        if (lane == 0) {
+                            const uint32_t d = pj - cj;
+                            *reinterpret_cast<volatile unsigned long long *>(&ctrl->runs[(d * 0x9E3779B1u) >> 26]) =
+                                (unsigned long long)d | ((unsigned long long)pj << 18) | ((unsigned long long)ej << 39);
+                        }
+                        if (lane == (uint32_t)j) ls[k0 & 3] = ej - pj;  // progress even if another warp reuses the slot
+                        __syncwarp();
+                        __threadfence_block();
+                    }
+                    uint32_t word = 0;
+                    if (act && best_len) {
+                        if (n_sat >= 2) {  // candidates are in newest-first order: strictly longer wins
+                            uint32_t bl = 0;
+                            for (uint32_t k = 0; k < n_sat; k++)
+                                if (ls[k] > bl) { bl = ls[k]; best_c = cs[k]; }
+                            best_len = bl;
+                        }
+                        uint32_t bw = 0;
+                        const uint32_t blim = best_c < kWordBwSat ? best_c : kWordBwSat;
+                        while (bw < blim && lds_b8(s + p - bw - 1) == lds_b8(s + best_c - bw - 1)) bw++;
+                        word = (p - best_c) | ((best_len < kWordLenSat ? best_len : kWordLenSat) << 18) | (bw << 28);
+                    }
+                    if (act) wout[p] = word;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// The sequential front end, one THREAD per stream (32 streams per warp): FrontendBytes::match_any's control flow
+// (encode/frontend_bytes.rs:160-211,261-317), Match::select (encode/match_object.rs:12-33), FseBackend::push_match /
+// Buffer::push (fse/backend.rs:66-96, fse/buffer.rs:45-117) over the per-position words of k_enc_find.
+struct TSink {
+    uint2 *packs;
+    uint32_t n_packs_total, n_lits_total, blk_pack0, blk_lit0, n_match_bytes, match_distance, n_blocks, out_used, blk_src0;
+};
+struct TEnv {
+    StreamCounts base;
+    EncBlock *blocks;
+    uint32_t *block_ids;
+    uint32_t *block_counter;
+    uint64_t src_off;
+};
+__device__ __forceinline__ void tsink_emit_block(TSink &s, const TEnv &env) {
+    EncBlock b;
+    b.pack_off = env.base.n_blocks + s.blk_pack0;
+    b.lit_off = env.base.n_fse + s.blk_lit0;
+    b.out_off = env.base.n_lmds + s.out_used;
+    b.src_pos = env.src_off + s.blk_src0;
+    b.n_packs = s.n_packs_total - s.blk_pack0;
+    b.n_lits = s.n_lits_total - s.blk_lit0;
+    b.n_match_bytes = s.n_match_bytes;
+    b.out_size = 0; b.gather = 1; b.pad = 0;
+    const uint32_t id = atomicAdd(env.block_counter, 1u);
+    env.blocks[id] = b;
+    env.block_ids[env.base.n_literals + s.n_blocks] = id;
+    s.out_used += (uint32_t)((block_bound(b.n_lits, b.n_packs) + 15) & ~15ull);
+    s.n_blocks++;
+    s.blk_src0 += b.n_lits + b.n_match_bytes;
+    s.blk_pack0 = s.n_packs_total; s.blk_lit0 = s.n_lits_total;
+    s.n_match_bytes = 0; s.match_distance = 0;
+}
+__device__ __forceinline__ void tsink_push_l(TSink &s, uint32_t l) {
+    s.match_distance = 1;
+    s.packs[s.n_packs_total++] = make_uint2(l, 1);
+}
+__device__ __forceinline__ void tsink_push_lmd(TSink &s, uint32_t l, uint32_t m, uint32_t d) {
+    if (s.match_distance == d) d = 0; else s.match_distance = d;
+    s.packs[s.n_packs_total++] = make_uint2(l | (m << 16), d);
+    s.n_match_bytes += m;
+}
+__device__ __forceinline__ bool tsink_buffer_push(TSink &s, uint32_t &lit_len, uint32_t &match_len, uint32_t d) {  // Buffer::push
+    while (lit_len > kMaxLValue) {
+        if (s.n_packs_total - s.blk_pack0 == kLmdsPerBlock) return false;
+        const uint32_t limit = kLiteralsPerBlock - (s.n_lits_total - s.blk_lit0);
+        if (kMaxLValue <= limit) { s.n_lits_total += kMaxLValue; lit_len -= kMaxLValue; tsink_push_l(s, kMaxLValue); }
+        else if (limit != 0) { s.n_lits_total += limit; lit_len -= limit; tsink_push_l(s, limit); return false; }
+        else return false;
+    }
+    if (s.n_packs_total - s.blk_pack0 == kLmdsPerBlock) return false;
+    uint32_t literal_len = lit_len;
+    const uint32_t limit = kLiteralsPerBlock - (s.n_lits_total - s.blk_lit0);
+    if (literal_len <= limit) { s.n_lits_total += literal_len; lit_len = 0; }
+    else if (limit != 0) { s.n_lits_total += limit; lit_len -= limit; tsink_push_l(s, limit); return false; }
+    else return false;
+    while (match_len > kMaxMValue) {
+        tsink_push_lmd(s, literal_len, kMaxMValue, d);
+        match_len -= kMaxMValue; literal_len = 0;
+        if (s.n_packs_total - s.blk_pack0 == kLmdsPerBlock) return false;
+    }
+    tsink_push_lmd(s, literal_len, match_len, d);
+    match_len = 0;
+    return true;
+}
+__device__ __forceinline__ void tsink_push_match(TSink &s, const TEnv &env, uint32_t lit_len, uint32_t match_len, uint32_t d) {
+    if (lit_len <= kMaxLValue && match_len <= kMaxMValue && s.n_packs_total - s.blk_pack0 < kLmdsPerBlock &&
+        s.n_lits_total - s.blk_lit0 + lit_len <= kLiteralsPerBlock) {
+        s.n_lits_total += lit_len;
+        tsink_push_lmd(s, lit_len, match_len, d);
+        return;
+    }
+    while (!tsink_buffer_push(s, lit_len, match_len, d)) tsink_emit_block(s, env);
+}
+
+constexpr int kReplayThreads = 32;
+__global__ void __launch_bounds__(kReplayThreads)
+k_enc_replay(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ src_off, const uint64_t *__restrict__ src_len, size_t n_streams,
+             EncStream *streams, const StreamCounts *__restrict__ bases, const uint32_t *__restrict__ words, uint2 *pack_scratch, uint32_t *block_ids,
+             EncBlock *blocks, uint32_t *block_counter) {
+    const size_t si = (size_t)blockIdx.x * kReplayThreads + threadIdx.x;
+    if (si >= n_streams || !streams[si].fast) return;
+    const uint8_t *src = src_base + src_off[si];
+    const uint32_t len = (uint32_t)src_len[si], end = len - 3;
+    TEnv env;
+    env.base = bases[si]; env.blocks = blocks; env.block_ids = block_ids; env.block_counter = block_counter; env.src_off = src_off[si];
+    TSink fs;
+    fs.packs = pack_scratch + env.base.n_blocks;
+    fs.n_packs_total = 0; fs.n_lits_total = 0; fs.blk_pack0 = 0; fs.blk_lit0 = 0; fs.n_match_bytes = 0; fs.match_distance = 0;
+    fs.n_blocks = 0; fs.out_used = 0; fs.blk_src0 = 0;
+    const uint32_t *W = words + env.base.n_fse;
+    uint32_t cur = 0, literal_index = 0;
+    Match pending = {0, 0, 0};
+    while (cur < end) {
+        const uint32_t w = __ldg(W + cur);
+        if (w == 0) { cur++; continue; }  // find_match came back empty (:203-209)
+        Match inc;
+        inc.idx = cur;
+        inc.match_idx = cur - (w & 0x3FFFFu);
+        inc.match_len = (w >> 18) & 0x3FFu;
+        if (inc.match_len == kWordLenSat) {  // the word's length field is saturated: finish the extension here
+            const uint32_t maxl = len - cur;
+            while (inc.match_len < maxl && src[cur + inc.match_len] == src[inc.match_idx + inc.match_len]) inc.match_len++;
+        }
+        {   // match_dec (:261-268)
+            const uint32_t lit = cur - literal_index;
+            const uint32_t lim = lit < inc.match_idx ? lit : inc.match_idx;
+            const uint32_t bw = w >> 28;
+            uint32_t dec = bw < lim ? bw : lim;
+            if (bw == kWordBwSat) while (dec < lim && src[inc.idx - dec - 1] == src[inc.match_idx - dec - 1]) dec++;
+            inc.idx -= dec; inc.match_idx -= dec; inc.match_len += dec;
+        }
+        bool have = true;
+        Match sel = pending;
+        if (inc.match_len >= kGoodMatchLen) { sel = inc; pending.match_len = 0; }
+        else if (pending.match_len == 0) { pending = inc; have = false; }
+        else if ((int32_t)(pending.idx + pending.match_len - inc.idx) <= 0) { pending = inc; }
+        else if (inc.match_len > pending.match_len) { sel = inc; pending.match_len = 0; }
+        else { pending.match_len = 0; }
+        if (have) {
+            tsink_push_match(fs, env, sel.idx - literal_index, sel.match_len, sel.idx - sel.match_idx);
+            literal_index = sel.idx + sel.match_len;
+            if (literal_index >= end) break;
+            cur = cur + 1 > literal_index ? cur + 1 : literal_index;
+        } else {
+            cur++;
+        }
+    }
+    if (pending.match_len != 0) {
+        tsink_push_match(fs, env, pending.idx - literal_index, pending.match_len, pending.idx - pending.match_idx);
+        literal_index = pending.idx + pending.match_len;
+    }
+    if (len - literal_index != 0) tsink_push_match(fs, env, len - literal_index, 0, 1);
+    tsink_emit_block(fs, env);
+    streams[si].n_blocks = fs.n_blocks;
+}
+
+// ------------------------------------------------------------------------------------------------
 // FSE block encode: warp per block.
 //
 // The seven FSE state machines of a block (4 literal states, L, M, D) are independent chains: each
@@ -752,7 +1139,7 @@ __device__ __forceinline__ void warp_emit(uint32_t *bitbuf, uint64_t v, uint32_t
 
 __global__ void __launch_bounds__(kFseEncWarps * 32)
 k_enc_fse_blocks(EncBlock *blocks, const uint32_t *__restrict__ n_blocks_p, const uint2 *__restrict__ pack_scratch,
-                 const uint8_t *__restrict__ lit_scratch, uint8_t *out_scratch, uint32_t *work_counter) {
+                 uint8_t *lit_scratch, uint8_t *out_scratch, uint32_t *work_counter, const uint8_t *__restrict__ src_base) {
     __shared__ FseEncSmem sm_all[kFseEncWarps];
     FseEncSmem &sm = sm_all[threadIdx.x >> 5];
     const uint32_t lane = lane_id();
@@ -764,8 +1151,40 @@ k_enc_fse_blocks(EncBlock *blocks, const uint32_t *__restrict__ n_blocks_p, cons
         if (bi >= n_blocks) break;
         const EncBlock b = blocks[bi];
         const uint2 *packs = pack_scratch + b.pack_off;
-        const uint8_t *lits = lit_scratch + b.lit_off;
+        uint8_t *lits = lit_scratch + b.lit_off;
         uint8_t *out = out_scratch + b.out_off;
+        if (b.gather) {
+            // Blocks of k_enc_replay: the literal bytes are still in the source.  Pack i's literals start at the block's
+            // first source byte + the (L + M) of the packs before it (Buffer::push appends them in that order).
+            const uint8_t *sp = src_base + b.src_pos;
+            uint32_t lit_run = 0, src_run = 0;
+            for (uint32_t i0 = 0; i0 < b.n_packs; i0 += 32) {
+                uint32_t L = 0, M = 0;
+                if (i0 + lane < b.n_packs) { const uint2 p = packs[i0 + lane]; L = p.x & 0xFFFF; M = p.x >> 16; }
+                const uint32_t v = (L << 17) + (L + M);  // 32 * 315 < 2^14, 32 * (315 + 2359) < 2^17
+                uint32_t inc = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+                    if (lane >= (uint32_t)o) inc += t;
+                }
+                const uint32_t exc = inc - v, tot = __shfl_sync(0xFFFFFFFFu, inc, 31);
+                const uint32_t my_lit = lit_run + (exc >> 17), my_src = src_run + (exc & 0x1FFFF);
+                const uint32_t sl = L <= 16 ? L : 0;
+                const uint32_t max_l = __reduce_max_sync(0xFFFFFFFFu, sl);
+                for (uint32_t t = 0; t < max_l; t++)
+                    if (t < sl) lits[my_lit + t] = sp[my_src + t];
+                uint32_t mask = __ballot_sync(0xFFFFFFFFu, L > 16);
+                while (mask) {
+                    const int j = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const uint32_t o = __shfl_sync(0xFFFFFFFFu, my_lit, j), f = __shfl_sync(0xFFFFFFFFu, my_src, j), nn = __shfl_sync(0xFFFFFFFFu, L, j);
+                    for (uint32_t t = lane; t < nn; t += 32) lits[o + t] = sp[f + t];
+                }
+                lit_run += tot >> 17; src_run += tot & 0x1FFFF;
+            }
+            __syncwarp();
+        }
         // ---- Weights::load (fse/weights.rs:25-64): histograms of the real packs / literals ----
         for (uint32_t t = lane; t < 360; t += 32) sm.W[t] = 0;
         __syncwarp();
@@ -967,7 +1386,8 @@ struct lzfse_b200_encoder {
     cudaStream_t own_stream = nullptr;
     std::string last_error;
     uint64_t launches = 0;
-    DevBuf streams, counts, totals_dev, tables, packs, lits, block_ids, blocks, out, counters;
+    DevBuf streams, counts, totals_dev, tables, packs, lits, block_ids, blocks, out, counters, words;
+    int allow_fast = 1;  // LZB_ENC_FAST=0 sends every stream through k_enc_parse (measurements, tests)
     PinnedBuf totals_host;
     HostStage stage;
     StageTimer timer;
@@ -985,43 +1405,63 @@ int encode_batch_device_impl(lzfse_b200_encoder *e, const uint8_t *src, const ui
     LZB_CK(e, e->streams.reserve(n * sizeof(EncStream)));
     LZB_CK(e, e->counts.reserve((n + 1 + n / 1024 + 2) * sizeof(StreamCounts)));  // + tile sums of the scan
     LZB_CK(e, e->totals_dev.reserve(sizeof(StreamCounts)));
-    LZB_CK(e, e->totals_host.reserve(sizeof(StreamCounts)));
-    LZB_CK(e, e->counters.reserve(4 * sizeof(uint32_t)));
+    LZB_CK(e, e->totals_host.reserve(2 * sizeof(StreamCounts)));
+    LZB_CK(e, e->counters.reserve(8 * sizeof(uint32_t)));
     const int tb = 128;
     e->timer.begin(s);
-    k_enc_prep<<<(unsigned)((n + tb - 1) / tb), tb, 0, s>>>(src_len, n, e->streams.as<EncStream>(), e->counts.as<StreamCounts>(), status);
+    LZB_CK(e, cudaMemsetAsync(e->counters.p, 0, 8 * sizeof(uint32_t), s));
+    uint32_t *ctr = e->counters.as<uint32_t>();  // [0] blocks produced, [1] parse cursor, [2] fse-encode cursor, [3] find cursor, [4] fast streams, [5] k_enc_parse streams
+    k_enc_prep<<<(unsigned)((n + tb - 1) / tb), tb, 0, s>>>(src_len, n, e->streams.as<EncStream>(), e->counts.as<StreamCounts>(), status, ctr + 4, e->allow_fast);
     launch_exclusive_scan(e->counts.as<StreamCounts>(), n, e->totals_host.as<StreamCounts>(), s);  // pinned host memory (UVA)
-    e->launches += n > 8192 ? 4 : 2;  // prep + the exclusive scan (three launches for large batches)
+    k_enc_publish_counts<<<1, 1, 0, s>>>(ctr + 4, reinterpret_cast<uint32_t *>(e->totals_host.as<StreamCounts>() + 1));
+    e->launches += n > 8192 ? 5 : 3;  // prep + the exclusive scan (three launches for large batches) + publish
     LZB_CK(e, cudaStreamSynchronize(s));
     const StreamCounts tot = *e->totals_host.as<StreamCounts>();  // {packs, literal bytes, block slots, out bytes}
+    const uint32_t n_fast = reinterpret_cast<const uint32_t *>(e->totals_host.as<StreamCounts>() + 1)[0];
+    const uint32_t n_slow = reinterpret_cast<const uint32_t *>(e->totals_host.as<StreamCounts>() + 1)[1];
     if (tot.n_literals > 0xFFFFFFF0ull) { e->last_error = "too many blocks in one batch"; return LZFSE_B200_INVALID_ARGUMENT; }
     const unsigned parse_ctas = (unsigned)e->n_sms * kParseWarpsPerSm / kParseWarps;
     const size_t n_slots = (size_t)parse_ctas * kParseWarps;
-    {   // history tables + one epoch word per table; zeroed when (re)allocated, never again (see k_enc_parse)
+    if (n_slow) {   // history tables + one epoch word per table; zeroed when (re)allocated, never again (see k_enc_parse)
         const void *before = e->tables.p;
         LZB_CK(e, e->tables.reserve(n_slots * (kTableWords + 1) * sizeof(uint32_t)));
         if (e->tables.p != before) LZB_CK(e, cudaMemsetAsync(e->tables.p, 0, e->tables.cap, s));
     }
+    if (n_fast) LZB_CK(e, e->words.reserve((tot.n_fse + 64) * sizeof(uint32_t)));  // one word per position (k_enc_find -> k_enc_replay)
     LZB_CK(e, e->packs.reserve((tot.n_blocks + 1) * sizeof(uint2)));
     LZB_CK(e, e->lits.reserve(tot.n_fse + 64));
     LZB_CK(e, e->block_ids.reserve((tot.n_literals + 1) * sizeof(uint32_t)));
     LZB_CK(e, e->blocks.reserve((tot.n_literals + 1) * sizeof(EncBlock)));
     LZB_CK(e, e->out.reserve(tot.n_lmds + 64));
-    LZB_CK(e, cudaMemsetAsync(e->counters.p, 0, 4 * sizeof(uint32_t), s));
-    uint32_t *ctr = e->counters.as<uint32_t>();  // [0] blocks produced, [1] parse stream cursor, [2] fse-encode cursor
     e->timer.mark(s);  // prep
 
-    k_enc_parse<<<parse_ctas, kParseWarps * 32, 0, s>>>(src, src_off, src_len, n, e->streams.as<EncStream>(), e->counts.as<StreamCounts>(),
-                                                       e->tables.as<uint32_t>(), e->tables.as<uint32_t>() + n_slots * kTableWords, e->packs.as<uint2>(),
-                                                       e->lits.as<uint8_t>(),
-                                                       e->block_ids.as<uint32_t>(), e->blocks.as<EncBlock>(), ctr, e->out.as<uint8_t>(), ctr + 1);
-    e->launches += 1;
+    if (n_fast) {
+        const unsigned g = n_fast < (unsigned)e->n_sms ? n_fast : (unsigned)e->n_sms;
+        k_enc_find<<<g, kFindThreads, kFindSmemBytes, s>>>(src, src_off, src_len, n, e->streams.as<EncStream>(), e->counts.as<StreamCounts>(),
+                                                           e->words.as<uint32_t>(), ctr + 3);
+        e->launches += 1;
+    }
+    e->timer.mark(s);  // find
+    if (n_fast) {
+        k_enc_replay<<<(unsigned)((n + kReplayThreads - 1) / kReplayThreads), kReplayThreads, 0, s>>>(
+            src, src_off, src_len, n, e->streams.as<EncStream>(), e->counts.as<StreamCounts>(), e->words.as<uint32_t>(), e->packs.as<uint2>(),
+            e->block_ids.as<uint32_t>(), e->blocks.as<EncBlock>(), ctr);
+        e->launches += 1;
+    }
+    e->timer.mark(s);  // replay
+    if (n_slow) {
+        k_enc_parse<<<parse_ctas, kParseWarps * 32, 0, s>>>(src, src_off, src_len, n, e->streams.as<EncStream>(), e->counts.as<StreamCounts>(),
+                                                           e->tables.as<uint32_t>(), e->tables.as<uint32_t>() + n_slots * kTableWords, e->packs.as<uint2>(),
+                                                           e->lits.as<uint8_t>(),
+                                                           e->block_ids.as<uint32_t>(), e->blocks.as<EncBlock>(), ctr, e->out.as<uint8_t>(), ctr + 1);
+        e->launches += 1;
+    }
     e->timer.mark(s);  // parse
     if (tot.n_literals) {
         unsigned g = (unsigned)((tot.n_literals + kFseEncWarps - 1) / kFseEncWarps);
         if (g > (unsigned)e->n_sms * 4) g = (unsigned)e->n_sms * 4;
         k_enc_fse_blocks<<<g, kFseEncWarps * 32, 0, s>>>(e->blocks.as<EncBlock>(), ctr, e->packs.as<uint2>(),
-                                                                                        e->lits.as<uint8_t>(), e->out.as<uint8_t>(), ctr + 2);
+                                                                                        e->lits.as<uint8_t>(), e->out.as<uint8_t>(), ctr + 2, src);
         e->launches += 1;
     }
     e->timer.mark(s);  // fse_blocks
@@ -1054,8 +1494,10 @@ int lzfse_b200_encoder_create(int device, lzfse_b200_encoder **out) {
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete e; return LZFSE_B200_NO_DEVICE; }
     e->n_sms = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete e; return LZFSE_B200_CUDA_ERROR; }
+    if (const char *ef = getenv("LZB_ENC_FAST")) e->allow_fast = atoi(ef) != 0;
     cudaFuncAttributes fa;
-    if (cudaFuncGetAttributes(&fa, k_enc_fse_blocks) != cudaSuccess) {
+    if (cudaFuncGetAttributes(&fa, k_enc_fse_blocks) != cudaSuccess ||
+        cudaFuncSetAttribute(k_enc_find, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFindSmemBytes) != cudaSuccess) {
         cudaGetLastError();  // no sm_100a image for this device: there is no fallback path
         cudaStreamDestroy(e->own_stream);
         delete e;
@@ -1068,7 +1510,7 @@ int lzfse_b200_encoder_create(int device, lzfse_b200_encoder **out) {
 void lzfse_b200_encoder_destroy(lzfse_b200_encoder *e) {
     if (!e) return;
     DeviceGuard g(e->device);
-    for (DevBuf *b : {&e->streams, &e->counts, &e->totals_dev, &e->tables, &e->packs, &e->lits, &e->block_ids, &e->blocks, &e->out, &e->counters}) b->release();
+    for (DevBuf *b : {&e->streams, &e->counts, &e->totals_dev, &e->tables, &e->packs, &e->lits, &e->block_ids, &e->blocks, &e->out, &e->counters, &e->words}) b->release();
     e->totals_host.release();
     e->stage.release();
     e->timer.release();
