@@ -666,12 +666,13 @@ constexpr uint32_t kNone = 0xFFFFu;       // chain end (positions are < kFastMax
 constexpr uint32_t kLaneCap = 1024;       // per-lane forward extension stops here; longer ones are finished warp-wide
 constexpr uint32_t kWordLenSat = 1023, kWordBwSat = 15;
 constexpr uint32_t kRunSlots = 64;        // (distance, start, end) of long runs already measured, per stream
-constexpr uint32_t kFsSrc = 0, kFsSrcBytes = kFastMaxLen + 48;  // up to 15 bytes of alignment in front, over-read slack behind
-constexpr uint32_t kFsHead = kFsSrc + kFsSrcBytes, kFsPrev = kFsHead + (1u << kHashBits) * 2, kFsCtrl = kFsPrev + kFastMaxLen * 2;
+constexpr uint32_t kFsSrc = 16, kFsSrcBytes = kFastMaxLen + 48;  // 16 bytes below the stream (backward reads), up to 15 of alignment, over-read slack behind
+constexpr uint32_t kFsHead = kFsSrc + kFsSrcBytes + 16, kFsPrev = kFsHead + (1u << kHashBits) * 2, kFsCtrl = kFsPrev + kFastMaxLen * 2;
 struct FindCtrl {
     unsigned long long mbar;
-    uint32_t chain_done, next_unit, stream, pad;
+    uint32_t chain_done, next_ticket, stream, pad;
     unsigned long long runs[kRunSlots];
+    uint8_t pre_done[kFastMaxLen / kFindUnit];  // per unit: peer info written
 };
 constexpr uint32_t kFindSmemBytes = kFsCtrl + sizeof(FindCtrl);
 static_assert(kFindSmemBytes <= 232448, "k_enc_find shared memory");
@@ -749,6 +750,7 @@ k_enc_find(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ sr
         if (si >= n_streams) break;
         if (!streams[si].fast) { __syncthreads(); continue; }
         const uint32_t len = (uint32_t)src_len[si], end = len - 3;
+        const uint32_t n_units = (end + kFindUnit - 1) / kFindUnit;
         const uint8_t *g = src_base + src_off[si];
         const uint32_t mis = (uint32_t)reinterpret_cast<uintptr_t>(g) & 15u;
         const uint32_t s = sm0 + kFsSrc + mis;  // shared address of stream byte 0
@@ -761,48 +763,84 @@ k_enc_find(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ sr
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sm0 + kFsSrc),
                          "l"(g - mis), "r"(bytes), "r"(mbar)
                          : "memory");
-            ctrl->chain_done = 0; ctrl->next_unit = 0;
+            ctrl->chain_done = 0; ctrl->next_ticket = 0;
         }
-        // meanwhile: empty bucket heads and run cache
+        // meanwhile: empty bucket heads, run cache, unit flags
         for (uint32_t t = tid; t < (1u << kHashBits) * 2 / 16; t += kFindThreads)
             *reinterpret_cast<uint4 *>(fsm + kFsHead + t * 16) = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
         if (tid < kRunSlots) ctrl->runs[tid] = 0;
+        if (tid < kFastMaxLen / kFindUnit / 4) reinterpret_cast<uint32_t *>(ctrl->pre_done)[tid] = 0;
         mbar_wait(mbar, phase);
         phase ^= 1;
         __syncthreads();
         uint32_t *wout = words + bases[si].n_fse;
         if (warp == 0) {
             // ---- the chain: HistoryTable::push for every position, in order, 32 per step ----
-            uint32_t val_n = lds4u(s + lane);  // end >= 4094
-            for (uint32_t b0 = 0; b0 < end; b0 += 32) {
-                const uint32_t p = b0 + lane;
-                const bool act = p < end;
-                const uint32_t val = val_n;
-                if (b0 + 32 < end) val_n = lds4u(s + (p + 32 < end ? p + 32 : end - 1));
-                const uint32_t h = act ? hash_u(val, false) : (0xFFFF0000u + lane);
-                const uint32_t peers = __match_any_sync(0xFFFFFFFFu, h);
-                const uint32_t lower = peers & lanemask_lt();
-                if (act) {
+            // The bucket index of every position and which lanes of a step share a bucket were worked out by the other
+            // warps (info word parked in prev[p], see below), so a step is: bucket head -> prev[p]; newest position of each
+            // bucket -> head.  One warp runs this serial chain; what it costs is instructions on its dependent path
+            // (a lone warp issues one every ~4 cycles), hence everything that can be precomputed is.
+            for (uint32_t u = 0; u < n_units; u++) {
+                while (*reinterpret_cast<volatile uint8_t *>(&ctrl->pre_done[u]) == 0) {}
+                __threadfence_block();
+                const uint32_t ub = u * kFindUnit;
+                uint32_t info = lds_u16(s_prev + (ub + lane) * 2);
+#pragma unroll
+                for (uint32_t k = 0; k < kFindUnit / 32; k++) {
+                    const uint32_t b0 = ub + k * 32, p = b0 + lane;
+                    uint32_t info_n = 0;
+                    if (k + 1 < kFindUnit / 32) info_n = lds_u16(s_prev + (p + 32) * 2);  // stays inside prev[]: ub + 255 <= 65535
+                    const uint32_t hb = __shfl_sync(0xFFFFFFFFu, info, (info >> 5) & 31u);  // the bucket index lives in the group's lowest lane
+                    const uint32_t h = ((info & 0x8000u) ? hb : info) & 0x3FFFu;
                     const uint32_t old = lds_u16(s_head + h * 2);
-                    sts_u16(s_prev + p * 2, lower ? b0 + (31 - __clz(lower)) : old);
-                    if ((peers >> lane) == 1u) sts_u16(s_head + h * 2, p);  // newest position of its bucket in this step
+                    if (p < end) {
+                        sts_u16(s_prev + p * 2, (info & 0x8000u) ? b0 + (info & 31u) : old);
+                        if (info & 0x4000u) sts_u16(s_head + h * 2, p);  // newest position of its bucket in this step
+                    }
+                    __syncwarp();
+                    info = info_n;
                 }
-                __syncwarp();
-                if (((b0 + 32) & (kFindUnit - 1)) == 0 || b0 + 32 >= end) {
-                    __threadfence_block();
-                    if (lane == 0) *reinterpret_cast<volatile uint32_t *>(&ctrl->chain_done) = b0 + 32 < end ? b0 + 32 : end;
-                }
+                __threadfence_block();
+                if (lane == 0) *reinterpret_cast<volatile uint32_t *>(&ctrl->chain_done) = ub + kFindUnit < end ? ub + kFindUnit : end;
             }
         } else {
-            // ---- find_match for every position, unit by unit behind the chain ----
             for (;;) {
-                uint32_t u = 0;
-                if (lane == 0) u = atomicAdd(&ctrl->next_unit, 1u);
-                u = __shfl_sync(0xFFFFFFFFu, u, 0);
-                const uint32_t p0 = u * kFindUnit;
-                if (p0 >= end) break;
+                uint32_t t = 0;
+                if (lane == 0) t = atomicAdd(&ctrl->next_ticket, 1u);
+                t = __shfl_sync(0xFFFFFFFFu, t, 0);
+                if (t >= 2 * n_units) break;
+                if (t < n_units) {
+                    // ---- info for the chain: bucket index, and which lanes of each 32-position step share a bucket ----
+                    // (__match_any_sync takes ~350 cycles when all 32 values differ, which they nearly always do; 14 ballots
+                    // over the bits of the bucket index give the same mask.)  Parked in prev[p] until the chain gets there:
+                    //   no lower lane in my bucket:  bit 14 = no higher lane either (I am the newest), bits 0..13 = bucket
+                    //   otherwise: bit 15, bit 14 as above, bits 5..9 = lowest lane of the group, bits 0..4 = next lower lane
+                    const uint32_t p0 = t * kFindUnit, p1 = p0 + kFindUnit < end ? p0 + kFindUnit : end;
+                    for (uint32_t b0 = p0; b0 < p1; b0 += 32) {
+                        const uint32_t p = b0 + lane;
+                        const bool act = p < end;
+                        const uint32_t h = hash_u(lds4u(s + (act ? p : end - 1)), false);
+                        uint32_t m = __ballot_sync(0xFFFFFFFFu, act);
+#pragma unroll
+                        for (int bit = 0; bit < (int)kHashBits; bit++) {
+                            const bool on = (h >> bit) & 1u;
+                            const uint32_t bl = __ballot_sync(0xFFFFFFFFu, on);
+                            m &= on ? bl : ~bl;
+                        }
+                        const uint32_t lower = m & lanemask_lt();
+                        const uint32_t newest = (m >> lane) == 1u ? 0x4000u : 0u;
+                        const uint32_t info = lower ? (0x8000u | newest | ((uint32_t)(__ffs(m) - 1) << 5) | (31 - __clz(lower))) : (newest | h);
+                        if (act) sts_u16(s_prev + p * 2, info);
+                    }
+                    __syncwarp();
+                    __threadfence_block();
+                    if (lane == 0) *reinterpret_cast<volatile uint8_t *>(&ctrl->pre_done[t]) = 1;
+                    continue;
+                }
+                // ---- find_match for every position of a unit, behind the chain ----
+                const uint32_t p0 = (t - n_units) * kFindUnit;
                 const uint32_t p1 = p0 + kFindUnit < end ? p0 + kFindUnit : end;
-                while (*reinterpret_cast<volatile uint32_t *>(&ctrl->chain_done) < p1) __nanosleep(200);
+                while (*reinterpret_cast<volatile uint32_t *>(&ctrl->chain_done) < p1) __nanosleep(100);
                 __threadfence_block();
                 for (uint32_t b0 = p0; b0 < p1; b0 += 32) {
                     const uint32_t p = b0 + lane;
@@ -814,16 +852,24 @@ k_enc_find(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ sr
                     if (act) {
                         const uint32_t val = lds4u(s + p);
                         uint32_t c = lds_u16(s_prev + p * 2);
+                        if (c != kNone) {
+                            const uint64_t p8 = lds8u(s + p + 4);  // bytes 4..11 of this position, shared by its candidates
+                            const uint32_t lim = maxl < kLaneCap ? maxl : kLaneCap;
 #pragma unroll
-                        for (int k = 0; k < 4; k++) {
-                            if (c == kNone) break;  // (the distance limit 262 139 cannot be exceeded inside 64 KiB)
-                            if (lds4u(s + c) == val) {
-                                const uint32_t lim = maxl < kLaneCap ? maxl : kLaneCap;
-                                const uint32_t l = smem_match_inc(s, p, c, 4, lim);
-                                if (l == kLaneCap && l < maxl) { cs[n_sat] = c; ls[n_sat] = 0; n_sat++; }
-                                if (l > best_len) { best_len = l; best_c = c; }
+                            for (int k = 0; k < 4; k++) {
+                                // (the distance limit 262 139 cannot be exceeded inside 64 KiB)
+                                const uint32_t cn = lds_u16(s_prev + c * 2);
+                                if (lds4u(s + c) == val) {
+                                    const uint64_t y = p8 ^ lds8u(s + c + 4);
+                                    uint32_t l;
+                                    if (y) { l = 4 + ((__ffsll((long long)y) - 1) >> 3); l = l < lim ? l : lim; }
+                                    else l = lim >= 12 ? smem_match_inc(s, p, c, 12, lim) : lim;
+                                    if (l == kLaneCap && l < maxl) { cs[n_sat] = c; ls[n_sat] = 0; n_sat++; }
+                                    if (l > best_len) { best_len = l; best_c = c; }
+                                }
+                                c = cn;
+                                if (c == kNone) break;
                             }
-                            c = lds_u16(s_prev + c * 2);
                         }
                     }
                     // Two or more candidates beyond the per-lane cap: their exact lengths decide (strictly longest, newest
@@ -867,9 +913,16 @@ k_enc_find(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ sr
                                 if (ls[k] > bl) { bl = ls[k]; best_c = cs[k]; }
                             best_len = bl;
                         }
+                        // backward length (match_kit/match_fast.rs:61-89), 4 bytes per step, up to what the word can hold
                         uint32_t bw = 0;
                         const uint32_t blim = best_c < kWordBwSat ? best_c : kWordBwSat;
-                        while (bw < blim && lds_b8(s + p - bw - 1) == lds_b8(s + best_c - bw - 1)) bw++;
+                        while (bw < blim) {
+                            const uint32_t x = lds4u(s + p - bw - 4) ^ lds4u(s + best_c - bw - 4);  // reads at most 4 bytes below the stream (padding)
+                            const uint32_t nb = x ? (uint32_t)__clz(x) >> 3 : 4u;
+                            bw += nb;
+                            if (nb < 4) break;
+                        }
+                        bw = bw < blim ? bw : blim;
                         word = (p - best_c) | ((best_len < kWordLenSat ? best_len : kWordLenSat) << 18) | (bw << 28);
                     }
                     if (act) wout[p] = word;
@@ -956,6 +1009,7 @@ __device__ __forceinline__ void tsink_push_match(TSink &s, const TEnv &env, uint
 }
 
 constexpr int kReplayThreads = 32;
+constexpr uint32_t kRingWords = 64, kRingStride = kRingWords * 4 + 16;  // per-lane ring of words (stride skews the banks)
 __global__ void __launch_bounds__(kReplayThreads)
 k_enc_replay(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ src_off, const uint64_t *__restrict__ src_len, size_t n_streams,
              EncStream *streams, const StreamCounts *__restrict__ bases, const uint32_t *__restrict__ words, uint2 *pack_scratch, uint32_t *block_ids,
@@ -973,8 +1027,34 @@ k_enc_replay(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ 
     const uint32_t *W = words + env.base.n_fse;
     uint32_t cur = 0, literal_index = 0;
     Match pending = {0, 0, 0};
+    // Every lane walks its own stream, so a plain load per position costs a memory round trip per step of this serial
+    // loop (and prefetch.global.L1 does not shorten it).  Each lane therefore owns a 64-word ring in shared memory that
+    // cp.async keeps filled 16 chunks ahead of its cursor; the cursor reads four words at a time.
+    __shared__ __align__(16) uint8_t rings[kReplayThreads * kRingStride];
+    const uint32_t ring = (uint32_t)__cvta_generic_to_shared(rings) + threadIdx.x * kRingStride;
+    const uint32_t w_limit = (end + 3u) & ~3u;  // chunks at or beyond this word index are never needed
+    uint32_t wbase = 0xFFFFFFFFu, fetched = 0;
+    uint4 wq = make_uint4(0, 0, 0, 0);
     while (cur < end) {
-        const uint32_t w = __ldg(W + cur);
+        if ((cur & ~3u) != wbase) {
+            wbase = cur & ~3u;
+            if (wbase >= fetched) {  // first use, or a jump past everything requested so far: older requests must not land on top of new ones
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                fetched = wbase;
+            }
+            const uint32_t want = wbase + kRingWords < w_limit ? wbase + kRingWords : w_limit;
+            while (fetched < want) {
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ring + (fetched & (kRingWords - 1)) * 4), "l"(W + fetched) : "memory");
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                fetched += 4;
+            }
+            // the chunk at wbase is the (fetched - wbase) / 4-th newest group; with a full window that is the 16th
+            if (fetched == wbase + kRingWords) asm volatile("cp.async.wait_group 14;" ::: "memory");
+            else asm volatile("cp.async.wait_group 0;" ::: "memory");
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(wq.x), "=r"(wq.y), "=r"(wq.z), "=r"(wq.w) : "r"(ring + (wbase & (kRingWords - 1)) * 4) : "memory");
+        }
+        const uint32_t k4 = cur & 3u;
+        const uint32_t w = k4 == 0 ? wq.x : (k4 == 1 ? wq.y : (k4 == 2 ? wq.z : wq.w));
         if (w == 0) { cur++; continue; }  // find_match came back empty (:203-209)
         Match inc;
         inc.idx = cur;
@@ -1427,7 +1507,7 @@ int encode_batch_device_impl(lzfse_b200_encoder *e, const uint8_t *src, const ui
         LZB_CK(e, e->tables.reserve(n_slots * (kTableWords + 1) * sizeof(uint32_t)));
         if (e->tables.p != before) LZB_CK(e, cudaMemsetAsync(e->tables.p, 0, e->tables.cap, s));
     }
-    if (n_fast) LZB_CK(e, e->words.reserve((tot.n_fse + 64) * sizeof(uint32_t)));  // one word per position (k_enc_find -> k_enc_replay)
+    if (n_fast) LZB_CK(e, e->words.reserve((tot.n_fse + 256) * sizeof(uint32_t)));  // one word per position (k_enc_find -> k_enc_replay)
     LZB_CK(e, e->packs.reserve((tot.n_blocks + 1) * sizeof(uint2)));
     LZB_CK(e, e->lits.reserve(tot.n_fse + 64));
     LZB_CK(e, e->block_ids.reserve((tot.n_literals + 1) * sizeof(uint32_t)));
