@@ -13,6 +13,7 @@
 //   k_enc_fse_blocks  lane / block      histogram, normalize_m1, weight varints, encode tables, 4-state
 //                                       literal stream, L/M/D stream, bvx2 header
 //   k_enc_assemble    warp / stream     compaction of the blocks into the caller's frame + bvx$
+#include <cstdio>
 #include <cstdlib>
 #include <new>
 #include <string>
@@ -660,6 +661,21 @@ k_enc_parse(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ s
 //                 with splits and block closing) over those words; emits packs and block records only -- the literal
 //                 bytes are collected by k_enc_fse_blocks from the packs.
 // ------------------------------------------------------------------------------------------------
+#ifndef LZB_CHAIN_MATES
+#define LZB_CHAIN_MATES 7   // find warps allowed on the chain warp's scheduler (0..7)
+#endif
+#ifndef LZB_PRE_AHEAD
+#define LZB_PRE_AHEAD 256   // info units handed out before the first find unit
+#endif
+#ifndef LZB_FENCE_SC
+#define LZB_FENCE_SC 0
+#endif
+#ifndef LZB_POLL_NS
+#define LZB_POLL_NS 100
+#endif
+#ifndef LZB_PRE_MATCH
+#define LZB_PRE_MATCH 2   // 0: 14 ballots, 1: match.any, 2: 5 ballots + shuffle compares (measured 114K / 130K / 90K cycles per stream)
+#endif
 constexpr int kFindThreads = 1024;
 constexpr uint32_t kFindUnit = 256;       // positions a find warp takes at a time
 constexpr uint32_t kNone = 0xFFFFu;       // chain end (positions are < kFastMaxLen - 3)
@@ -718,6 +734,14 @@ __device__ __forceinline__ uint32_t smem_warp_match_inc(uint32_t s, uint32_t a, 
     }
     return lim;
 }
+// release / acquire fence at CTA scope around the shared-memory flags (MEMBAR.SC.CTA, what __threadfence_block() emits, is heavier)
+__device__ __forceinline__ void fence_cta() {
+#if LZB_FENCE_SC
+    __threadfence_block();
+#else
+    asm volatile("fence.acq_rel.cta;" ::: "memory");
+#endif
+}
 __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t phase) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -774,41 +798,85 @@ k_enc_find(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ sr
         phase ^= 1;
         __syncthreads();
         uint32_t *wout = words + bases[si].n_fse;
+#ifdef LZB_FIND_DEBUG
+        const long long dbg_t0 = clock64();
+        long long dbg_chain = 0, dbg_pre = 0, dbg_find0 = 0;
+        bool dbg_passed = false;
+#endif
         if (warp == 0) {
             // ---- the chain: HistoryTable::push for every position, in order, 32 per step ----
             // The bucket index of every position and which lanes of a step share a bucket were worked out by the other
             // warps (info word parked in prev[p], see below), so a step is: bucket head -> prev[p]; newest position of each
             // bucket -> head.  One warp runs this serial chain; what it costs is instructions on its dependent path
             // (a lone warp issues one every ~4 cycles), hence everything that can be precomputed is.
+            // Only the bucket heads carry a dependency from one step to the next, and that one is satisfied by program order
+            // (a step's head stores are issued before the next step's head loads); nothing in the chain consumes the loaded
+            // values.  So a unit's eight steps issue their loads and stores back to back and prev[] is written at the end:
+            // one shared-memory round trip per unit instead of one per step.
             for (uint32_t u = 0; u < n_units; u++) {
                 while (*reinterpret_cast<volatile uint8_t *>(&ctrl->pre_done[u]) == 0) {}
-                __threadfence_block();
+                fence_cta();
                 const uint32_t ub = u * kFindUnit;
-                uint32_t info = lds_u16(s_prev + (ub + lane) * 2);
+                constexpr uint32_t kSteps = kFindUnit / 32;
+                uint32_t info[kSteps], h[kSteps], old[kSteps];
 #pragma unroll
-                for (uint32_t k = 0; k < kFindUnit / 32; k++) {
-                    const uint32_t b0 = ub + k * 32, p = b0 + lane;
-                    uint32_t info_n = 0;
-                    if (k + 1 < kFindUnit / 32) info_n = lds_u16(s_prev + (p + 32) * 2);  // stays inside prev[]: ub + 255 <= 65535
-                    const uint32_t hb = __shfl_sync(0xFFFFFFFFu, info, (info >> 5) & 31u);  // the bucket index lives in the group's lowest lane
-                    const uint32_t h = ((info & 0x8000u) ? hb : info) & 0x3FFFu;
-                    const uint32_t old = lds_u16(s_head + h * 2);
-                    if (p < end) {
-                        sts_u16(s_prev + p * 2, (info & 0x8000u) ? b0 + (info & 31u) : old);
-                        if (info & 0x4000u) sts_u16(s_head + h * 2, p);  // newest position of its bucket in this step
-                    }
-                    __syncwarp();
-                    info = info_n;
+                for (uint32_t k = 0; k < kSteps; k++) info[k] = lds_u16(s_prev + (ub + k * 32 + lane) * 2);  // stays inside prev[]: ub + 255 <= 65535
+#pragma unroll
+                for (uint32_t k = 0; k < kSteps; k++) {
+                    const uint32_t hb = __shfl_sync(0xFFFFFFFFu, info[k], (info[k] >> 5) & 31u);  // the bucket index lives in the group's lowest lane
+                    h[k] = ((info[k] & 0x8000u) ? hb : info[k]) & 0x3FFFu;
                 }
-                __threadfence_block();
+#pragma unroll
+                for (uint32_t k = 0; k < kSteps; k++) {
+                    const uint32_t p = ub + k * 32 + lane;
+                    old[k] = lds_u16(s_head + h[k] * 2);
+                    if ((info[k] & 0x4000u) && p < end) sts_u16(s_head + h[k] * 2, p);  // newest position of its bucket in this step
+                    __syncwarp();
+                }
+#pragma unroll
+                for (uint32_t k = 0; k < kSteps; k++) {
+                    const uint32_t b0 = ub + k * 32, p = b0 + lane;
+                    if (p < end) sts_u16(s_prev + p * 2, (info[k] & 0x8000u) ? b0 + (info[k] & 31u) : old[k]);
+                }
+                __syncwarp();
+                fence_cta();
                 if (lane == 0) *reinterpret_cast<volatile uint32_t *>(&ctrl->chain_done) = ub + kFindUnit < end ? ub + kFindUnit : end;
             }
-        } else {
+#ifdef LZB_FIND_DEBUG
+            dbg_chain = clock64() - dbg_t0;
+#endif
+#ifdef LZB_FIND_PHASED
+            __syncthreads();  // chain done
+#endif
+        } else if ((warp & 3u) != 0 || (warp >> 2) <= LZB_CHAIN_MATES) {
+            // (Warps that would share the chain warp's scheduler beyond LZB_CHAIN_MATES of them stay idle: the chain is one
+            // warp's dependent instruction stream, and every warp issuing next to it stretches it.)
             for (;;) {
                 uint32_t t = 0;
                 if (lane == 0) t = atomicAdd(&ctrl->next_ticket, 1u);
                 t = __shfl_sync(0xFFFFFFFFu, t, 0);
                 if (t >= 2 * n_units) break;
+#ifdef LZB_FIND_PHASED
+                if (t == n_units) {}  // handled below
+#endif
+                // ticket order: the info units run LZB_PRE_AHEAD units ahead of the find units, then alternate with them
+                {
+                    const uint32_t ahead = LZB_PRE_AHEAD < n_units ? LZB_PRE_AHEAD : n_units;
+                    if (t < ahead) {}                                            // info unit t
+                    else if (t < ahead + 2 * (n_units - ahead)) {                // alternate: find unit j, info unit ahead + j
+                        const uint32_t j = (t - ahead) >> 1;
+                        t = ((t - ahead) & 1u) ? ahead + j : n_units + j;
+                    } else t = n_units + (t - ahead - (n_units - ahead));        // the last `ahead` find units
+                }
+#ifdef LZB_FIND_PHASED
+                if (t >= n_units && !dbg_passed) {
+                    dbg_passed = true;
+                    dbg_pre = clock64() - dbg_t0;
+                    __syncthreads();  // all info units done (every warp gets here: tickets >= n_units exist for all of them or the loop ends)
+                    __syncthreads();  // chain done
+                    dbg_find0 = clock64() - dbg_t0;
+                }
+#endif
                 if (t < n_units) {
                     // ---- info for the chain: bucket index, and which lanes of each 32-position step share a bucket ----
                     // (__match_any_sync takes ~350 cycles when all 32 values differ, which they nearly always do; 14 ballots
@@ -820,6 +888,27 @@ k_enc_find(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ sr
                         const uint32_t p = b0 + lane;
                         const bool act = p < end;
                         const uint32_t h = hash_u(lds4u(s + (act ? p : end - 1)), false);
+#if LZB_PRE_MATCH == 1
+                        uint32_t m = __match_any_sync(0xFFFFFFFFu, act ? h : 0xFFFF0000u + lane);
+#elif LZB_PRE_MATCH == 2
+                        // five ballots split the lanes into classes by the low bits of the bucket index; the few lanes of a
+                        // class are then compared one by one (shuffle) -- VOTE is the scarce pipe here
+                        uint32_t mc = __ballot_sync(0xFFFFFFFFu, act);
+#pragma unroll
+                        for (int bit = 0; bit < 5; bit++) {
+                            const bool on = (h >> bit) & 1u;
+                            const uint32_t bl = __ballot_sync(0xFFFFFFFFu, on);
+                            mc &= on ? bl : ~bl;
+                        }
+                        uint32_t m = act ? (1u << lane) : 0u;
+                        uint32_t rest = mc & ~(1u << lane);
+                        while (__any_sync(0xFFFFFFFFu, rest != 0)) {
+                            const int j = rest ? __ffs(rest) - 1 : (int)lane;
+                            const uint32_t hj = __shfl_sync(0xFFFFFFFFu, h, j);
+                            if (rest && hj == h) m |= 1u << j;
+                            rest &= rest - 1;
+                        }
+#else
                         uint32_t m = __ballot_sync(0xFFFFFFFFu, act);
 #pragma unroll
                         for (int bit = 0; bit < (int)kHashBits; bit++) {
@@ -827,21 +916,25 @@ k_enc_find(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ sr
                             const uint32_t bl = __ballot_sync(0xFFFFFFFFu, on);
                             m &= on ? bl : ~bl;
                         }
+#endif
                         const uint32_t lower = m & lanemask_lt();
                         const uint32_t newest = (m >> lane) == 1u ? 0x4000u : 0u;
                         const uint32_t info = lower ? (0x8000u | newest | ((uint32_t)(__ffs(m) - 1) << 5) | (31 - __clz(lower))) : (newest | h);
                         if (act) sts_u16(s_prev + p * 2, info);
                     }
                     __syncwarp();
-                    __threadfence_block();
+                    fence_cta();
                     if (lane == 0) *reinterpret_cast<volatile uint8_t *>(&ctrl->pre_done[t]) = 1;
+#ifdef LZB_FIND_DEBUG
+                    dbg_pre = clock64() - dbg_t0;
+#endif
                     continue;
                 }
                 // ---- find_match for every position of a unit, behind the chain ----
                 const uint32_t p0 = (t - n_units) * kFindUnit;
                 const uint32_t p1 = p0 + kFindUnit < end ? p0 + kFindUnit : end;
-                while (*reinterpret_cast<volatile uint32_t *>(&ctrl->chain_done) < p1) __nanosleep(100);
-                __threadfence_block();
+                while (*reinterpret_cast<volatile uint32_t *>(&ctrl->chain_done) < p1) __nanosleep(LZB_POLL_NS);
+                fence_cta();
                 for (uint32_t b0 = p0; b0 < p1; b0 += 32) {
                     const uint32_t p = b0 + lane;
                     const bool act = p < p1;
@@ -903,7 +996,7 @@ k_enc_find(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ sr
                         }
                         if (lane == (uint32_t)j) ls[k0 & 3] = ej - pj;  // progress even if another warp reuses the slot
                         __syncwarp();
-                        __threadfence_block();
+                        fence_cta();
                     }
                     uint32_t word = 0;
                     if (act && best_len) {
@@ -925,11 +1018,30 @@ k_enc_find(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ sr
                         bw = bw < blim ? bw : blim;
                         word = (p - best_c) | ((best_len < kWordLenSat ? best_len : kWordLenSat) << 18) | (bw << 28);
                     }
+                    // positions without a candidate carry the distance to the next position of this 32-group that has one
+                    // (distance field 0, length field = skip), so the front end steps over empty runs in one go
+                    {
+                        const uint32_t nz = __ballot_sync(0xFFFFFFFFu, word != 0);
+                        if (word == 0) {
+                            const uint32_t next = lane == 31 ? 0u : nz & (0xFFFFFFFEu << lane);
+                            word = (next ? (uint32_t)__ffs(next) - 1u - lane : 32u - lane) << 18;
+                        }
+                    }
                     if (act) wout[p] = word;
                 }
             }
         }
+#ifdef LZB_FIND_DEBUG
+        const long long dbg_mine = clock64() - dbg_t0;
+#ifdef LZB_FIND_PHASED
+        if (warp != 0 && !dbg_passed) { __syncthreads(); __syncthreads(); }
+        if (blockIdx.x == 3 && lane == 0 && warp == 1) printf("  phased: pre_end %lld find_start %lld\n", dbg_pre, dbg_find0);
+#endif
         __syncthreads();
+        if (blockIdx.x == 3 && lane == 0 && (warp < 3 || warp == 31)) printf("stream %u warp %u: chain %lld lastpre %lld mywork_end %lld all_end %lld\n", si, warp, dbg_chain, dbg_pre, dbg_mine, clock64() - dbg_t0);
+#else
+        __syncthreads();
+#endif
     }
 }
 
@@ -1008,13 +1120,23 @@ __device__ __forceinline__ void tsink_push_match(TSink &s, const TEnv &env, uint
     while (!tsink_buffer_push(s, lit_len, match_len, d)) tsink_emit_block(s, env);
 }
 
+#ifndef LZB_REPLAY_STRIDE
+#define LZB_REPLAY_STRIDE 1   // measured 1/2/4/8/16: 11.1 / 11.4 / 12.4 / 15.4 / 23.8 ms -- fewer streams per warp do not help
+#endif
 constexpr int kReplayThreads = 32;
-constexpr uint32_t kRingWords = 64, kRingStride = kRingWords * 4 + 16;  // per-lane ring of words (stride skews the banks)
+constexpr int kReplayStride = LZB_REPLAY_STRIDE;
+#ifndef LZB_RING_WORDS
+#define LZB_RING_WORDS 64
+#endif
+constexpr uint32_t kRingWords = LZB_RING_WORDS, kRingStride = kRingWords * 4 + 16;  // per-lane ring of words (stride skews the banks)
 __global__ void __launch_bounds__(kReplayThreads)
 k_enc_replay(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ src_off, const uint64_t *__restrict__ src_len, size_t n_streams,
              EncStream *streams, const StreamCounts *__restrict__ bases, const uint32_t *__restrict__ words, uint2 *pack_scratch, uint32_t *block_ids,
              EncBlock *blocks, uint32_t *block_counter) {
-    const size_t si = (size_t)blockIdx.x * kReplayThreads + threadIdx.x;
+    // Only every kReplayStride-th lane works: the lanes of a warp run different streams, so a warp executes the union of
+    // their control paths; fewer streams per warp (and more warps) shorten that serial instruction stream.
+    if (threadIdx.x % kReplayStride != 0) return;
+    const size_t si = ((size_t)blockIdx.x * kReplayThreads + threadIdx.x) / kReplayStride;
     if (si >= n_streams || !streams[si].fast) return;
     const uint8_t *src = src_base + src_off[si];
     const uint32_t len = (uint32_t)src_len[si], end = len - 3;
@@ -1030,8 +1152,8 @@ k_enc_replay(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ 
     // Every lane walks its own stream, so a plain load per position costs a memory round trip per step of this serial
     // loop (and prefetch.global.L1 does not shorten it).  Each lane therefore owns a 64-word ring in shared memory that
     // cp.async keeps filled 16 chunks ahead of its cursor; the cursor reads four words at a time.
-    __shared__ __align__(16) uint8_t rings[kReplayThreads * kRingStride];
-    const uint32_t ring = (uint32_t)__cvta_generic_to_shared(rings) + threadIdx.x * kRingStride;
+    __shared__ __align__(16) uint8_t rings[kReplayThreads / kReplayStride * kRingStride];
+    const uint32_t ring = (uint32_t)__cvta_generic_to_shared(rings) + threadIdx.x / kReplayStride * kRingStride;
     const uint32_t w_limit = (end + 3u) & ~3u;  // chunks at or beyond this word index are never needed
     uint32_t wbase = 0xFFFFFFFFu, fetched = 0;
     uint4 wq = make_uint4(0, 0, 0, 0);
@@ -1049,13 +1171,13 @@ k_enc_replay(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ 
                 fetched += 4;
             }
             // the chunk at wbase is the (fetched - wbase) / 4-th newest group; with a full window that is the 16th
-            if (fetched == wbase + kRingWords) asm volatile("cp.async.wait_group 14;" ::: "memory");
+            if (fetched == wbase + kRingWords) asm volatile("cp.async.wait_group %0;" ::"n"(kRingWords / 4 - 2) : "memory");
             else asm volatile("cp.async.wait_group 0;" ::: "memory");
             asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(wq.x), "=r"(wq.y), "=r"(wq.z), "=r"(wq.w) : "r"(ring + (wbase & (kRingWords - 1)) * 4) : "memory");
         }
         const uint32_t k4 = cur & 3u;
         const uint32_t w = k4 == 0 ? wq.x : (k4 == 1 ? wq.y : (k4 == 2 ? wq.z : wq.w));
-        if (w == 0) { cur++; continue; }  // find_match came back empty (:203-209)
+        if ((w & 0x3FFFFu) == 0) { cur += (w >> 18) & 0x3FFu; continue; }  // find_match came back empty (:203-209) for this many positions
         Match inc;
         inc.idx = cur;
         inc.match_idx = cur - (w & 0x3FFFFu);
@@ -1523,7 +1645,7 @@ int encode_batch_device_impl(lzfse_b200_encoder *e, const uint8_t *src, const ui
     }
     e->timer.mark(s);  // find
     if (n_fast) {
-        k_enc_replay<<<(unsigned)((n + kReplayThreads - 1) / kReplayThreads), kReplayThreads, 0, s>>>(
+        k_enc_replay<<<(unsigned)((n * kReplayStride + kReplayThreads - 1) / kReplayThreads), kReplayThreads, 0, s>>>(
             src, src_off, src_len, n, e->streams.as<EncStream>(), e->counts.as<StreamCounts>(), e->words.as<uint32_t>(), e->packs.as<uint2>(),
             e->block_ids.as<uint32_t>(), e->blocks.as<EncBlock>(), ctr);
         e->launches += 1;

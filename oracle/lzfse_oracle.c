@@ -7,6 +7,7 @@
  */
 #include "lzfse_oracle.h"
 
+#include <immintrin.h>
 #include <pthread.h>
 #include <stdatomic.h>
 #include <stdlib.h>
@@ -82,10 +83,11 @@ static void init_tables_once(void) {
 static void init_tables(void) { pthread_once(&g_once, init_tables_once); }
 
 static inline uint32_t d_sym_from_value(uint32_t v) {
-    /* Largest symbol with base <= v: bases grow by 4 symbols per power of two. */
-    uint32_t lo = 0, hi = D_SYMBOLS - 1;
-    while (lo < hi) { uint32_t mid = (lo + hi + 1) >> 1; if (D_BASE_VALUE[mid] <= v) lo = mid; else hi = mid - 1; }
-    return lo;
+    /* Largest symbol with base <= v (fse/constants.rs:305-321 via d_index): four symbols per power of two,
+     * base(4e + r) = ((4 + r) << e) - 4, so e = floor(log2(v + 4)) - 2 and r = ((v + 4) >> e) - 4. */
+    if (v < 4) return v;
+    const uint32_t e = 29u - (uint32_t)__builtin_clz(v + 4);
+    return 4 * e + (((v + 4) >> e) - 4);
 }
 
 static inline uint16_t le16(const uint8_t *p) { return (uint16_t)(p[0] | (p[1] << 8)); }
@@ -311,6 +313,11 @@ static inline int out_match(dctx *d, uint32_t len, uint32_t distance) {
     if (len > d->dst_cap - d->out) return ORC_BUFFER_OVERFLOW;
     uint8_t *q = d->dst + d->out; const uint8_t *s = q - distance;
     uint32_t i = 0;
+    if (distance >= 16 && (size_t)len + 16 <= d->dst_cap - d->out) { /* 16-byte strides, over-copying into the slack like lz/writer.rs:156-177 */
+        for (; i < len; i += 16) memcpy(q + i, s + i, 16);
+        d->out += len;
+        return ORC_OK;
+    }
     if (distance >= 8) { /* 8-byte strides never read a byte this copy has not written yet (lz/object.rs:27-58) */
         for (; i + 8 <= len; i += 8) memcpy(q + i, s + i, 8);
     }
@@ -593,7 +600,9 @@ typedef struct { uint64_t accum; int64_t accum_bits; obuf *o; } bitwriter;
 static inline void bw_push(bitwriter *w, uint64_t bits, uint32_t n) { w->accum |= bits << w->accum_bits; w->accum_bits += n; }
 static inline void bw_flush(bitwriter *w) {
     size_t n_bytes = (size_t)w->accum_bits / 8; uint8_t b[8]; st64(b, w->accum);
-    ob_put(w->o, b, n_bytes);
+    obuf *o = w->o;
+    if (o->pos + 8 <= o->cap) { memcpy(o->p + o->pos, b, 8); o->pos += n_bytes; } /* whole word, the unused tail is overwritten by what follows */
+    else ob_put(o, b, n_bytes);
     w->accum = n_bytes == 8 ? 0 : w->accum >> (n_bytes * 8); w->accum_bits -= (int64_t)n_bytes * 8;
 }
 static inline uint32_t bw_finalize(bitwriter *w) {
@@ -875,11 +884,18 @@ static void be_finalize(backend *b) {
 }
 
 /* encode/history.rs:144-154, 101-131 */
-typedef struct { uint32_t val, idx; } hitem;
-typedef struct { hitem q[HASH_WIDTH]; } history;
+/* Item {val, idx} x 4, newest first; kept as two 4-lane vectors (the layout is private to the table) so that push is two
+ * shift-inserts. */
+typedef struct { uint32_t idx[HASH_WIDTH], val[HASH_WIDTH]; } __attribute__((aligned(32))) history;
 struct orc_encoder { history table[1 << HASH_BITS]; fse_backend fse; };
 
-orc_encoder *orc_encoder_create(void) { init_tables(); return (orc_encoder *)calloc(1, sizeof(orc_encoder)); }
+orc_encoder *orc_encoder_create(void) {
+    init_tables();
+    const size_t sz = (sizeof(orc_encoder) + 63) & ~(size_t)63;
+    orc_encoder *e = (orc_encoder *)aligned_alloc(64, sz); /* the table's buckets are 32-byte vectors */
+    if (e) memset(e, 0, sz);
+    return e;
+}
 void orc_encoder_destroy(orc_encoder *e) { free(e); }
 
 typedef struct { uint32_t idx, match_idx, match_len; } match_t; /* encode/match_object.rs:4-8 */
@@ -917,23 +933,26 @@ static inline uint32_t fe_hash(uint32_t val, int vn) { /* fse/object.rs:38-43, v
     return (val * 0x9E3779B1u) >> (32 - HASH_BITS);
 }
 /* encode/history.rs:24-31 */
-static inline history fe_push(frontend *f, uint32_t val, uint32_t idx) {
-    history *q = &f->table[fe_hash(val, f->vn)], copy = *q;
-    q->q[3] = q->q[2]; q->q[2] = q->q[1]; q->q[1] = q->q[0]; q->q[0].val = val; q->q[0].idx = idx;
+static inline __attribute__((always_inline)) history fe_push(frontend *f, uint32_t val, uint32_t idx, const int vn) {
+    history *q = &f->table[fe_hash(val, vn)], copy;
+    const __m128i qi = _mm_load_si128((const __m128i *)q->idx), qv = _mm_load_si128((const __m128i *)q->val);
+    _mm_store_si128((__m128i *)copy.idx, qi); _mm_store_si128((__m128i *)copy.val, qv);
+    _mm_store_si128((__m128i *)q->idx, _mm_insert_epi32(_mm_slli_si128(qi, 4), (int)idx, 0));
+    _mm_store_si128((__m128i *)q->val, _mm_insert_epi32(_mm_slli_si128(qv, 4), (int)val, 0));
     return copy;
 }
 /* encode/frontend_bytes.rs:214-268 */
-static match_t fe_find_match(frontend *f, const history *queue, uint32_t val, uint32_t idx) {
+static inline __attribute__((always_inline)) match_t fe_find_match(frontend *f, const history *queue, uint32_t val, uint32_t idx, const int vn) {
     match_t m = {0, 0, 0};
-    uint32_t max_d = f->vn ? VN_MAX_D : MAX_D_VALUE;
+    uint32_t max_d = vn ? VN_MAX_D : MAX_D_VALUE;
     for (int i = 0; i < HASH_WIDTH; i++) {
-        uint32_t distance = idx - queue->q[i].idx;
+        uint32_t distance = idx - queue->idx[i];
         if (distance > max_d) break;
-        uint32_t x = val ^ queue->q[i].val, len;
-        if (x == 0) len = match_inc(f->src, idx, queue->q[i].idx, 4, f->len - idx);
-        else if (f->vn && (x & 0x00FFFFFFu) == 0) len = 3;
+        uint32_t x = val ^ queue->val[i], len;
+        if (x == 0) len = match_inc(f->src, idx, queue->idx[i], 4, f->len - idx);
+        else if (vn && (x & 0x00FFFFFFu) == 0) len = 3;
         else len = 0;
-        if (len > m.match_len) { m.match_len = len; m.match_idx = queue->q[i].idx; }
+        if (len > m.match_len) { m.match_len = len; m.match_idx = queue->idx[i]; }
     }
     if (m.match_len != 0) {
         m.idx = idx;
@@ -962,17 +981,17 @@ static void fe_push_match(frontend *f, match_t m) {
 /* encode/frontend_bytes.rs:121-211,271-284,305-344 (finalize = match_blocks + flush_pending +
  * flush_literals + backend.finalize).  Inputs above BLOCK_GUIDE (2 GiB, :160-182,348-375) are out
  * of scope for the batched path and rejected by the caller. */
-static void fe_finalize(frontend *f) {
+static inline __attribute__((always_inline)) void fe_finalize_k(frontend *f, const int vn) {
     uint32_t end = (uint32_t)f->len - 3, index = 0;
     for (;;) {
         uint32_t val = le32(f->src + index);
-        history queue = fe_push(f, val, index);
-        match_t incoming = fe_find_match(f, &queue, val, index), sel;
+        history queue = fe_push(f, val, index, vn);
+        match_t incoming = fe_find_match(f, &queue, val, index, vn), sel;
         if (match_select(&f->pending, incoming, &sel)) {
             fe_push_match(f, sel);
             if (f->literal_index >= end) break;
             index++;
-            while (index < f->literal_index) { fe_push(f, le32(f->src + index), index); index++; } /* sync_history */
+            while (index < f->literal_index) { fe_push(f, le32(f->src + index), index, vn); index++; } /* sync_history */
             if (index >= end) break;
         } else {
             index++;
@@ -986,9 +1005,12 @@ static void fe_finalize(frontend *f) {
     }
     be_finalize(f->be);
 }
+/* the 3-byte-key (LZVN) and 4-byte-key (FSE) front ends as two specialised copies of the loop */
+static void fe_finalize(frontend *f) { if (f->vn) fe_finalize_k(f, 1); else fe_finalize_k(f, 0); }
 static void fe_init(frontend *f, orc_encoder *e, const uint8_t *src, size_t len, int vn, backend *be) {
-    for (size_t i = 0; i < (1u << HASH_BITS); i++) /* encode/history.rs:72-83: idx = Q0 - Q1 */
-        for (int j = 0; j < HASH_WIDTH; j++) { e->table[i].q[j].val = 0; e->table[i].q[j].idx = 0u - Q1; }
+    const __m256i reset = _mm256_setr_epi32((int)(0u - Q1), (int)(0u - Q1), (int)(0u - Q1), (int)(0u - Q1), 0, 0, 0, 0);
+    for (size_t i = 0; i < (1u << HASH_BITS); i++) /* encode/history.rs:72-83: idx = Q0 - Q1, val = 0 */
+        _mm256_store_si256((__m256i *)&e->table[i], reset);
     f->table = e->table; f->src = src; f->len = len; f->vn = vn; f->literal_index = 0; f->be = be;
     f->pending.idx = f->pending.match_idx = f->pending.match_len = 0;
 }
