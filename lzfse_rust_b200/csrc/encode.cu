@@ -679,7 +679,7 @@ k_enc_parse(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ s
 constexpr int kFindThreads = 1024;
 constexpr uint32_t kFindUnit = 256;       // positions a find warp takes at a time
 constexpr uint32_t kNone = 0xFFFFu;       // chain end (positions are < kFastMaxLen - 3)
-constexpr uint32_t kLaneCap = 1024;       // per-lane forward extension stops here; longer ones are finished warp-wide
+constexpr uint32_t kLaneCap = 64;         // per-lane forward extension stops here; longer ones are finished warp-wide (or inherited from a run already measured)
 constexpr uint32_t kWordLenSat = 1023, kWordBwSat = 15;
 constexpr uint32_t kRunSlots = 64;        // (distance, start, end) of long runs already measured, per stream
 constexpr uint32_t kFsSrc = 16, kFsSrcBytes = kFastMaxLen + 48;  // 16 bytes below the stream (backward reads), up to 15 of alignment, over-read slack behind
@@ -965,10 +965,10 @@ k_enc_find(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ sr
                             }
                         }
                     }
-                    // Two or more candidates beyond the per-lane cap: their exact lengths decide (strictly longest, newest
-                    // first).  Runs are measured once per (distance, start) with the whole warp and remembered: inside a
-                    // run every later position inherits end - p, which keeps periodic data linear.
-                    bool need = n_sat >= 2;
+                    // Candidates beyond the per-lane cap need their exact lengths (strictly longest wins, newest first, and the
+                    // word stores up to 1023).  Runs are measured once per (distance, start) with the whole warp and remembered:
+                    // inside a run every later position inherits end - p, which keeps periodic data linear.
+                    bool need = n_sat >= 1;
                     while (__any_sync(0xFFFFFFFFu, need)) {
                         if (need) {
                             bool open = false;
@@ -1000,7 +1000,7 @@ k_enc_find(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ sr
                     }
                     uint32_t word = 0;
                     if (act && best_len) {
-                        if (n_sat >= 2) {  // candidates are in newest-first order: strictly longer wins
+                        if (n_sat >= 1) {  // candidates are in newest-first order: strictly longer wins (any capped one beats the others)
                             uint32_t bl = 0;
                             for (uint32_t k = 0; k < n_sat; k++)
                                 if (ls[k] > bl) { bl = ls[k]; best_c = cs[k]; }
@@ -1186,7 +1186,13 @@ k_enc_replay(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ 
         inc.match_len = (w >> 18) & 0x3FFu;
         if (inc.match_len == kWordLenSat) {  // the word's length field is saturated: finish the extension here
             const uint32_t maxl = len - cur;
+            while (inc.match_len + 8 <= maxl) {
+                const uint64_t y = ld8u(src + cur + inc.match_len) ^ ld8u(src + inc.match_idx + inc.match_len);
+                if (y) { inc.match_len += (__ffsll((long long)y) - 1) >> 3; goto fwd_done; }
+                inc.match_len += 8;
+            }
             while (inc.match_len < maxl && src[cur + inc.match_len] == src[inc.match_idx + inc.match_len]) inc.match_len++;
+        fwd_done:;
         }
         {   // match_dec (:261-268)
             const uint32_t lit = cur - literal_index;

@@ -165,3 +165,61 @@ def test_patchwork_frames_equal(enc, dec):
         assert f == oenc.encode(d)[1], (i, len(d))
     outs, dst = dec.decode_batch(list(frames))
     assert (dst == 0).all() and list(outs) == datas
+
+
+def _fast_path_cases():
+    """Inputs for the shared-memory parse (k_enc_find / k_enc_replay: bvx2 streams of 4097..65536 bytes): the length
+    limits on both sides, runs longer than the per-lane extension cap (1024) and than one pack's M (2359), several
+    candidates beyond the cap at once (periodic data: exact lengths decide), literal runs beyond 315 and beyond a
+    block's 40 000, and a duplicate that sends the backward extension past what a word stores (15)."""
+    rnd = tk.rng_gen_vec(7, 70000)
+    txt = tk.synth_text(0xFA57, 65536)
+    yield "len4097", txt[:4097]
+    yield "len4100", rnd[:4100]
+    yield "len65535", txt[:65535]
+    yield "len65536_text", txt
+    yield "len65536_noise", rnd[:65536]
+    yield "len65537_slow_path", (txt + b"x")[:65537]
+    yield "zeros65536", bytes(65536)
+    for p in (1, 2, 3, 4, 5, 7, 16, 64, 333, 1000, 5000):
+        yield "period%d" % p, (rnd[:p] * (65536 // p + 1))[:65536]
+    yield "long_dup", txt[:20000] + txt[:20000] + txt[:20000]
+    yield "dup_after_noise", rnd[:30000] + txt[1000:9000] + rnd[30000:40000] + txt[1000:9000]
+    yield "two_periods", (rnd[:3] * 4000)[:9000] + (rnd[10:17] * 4000)[:30000] + (rnd[:3] * 4000)[:9000]
+    yield "noise_then_zeros", rnd[:41000] + bytes(24000)
+    yield "back_ext", rnd[:500] + txt[:3000] + rnd[500:520] + txt[:3000] + rnd[600:5000]
+
+
+def test_fast_parse_cases(enc, dec):
+    names, datas = zip(*_fast_path_cases())
+    frames, status = enc.encode_batch(list(datas))
+    oenc = ob.Encoder()
+    for name, data, frame, st in zip(names, datas, frames, status):
+        ost, oframe = oenc.encode(data)
+        assert st == 0 and ost == 0, name
+        assert frame == oframe, (name, len(frame), len(oframe))
+    outs, dstat = dec.decode_batch(list(frames))
+    assert (dstat == 0).all() and list(outs) == list(datas)
+
+
+def test_fast_and_general_parse_agree(dec):
+    """LZB_ENC_FAST=0 sends every stream through the general kernel (k_enc_parse): same frames."""
+    import lzfse_rust_b200 as L
+
+    datas = [d for _, d in _fast_path_cases()] + [tk.synth_text(0x5EED0000 + i, 65536) for i in range(40)]
+    old = os.environ.get("LZB_ENC_FAST")
+    try:
+        os.environ["LZB_ENC_FAST"] = "0"
+        e0 = L.LzfseEncoder(0)
+        f0, s0 = e0.encode_batch(datas)
+        e0.close()
+        os.environ["LZB_ENC_FAST"] = "1"
+        e1 = L.LzfseEncoder(0)
+        f1, s1 = e1.encode_batch(datas)
+        e1.close()
+    finally:
+        if old is None:
+            os.environ.pop("LZB_ENC_FAST", None)
+        else:
+            os.environ["LZB_ENC_FAST"] = old
+    assert (s0 == 0).all() and (s1 == 0).all() and list(f0) == list(f1)
