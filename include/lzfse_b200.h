@@ -27,8 +27,17 @@
  * returns LZFSE_B200_NO_DEVICE (create) or LZFSE_B200_CUDA_ERROR.
  *
  * Threading: a handle is single-caller (`&mut self` in the reference).  Distinct handles may be
- * used concurrently.  *_device calls enqueue on the given CUDA stream and synchronise it once
- * internally (to size scratch memory); results are complete when they return.
+ * used concurrently.  *_batch_device calls enqueue on the given CUDA stream, synchronise it once
+ * internally after the header scan (scratch sizes depend on what the headers announce) and once at
+ * the end; results are complete when they return.  The *_batch_device_async variants skip the
+ * second wait: they return as soon as every kernel is enqueued (the header scan, a few tens of
+ * microseconds of device time, is the only thing they wait for); out_len / status / dst are valid
+ * once `cuda_stream` reaches that point -- lzfse_b200_{decoder,encoder}_sync waits for it, or the
+ * caller orders its own work on the same stream.  One asynchronous call may be in flight per handle
+ * (its scratch is the handle's); use one handle per stream to overlap batches.
+ *
+ * `cuda_stream` is a cudaStream_t.  NULL is CUDA's legacy default stream (stream 0), with its usual
+ * ordering against other blocking streams -- e.g. what torch.cuda.current_stream() is by default.
  */
 #ifndef LZFSE_B200_H
 #define LZFSE_B200_H
@@ -97,7 +106,7 @@ int lzfse_b200_decode_bytes(lzfse_b200_decoder *d, const uint8_t *src, size_t sr
  * dst_base[dst_off[i] ..), at most dst_cap[i] bytes; out_len[i] and status[i] receive the result.
  * Output regions of different streams must not overlap.  A failing stream does not disturb others;
  * its output region's contents are unspecified (as in the reference, src/lz/writer.rs:18,28).
- * _device: every pointer is device memory on the handle's GPU; `cuda_stream` is a cudaStream_t (or NULL).
+ * _device: every pointer is device memory on the handle's GPU; `cuda_stream` is a cudaStream_t (NULL = stream 0).
  * _host:   every pointer is host memory; H2D/D2H copies happen inside the call.
  * Return value: call-level status (LZFSE_B200_OK even if individual streams failed).
  * Limit (no reference counterpart): a frame that decodes to more than 0xF0000000 bytes fails with
@@ -109,6 +118,12 @@ int lzfse_b200_decode_batch_device(lzfse_b200_decoder *d, const uint8_t *src_bas
 int lzfse_b200_decode_batch_host(lzfse_b200_decoder *d, const uint8_t *src_base, const uint64_t *src_off,
                                  const uint64_t *src_len, uint8_t *dst_base, const uint64_t *dst_off,
                                  const uint64_t *dst_cap, uint64_t *out_len, int32_t *status, size_t n);
+/* Asynchronous form of _device (see "Threading" above) and the wait that completes it. */
+int lzfse_b200_decode_batch_device_async(lzfse_b200_decoder *d, const uint8_t *src_base, const uint64_t *src_off,
+                                         const uint64_t *src_len, uint8_t *dst_base, const uint64_t *dst_off,
+                                         const uint64_t *dst_cap, uint64_t *out_len, int32_t *status, size_t n,
+                                         void *cuda_stream);
+int lzfse_b200_decoder_sync(lzfse_b200_decoder *d);
 
 /* Header-only walk: raw_len[i] = sum of the blocks' n_raw_bytes, n_blocks[i] = block count.
  * (Unlike the reference's dead-code probe, LZVN blocks advance by n_payload_bytes; cf. src/vn/ops.rs:13.) */
@@ -148,6 +163,11 @@ int lzfse_b200_encode_batch_device(lzfse_b200_encoder *e, const uint8_t *src_bas
 int lzfse_b200_encode_batch_host(lzfse_b200_encoder *e, const uint8_t *src_base, const uint64_t *src_off,
                                  const uint64_t *src_len, uint8_t *dst_base, const uint64_t *dst_off,
                                  const uint64_t *dst_cap, uint64_t *out_len, int32_t *status, size_t n);
+int lzfse_b200_encode_batch_device_async(lzfse_b200_encoder *e, const uint8_t *src_base, const uint64_t *src_off,
+                                         const uint64_t *src_len, uint8_t *dst_base, const uint64_t *dst_off,
+                                         const uint64_t *dst_cap, uint64_t *out_len, int32_t *status, size_t n,
+                                         void *cuda_stream);
+int lzfse_b200_encoder_sync(lzfse_b200_encoder *e);
 uint64_t lzfse_b200_encoder_last_launches(const lzfse_b200_encoder *e);
 void lzfse_b200_encoder_set_timing(lzfse_b200_encoder *e, int enabled);
 int lzfse_b200_encoder_last_stage_ms(const lzfse_b200_encoder *e, float *stage_ms, int cap);

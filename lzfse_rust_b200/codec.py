@@ -102,6 +102,10 @@ class _Handle:
         self._check(fn(self._h, _ptr(src), _ptr(src_off), _ptr(src_len), _ptr(dst), _ptr(dst_off), _ptr(dst_cap), _ptr(out_len), _ptr(status), n))
         return out_len, status
 
+    def sync(self):
+        """Waits for the last `wait=False` batch call on this object (lzfse_b200_{decoder,encoder}_sync)."""
+        self._check(getattr(self._lib, "lzfse_b200_%s_sync" % self._kind)(self._h))
+
     def _batch_device(self, fn, src, src_off, src_len, dst, dst_off, dst_cap, stream=None):
         import torch
 
@@ -127,7 +131,7 @@ class LzfseDecoder(_Handle):
         """Decode the frame `src` and append it to the bytearray `dst`; returns the bytes appended."""
         src = _as_u8(src)
         raw, _, st = self.probe_batch(src, [0], [len(src)])
-        cap = int(raw[0]) if st[0] == 0 else 0
+        cap = min(int(raw[0]), len(src) * self.MAX_RATIO + self.MAX_SLACK) if st[0] == 0 else 0
         out = np.empty(max(cap, 1), dtype=np.uint8)
         n = C.c_size_t(0)
         rc = self._lib.lzfse_b200_decode_bytes(self._h, _ptr(src), len(src), _ptr(out), cap, C.byref(n))
@@ -149,6 +153,12 @@ class LzfseDecoder(_Handle):
         """Batched decode on host buffers (numpy uint8 arrays).  Returns (out_len[n], status[n])."""
         return self._batch_host(self._lib.lzfse_b200_decode_batch_host, _as_u8(src), src_off, src_len, dst, dst_off, dst_cap)
 
+    # The most an LZFSE frame can legitimately expand: 10 000 matches of 2 359 bytes from a block of a few hundred bytes.
+    # decode_batch / decode_bytes size their buffers from the frames' own (untrusted) headers, so what a frame may
+    # announce is capped at MAX_RATIO x its size + MAX_SLACK; a frame that really produces more fails with
+    # BufferOverflow on its own, the rest of the batch is untouched.  Pass `caps` to lift the cap.
+    MAX_RATIO, MAX_SLACK = 65536, 1 << 16
+
     def decode_batch(self, frames, caps=None):
         """Decode a list of frames; returns (list of bytes-or-None, status array)."""
         n = len(frames)
@@ -157,7 +167,7 @@ class LzfseDecoder(_Handle):
         src = np.frombuffer(b"".join(bytes(f) for f in frames) or b"\0", dtype=np.uint8)
         if caps is None:
             raw, _, _ = self.probe_batch(src, offs, lens)
-            caps = np.minimum(raw, np.uint64(1 << 32))
+            caps = np.minimum(raw, lens * np.uint64(self.MAX_RATIO) + np.uint64(self.MAX_SLACK))
         caps = _u64(caps)
         doff = np.concatenate([[0], np.cumsum(caps)[:-1]]).astype(np.uint64) if n else np.zeros(0, np.uint64)
         dst = np.empty(max(int(caps.sum()), 1), dtype=np.uint8)
@@ -165,9 +175,12 @@ class LzfseDecoder(_Handle):
         outs = [dst[int(doff[i]) : int(doff[i]) + int(out_len[i])].tobytes() if status[i] == 0 else None for i in range(n)]
         return outs, status
 
-    def decode_batch_device(self, src, src_off, src_len, dst, dst_off, dst_cap, stream=None):
-        """Batched decode on CUDA tensors (uint8 data, int64 descriptors).  Returns (out_len, status) tensors."""
-        return self._batch_device(self._lib.lzfse_b200_decode_batch_device, src, src_off, src_len, dst, dst_off, dst_cap, stream)
+    def decode_batch_device(self, src, src_off, src_len, dst, dst_off, dst_cap, stream=None, wait=True):
+        """Batched decode on CUDA tensors (uint8 data, int64 descriptors).  Returns (out_len, status) tensors.  The work
+        is enqueued on `stream` (default: torch's current stream).  wait=False returns once everything is enqueued; the
+        results are valid after sync() or for work ordered behind it on the same stream."""
+        fn = self._lib.lzfse_b200_decode_batch_device if wait else self._lib.lzfse_b200_decode_batch_device_async
+        return self._batch_device(fn, src, src_off, src_len, dst, dst_off, dst_cap, stream)
 
 
 class LzfseEncoder(_Handle):
@@ -207,8 +220,9 @@ class LzfseEncoder(_Handle):
         outs = [dst[int(doff[i]) : int(doff[i]) + int(out_len[i])].tobytes() if status[i] == 0 else None for i in range(n)]
         return outs, status
 
-    def encode_batch_device(self, src, src_off, src_len, dst, dst_off, dst_cap, stream=None):
-        return self._batch_device(self._lib.lzfse_b200_encode_batch_device, src, src_off, src_len, dst, dst_off, dst_cap, stream)
+    def encode_batch_device(self, src, src_off, src_len, dst, dst_off, dst_cap, stream=None, wait=True):
+        fn = self._lib.lzfse_b200_encode_batch_device if wait else self._lib.lzfse_b200_encode_batch_device_async
+        return self._batch_device(fn, src, src_off, src_len, dst, dst_off, dst_cap, stream)
 
 
 def decode_bytes(src, dst, device=0):

@@ -15,23 +15,28 @@
 
 namespace lzb {
 // decode.cu
+uint32_t long_stream_threshold(size_t, int);
 void launch_scan_count(const uint8_t *, const uint64_t *, const uint64_t *, const uint64_t *, size_t, StreamCounts *, uint32_t *, uint64_t *,
-                       uint32_t *, StreamCounts *, cudaStream_t);
+                       uint32_t *, StreamCounts *, uint32_t *, uint32_t, cudaStream_t);
 void launch_scan_fill(const uint8_t *, const uint64_t *, const uint64_t *, const uint64_t *, const uint64_t *, size_t, StreamCounts *, BlockDesc *, FseDesc *,
-                      uint32_t *, cudaStream_t);
+                      uint32_t *, uint64_t *, uint32_t *, uint32_t, uint64_t *, uint32_t *, uint32_t *, cudaStream_t);
 int setup_decode_kernels();
 void launch_fse_stages(const uint8_t *, const uint64_t *, const uint64_t *, const uint64_t *, const uint64_t *, const BlockDesc *, FseDesc *, uint32_t, uint8_t *,
-                       LmdRec *, uint32_t *, uint32_t *, int, cudaStream_t, cudaEvent_t);
+                       LmdRec *, uint32_t *, uint32_t *, uint32_t *, int, cudaStream_t, cudaEvent_t);
 void launch_expand(const uint8_t *, const uint64_t *, const uint64_t *, uint8_t *, const uint64_t *, const uint64_t *, const StreamCounts *, const BlockDesc *,
-                   const FseDesc *, const uint8_t *, const LmdRec *, uint32_t *, size_t, uint32_t *, int, cudaStream_t);
+                   const FseDesc *, const uint8_t *, const LmdRec *, uint32_t *, size_t, uint32_t *, const uint64_t *, int, cudaStream_t);
 void launch_expand_vn(const uint8_t *, const uint64_t *, const uint64_t *, uint8_t *, const uint64_t *, const uint64_t *, const StreamCounts *,
                       const BlockDesc *, uint32_t *, size_t, uint32_t *, int, cudaStream_t);
 void launch_finish(const uint32_t *, const uint64_t *, uint64_t *, int32_t *, size_t, cudaStream_t);
 // expand.cu
 int setup_expand_kernel();
 void launch_expand_cta(const uint8_t *, const uint64_t *, const uint64_t *, uint8_t *, const uint64_t *, const uint64_t *, const StreamCounts *,
-                       const BlockDesc *, const FseDesc *, const uint8_t *, const LmdRec *, const uint64_t *, uint32_t *, size_t, uint32_t *, int,
-                       cudaStream_t);
+                       const BlockDesc *, const FseDesc *, const uint8_t *, const LmdRec *, const uint64_t *, uint32_t *, size_t, uint32_t *,
+                       const uint64_t *, int, cudaStream_t);
+// expand_long.cu
+void launch_expand_long(const uint8_t *, const uint64_t *, const uint64_t *, uint8_t *, const uint64_t *, const uint64_t *, const StreamCounts *,
+                        const BlockDesc *, const FseDesc *, const uint8_t *, const LmdRec *, const uint32_t *, const uint32_t *, const uint64_t *, uint32_t *,
+                        uint32_t *, uint32_t, uint32_t, uint32_t *, int, cudaStream_t);
 }  // namespace lzb
 
 using namespace lzb;
@@ -39,11 +44,12 @@ using namespace lzb;
 // Device scratch of one kernel chain.  The host entry point runs several chains (one per slice of the batch) at the
 // same time, each with its own scratch and stream; everything else uses chain 0.
 struct DecodeScratch {
-    DevBuf counts, err, raw_total, totals_dev, blocks, fse, lits, lmds, work;
+    DevBuf counts, err, raw_total, totals_dev, blocks, fse, lits, lmds, work, slow;
+    DevBuf long_base, long_blocks, long_streams, image;  // two-pass expansion of long streams (expand_long.cu)
     PinnedBuf totals_host;
     cudaStream_t stream = nullptr;  // chains 1.. only
     void release() {
-        for (DevBuf *b : {&counts, &err, &raw_total, &totals_dev, &blocks, &fse, &lits, &lmds, &work}) b->release();
+        for (DevBuf *b : {&counts, &err, &raw_total, &totals_dev, &blocks, &fse, &lits, &lmds, &work, &slow, &long_base, &long_blocks, &long_streams, &image}) b->release();
         totals_host.release();
         if (stream) cudaStreamDestroy(stream);
         stream = nullptr;
@@ -57,6 +63,8 @@ struct lzfse_b200_decoder {
     cudaStream_t own_stream = nullptr;
     std::string last_error;
     uint64_t launches = 0;
+    bool pending = false;             // an *_async call has been enqueued and not yet synchronised
+    cudaStream_t pending_stream = nullptr;
     int expand_mode = 0;  // 0 = choose per batch, 1 = warp per stream, 2 = CTA per stream (LZB_EXPAND=warp|cta: measurements only)
     DecodeScratch chain[kMaxChains];
     // staging for the *_host entry points
@@ -75,13 +83,14 @@ int decode_launch_scan(lzfse_b200_decoder *d, DecodeScratch &c, const uint8_t *s
     CK(d, c.err.reserve(n * sizeof(uint32_t)));
     CK(d, c.raw_total.reserve(n * sizeof(uint64_t)));
     CK(d, c.totals_dev.reserve(sizeof(StreamCounts)));
-    CK(d, c.totals_host.reserve(sizeof(StreamCounts)));
-    CK(d, c.work.reserve(4 * sizeof(uint32_t)));
+    CK(d, c.totals_host.reserve(sizeof(StreamCounts) + sizeof(LongTotals)));
+    CK(d, c.work.reserve(kWorkWords * sizeof(uint32_t)));
+    CK(d, cudaMemsetAsync(c.work.p, 0, kWorkWords * sizeof(uint32_t), s));
     uint64_t *raw_total = raw_len ? raw_len : c.raw_total.as<uint64_t>();
     // Totals go straight into pinned host memory (UVA): no device-to-host copy that could queue behind a bulk
     // download on the copy engine.
     launch_scan_count(src, src_off, src_len, probe_only ? nullptr : dst_cap, n, c.counts.as<StreamCounts>(), c.err.as<uint32_t>(), raw_total,
-                      n_blocks, c.totals_host.as<StreamCounts>(), s);
+                      n_blocks, c.totals_host.as<StreamCounts>(), c.work.as<uint32_t>(), long_stream_threshold(n, d->n_sms), s);
     d->launches += n > 8192 ? 4 : 2;  // k_scan + the exclusive scan (three launches for large batches)
     return LZFSE_B200_OK;
 }
@@ -94,23 +103,29 @@ int decode_launch_rest(lzfse_b200_decoder *d, DecodeScratch &c, const uint8_t *s
     uint64_t *raw_total = c.raw_total.as<uint64_t>();
     CK(d, cudaStreamSynchronize(s));
     const StreamCounts tot = *c.totals_host.as<StreamCounts>();
+    const LongTotals lt = *reinterpret_cast<const LongTotals *>(c.totals_host.as<StreamCounts>() + 1);
     if (tot.n_fse > 0xFFFFFFFFull) { d->last_error = "too many FSE blocks in one batch"; return LZFSE_B200_INVALID_ARGUMENT; }
     CK(d, c.blocks.reserve((tot.n_blocks + 1) * sizeof(BlockDesc)));
     CK(d, c.fse.reserve((tot.n_fse + 1) * sizeof(FseDesc)));
     CK(d, c.lits.reserve(tot.n_literals + 512));  // slack: the expander prefetches up to 128 bytes past a block's run
     CK(d, c.lmds.reserve((tot.n_lmds + 1) * sizeof(LmdRec)));
-    CK(d, cudaMemsetAsync(c.work.p, 0, 4 * sizeof(uint32_t), s));
+    CK(d, c.slow.reserve((2 * tot.n_fse + 2) * sizeof(uint32_t)));
+    CK(d, c.long_base.reserve(n * sizeof(uint64_t)));
+    CK(d, c.long_blocks.reserve(((size_t)lt.n_blocks + 1) * sizeof(uint32_t)));
+    CK(d, c.long_streams.reserve(((size_t)lt.n_streams + 1) * sizeof(uint32_t)));
+    CK(d, c.image.reserve((lt.elements + 4) * sizeof(uint32_t)));  // four bytes per output byte of the long streams
 
     launch_scan_fill(src, src_off, src_len, dst_off, dst_cap, n, c.counts.as<StreamCounts>(), c.blocks.as<BlockDesc>(), c.fse.as<FseDesc>(),
-                     c.err.as<uint32_t>(), s);
+                     c.err.as<uint32_t>(), raw_total, c.work.as<uint32_t>(), long_stream_threshold(n, d->n_sms), c.long_base.as<uint64_t>(),
+                     c.long_blocks.as<uint32_t>(), c.long_streams.as<uint32_t>(), s);
     d->launches += 1;
     if (timer) timer->mark(s);  // scan (count + host round trip + fill)
     if (tot.n_fse) {
         launch_fse_stages(src, src_off, src_len, dst_off, dst_cap, c.blocks.as<BlockDesc>(), c.fse.as<FseDesc>(), (uint32_t)tot.n_fse,
-                          c.lits.as<uint8_t>(), c.lmds.as<LmdRec>(), c.err.as<uint32_t>(), c.work.as<uint32_t>(), d->n_sms, s,
+                          c.lits.as<uint8_t>(), c.lmds.as<LmdRec>(), c.err.as<uint32_t>(), c.work.as<uint32_t>(), c.slow.as<uint32_t>(), d->n_sms, s,
                           timer && timer->enabled ? timer->ev[timer->n] : nullptr);
         if (timer && timer->enabled) timer->n++;  // literals
-        d->launches += 2;
+        d->launches += 3;
     } else if (timer) {
         timer->mark(s);
     }
@@ -124,26 +139,37 @@ int decode_launch_rest(lzfse_b200_decoder *d, DecodeScratch &c, const uint8_t *s
     }
     // Everything else: a warp per stream when there are enough streams to fill the machine that way (32 warps x 148
     // SMs); otherwise a CTA per stream, whose 7 worker warps share one stream through a shared-memory window.
+    // Long streams (many blocks): two passes, all their blocks side by side (expand_long.cu); the kernels below skip them.
+    if (lt.n_streams) {
+        launch_expand_long(src, src_off, src_len, dst, dst_off, dst_cap, c.counts.as<StreamCounts>(), c.blocks.as<BlockDesc>(), c.fse.as<FseDesc>(),
+                           c.lits.as<uint8_t>(), c.lmds.as<LmdRec>(), c.long_blocks.as<uint32_t>(), c.long_streams.as<uint32_t>(),
+                           c.long_base.as<uint64_t>(), c.image.as<uint32_t>(), c.err.as<uint32_t>(), lt.n_streams, lt.n_blocks, c.work.as<uint32_t>(),
+                           d->n_sms, s);
+        d->launches += 2;
+    }
     const bool use_cta = d->expand_mode == 2 || (d->expand_mode == 0 && n < (size_t)d->n_sms * 16);
-    if (!use_cta)
+    if (lt.n_streams == n) {
+        // nothing left for the in-order kernels
+    } else if (!use_cta)
         launch_expand(src, src_off, src_len, dst, dst_off, dst_cap, c.counts.as<StreamCounts>(), c.blocks.as<BlockDesc>(), c.fse.as<FseDesc>(),
-                      c.lits.as<uint8_t>(), c.lmds.as<LmdRec>(), c.err.as<uint32_t>(), n, c.work.as<uint32_t>() + 2, d->n_sms, s);
+                      c.lits.as<uint8_t>(), c.lmds.as<LmdRec>(), c.err.as<uint32_t>(), n, c.work.as<uint32_t>() + 2, c.long_base.as<uint64_t>(), d->n_sms, s);
     else
         launch_expand_cta(src, src_off, src_len, dst, dst_off, dst_cap, c.counts.as<StreamCounts>(), c.blocks.as<BlockDesc>(),
                           c.fse.as<FseDesc>(), c.lits.as<uint8_t>(), c.lmds.as<LmdRec>(), raw_total, c.err.as<uint32_t>(), n, c.work.as<uint32_t>() + 2,
-                          d->n_sms, s);
+                          c.long_base.as<uint64_t>(), d->n_sms, s);
     if (timer) timer->mark(s);  // expand
     launch_finish(c.err.as<uint32_t>(), raw_total, out_len, status, n, s);
     if (timer) timer->mark(s);  // finish
-    d->launches += 2;
+    d->launches += lt.n_streams == n ? 1 : 2;
     CK(d, cudaGetLastError());
     return LZFSE_B200_OK;
 }
 
 int decode_batch_device_impl(lzfse_b200_decoder *d, const uint8_t *src, const uint64_t *src_off, const uint64_t *src_len, uint8_t *dst,
                              const uint64_t *dst_off, const uint64_t *dst_cap, uint64_t *out_len, int32_t *status, uint64_t *raw_len,
-                             uint32_t *n_blocks, size_t n, cudaStream_t s, bool probe_only) {
+                             uint32_t *n_blocks, size_t n, cudaStream_t s, bool probe_only, bool wait = true) {
     d->launches = 0;
+    d->pending = false;
     if (n == 0) return LZFSE_B200_OK;
     DecodeScratch &c = d->chain[0];
     d->timer.begin(s);
@@ -158,6 +184,11 @@ int decode_batch_device_impl(lzfse_b200_decoder *d, const uint8_t *src, const ui
     }
     rc = decode_launch_rest(d, c, src, src_off, src_len, dst, dst_off, dst_cap, out_len, status, n, s, &d->timer);
     if (rc) return rc;
+    if (!wait) {  // lzfse_b200_decoder_sync (or the caller's own wait on `s`) completes the call
+        d->pending = true;
+        d->pending_stream = s;
+        return LZFSE_B200_OK;
+    }
     CK(d, cudaStreamSynchronize(s));
     d->timer.finish();
     return LZFSE_B200_OK;
@@ -250,14 +281,38 @@ int lzfse_b200_decoder_last_stage_ms(const lzfse_b200_decoder *d, float *ms, int
     return d->timer.n_done;
 }
 uint64_t lzfse_b200_decoder_last_launches(const lzfse_b200_decoder *d) { return d ? d->launches : 0; }
+// Test hook (not part of the public header): the work counters of chain 0 after the last call (common.cuh, kWorkWords).
+int lzfse_b200_debug_decoder_counters(lzfse_b200_decoder *d, uint32_t *out) {
+    if (!d || !d->chain[0].work.p) return 0;
+    DeviceGuard g(d->device);
+    return cudaMemcpy(out, d->chain[0].work.p, kWorkWords * sizeof(uint32_t), cudaMemcpyDeviceToHost) == cudaSuccess ? (int)kWorkWords : 0;
+}
 
 int lzfse_b200_decode_batch_device(lzfse_b200_decoder *d, const uint8_t *src, const uint64_t *src_off, const uint64_t *src_len, uint8_t *dst,
                                    const uint64_t *dst_off, const uint64_t *dst_cap, uint64_t *out_len, int32_t *status, size_t n, void *stream) {
     if (!d || (n && (!src_off || !src_len || !dst_off || !dst_cap || !out_len || !status))) return LZFSE_B200_INVALID_ARGUMENT;
     DeviceGuard g(d->device);
     if (!g.ok) return LZFSE_B200_CUDA_ERROR;
-    cudaStream_t s = stream ? (cudaStream_t)stream : d->own_stream;
-    return decode_batch_device_impl(d, src, src_off, src_len, dst, dst_off, dst_cap, out_len, status, nullptr, nullptr, n, s, false);
+    return decode_batch_device_impl(d, src, src_off, src_len, dst, dst_off, dst_cap, out_len, status, nullptr, nullptr, n, (cudaStream_t)stream, false);
+}
+
+int lzfse_b200_decode_batch_device_async(lzfse_b200_decoder *d, const uint8_t *src, const uint64_t *src_off, const uint64_t *src_len, uint8_t *dst,
+                                         const uint64_t *dst_off, const uint64_t *dst_cap, uint64_t *out_len, int32_t *status, size_t n, void *stream) {
+    if (!d || (n && (!src_off || !src_len || !dst_off || !dst_cap || !out_len || !status))) return LZFSE_B200_INVALID_ARGUMENT;
+    DeviceGuard g(d->device);
+    if (!g.ok) return LZFSE_B200_CUDA_ERROR;
+    return decode_batch_device_impl(d, src, src_off, src_len, dst, dst_off, dst_cap, out_len, status, nullptr, nullptr, n, (cudaStream_t)stream, false, false);
+}
+
+int lzfse_b200_decoder_sync(lzfse_b200_decoder *d) {
+    if (!d) return LZFSE_B200_INVALID_ARGUMENT;
+    if (!d->pending) return LZFSE_B200_OK;
+    DeviceGuard g(d->device);
+    if (!g.ok) return LZFSE_B200_CUDA_ERROR;
+    d->pending = false;
+    CK(d, cudaStreamSynchronize(d->pending_stream));
+    d->timer.finish();
+    return LZFSE_B200_OK;
 }
 
 int lzfse_b200_decode_probe_batch_device(lzfse_b200_decoder *d, const uint8_t *src, const uint64_t *src_off, const uint64_t *src_len,
@@ -265,8 +320,7 @@ int lzfse_b200_decode_probe_batch_device(lzfse_b200_decoder *d, const uint8_t *s
     if (!d || (n && (!src_off || !src_len || !raw_len || !status))) return LZFSE_B200_INVALID_ARGUMENT;
     DeviceGuard g(d->device);
     if (!g.ok) return LZFSE_B200_CUDA_ERROR;
-    cudaStream_t s = stream ? (cudaStream_t)stream : d->own_stream;
-    return decode_batch_device_impl(d, src, src_off, src_len, nullptr, nullptr, nullptr, nullptr, status, raw_len, n_blocks, n, s, true);
+    return decode_batch_device_impl(d, src, src_off, src_len, nullptr, nullptr, nullptr, nullptr, status, raw_len, n_blocks, n, (cudaStream_t)stream, true);
 }
 
 // Host-buffer variants: stage the bytes on the device (host_util.h), run the device path, copy back.

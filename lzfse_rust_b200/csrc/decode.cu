@@ -97,7 +97,9 @@ template <bool FILL>
 __global__ void k_scan(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ src_off,
                        const uint64_t *__restrict__ src_len, const uint64_t *__restrict__ dst_off,
                        const uint64_t *__restrict__ dst_cap, size_t n, StreamCounts *counts /* in FILL: scanned bases */,
-                       BlockDesc *blocks, FseDesc *fse, uint32_t *err, uint64_t *raw_total, uint32_t *n_blocks_out) {
+                       BlockDesc *blocks, FseDesc *fse, uint32_t *err, uint64_t *raw_total, uint32_t *n_blocks_out,
+                       uint32_t *work /* kWorkWords counters, or null (probe) */, uint32_t long_fse /* streams with at least this many bvx blocks are long */,
+                       uint64_t *long_base, uint32_t *long_blocks, uint32_t *long_streams) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint8_t *s = src_base + src_off[i];
@@ -107,7 +109,20 @@ __global__ void k_scan(const uint8_t *__restrict__ src_base, const uint64_t *__r
     uint64_t n_lit = 0, n_lmd = 0;
     uint32_t key = kNoError;
     StreamCounts base;
-    if (FILL) base = counts[i];
+    bool is_long = false;   // expanded by the two-pass kernels (expand_long.cu)
+    uint32_t long_slot = 0;
+    if (FILL) {
+        base = counts[i];
+        const StreamCounts next = counts[i + 1];
+        is_long = next.n_fse - base.n_fse >= long_fse;
+        if (is_long) {  // image range, slots in the block list, entry in the stream list
+            long_base[i] = atomicAdd(reinterpret_cast<unsigned long long *>(work + 12), (unsigned long long)((raw_total[i] + 3) & ~3ull));
+            long_slot = atomicAdd(work + 14, (uint32_t)(next.n_blocks - base.n_blocks));
+            long_streams[atomicAdd(work + 15, 1u)] = (uint32_t)i;
+        } else {
+            long_base[i] = ~0ull;
+        }
+    }
     for (;;) {
         uint64_t rest = len - pos;
         uint32_t kb = blk < 0x1FFFFFu ? blk : 0x1FFFFFu;
@@ -199,7 +214,10 @@ __global__ void k_scan(const uint8_t *__restrict__ src_base, const uint64_t *__r
         }
         // C-ABI limit: the expansion stage keeps stream positions in 32 bits
         if (raw + bd.n_raw > kMaxStreamRaw) { key = err_key(kb, PH_HEADER, LZFSE_B200_BUFFER_OVERFLOW); break; }
-        if (FILL) blocks[base.n_blocks + blk] = bd;
+        if (FILL) {
+            blocks[base.n_blocks + blk] = bd;
+            if (is_long) long_blocks[long_slot + blk] = (uint32_t)(base.n_blocks + blk);
+        }
         raw += bd.n_raw;
         blk++;
         pos += blen;
@@ -212,6 +230,11 @@ __global__ void k_scan(const uint8_t *__restrict__ src_base, const uint64_t *__r
         err[i] = key;
         raw_total[i] = raw;
         if (n_blocks_out) n_blocks_out[i] = blk;
+        if (work && n_fse >= long_fse) {  // totals of the long streams: the host sizes their image from these
+            atomicAdd(reinterpret_cast<unsigned long long *>(work + 8), (unsigned long long)((raw + 3) & ~3ull));
+            atomicAdd(work + 10, blk);
+            atomicAdd(work + 11, 1u);
+        }
     }
 }
 
@@ -235,7 +258,7 @@ __device__ __forceinline__ StreamCounts sc_warp_inclusive(StreamCounts v, uint32
     }
     return v;
 }
-__global__ void __launch_bounds__(1024) k_exclusive_scan(StreamCounts *counts, size_t n, StreamCounts *totals) {
+__global__ void __launch_bounds__(1024) k_exclusive_scan(StreamCounts *counts, size_t n, StreamCounts *totals, const uint32_t *work) {
     __shared__ StreamCounts warp_tot[32];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t per = (n + blockDim.x - 1) / blockDim.x;
@@ -255,6 +278,7 @@ __global__ void __launch_bounds__(1024) k_exclusive_scan(StreamCounts *counts, s
     if (warp == 0) {
         const StreamCounts w = sc_warp_inclusive(warp_tot[lane], lane);
         if (lane == 31) { *totals = w; counts[n] = w; }
+        if (work && lane < 4) reinterpret_cast<uint32_t *>(totals + 1)[lane] = work[8 + lane];  // LongTotals (see api.cu)
         StreamCounts ex = sc_shfl_up(w, 1);
         if (lane == 0) ex = StreamCounts{0, 0, 0, 0};
         warp_tot[lane] = ex;
@@ -309,15 +333,15 @@ __global__ void __launch_bounds__(1024) k_scan_tile_apply(StreamCounts *counts, 
     if (i == n) counts[n] = tile_offsets[n_tiles];  // grand totals (the tile holding index n exists: see the launcher)
 }
 // counts must have room for n + 1 + (n / 1024 + 2) elements.
-void launch_exclusive_scan(StreamCounts *counts, size_t n, StreamCounts *totals, cudaStream_t s) {
+void launch_exclusive_scan(StreamCounts *counts, size_t n, StreamCounts *totals, const uint32_t *work, cudaStream_t s) {
     if (n <= 8192) {
-        k_exclusive_scan<<<1, 1024, 0, s>>>(counts, n, totals);
+        k_exclusive_scan<<<1, 1024, 0, s>>>(counts, n, totals, work);
         return;
     }
     const size_t n_tiles = (n + 1 + 1023) / 1024;  // covers index n as well
     StreamCounts *tiles = counts + n + 1;
     k_scan_tile_sums<<<(unsigned)n_tiles, 1024, 0, s>>>(counts, n, tiles);
-    k_exclusive_scan<<<1, 1024, 0, s>>>(tiles, n_tiles, totals);
+    k_exclusive_scan<<<1, 1024, 0, s>>>(tiles, n_tiles, totals, work);
     k_scan_tile_apply<<<(unsigned)n_tiles, 1024, 0, s>>>(counts, n, tiles, n_tiles);
 }
 
@@ -544,7 +568,9 @@ constexpr size_t kLitSmemPerWarp = 1024 * 32 * 3 + kRingBytesPerWarp;
 __global__ void __launch_bounds__(kLitWarps * 32, 1)
 k_fse_literals(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ src_off, const uint64_t *__restrict__ src_len,
                const BlockDesc *__restrict__ blocks, FseDesc *__restrict__ fse, uint32_t n_fse, uint8_t *__restrict__ lit_scratch,
-               uint32_t *err, uint32_t *work_counter) {
+               uint32_t *err, uint32_t *work_counter, const uint32_t *__restrict__ list, const uint32_t *__restrict__ list_count) {
+    // With a list: only the blocks the quad kernel (k_fse_literals4) handed over -- anything it did not like.
+    if (list) n_fse = *list_count;
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
     uint16_t *kd = reinterpret_cast<uint16_t *>(smem + warp * kLitSmemPerWarp);
@@ -555,8 +581,8 @@ k_fse_literals(const uint8_t *__restrict__ src_base, const uint64_t *__restrict_
         if (lane == 0) base = atomicAdd(work_counter, 32u);
         base = __shfl_sync(0xFFFFFFFFu, base, 0);
         if (base >= n_fse) break;
-        const uint32_t f = base + lane;
-        if (f < n_fse) {
+        if (base + lane < n_fse) {
+            const uint32_t f = list ? list[base + lane] : base + lane;
             FseDesc fd = fse[f];
             const BlockDesc bd = blocks[fd.block];
             const uint8_t *blk = src_base + bd.src_off;
@@ -639,6 +665,162 @@ k_fse_literals(const uint8_t *__restrict__ src_base, const uint64_t *__restrict_
                     else fse[f].ok_lit = 1;
                 }
             }
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Literal stage, fast kernel: FOUR lanes per block, lane q of a quad carries interleaved state q.
+//
+// The lane-per-block kernel above spends ~300 cycles per 4-literal step: one warp per scheduler issues all ~90
+// instructions of the step itself, its 64 table slots per SM leave two schedulers empty, and the 111 blocks per SM of
+// the headline workload need two waves.  A block's four FSE states are independent except for the bit cursor, so a
+// quad decodes one step with ONE table lookup per lane; the four k values travel through three butterfly shuffles
+// (prefix for the lane's bit position, total for the cursor).  8 blocks per warp, 8 warps per SM: the same 64 table
+// slots, but all four schedulers issue and a step is ~1/3 of the dependent chain.
+//
+// This kernel only decodes blocks that are plainly well formed.  Whatever else it meets -- truncated payloads, bad
+// weights, a reader that comes within 57 bits of the pad, non-zero final states -- it leaves untouched and appends to
+// `slow_list`; the lane-per-block kernel then runs over that list with the reference's exact flush semantics and
+// reports the error the reference reports (fse/literals.rs:49-91, bits/bit_reader.rs:20-71).
+// ------------------------------------------------------------------------------------------------
+constexpr int kLit4Warps = 8;
+constexpr uint32_t kLit4Blocks = 8;  // per warp
+constexpr size_t kLit4TabBytes = 1024 * 3;  // u16 plane (k << 12 | delta), u8 plane (symbol)
+constexpr size_t kLit4SmemPerWarp = kLit4Blocks * (kLit4TabBytes + kRingStride);
+
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u8v(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+
+__global__ void __launch_bounds__(kLit4Warps * 32, 1)
+k_fse_literals4(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ src_off, const uint64_t *__restrict__ src_len,
+                const BlockDesc *__restrict__ blocks, FseDesc *__restrict__ fse, uint32_t n_fse, uint8_t *__restrict__ lit_scratch,
+                uint32_t *work_counter, uint32_t *__restrict__ slow_list, uint32_t *slow_count) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    constexpr uint32_t kFull = 0xFFFFFFFFu;
+    const uint32_t warp = threadIdx.x >> 5, lane = lane_id(), q = lane & 3, b = lane >> 2;
+    uint8_t *wbase = smem + warp * kLit4SmemPerWarp;
+    uint16_t *kd = reinterpret_cast<uint16_t *>(wbase + b * kLit4TabBytes);
+    uint8_t *sy = wbase + b * kLit4TabBytes + 2048;
+    const uint32_t kd_s = (uint32_t)__cvta_generic_to_shared(kd), sy_s = kd_s + 2048;
+    const uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(wbase + kLit4Blocks * kLit4TabBytes) + b * kRingStride;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(work_counter, kLit4Blocks);
+        base = __shfl_sync(kFull, base, 0);
+        if (base >= n_fse) break;
+        const uint32_t f = base + b;
+        const bool have = f < n_fse;
+        bool good = false;  // the quad decodes this block
+        uint64_t lit_off = 0;
+        RingWindow br;
+        br.P = 0; br.dead = false; br.g0 = 0; br.a_base = 0; br.lo16 = 0; br.hi = 0; br.next_chunk = 0; br.ring = ring_addr;
+        uint32_t s = 0, n_it = 0;
+        if (have) {
+            const FseDesc fd = fse[f];
+            const BlockDesc bd = blocks[fd.block];
+            const uint8_t *blk = src_base + bd.src_off;
+            const bool v1 = fd.flags & FSE_V1;
+            const uint8_t *wp = blk + (v1 ? kV1HeaderSize : kV2HeaderSize);
+            lit_off = fd.lit_off;
+            good = !(fd.flags & FSE_TRUNC_LIT) && validate_weights(wp, fd.n_weight_bytes, v1) == 0;
+            if (good) {
+                // build_u_table (fse/decoder.rs:299-335): every lane of the quad walks the weights, lane q writes the
+                // states congruent to q
+                WeightReader r;
+                r.init(wp, fd.n_weight_bytes, v1);
+                for (int k = 0; k < 104; k++) r.next();
+                uint32_t total = 0;
+                for (uint32_t sym = 0; sym < 256; sym++) {
+                    const uint32_t w = r.next();
+                    if (w == 0) continue;
+                    const uint32_t k = __clz(w) - 21;
+                    const uint32_t x = (2048u >> k) - w;
+                    for (uint32_t j = (q - total) & 3u; j < w; j += 4) {
+                        uint32_t kk, delta;
+                        if (j < x) { kk = k; delta = ((w + j) << k) - 1024u; }
+                        else { kk = k - 1; delta = (j - x) << (k - 1); }
+                        kd[total + j] = (uint16_t)(delta | (kk << 12));
+                        sy[total + j] = (uint8_t)sym;
+                    }
+                    total += w;
+                }
+                for (uint32_t t = total + ((q - total) & 3u); t < 1024; t += 4) { kd[t] = (uint16_t)t; sy[t] = 0; }
+                // the reader: the quad shares one ring; lane q requests chunks q and q + 4 of the first eight
+                const uint8_t *s_lo = src_base + src_off[bd.stream], *s_hi = s_lo + src_len[bd.stream];
+                const uint8_t *start = blk + fd.header_size - 8;
+                const uint32_t len = fd.n_lit_payload + 8, off = fd.lit_bits;
+                br.g0 = (reinterpret_cast<uintptr_t>(s_lo) & ~(uintptr_t)15) - 256;
+                br.lo16 = (uint32_t)(((reinterpret_cast<uintptr_t>(s_lo) + 15) & ~(uintptr_t)15) - br.g0);
+                br.hi = (uint32_t)(reinterpret_cast<uintptr_t>(s_hi) - br.g0);
+                br.a_base = (uint32_t)(reinterpret_cast<uintptr_t>(start) - br.g0);
+                br.P = (int)len * 8 - (int)off;
+                const uint32_t last = start[len - 1];
+                if (off != 0 && (last >> (8 - off)) != 0) good = false;  // BitReader::new would refuse
+                const uint32_t a = br.a_base + (uint32_t)((br.P - 57) >> 3);
+                const uint32_t top = ((a & ~3u) + 11) & ~15u;
+                br.fetch_chunk(top - 16 * q);
+                br.fetch_chunk(top - 16 * (q + 4));
+                br.next_chunk = top - kRing;
+                s = fse[f].lit_state[q];  // (indexing the register copy would push it to the stack)
+                n_it = good ? fd.n_literals >> 2 : 0;
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        uint8_t *out = lit_scratch + lit_off + q;
+        asm volatile("" : "+l"(out));
+        const uint32_t max_it = __reduce_max_sync(kFull, n_it);
+        uint32_t it = 0;
+        bool stopped = false;
+        for (uint32_t step = 0; step < max_it; step++) {
+            const bool live = step < n_it && !stopped && br.P >= 57;  // same in all four lanes of a quad
+            stopped |= step < n_it && !live;
+            if (live) {
+                const uint32_t a4 = (br.a_base + (uint32_t)((br.P - 57) >> 3)) & ~3u;
+                if (a4 + 12 <= br.next_chunk + kRing) {
+                    if (q == 0) br.fetch_chunk(br.next_chunk);
+                    br.next_chunk -= 16;
+                }
+            }
+            // One group per STEP, committed by the whole warp (the hardware counts a warp's groups, not a lane's: with a
+            // group per refill of one quad, "at most five pending" made every refill wait for the requests the other
+            // quads had issued a few steps earlier -- a full memory round trip per step).  A chunk is requested when the
+            // window's base is <= 116 bytes above it and first read when the base is <= 15 above it; a step consumes at
+            // most 5 bytes, so at least 20 younger groups exist by then and 16 pending ones are safe.
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 16;" ::: "memory");
+            __syncwarp();  // lane 0's chunks become visible to the quad
+            int cur;
+            const uint64_t win = br.window_fast(cur);
+            const uint32_t e = lds_u16(kd_s + s * 2), y = lds_u8v(sy_s + s);
+            const uint32_t k = live ? e >> 12 : 0u;
+            const uint32_t x1 = __shfl_xor_sync(kFull, k, 1), x2 = __shfl_xor_sync(kFull, k, 2), x3 = __shfl_xor_sync(kFull, k, 3);
+            const uint32_t pre = ((q & 1) ? x1 : 0u) + ((q & 2) ? x2 + x3 : 0u);  // bits taken by the lower states of this step
+            const int p = cur - (int)pre - (int)k;
+            if (live) {
+                s = bits_at(win, p, k) + (e & 0xFFF);
+                br.P -= (int)(k + x1 + x2 + x3);
+                out[step * 4] = (uint8_t)y;
+                it = step + 1;
+            }
+        }
+        // Literals::load's tail: final flush, reader not underflown, all four states back at zero
+        const bool lane_ok = good && it == n_it && br.P >= 64 && s == 0;
+        const bool ok = ((__ballot_sync(kFull, lane_ok) >> (b * 4)) & 0xFu) == 0xFu;
+        if (have && q == 0) {
+            if (ok) fse[f].ok_lit = 1;
+            else slow_list[atomicAdd(slow_count, 1u)] = f;
         }
         __syncwarp();
     }
@@ -1013,7 +1195,7 @@ k_expand(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ src_
          uint8_t *__restrict__ dst_base, const uint64_t *__restrict__ dst_off, const uint64_t *__restrict__ dst_cap,
          const StreamCounts *__restrict__ bases,
          const BlockDesc *__restrict__ blocks, const FseDesc *__restrict__ fse, const uint8_t *__restrict__ lit_scratch,
-         const LmdRec *__restrict__ lmd_scratch, uint32_t *err, size_t n_streams, uint32_t *work_counter) {
+         const LmdRec *__restrict__ lmd_scratch, uint32_t *err, size_t n_streams, uint32_t *work_counter, const uint64_t *__restrict__ long_base) {
     __shared__ __align__(16) uint8_t stage[kExpandWarps][kStageStride];
     const uint32_t lane = lane_id();
     uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage[threadIdx.x >> 5]);
@@ -1025,6 +1207,7 @@ k_expand(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ src_
     if (lane == 0) stream = atomicAdd(work_counter, 1u);
     stream = __shfl_sync(0xFFFFFFFFu, (uint32_t)stream, 0);
     if (stream >= n_streams) return;
+    if (long_base[stream] != ~0ull) continue;  // expand_long.cu
     const uint64_t b0 = bases[stream].n_blocks, b1 = bases[stream + 1].n_blocks;
     uint8_t *stream_out = dst_base + dst_off[stream];
     if (b1 - b0 == 1 && vn_fast_eligible(1, blocks[b0], src_off[stream] + src_len[stream] - blocks[b0].src_off, dst_cap[stream])) continue;  // k_expand_vn
@@ -1276,46 +1459,74 @@ __global__ void k_finish(const uint32_t *__restrict__ err, const uint64_t *__res
 // ------------------------------------------------------------------------------------------------
 // Host-side launchers (called from api.cu)
 // ------------------------------------------------------------------------------------------------
+// Streams with at least this many bvx blocks take the two-pass expansion (expand_long.cu): a handful in a batch that
+// cannot fill the machine with one warp per stream, many when it can (the image costs four bytes per output byte).
+uint32_t long_stream_threshold(size_t n, int n_sms) {
+    static const int forced = [] { const char *e = getenv("LZB_LONG_FSE"); return e ? atoi(e) : 0; }();  // measurements / tests
+    if (forced > 0) return (uint32_t)forced;
+    return n < (size_t)n_sms * 16 ? 4u : 64u;
+}
 void launch_scan_count(const uint8_t *src, const uint64_t *src_off, const uint64_t *src_len, const uint64_t *dst_cap, size_t n,
-                       StreamCounts *counts, uint32_t *err, uint64_t *raw_total, uint32_t *n_blocks_out, StreamCounts *totals, cudaStream_t s) {
+                       StreamCounts *counts, uint32_t *err, uint64_t *raw_total, uint32_t *n_blocks_out, StreamCounts *totals, uint32_t *work,
+                       uint32_t long_fse, cudaStream_t s) {
     if (n == 0) return;
     const int tb = 128;
-    k_scan<false><<<(unsigned)((n + tb - 1) / tb), tb, 0, s>>>(src, src_off, src_len, nullptr, dst_cap, n, counts, nullptr, nullptr, err, raw_total, n_blocks_out);
-    launch_exclusive_scan(counts, n, totals, s);
+    k_scan<false><<<(unsigned)((n + tb - 1) / tb), tb, 0, s>>>(src, src_off, src_len, nullptr, dst_cap, n, counts, nullptr, nullptr, err, raw_total, n_blocks_out,
+                                                               work, long_fse, nullptr, nullptr, nullptr);
+    launch_exclusive_scan(counts, n, totals, work, s);
 }
 void launch_scan_fill(const uint8_t *src, const uint64_t *src_off, const uint64_t *src_len, const uint64_t *dst_off, const uint64_t *dst_cap, size_t n,
-                      StreamCounts *bases, BlockDesc *blocks, FseDesc *fse, uint32_t *err, cudaStream_t s) {
+                      StreamCounts *bases, BlockDesc *blocks, FseDesc *fse, uint32_t *err, uint64_t *raw_total, uint32_t *work, uint32_t long_fse,
+                      uint64_t *long_base, uint32_t *long_blocks, uint32_t *long_streams, cudaStream_t s) {
     if (n == 0) return;
     const int tb = 128;
-    k_scan<true><<<(unsigned)((n + tb - 1) / tb), tb, 0, s>>>(src, src_off, src_len, dst_off, dst_cap, n, bases, blocks, fse, err, nullptr, nullptr);
+    k_scan<true><<<(unsigned)((n + tb - 1) / tb), tb, 0, s>>>(src, src_off, src_len, dst_off, dst_cap, n, bases, blocks, fse, err, raw_total, nullptr, work,
+                                                              long_fse, long_base, long_blocks, long_streams);
 }
 int setup_decode_kernels() {
     cudaError_t e = cudaFuncSetAttribute(k_fse_literals, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kLitWarps * kLitSmemPerWarp));
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(k_fse_lmds, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kLmdWarps * kLmdSmemPerWarp));
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(k_fse_literals4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kLit4Warps * kLit4SmemPerWarp));
     return (int)e;
 }
 void launch_fse_stages(const uint8_t *src, const uint64_t *src_off, const uint64_t *src_len, const uint64_t *dst_off, const uint64_t *dst_cap,
                        const BlockDesc *blocks, FseDesc *fse, uint32_t n_fse, uint8_t *lit_scratch, LmdRec *lmd_scratch, uint32_t *err,
-                       uint32_t *work_counters /* 2 zeroed u32 */, int n_sms, cudaStream_t s, cudaEvent_t between) {
+                       uint32_t *work_counters /* kWorkWords zeroed u32 */, uint32_t *slow_lists /* 2 * n_fse u32 */, int n_sms, cudaStream_t s,
+                       cudaEvent_t between) {
     if (n_fse == 0) return;
     unsigned need_lit = (n_fse + 32 * kLitWarps - 1) / (32 * kLitWarps), need_lmd = (n_fse + 32 * kLmdWarps - 1) / (32 * kLmdWarps);
     unsigned g_lit = need_lit < (unsigned)n_sms ? need_lit : (unsigned)n_sms;
     unsigned g_lmd = need_lmd < (unsigned)n_sms ? need_lmd : (unsigned)n_sms;
-    k_fse_literals<<<g_lit, kLitWarps * 32, kLitWarps * kLitSmemPerWarp, s>>>(src, src_off, src_len, blocks, fse, n_fse, lit_scratch, err, work_counters);
+    // literals: quad kernel first, then the exact lane-per-block kernel over whatever the quad kernel handed over
+    // (usually nothing: its CTAs read a zero count and leave)
+    static const bool lit4 = [] { const char *e = getenv("LZB_LIT4"); return !e || atoi(e) != 0; }();  // LZB_LIT4=0: measurements only
+    if (lit4) {
+        unsigned need4 = (n_fse + kLit4Blocks * kLit4Warps - 1) / (kLit4Blocks * kLit4Warps);
+        unsigned g4 = need4 < (unsigned)n_sms ? need4 : (unsigned)n_sms;
+        k_fse_literals4<<<g4, kLit4Warps * 32, kLit4Warps * kLit4SmemPerWarp, s>>>(src, src_off, src_len, blocks, fse, n_fse, lit_scratch,
+                                                                                  work_counters + 4, slow_lists, work_counters + 5);
+        k_fse_literals<<<g_lit, kLitWarps * 32, kLitWarps * kLitSmemPerWarp, s>>>(src, src_off, src_len, blocks, fse, n_fse, lit_scratch, err, work_counters,
+                                                                                  slow_lists, work_counters + 5);
+    } else {
+        k_fse_literals<<<g_lit, kLitWarps * 32, kLitWarps * kLitSmemPerWarp, s>>>(src, src_off, src_len, blocks, fse, n_fse, lit_scratch, err, work_counters,
+                                                                                  nullptr, nullptr);
+    }
     if (between) cudaEventRecord(between, s);
     k_fse_lmds<<<g_lmd, kLmdWarps * 32, kLmdWarps * kLmdSmemPerWarp, s>>>(src, src_off, src_len, dst_off, dst_cap, blocks, fse, n_fse, lmd_scratch, err, work_counters + 1);
 }
 void launch_expand(const uint8_t *src, const uint64_t *src_off, const uint64_t *src_len, uint8_t *dst, const uint64_t *dst_off,
                    const uint64_t *dst_cap, const StreamCounts *bases, const BlockDesc *blocks, const FseDesc *fse, const uint8_t *lit_scratch,
-                   const LmdRec *lmd_scratch, uint32_t *err, size_t n, uint32_t *work_counter /* zeroed */, int n_sms, cudaStream_t s) {
+                   const LmdRec *lmd_scratch, uint32_t *err, size_t n, uint32_t *work_counter /* zeroed */, const uint64_t *long_base, int n_sms,
+                   cudaStream_t s) {
     if (n == 0) return;
     // Tuning aid: LZB_EXPAND_PAD_KB adds unused dynamic shared memory per CTA and so caps the resident CTAs per SM.
     static const int pad_kb = [] { const char *e = getenv("LZB_EXPAND_PAD_KB"); return e ? atoi(e) : 0; }();
     if (pad_kb > 48) cudaFuncSetAttribute(k_expand, cudaFuncAttributeMaxDynamicSharedMemorySize, pad_kb * 1024);
     const size_t need = (n + kExpandWarps - 1) / kExpandWarps, resident = (size_t)n_sms * LZB_EXPAND_CTAS;
     k_expand<<<(unsigned)(need < resident ? need : resident), kExpandWarps * 32, (size_t)pad_kb * 1024, s>>>(src, src_off, src_len, dst, dst_off, dst_cap, bases, blocks, fse,
-                                                                                                        lit_scratch, lmd_scratch, err, n, work_counter);
+                                                                                                        lit_scratch, lmd_scratch, err, n, work_counter, long_base);
 }
 void launch_expand_vn(const uint8_t *src, const uint64_t *src_off, const uint64_t *src_len, uint8_t *dst, const uint64_t *dst_off,
                       const uint64_t *dst_cap, const StreamCounts *bases, const BlockDesc *blocks, uint32_t *err, size_t n,

@@ -23,7 +23,7 @@
 
 namespace lzb {
 
-void launch_exclusive_scan(StreamCounts *counts, size_t n, StreamCounts *totals, cudaStream_t s);  // decode.cu
+void launch_exclusive_scan(StreamCounts *counts, size_t n, StreamCounts *totals, const uint32_t *work, cudaStream_t s);  // decode.cu
 
 constexpr uint32_t kEmptyIdx = 0xC0C0C0C0u;  // history reset marker (encode/history.rs:72-83: any idx whose distance is out of range)
 // A bucket is one 32-byte sector: 4 positions (newest first) followed by the 4 source bytes found at each of them --
@@ -1150,31 +1150,40 @@ k_enc_replay(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ 
     uint32_t cur = 0, literal_index = 0;
     Match pending = {0, 0, 0};
     // Every lane walks its own stream, so a plain load per position costs a memory round trip per step of this serial
-    // loop (and prefetch.global.L1 does not shorten it).  Each lane therefore owns a 64-word ring in shared memory that
-    // cp.async keeps filled 16 chunks ahead of its cursor; the cursor reads four words at a time into registers (one
-    // ld.shared per position instead -- measured with 128- and 256-word rings -- puts 30 cycles more on every step of
-    // the serial chain: 11.6 / 13.1 ms against 11.1 ms).
+    // loop (and prefetch.global.L1 does not shorten it).  Each lane therefore owns a 64-word ring in shared memory, two
+    // halves of 32 words: on entering a half it waits for everything it has requested (cp.async.wait_group 0) and then
+    // requests the half after, which so has 32 positions of time to arrive.  The cursor reads four words at a time into
+    // registers.
+    // Only wait_group 0 is used, on purpose.  The first version kept 16 single-chunk groups in flight and waited with
+    // wait_group 14 ("my 16th newest group is complete"): right by PTX's per-thread wording, but the lanes of this
+    // kernel are divergent and about ten of 16 384 streams per run then read a chunk before it had arrived (frames
+    // still valid, but not the reference's bytes, and different ones from run to run -- found by scripts/enc_words_diff.py:
+    // identical words, different packs; gone with a full drain).
     __shared__ __align__(16) uint8_t rings[kReplayThreads / kReplayStride * kRingStride];
+    static_assert(kRingWords == 64, "two halves of 32 words");
     const uint32_t ring = (uint32_t)__cvta_generic_to_shared(rings) + threadIdx.x / kReplayStride * kRingStride;
     const uint32_t w_limit = (end + 3u) & ~3u;  // chunks at or beyond this word index are never needed
-    uint32_t wbase = 0xFFFFFFFFu, fetched = 0;
+    uint32_t wbase = 0xFFFFFFFFu, half = 0xFFFFFFFFu, pre_half = 0xFFFFFFFFu;
     uint4 wq = make_uint4(0, 0, 0, 0);
+    auto request_half = [&](uint32_t h) {  // words [h, h + 32) below w_limit, eight 16-byte chunks at most
+        const uint32_t hi = h + 32u < w_limit ? h + 32u : w_limit;
+        for (uint32_t c = h; c < hi; c += 4)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ring + (c & (kRingWords - 1)) * 4), "l"(W + c) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
     while (cur < end) {
         if ((cur & ~3u) != wbase) {
             wbase = cur & ~3u;
-            if (wbase >= fetched) {  // first use, or a jump past everything requested so far: older requests must not land on top of new ones
+            if ((wbase & ~31u) != half) {
+                half = wbase & ~31u;
+                if (half != pre_half) {  // first use, or a jump past the half requested ahead: nothing in flight may land on the new requests
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
+                    request_half(half);
+                }
                 asm volatile("cp.async.wait_group 0;" ::: "memory");
-                fetched = wbase;
+                pre_half = half + 32u;
+                if (pre_half < w_limit) request_half(pre_half);  // into the half just left
             }
-            const uint32_t want = wbase + kRingWords < w_limit ? wbase + kRingWords : w_limit;
-            while (fetched < want) {
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ring + (fetched & (kRingWords - 1)) * 4), "l"(W + fetched) : "memory");
-                asm volatile("cp.async.commit_group;" ::: "memory");
-                fetched += 4;
-            }
-            // the chunk at wbase is the (fetched - wbase) / 4-th newest group; with a full window that is the 16th
-            if (fetched == wbase + kRingWords) asm volatile("cp.async.wait_group %0;" ::"n"(kRingWords / 4 - 2) : "memory");
-            else asm volatile("cp.async.wait_group 0;" ::: "memory");
             asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(wq.x), "=r"(wq.y), "=r"(wq.z), "=r"(wq.w) : "r"(ring + (wbase & (kRingWords - 1)) * 4) : "memory");
         }
         const uint32_t k4 = cur & 3u;
@@ -1597,6 +1606,8 @@ struct lzfse_b200_encoder {
     std::string last_error;
     uint64_t launches = 0;
     DevBuf streams, counts, totals_dev, tables, packs, lits, block_ids, blocks, out, counters, words;
+    bool pending = false;             // an *_async call has been enqueued and not yet synchronised
+    cudaStream_t pending_stream = nullptr;
     int allow_fast = 1;  // LZB_ENC_FAST=0 sends every stream through k_enc_parse (measurements, tests)
     PinnedBuf totals_host;
     HostStage stage;
@@ -1608,8 +1619,10 @@ namespace {
 constexpr int kParseWarpsPerSm = LZB_PARSE_CTAS * 4;  // resident history tables: 148 * 28 * 512 KiB = 2072 MiB
 
 int encode_batch_device_impl(lzfse_b200_encoder *e, const uint8_t *src, const uint64_t *src_off, const uint64_t *src_len, uint8_t *dst,
-                             const uint64_t *dst_off, const uint64_t *dst_cap, uint64_t *out_len, int32_t *status, size_t n, cudaStream_t s) {
+                             const uint64_t *dst_off, const uint64_t *dst_cap, uint64_t *out_len, int32_t *status, size_t n, cudaStream_t s,
+                             bool wait = true) {
     e->launches = 0;
+    e->pending = false;
     if (n == 0) return LZFSE_B200_OK;
     if (n > 0x7FFFFFFFull) { e->last_error = "too many streams in one batch"; return LZFSE_B200_INVALID_ARGUMENT; }
     LZB_CK(e, e->streams.reserve(n * sizeof(EncStream)));
@@ -1622,7 +1635,7 @@ int encode_batch_device_impl(lzfse_b200_encoder *e, const uint8_t *src, const ui
     LZB_CK(e, cudaMemsetAsync(e->counters.p, 0, 8 * sizeof(uint32_t), s));
     uint32_t *ctr = e->counters.as<uint32_t>();  // [0] blocks produced, [1] parse cursor, [2] fse-encode cursor, [3] find cursor, [4] fast streams, [5] k_enc_parse streams
     k_enc_prep<<<(unsigned)((n + tb - 1) / tb), tb, 0, s>>>(src_len, n, e->streams.as<EncStream>(), e->counts.as<StreamCounts>(), status, ctr + 4, e->allow_fast);
-    launch_exclusive_scan(e->counts.as<StreamCounts>(), n, e->totals_host.as<StreamCounts>(), s);  // pinned host memory (UVA)
+    launch_exclusive_scan(e->counts.as<StreamCounts>(), n, e->totals_host.as<StreamCounts>(), nullptr, s);  // pinned host memory (UVA)
     k_enc_publish_counts<<<1, 1, 0, s>>>(ctr + 4, reinterpret_cast<uint32_t *>(e->totals_host.as<StreamCounts>() + 1));
     e->launches += n > 8192 ? 5 : 3;  // prep + the exclusive scan (three launches for large batches) + publish
     LZB_CK(e, cudaStreamSynchronize(s));
@@ -1681,6 +1694,11 @@ int encode_batch_device_impl(lzfse_b200_encoder *e, const uint8_t *src, const ui
     e->launches += 1;
     e->timer.mark(s);  // assemble
     LZB_CK(e, cudaGetLastError());
+    if (!wait) {  // lzfse_b200_encoder_sync (or the caller's own wait on `s`) completes the call
+        e->pending = true;
+        e->pending_stream = s;
+        return LZFSE_B200_OK;
+    }
     LZB_CK(e, cudaStreamSynchronize(s));
     e->timer.finish();
     return LZFSE_B200_OK;
@@ -1736,6 +1754,23 @@ int lzfse_b200_encoder_last_stage_ms(const lzfse_b200_encoder *e, float *ms, int
     for (int i = 0; i < e->timer.n_done && i < cap; i++) ms[i] = e->timer.ms[i];
     return e->timer.n_done;
 }
+// Test hook (not part of the public header): copies the per-position words of the last fast parse to the host.
+size_t lzfse_b200_debug_encoder_words(lzfse_b200_encoder *e, uint32_t *host, size_t max_words) {
+    if (!e || !e->words.p) return 0;
+    DeviceGuard g(e->device);
+    size_t n = e->words.cap / sizeof(uint32_t);
+    if (n > max_words) n = max_words;
+    if (cudaMemcpy(host, e->words.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+    return n;
+}
+size_t lzfse_b200_debug_encoder_packs(lzfse_b200_encoder *e, uint64_t *host, size_t max_packs) {
+    if (!e || !e->packs.p) return 0;
+    DeviceGuard g(e->device);
+    size_t n = e->packs.cap / sizeof(uint2);
+    if (n > max_packs) n = max_packs;
+    if (cudaMemcpy(host, e->packs.p, n * sizeof(uint2), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+    return n;
+}
 size_t lzfse_b200_encode_bound(size_t n) { return n + n / 4 + (n / 16384 + 2) * 768 + 64; }
 
 int lzfse_b200_encode_batch_device(lzfse_b200_encoder *e, const uint8_t *src, const uint64_t *src_off, const uint64_t *src_len, uint8_t *dst,
@@ -1743,8 +1778,26 @@ int lzfse_b200_encode_batch_device(lzfse_b200_encoder *e, const uint8_t *src, co
     if (!e || (n && (!src_off || !src_len || !dst_off || !dst_cap || !out_len || !status))) return LZFSE_B200_INVALID_ARGUMENT;
     DeviceGuard g(e->device);
     if (!g.ok) return LZFSE_B200_CUDA_ERROR;
-    cudaStream_t s = stream ? (cudaStream_t)stream : e->own_stream;
-    return encode_batch_device_impl(e, src, src_off, src_len, dst, dst_off, dst_cap, out_len, status, n, s);
+    return encode_batch_device_impl(e, src, src_off, src_len, dst, dst_off, dst_cap, out_len, status, n, (cudaStream_t)stream);
+}
+
+int lzfse_b200_encode_batch_device_async(lzfse_b200_encoder *e, const uint8_t *src, const uint64_t *src_off, const uint64_t *src_len, uint8_t *dst,
+                                         const uint64_t *dst_off, const uint64_t *dst_cap, uint64_t *out_len, int32_t *status, size_t n, void *stream) {
+    if (!e || (n && (!src_off || !src_len || !dst_off || !dst_cap || !out_len || !status))) return LZFSE_B200_INVALID_ARGUMENT;
+    DeviceGuard g(e->device);
+    if (!g.ok) return LZFSE_B200_CUDA_ERROR;
+    return encode_batch_device_impl(e, src, src_off, src_len, dst, dst_off, dst_cap, out_len, status, n, (cudaStream_t)stream, false);
+}
+
+int lzfse_b200_encoder_sync(lzfse_b200_encoder *e) {
+    if (!e) return LZFSE_B200_INVALID_ARGUMENT;
+    if (!e->pending) return LZFSE_B200_OK;
+    DeviceGuard g(e->device);
+    if (!g.ok) return LZFSE_B200_CUDA_ERROR;
+    e->pending = false;
+    LZB_CK(e, cudaStreamSynchronize(e->pending_stream));
+    e->timer.finish();
+    return LZFSE_B200_OK;
 }
 
 int lzfse_b200_encode_batch_host(lzfse_b200_encoder *e, const uint8_t *src, const uint64_t *src_off, const uint64_t *src_len, uint8_t *dst,

@@ -306,7 +306,7 @@ k_expand_cta(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ 
              uint8_t *__restrict__ dst_base, const uint64_t *__restrict__ dst_off, const uint64_t *__restrict__ dst_cap,
              const StreamCounts *__restrict__ bases, const BlockDesc *__restrict__ blocks, const FseDesc *__restrict__ fse,
              const uint8_t *__restrict__ lit_scratch, const LmdRec *__restrict__ lmd_scratch, const uint64_t *__restrict__ raw_total,
-             uint32_t *err, uint32_t n_streams, uint32_t *work_counter) {
+             uint32_t *err, uint32_t n_streams, uint32_t *work_counter, const uint64_t *__restrict__ long_base) {
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool flusher = warp == kXWorkers;
     XEnv e;
@@ -333,6 +333,7 @@ k_expand_cta(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ 
         const uint64_t b0 = bases[stream].n_blocks;
         uint64_t b1 = bases[stream + 1].n_blocks;
         if (b1 - b0 == 1 && vn_fast_eligible(1, blocks[b0], src_off[stream] + src_len[stream] - blocks[b0].src_off, dst_cap[stream])) b1 = b0;  // k_expand_vn
+        if (long_base[stream] != ~0ull) b1 = b0;  // expand_long.cu
         uint32_t fl = 0;   // flusher's copy of ctl->flushed
         for (uint64_t b = b0; b < b1; b++) {
             const BlockDesc bd = blocks[b];
@@ -456,12 +457,12 @@ int setup_expand_kernel() {
 void launch_expand_cta(const uint8_t *src, const uint64_t *src_off, const uint64_t *src_len, uint8_t *dst, const uint64_t *dst_off,
                        const uint64_t *dst_cap, const StreamCounts *bases, const BlockDesc *blocks, const FseDesc *fse, const uint8_t *lit_scratch,
                        const LmdRec *lmd_scratch, const uint64_t *raw_total, uint32_t *err, size_t n, uint32_t *work_counter /* zeroed */,
-                       int n_sms, cudaStream_t s) {
+                       const uint64_t *long_base, int n_sms, cudaStream_t s) {
     if (n == 0) return;
     const size_t resident = (size_t)n_sms * LZB_XCTAS;
     const unsigned grid = (unsigned)(n < resident ? n : resident);
     k_expand_cta<<<grid, kXThreads, kXSmem, s>>>(src, src_off, src_len, dst, dst_off, dst_cap, bases, blocks, fse, lit_scratch, lmd_scratch, raw_total,
-                                                 err, (uint32_t)n, work_counter);
+                                                 err, (uint32_t)n, work_counter, long_base);
 }
 
 }  // namespace lzb

@@ -99,3 +99,43 @@ def test_many_small_streams(codec):
     outs, dst = dec.decode_batch(frames)
     assert not dst.any() and outs == chunks
     assert {f[:4] for f in frames} >= {b"bvx-", b"bvxn", b"bvx2"}
+
+
+def test_long_stream_compound_and_hostile(codec):
+    """The two-pass expansion of long streams (expand_long.cu): bvx2 blocks with a raw and an LZVN block between them
+    (blocks of independent frames concatenated: their matches still reach the same bytes), next to short streams that
+    take the in-order kernels; then the same long stream with one bit flipped in many places and cut short -- statuses
+    and bytes must equal the oracle's."""
+    from bench_support import workload as W
+
+    enc, dec = codec
+    pool, woff = W.word_pool(dec)
+    parts = [W.text_chunks(pool, woff, 1, 640 << 10, seed0=0x17000000).tobytes(), b"0123456789", tk.synth_text(77, 2000),
+             W.text_chunks(pool, woff, 1, 512 << 10, seed0=0x17000001).tobytes(), tk.rng_gen_vec(9, 70000), bytes(400000)]
+    pf, st = enc.encode_batch(parts)
+    assert not st.any() and all(f.endswith(b"bvx$") for f in pf)
+    compound = b"".join(f[:-4] for f in pf) + b"bvx$"
+    want = b"".join(parts)
+    assert ob.decode(compound) == (0, want)
+    shorts = [tk.synth_text(500 + i, 65536) for i in range(3)]
+    sf, st = enc.encode_batch(shorts)
+    assert not st.any()
+    outs, dst = dec.decode_batch([compound, sf[0], pf[0], sf[1], pf[3], sf[2]])
+    assert not dst.any() and outs == [want, shorts[0], parts[0], shorts[1], parts[3], shorts[2]]
+    # hostile: bit flips spread over the long frame (headers, weights, payloads of different blocks), truncations
+    frames = []
+    for k in range(96):
+        b = bytearray(compound)
+        pos = (k * 7919 * 131) % len(b)
+        b[pos] ^= 1 << (k % 8)
+        frames.append(bytes(b))
+    for k in range(16):
+        frames.append(compound[: (len(compound) * (k + 1)) // 17])
+    frames.append(compound)
+    caps = [len(want)] * len(frames)
+    outs, dst = dec.decode_batch(frames, caps=caps)
+    for f, o, s in zip(frames, outs, dst):
+        es, eo = ob.decode(f, cap=len(want))
+        assert int(s) == es, (int(s), es)
+        if es == 0:
+            assert o == eo

@@ -118,3 +118,24 @@ def test_two_rank_sharding_gloo(tmp_path):
                         "--master-port", "29531", str(script)], capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("ok") == 2
+
+
+def test_rust_sys_crate_matches_header():
+    """rust/lzfse_b200_sys declares exactly the functions include/lzfse_b200.h declares, with the same number of
+    parameters (the crates are source only: no rustc in this image), and its build.rs compiles every CUDA source the
+    Python build does."""
+    from lzfse_rust_b200 import build
+
+    header = open(os.path.join(ROOT, "include", "lzfse_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    c_decl = {m.group(1): m.group(2) for m in re.finditer(r"\b(lzfse_b200_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", header)}
+    rs = open(os.path.join(ROOT, "rust", "lzfse_b200_sys", "src", "lib.rs")).read()
+    rs_decl = {m.group(1): m.group(2) for m in re.finditer(r"pub fn (lzfse_b200_[a-z0-9_]+)\s*\(([^)]*)\)", rs)}
+    assert set(c_decl) == set(rs_decl), set(c_decl) ^ set(rs_decl)
+    count = lambda a: 0 if a.strip() in ("", "void") else a.count(",") + 1
+    for name in c_decl:
+        assert count(c_decl[name]) == count(rs_decl[name]), name
+    build_rs = open(os.path.join(ROOT, "rust", "lzfse_b200_sys", "build.rs")).read()
+    for src in build.SOURCES:
+        assert '"%s"' % src in build_rs, src
+    assert "compute_100a" in build_rs
