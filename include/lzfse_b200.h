@@ -77,7 +77,7 @@ enum lzfse_b200_status {
     LZFSE_B200_VN_BAD_PAYLOAD_COUNT = 32, /* Error::Vn(VnErrorKind::...) = 32 + discriminant */
     LZFSE_B200_VN_BAD_PAYLOAD = 33,
     LZFSE_B200_VN_BAD_OPCODE = 34,
-    /* call-level failures (return values only, never per-stream) */
+    /* call-level failures (return values; per-stream only where a function says so) */
     LZFSE_B200_INVALID_ARGUMENT = 64,
     LZFSE_B200_NO_DEVICE = 65,
     LZFSE_B200_CUDA_ERROR = 66,
@@ -148,8 +148,18 @@ int lzfse_b200_decoder_last_stage_ms(const lzfse_b200_decoder *d, float *stage_m
 int lzfse_b200_encoder_create(int cuda_device, lzfse_b200_encoder **out);
 void lzfse_b200_encoder_destroy(lzfse_b200_encoder *e);
 
-/* Upper bound of the frame size encode produces for src_len input bytes. */
+/* Frame-size bounds for src_len input bytes.
+ * lzfse_b200_encode_bound is the working bound: 1.25 x the input plus 768 bytes per 16 KiB, which no input we know of
+ * exceeds (incompressible data costs ~8.2 bits per byte plus one block header per 40 000 literals) but which is not
+ * derived from the format's worst case; a frame that did exceed it fails with LZFSE_B200_BUFFER_OVERFLOW, where the
+ * reference's Vec would have grown.  lzfse_b200_encode_bound_strict is that worst case (10 bits per literal, 54 bits per
+ * L/M/D triple, a header and weight table per block: ~3 x the input); a caller that must never see BufferOverflow retries
+ * the failing streams with it (the Python wrappers do).
+ * Inputs of more than 0x7FFFFFFF bytes per stream are not supported (the reference repositions its history there,
+ * src/encode/frontend_bytes.rs:348-375): such a stream gets the per-stream status LZFSE_B200_INVALID_ARGUMENT -- the one
+ * case where a code >= 64 appears in status[]. */
 size_t lzfse_b200_encode_bound(size_t src_len);
+size_t lzfse_b200_encode_bound_strict(size_t src_len);
 
 /* encode_bytes: one frame, host buffers. */
 int lzfse_b200_encode_bytes(lzfse_b200_encoder *e, const uint8_t *src, size_t src_len, uint8_t *dst,

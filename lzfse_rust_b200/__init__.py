@@ -6,6 +6,8 @@ There is no CPU implementation in here: creating a decoder/encoder without a CUD
 """
 from .codec import LzfseDecoder, LzfseEncoder, LzfseError, STATUS_NAMES, decode_bytes, encode_bytes
 from .sharding import shard_ranges
+from .streaming import LzfseReader, LzfseRingDecoder, LzfseRingEncoder, LzfseWriter
 
-__all__ = ["LzfseDecoder", "LzfseEncoder", "LzfseError", "STATUS_NAMES", "decode_bytes", "encode_bytes", "shard_ranges"]
-__version__ = "0.1.0"
+__all__ = ["LzfseDecoder", "LzfseEncoder", "LzfseError", "STATUS_NAMES", "decode_bytes", "encode_bytes", "shard_ranges",
+           "LzfseRingDecoder", "LzfseRingEncoder", "LzfseReader", "LzfseWriter"]
+__version__ = "0.2.0"

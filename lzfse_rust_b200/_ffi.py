@@ -13,7 +13,7 @@ SYMBOLS = [
     "lzfse_b200_decoder_last_launches", "lzfse_b200_encoder_create", "lzfse_b200_encoder_destroy", "lzfse_b200_encode_bound",
     "lzfse_b200_encode_bytes", "lzfse_b200_encode_batch_device", "lzfse_b200_encode_batch_host", "lzfse_b200_encoder_last_launches",
     "lzfse_b200_decoder_set_timing", "lzfse_b200_decoder_last_stage_ms", "lzfse_b200_encoder_set_timing", "lzfse_b200_encoder_last_stage_ms",
-    "lzfse_b200_decode_batch_device_async", "lzfse_b200_decoder_sync", "lzfse_b200_encode_batch_device_async", "lzfse_b200_encoder_sync",
+    "lzfse_b200_encode_bound_strict", "lzfse_b200_decode_batch_device_async", "lzfse_b200_decoder_sync", "lzfse_b200_encode_batch_device_async", "lzfse_b200_encoder_sync",
 ]
 
 _lib = None
@@ -52,6 +52,8 @@ def load(build_if_missing=True):
         getattr(lib, "lzfse_b200_%s_last_stage_ms" % n).argtypes = [vp, C.POINTER(C.c_float), C.c_int]
     lib.lzfse_b200_encode_bound.argtypes = [C.c_size_t]
     lib.lzfse_b200_encode_bound.restype = C.c_size_t
+    lib.lzfse_b200_encode_bound_strict.argtypes = [C.c_size_t]
+    lib.lzfse_b200_encode_bound_strict.restype = C.c_size_t
     for n in ("decode", "encode"):
         getattr(lib, "lzfse_b200_%s_bytes" % n).argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, szp]
         getattr(lib, "lzfse_b200_%s_batch_device" % n).argtypes = [vp, vp, u64p, u64p, vp, u64p, u64p, u64p, i32p, C.c_size_t, vp]

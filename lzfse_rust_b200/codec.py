@@ -199,6 +199,10 @@ class LzfseEncoder(_Handle):
         out = np.empty(cap, dtype=np.uint8)
         n = C.c_size_t(0)
         rc = self._lib.lzfse_b200_encode_bytes(self._h, _ptr(src) if len(src) else None, len(src), _ptr(out), cap, C.byref(n))
+        if rc == 5:  # BufferOverflow under the working bound: once more with the format's worst case
+            cap = int(self._lib.lzfse_b200_encode_bound_strict(len(src)))
+            out = np.empty(cap, dtype=np.uint8)
+            rc = self._lib.lzfse_b200_encode_bytes(self._h, _ptr(src) if len(src) else None, len(src), _ptr(out), cap, C.byref(n))
         if rc != 0:
             raise LzfseError(rc, self._lib.lzfse_b200_encoder_last_error(self._h).decode() if rc >= 64 else "")
         dst += out[: n.value].tobytes()
@@ -218,6 +222,15 @@ class LzfseEncoder(_Handle):
         dst = np.empty(max(int(caps.sum()), 1), dtype=np.uint8)
         out_len, status = self.encode_batch_into(src, offs, lens, dst, doff, caps)
         outs = [dst[int(doff[i]) : int(doff[i]) + int(out_len[i])].tobytes() if status[i] == 0 else None for i in range(n)]
+        over = [i for i in range(n) if status[i] == 5]  # BufferOverflow under the working bound: once more with the format's worst case
+        if over:
+            caps2 = np.array([int(self._lib.lzfse_b200_encode_bound_strict(int(lens[i]))) for i in over], dtype=np.uint64)
+            doff2 = np.concatenate([[0], np.cumsum(caps2)[:-1]]).astype(np.uint64)
+            dst2 = np.empty(int(caps2.sum()), dtype=np.uint8)
+            ol2, st2 = self.encode_batch_into(src, offs[over], lens[over], dst2, doff2, caps2)
+            for k, i in enumerate(over):
+                status[i] = st2[k]
+                outs[i] = dst2[int(doff2[k]) : int(doff2[k]) + int(ol2[k])].tobytes() if st2[k] == 0 else None
         return outs, status
 
     def encode_batch_device(self, src, src_off, src_len, dst, dst_off, dst_cap, stream=None, wait=True):

@@ -22,7 +22,7 @@ void launch_scan_fill(const uint8_t *, const uint64_t *, const uint64_t *, const
                       uint32_t *, uint64_t *, uint32_t *, uint32_t, uint64_t *, uint32_t *, uint32_t *, cudaStream_t);
 int setup_decode_kernels();
 void launch_fse_stages(const uint8_t *, const uint64_t *, const uint64_t *, const uint64_t *, const uint64_t *, const BlockDesc *, FseDesc *, uint32_t, uint8_t *,
-                       LmdRec *, uint32_t *, uint32_t *, uint32_t *, int, cudaStream_t, cudaEvent_t);
+                       LmdRec *, uint32_t *, uint32_t *, int, cudaStream_t, cudaEvent_t);
 void launch_expand(const uint8_t *, const uint64_t *, const uint64_t *, uint8_t *, const uint64_t *, const uint64_t *, const StreamCounts *, const BlockDesc *,
                    const FseDesc *, const uint8_t *, const LmdRec *, uint32_t *, size_t, uint32_t *, const uint64_t *, int, cudaStream_t);
 void launch_expand_vn(const uint8_t *, const uint64_t *, const uint64_t *, uint8_t *, const uint64_t *, const uint64_t *, const StreamCounts *,
@@ -44,12 +44,12 @@ using namespace lzb;
 // Device scratch of one kernel chain.  The host entry point runs several chains (one per slice of the batch) at the
 // same time, each with its own scratch and stream; everything else uses chain 0.
 struct DecodeScratch {
-    DevBuf counts, err, raw_total, totals_dev, blocks, fse, lits, lmds, work, slow;
+    DevBuf counts, err, raw_total, totals_dev, blocks, fse, lits, lmds, work;
     DevBuf long_base, long_blocks, long_streams, image;  // two-pass expansion of long streams (expand_long.cu)
     PinnedBuf totals_host;
     cudaStream_t stream = nullptr;  // chains 1.. only
     void release() {
-        for (DevBuf *b : {&counts, &err, &raw_total, &totals_dev, &blocks, &fse, &lits, &lmds, &work, &slow, &long_base, &long_blocks, &long_streams, &image}) b->release();
+        for (DevBuf *b : {&counts, &err, &raw_total, &totals_dev, &blocks, &fse, &lits, &lmds, &work, &long_base, &long_blocks, &long_streams, &image}) b->release();
         totals_host.release();
         if (stream) cudaStreamDestroy(stream);
         stream = nullptr;
@@ -109,7 +109,6 @@ int decode_launch_rest(lzfse_b200_decoder *d, DecodeScratch &c, const uint8_t *s
     CK(d, c.fse.reserve((tot.n_fse + 1) * sizeof(FseDesc)));
     CK(d, c.lits.reserve(tot.n_literals + 512));  // slack: the expander prefetches up to 128 bytes past a block's run
     CK(d, c.lmds.reserve((tot.n_lmds + 1) * sizeof(LmdRec)));
-    CK(d, c.slow.reserve((2 * tot.n_fse + 2) * sizeof(uint32_t)));
     CK(d, c.long_base.reserve(n * sizeof(uint64_t)));
     CK(d, c.long_blocks.reserve(((size_t)lt.n_blocks + 1) * sizeof(uint32_t)));
     CK(d, c.long_streams.reserve(((size_t)lt.n_streams + 1) * sizeof(uint32_t)));
@@ -122,10 +121,10 @@ int decode_launch_rest(lzfse_b200_decoder *d, DecodeScratch &c, const uint8_t *s
     if (timer) timer->mark(s);  // scan (count + host round trip + fill)
     if (tot.n_fse) {
         launch_fse_stages(src, src_off, src_len, dst_off, dst_cap, c.blocks.as<BlockDesc>(), c.fse.as<FseDesc>(), (uint32_t)tot.n_fse,
-                          c.lits.as<uint8_t>(), c.lmds.as<LmdRec>(), c.err.as<uint32_t>(), c.work.as<uint32_t>(), c.slow.as<uint32_t>(), d->n_sms, s,
+                          c.lits.as<uint8_t>(), c.lmds.as<LmdRec>(), c.err.as<uint32_t>(), c.work.as<uint32_t>(), d->n_sms, s,
                           timer && timer->enabled ? timer->ev[timer->n] : nullptr);
         if (timer && timer->enabled) timer->n++;  // literals
-        d->launches += 3;
+        d->launches += 2;
     } else if (timer) {
         timer->mark(s);
     }
@@ -331,8 +330,23 @@ int lzfse_b200_decode_probe_batch_device(lzfse_b200_decoder *d, const uint8_t *s
 // machine, hence a chain takes ~2.5 ms however small its slice is, and running the chains one after the other would
 // leave the download engine idle between slices.  The download (the bound: ~56 GB/s) starts as soon as the first,
 // small slice is done; by then the other chains have been running next to it.
+static int decode_batch_host_pipelined_impl(lzfse_b200_decoder *d, const uint8_t *src, const uint64_t *src_off, const uint64_t *src_len, uint8_t *dst,
+                                            const uint64_t *dst_off, uint64_t *out_len, int32_t *status, size_t n);
 static int decode_batch_host_pipelined(lzfse_b200_decoder *d, const uint8_t *src, const uint64_t *src_off, const uint64_t *src_len, uint8_t *dst,
                                        const uint64_t *dst_off, uint64_t *out_len, int32_t *status, size_t n) {
+    const int rc = decode_batch_host_pipelined_impl(d, src, src_off, src_len, dst, dst_off, out_len, status, n);
+    if (rc) {  // a call-level failure: nothing of this call may still be running (or copying into the caller's buffers) when it returns
+        for (auto &c : d->chain)
+            if (c.stream) cudaStreamSynchronize(c.stream);
+        if (d->stage.copy_in) cudaStreamSynchronize(d->stage.copy_in);
+        if (d->stage.copy_out) cudaStreamSynchronize(d->stage.copy_out);
+        cudaStreamSynchronize(d->own_stream);
+        cudaGetLastError();
+    }
+    return rc;
+}
+static int decode_batch_host_pipelined_impl(lzfse_b200_decoder *d, const uint8_t *src, const uint64_t *src_off, const uint64_t *src_len, uint8_t *dst,
+                                            const uint64_t *dst_off, uint64_t *out_len, int32_t *status, size_t n) {
     uint32_t share_pct[kMaxChains] = {4, 12, 28, 52, 76, 100};  // cumulative share of the bytes crossing the bus
     int n_slices = kMaxChains;
     if (const char *ov = getenv("LZB_SLICES")) {  // tuning aid: comma-separated cumulative percentages

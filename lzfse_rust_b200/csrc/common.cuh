@@ -38,7 +38,7 @@ enum BlockType : uint32_t { BT_RAW = 0, BT_VXN = 1, BT_VX1 = 2, BT_VX2 = 3 };
 enum Phase : uint32_t { PH_HEADER = 0, PH_WEIGHTS = 1, PH_LIT_TAKE = 2, PH_LIT = 3, PH_LMD_TAKE = 4, PH_LMD = 5 };
 constexpr uint32_t kNoError = 0xFFFFFFFFu;
 // Work counters of one decode chain (zeroed per call): 0 literals (exact kernel), 1 LMDs, 2 expansion, 3 LZVN expansion,
-// 4 literals (quad kernel), 5 number of blocks the quad kernel handed to the exact kernel, 6-7 spare;
+// 4-7 spare;
 // long streams (expand_long.cu): 8-9 image elements (u64), 10 blocks, 11 streams as counted by k_scan<false>;
 // 12-13 / 14 / 15 the same three as allocation cursors of k_scan<true>; 16 pass-1 work counter
 constexpr uint32_t kWorkWords = 32;

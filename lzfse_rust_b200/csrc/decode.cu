@@ -568,9 +568,7 @@ constexpr size_t kLitSmemPerWarp = 1024 * 32 * 3 + kRingBytesPerWarp;
 __global__ void __launch_bounds__(kLitWarps * 32, 1)
 k_fse_literals(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ src_off, const uint64_t *__restrict__ src_len,
                const BlockDesc *__restrict__ blocks, FseDesc *__restrict__ fse, uint32_t n_fse, uint8_t *__restrict__ lit_scratch,
-               uint32_t *err, uint32_t *work_counter, const uint32_t *__restrict__ list, const uint32_t *__restrict__ list_count) {
-    // With a list: only the blocks the quad kernel (k_fse_literals4) handed over -- anything it did not like.
-    if (list) n_fse = *list_count;
+               uint32_t *err, uint32_t *work_counter) {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
     uint16_t *kd = reinterpret_cast<uint16_t *>(smem + warp * kLitSmemPerWarp);
@@ -581,8 +579,8 @@ k_fse_literals(const uint8_t *__restrict__ src_base, const uint64_t *__restrict_
         if (lane == 0) base = atomicAdd(work_counter, 32u);
         base = __shfl_sync(0xFFFFFFFFu, base, 0);
         if (base >= n_fse) break;
-        if (base + lane < n_fse) {
-            const uint32_t f = list ? list[base + lane] : base + lane;
+        const uint32_t f = base + lane;
+        if (f < n_fse) {
             FseDesc fd = fse[f];
             const BlockDesc bd = blocks[fd.block];
             const uint8_t *blk = src_base + bd.src_off;
@@ -665,162 +663,6 @@ k_fse_literals(const uint8_t *__restrict__ src_base, const uint64_t *__restrict_
                     else fse[f].ok_lit = 1;
                 }
             }
-        }
-        __syncwarp();
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Literal stage, fast kernel: FOUR lanes per block, lane q of a quad carries interleaved state q.
-//
-// The lane-per-block kernel above spends ~300 cycles per 4-literal step: one warp per scheduler issues all ~90
-// instructions of the step itself, its 64 table slots per SM leave two schedulers empty, and the 111 blocks per SM of
-// the headline workload need two waves.  A block's four FSE states are independent except for the bit cursor, so a
-// quad decodes one step with ONE table lookup per lane; the four k values travel through three butterfly shuffles
-// (prefix for the lane's bit position, total for the cursor).  8 blocks per warp, 8 warps per SM: the same 64 table
-// slots, but all four schedulers issue and a step is ~1/3 of the dependent chain.
-//
-// This kernel only decodes blocks that are plainly well formed.  Whatever else it meets -- truncated payloads, bad
-// weights, a reader that comes within 57 bits of the pad, non-zero final states -- it leaves untouched and appends to
-// `slow_list`; the lane-per-block kernel then runs over that list with the reference's exact flush semantics and
-// reports the error the reference reports (fse/literals.rs:49-91, bits/bit_reader.rs:20-71).
-// ------------------------------------------------------------------------------------------------
-constexpr int kLit4Warps = 8;
-constexpr uint32_t kLit4Blocks = 8;  // per warp
-constexpr size_t kLit4TabBytes = 1024 * 3;  // u16 plane (k << 12 | delta), u8 plane (symbol)
-constexpr size_t kLit4SmemPerWarp = kLit4Blocks * (kLit4TabBytes + kRingStride);
-
-__device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
-    uint32_t v;
-    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ uint32_t lds_u8v(uint32_t a) {
-    uint32_t v;
-    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
-    return v;
-}
-
-__global__ void __launch_bounds__(kLit4Warps * 32, 1)
-k_fse_literals4(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ src_off, const uint64_t *__restrict__ src_len,
-                const BlockDesc *__restrict__ blocks, FseDesc *__restrict__ fse, uint32_t n_fse, uint8_t *__restrict__ lit_scratch,
-                uint32_t *work_counter, uint32_t *__restrict__ slow_list, uint32_t *slow_count) {
-    extern __shared__ __align__(16) uint8_t smem[];
-    constexpr uint32_t kFull = 0xFFFFFFFFu;
-    const uint32_t warp = threadIdx.x >> 5, lane = lane_id(), q = lane & 3, b = lane >> 2;
-    uint8_t *wbase = smem + warp * kLit4SmemPerWarp;
-    uint16_t *kd = reinterpret_cast<uint16_t *>(wbase + b * kLit4TabBytes);
-    uint8_t *sy = wbase + b * kLit4TabBytes + 2048;
-    const uint32_t kd_s = (uint32_t)__cvta_generic_to_shared(kd), sy_s = kd_s + 2048;
-    const uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(wbase + kLit4Blocks * kLit4TabBytes) + b * kRingStride;
-    for (;;) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(work_counter, kLit4Blocks);
-        base = __shfl_sync(kFull, base, 0);
-        if (base >= n_fse) break;
-        const uint32_t f = base + b;
-        const bool have = f < n_fse;
-        bool good = false;  // the quad decodes this block
-        uint64_t lit_off = 0;
-        RingWindow br;
-        br.P = 0; br.dead = false; br.g0 = 0; br.a_base = 0; br.lo16 = 0; br.hi = 0; br.next_chunk = 0; br.ring = ring_addr;
-        uint32_t s = 0, n_it = 0;
-        if (have) {
-            const FseDesc fd = fse[f];
-            const BlockDesc bd = blocks[fd.block];
-            const uint8_t *blk = src_base + bd.src_off;
-            const bool v1 = fd.flags & FSE_V1;
-            const uint8_t *wp = blk + (v1 ? kV1HeaderSize : kV2HeaderSize);
-            lit_off = fd.lit_off;
-            good = !(fd.flags & FSE_TRUNC_LIT) && validate_weights(wp, fd.n_weight_bytes, v1) == 0;
-            if (good) {
-                // build_u_table (fse/decoder.rs:299-335): every lane of the quad walks the weights, lane q writes the
-                // states congruent to q
-                WeightReader r;
-                r.init(wp, fd.n_weight_bytes, v1);
-                for (int k = 0; k < 104; k++) r.next();
-                uint32_t total = 0;
-                for (uint32_t sym = 0; sym < 256; sym++) {
-                    const uint32_t w = r.next();
-                    if (w == 0) continue;
-                    const uint32_t k = __clz(w) - 21;
-                    const uint32_t x = (2048u >> k) - w;
-                    for (uint32_t j = (q - total) & 3u; j < w; j += 4) {
-                        uint32_t kk, delta;
-                        if (j < x) { kk = k; delta = ((w + j) << k) - 1024u; }
-                        else { kk = k - 1; delta = (j - x) << (k - 1); }
-                        kd[total + j] = (uint16_t)(delta | (kk << 12));
-                        sy[total + j] = (uint8_t)sym;
-                    }
-                    total += w;
-                }
-                for (uint32_t t = total + ((q - total) & 3u); t < 1024; t += 4) { kd[t] = (uint16_t)t; sy[t] = 0; }
-                // the reader: the quad shares one ring; lane q requests chunks q and q + 4 of the first eight
-                const uint8_t *s_lo = src_base + src_off[bd.stream], *s_hi = s_lo + src_len[bd.stream];
-                const uint8_t *start = blk + fd.header_size - 8;
-                const uint32_t len = fd.n_lit_payload + 8, off = fd.lit_bits;
-                br.g0 = (reinterpret_cast<uintptr_t>(s_lo) & ~(uintptr_t)15) - 256;
-                br.lo16 = (uint32_t)(((reinterpret_cast<uintptr_t>(s_lo) + 15) & ~(uintptr_t)15) - br.g0);
-                br.hi = (uint32_t)(reinterpret_cast<uintptr_t>(s_hi) - br.g0);
-                br.a_base = (uint32_t)(reinterpret_cast<uintptr_t>(start) - br.g0);
-                br.P = (int)len * 8 - (int)off;
-                const uint32_t last = start[len - 1];
-                if (off != 0 && (last >> (8 - off)) != 0) good = false;  // BitReader::new would refuse
-                const uint32_t a = br.a_base + (uint32_t)((br.P - 57) >> 3);
-                const uint32_t top = ((a & ~3u) + 11) & ~15u;
-                br.fetch_chunk(top - 16 * q);
-                br.fetch_chunk(top - 16 * (q + 4));
-                br.next_chunk = top - kRing;
-                s = fse[f].lit_state[q];  // (indexing the register copy would push it to the stack)
-                n_it = good ? fd.n_literals >> 2 : 0;
-            }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncwarp();
-        uint8_t *out = lit_scratch + lit_off + q;
-        asm volatile("" : "+l"(out));
-        const uint32_t max_it = __reduce_max_sync(kFull, n_it);
-        uint32_t it = 0;
-        bool stopped = false;
-        for (uint32_t step = 0; step < max_it; step++) {
-            const bool live = step < n_it && !stopped && br.P >= 57;  // same in all four lanes of a quad
-            stopped |= step < n_it && !live;
-            if (live) {
-                const uint32_t a4 = (br.a_base + (uint32_t)((br.P - 57) >> 3)) & ~3u;
-                if (a4 + 12 <= br.next_chunk + kRing) {
-                    if (q == 0) br.fetch_chunk(br.next_chunk);
-                    br.next_chunk -= 16;
-                }
-            }
-            // One group per STEP, committed by the whole warp (the hardware counts a warp's groups, not a lane's: with a
-            // group per refill of one quad, "at most five pending" made every refill wait for the requests the other
-            // quads had issued a few steps earlier -- a full memory round trip per step).  A chunk is requested when the
-            // window's base is <= 116 bytes above it and first read when the base is <= 15 above it; a step consumes at
-            // most 5 bytes, so at least 20 younger groups exist by then and 16 pending ones are safe.
-            asm volatile("cp.async.commit_group;" ::: "memory");
-            asm volatile("cp.async.wait_group 16;" ::: "memory");
-            __syncwarp();  // lane 0's chunks become visible to the quad
-            int cur;
-            const uint64_t win = br.window_fast(cur);
-            const uint32_t e = lds_u16(kd_s + s * 2), y = lds_u8v(sy_s + s);
-            const uint32_t k = live ? e >> 12 : 0u;
-            const uint32_t x1 = __shfl_xor_sync(kFull, k, 1), x2 = __shfl_xor_sync(kFull, k, 2), x3 = __shfl_xor_sync(kFull, k, 3);
-            const uint32_t pre = ((q & 1) ? x1 : 0u) + ((q & 2) ? x2 + x3 : 0u);  // bits taken by the lower states of this step
-            const int p = cur - (int)pre - (int)k;
-            if (live) {
-                s = bits_at(win, p, k) + (e & 0xFFF);
-                br.P -= (int)(k + x1 + x2 + x3);
-                out[step * 4] = (uint8_t)y;
-                it = step + 1;
-            }
-        }
-        // Literals::load's tail: final flush, reader not underflown, all four states back at zero
-        const bool lane_ok = good && it == n_it && br.P >= 64 && s == 0;
-        const bool ok = ((__ballot_sync(kFull, lane_ok) >> (b * 4)) & 0xFu) == 0xFu;
-        if (have && q == 0) {
-            if (ok) fse[f].ok_lit = 1;
-            else slow_list[atomicAdd(slow_count, 1u)] = f;
         }
         __syncwarp();
     }
@@ -1115,9 +957,28 @@ __device__ __forceinline__ void expand_step(uint8_t *__restrict__ out, const uin
             }
         }
     }
+    mask = __ballot_sync(0xFFFFFFFFu, M != 0 && !solo);
     if constexpr (STAGED) {
-        // flush [out_base, out_base + tot_o): bytes up to the first 16-byte boundary, whole 16-byte units, the rest.
-        // (Positions of the matches still to come carry garbage; they are written next.)
+        // ---- the other matches (long, overlapping, or reading what this step produces), in order, INTO THE IMAGE ----
+        // A source byte at or above out_base is in the image (shared memory, ~30 cycles); below it, it is final and comes
+        // from global memory.  Before, these matches were copied global -> global after the flush: every one of them was a
+        // round trip to L2 (the line was only ever written by this SM, so it is not in L1) in the step's serial chain.
+        if (mask) __syncwarp();
+        while (mask) {
+            const int j = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const uint32_t o = __shfl_sync(0xFFFFFFFFu, my_dst, j), d = __shfl_sync(0xFFFFFFFFu, D, j), n = __shfl_sync(0xFFFFFFFFu, M, j);
+            const uint8_t *s = out + o - d;   // may point before `out` (earlier blocks of the stream)
+            const int32_t src0 = (int32_t)o - (int32_t)d, ob = (int32_t)out_base;  // block-relative; src0 may be negative
+            for (uint32_t t = lane; t < n; t += 32) {
+                const uint32_t u = d >= n ? t : t % d;  // byte i == byte i mod D of the D bytes before the match
+                const int32_t pp = src0 + (int32_t)u;
+                const uint32_t v = pp >= ob ? lds_u8(sbase + (uint32_t)pp) : (uint32_t)s[u];
+                sts_u8(sbase + o + t, v);
+            }
+            __syncwarp();
+        }
+        // flush [out_base, out_base + tot_o): bytes up to the first 16-byte boundary, whole 16-byte units, the rest
         __syncwarp();
         uint8_t *g0 = out + out_base;
         asm volatile("" : "+l"(g0));  // as above: one address, not one per store
@@ -1134,22 +995,23 @@ __device__ __forceinline__ void expand_step(uint8_t *__restrict__ out, const uin
         } else if (lane < tot_o) {
             g0[lane] = (uint8_t)lds_u8(stage_s + align + lane);
         }
-    }
-    mask = __ballot_sync(0xFFFFFFFFu, M != 0 && !solo);
-    if (mask || STAGED) __syncwarp();
-    while (mask) {
-        int j = __ffs(mask) - 1;
-        mask &= mask - 1;
-        uint32_t o = __shfl_sync(0xFFFFFFFFu, my_dst, j), d = __shfl_sync(0xFFFFFFFFu, D, j), n = __shfl_sync(0xFFFFFFFFu, M, j);
-        const uint8_t *s = out + o - d;
-        if (d >= n) {
-            for (uint32_t t = lane; t < n; t += 32) out[o + t] = s[t];
-        } else {
-            for (uint32_t t = lane; t < n; t += 32) out[o + t] = s[t % d];  // byte i == byte i mod D of the seed
+        __syncwarp();
+    } else {
+        if (mask) __syncwarp();
+        while (mask) {
+            int j = __ffs(mask) - 1;
+            mask &= mask - 1;
+            uint32_t o = __shfl_sync(0xFFFFFFFFu, my_dst, j), d = __shfl_sync(0xFFFFFFFFu, D, j), n = __shfl_sync(0xFFFFFFFFu, M, j);
+            const uint8_t *s = out + o - d;
+            if (d >= n) {
+                for (uint32_t t = lane; t < n; t += 32) out[o + t] = s[t];
+            } else {
+                for (uint32_t t = lane; t < n; t += 32) out[o + t] = s[t % d];  // byte i == byte i mod D of the seed
+            }
+            __syncwarp();
         }
         __syncwarp();
     }
-    __syncwarp();
 }
 
 // One bvx1/bvx2 block, 32 LMDs per step.
@@ -1487,32 +1349,16 @@ int setup_decode_kernels() {
     cudaError_t e = cudaFuncSetAttribute(k_fse_literals, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kLitWarps * kLitSmemPerWarp));
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(k_fse_lmds, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kLmdWarps * kLmdSmemPerWarp));
-    if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(k_fse_literals4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kLit4Warps * kLit4SmemPerWarp));
     return (int)e;
 }
 void launch_fse_stages(const uint8_t *src, const uint64_t *src_off, const uint64_t *src_len, const uint64_t *dst_off, const uint64_t *dst_cap,
                        const BlockDesc *blocks, FseDesc *fse, uint32_t n_fse, uint8_t *lit_scratch, LmdRec *lmd_scratch, uint32_t *err,
-                       uint32_t *work_counters /* kWorkWords zeroed u32 */, uint32_t *slow_lists /* 2 * n_fse u32 */, int n_sms, cudaStream_t s,
-                       cudaEvent_t between) {
+                       uint32_t *work_counters /* kWorkWords zeroed u32 */, int n_sms, cudaStream_t s, cudaEvent_t between) {
     if (n_fse == 0) return;
     unsigned need_lit = (n_fse + 32 * kLitWarps - 1) / (32 * kLitWarps), need_lmd = (n_fse + 32 * kLmdWarps - 1) / (32 * kLmdWarps);
     unsigned g_lit = need_lit < (unsigned)n_sms ? need_lit : (unsigned)n_sms;
     unsigned g_lmd = need_lmd < (unsigned)n_sms ? need_lmd : (unsigned)n_sms;
-    // literals: quad kernel first, then the exact lane-per-block kernel over whatever the quad kernel handed over
-    // (usually nothing: its CTAs read a zero count and leave)
-    static const bool lit4 = [] { const char *e = getenv("LZB_LIT4"); return !e || atoi(e) != 0; }();  // LZB_LIT4=0: measurements only
-    if (lit4) {
-        unsigned need4 = (n_fse + kLit4Blocks * kLit4Warps - 1) / (kLit4Blocks * kLit4Warps);
-        unsigned g4 = need4 < (unsigned)n_sms ? need4 : (unsigned)n_sms;
-        k_fse_literals4<<<g4, kLit4Warps * 32, kLit4Warps * kLit4SmemPerWarp, s>>>(src, src_off, src_len, blocks, fse, n_fse, lit_scratch,
-                                                                                  work_counters + 4, slow_lists, work_counters + 5);
-        k_fse_literals<<<g_lit, kLitWarps * 32, kLitWarps * kLitSmemPerWarp, s>>>(src, src_off, src_len, blocks, fse, n_fse, lit_scratch, err, work_counters,
-                                                                                  slow_lists, work_counters + 5);
-    } else {
-        k_fse_literals<<<g_lit, kLitWarps * 32, kLitWarps * kLitSmemPerWarp, s>>>(src, src_off, src_len, blocks, fse, n_fse, lit_scratch, err, work_counters,
-                                                                                  nullptr, nullptr);
-    }
+    k_fse_literals<<<g_lit, kLitWarps * 32, kLitWarps * kLitSmemPerWarp, s>>>(src, src_off, src_len, blocks, fse, n_fse, lit_scratch, err, work_counters);
     if (between) cudaEventRecord(between, s);
     k_fse_lmds<<<g_lmd, kLmdWarps * 32, kLmdWarps * kLmdSmemPerWarp, s>>>(src, src_off, src_len, dst_off, dst_cap, blocks, fse, n_fse, lmd_scratch, err, work_counters + 1);
 }

@@ -1126,7 +1126,7 @@ __device__ __forceinline__ void tsink_push_match(TSink &s, const TEnv &env, uint
 constexpr int kReplayThreads = 32;
 constexpr int kReplayStride = LZB_REPLAY_STRIDE;
 #ifndef LZB_RING_WORDS
-#define LZB_RING_WORDS 64
+#define LZB_RING_WORDS 128   // 64: replay 14.6 ms per GiB (half a ring of lead time is about one memory round trip on text)
 #endif
 constexpr uint32_t kRingWords = LZB_RING_WORDS, kRingStride = kRingWords * 4 + 16;  // per-lane ring of words (stride skews the banks)
 __global__ void __launch_bounds__(kReplayThreads)
@@ -1150,9 +1150,9 @@ k_enc_replay(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ 
     uint32_t cur = 0, literal_index = 0;
     Match pending = {0, 0, 0};
     // Every lane walks its own stream, so a plain load per position costs a memory round trip per step of this serial
-    // loop (and prefetch.global.L1 does not shorten it).  Each lane therefore owns a 64-word ring in shared memory, two
-    // halves of 32 words: on entering a half it waits for everything it has requested (cp.async.wait_group 0) and then
-    // requests the half after, which so has 32 positions of time to arrive.  The cursor reads four words at a time into
+    // loop (and prefetch.global.L1 does not shorten it).  Each lane therefore owns a ring of words in shared memory, two
+    // halves: on entering a half it waits for everything it has requested (cp.async.wait_group 0) and then requests the
+    // half after, which so has half a ring of positions to arrive.  The cursor reads four words at a time into
     // registers.
     // Only wait_group 0 is used, on purpose.  The first version kept 16 single-chunk groups in flight and waited with
     // wait_group 14 ("my 16th newest group is complete"): right by PTX's per-thread wording, but the lanes of this
@@ -1160,13 +1160,14 @@ k_enc_replay(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ 
     // still valid, but not the reference's bytes, and different ones from run to run -- found by scripts/enc_words_diff.py:
     // identical words, different packs; gone with a full drain).
     __shared__ __align__(16) uint8_t rings[kReplayThreads / kReplayStride * kRingStride];
-    static_assert(kRingWords == 64, "two halves of 32 words");
+    constexpr uint32_t kHalf = kRingWords / 2;
+    static_assert((kRingWords & (kRingWords - 1)) == 0 && kHalf % 4 == 0, "two halves of whole chunks");
     const uint32_t ring = (uint32_t)__cvta_generic_to_shared(rings) + threadIdx.x / kReplayStride * kRingStride;
     const uint32_t w_limit = (end + 3u) & ~3u;  // chunks at or beyond this word index are never needed
     uint32_t wbase = 0xFFFFFFFFu, half = 0xFFFFFFFFu, pre_half = 0xFFFFFFFFu;
     uint4 wq = make_uint4(0, 0, 0, 0);
-    auto request_half = [&](uint32_t h) {  // words [h, h + 32) below w_limit, eight 16-byte chunks at most
-        const uint32_t hi = h + 32u < w_limit ? h + 32u : w_limit;
+    auto request_half = [&](uint32_t h) {  // words [h, h + kHalf) below w_limit, in 16-byte chunks
+        const uint32_t hi = h + kHalf < w_limit ? h + kHalf : w_limit;
         for (uint32_t c = h; c < hi; c += 4)
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ring + (c & (kRingWords - 1)) * 4), "l"(W + c) : "memory");
         asm volatile("cp.async.commit_group;" ::: "memory");
@@ -1174,14 +1175,14 @@ k_enc_replay(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ 
     while (cur < end) {
         if ((cur & ~3u) != wbase) {
             wbase = cur & ~3u;
-            if ((wbase & ~31u) != half) {
-                half = wbase & ~31u;
+            if ((wbase & ~(kHalf - 1)) != half) {
+                half = wbase & ~(kHalf - 1);
                 if (half != pre_half) {  // first use, or a jump past the half requested ahead: nothing in flight may land on the new requests
                     asm volatile("cp.async.wait_group 0;" ::: "memory");
                     request_half(half);
                 }
                 asm volatile("cp.async.wait_group 0;" ::: "memory");
-                pre_half = half + 32u;
+                pre_half = half + kHalf;
                 if (pre_half < w_limit) request_half(pre_half);  // into the half just left
             }
             asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(wq.x), "=r"(wq.y), "=r"(wq.z), "=r"(wq.w) : "r"(ring + (wbase & (kRingWords - 1)) * 4) : "memory");
@@ -1608,6 +1609,7 @@ struct lzfse_b200_encoder {
     DevBuf streams, counts, totals_dev, tables, packs, lits, block_ids, blocks, out, counters, words;
     bool pending = false;             // an *_async call has been enqueued and not yet synchronised
     cudaStream_t pending_stream = nullptr;
+    bool tables_dirty = false;        // a call that ran k_enc_parse did not complete: entries of unknown epochs may be in the tables
     int allow_fast = 1;  // LZB_ENC_FAST=0 sends every stream through k_enc_parse (measurements, tests)
     PinnedBuf totals_host;
     HostStage stage;
@@ -1648,7 +1650,11 @@ int encode_batch_device_impl(lzfse_b200_encoder *e, const uint8_t *src, const ui
     if (n_slow) {   // history tables + one epoch word per table; zeroed when (re)allocated, never again (see k_enc_parse)
         const void *before = e->tables.p;
         LZB_CK(e, e->tables.reserve(n_slots * (kTableWords + 1) * sizeof(uint32_t)));
-        if (e->tables.p != before) LZB_CK(e, cudaMemsetAsync(e->tables.p, 0, e->tables.cap, s));
+        // The epochs are written back when a stream's parse ends; after a call that did not get that far (a CUDA error, a
+        // fault) the tables may hold positions biased with epochs the epoch words do not know about, which a later stream
+        // could take for valid candidates.  Such a call leaves the flag set and the next one starts from zeroed tables.
+        if (e->tables.p != before || e->tables_dirty) LZB_CK(e, cudaMemsetAsync(e->tables.p, 0, e->tables.cap, s));
+        e->tables_dirty = true;
     }
     if (n_fast) LZB_CK(e, e->words.reserve((tot.n_fse + 256) * sizeof(uint32_t)));  // one word per position (k_enc_find -> k_enc_replay)
     LZB_CK(e, e->packs.reserve((tot.n_blocks + 1) * sizeof(uint2)));
@@ -1700,6 +1706,7 @@ int encode_batch_device_impl(lzfse_b200_encoder *e, const uint8_t *src, const ui
         return LZFSE_B200_OK;
     }
     LZB_CK(e, cudaStreamSynchronize(s));
+    e->tables_dirty = false;
     e->timer.finish();
     return LZFSE_B200_OK;
 }
@@ -1772,6 +1779,7 @@ size_t lzfse_b200_debug_encoder_packs(lzfse_b200_encoder *e, uint64_t *host, siz
     return n;
 }
 size_t lzfse_b200_encode_bound(size_t n) { return n + n / 4 + (n / 16384 + 2) * 768 + 64; }
+size_t lzfse_b200_encode_bound_strict(size_t n) { return (size_t)out_cap(n) + 64; }
 
 int lzfse_b200_encode_batch_device(lzfse_b200_encoder *e, const uint8_t *src, const uint64_t *src_off, const uint64_t *src_len, uint8_t *dst,
                                    const uint64_t *dst_off, const uint64_t *dst_cap, uint64_t *out_len, int32_t *status, size_t n, void *stream) {
@@ -1796,6 +1804,7 @@ int lzfse_b200_encoder_sync(lzfse_b200_encoder *e) {
     if (!g.ok) return LZFSE_B200_CUDA_ERROR;
     e->pending = false;
     LZB_CK(e, cudaStreamSynchronize(e->pending_stream));
+    e->tables_dirty = false;
     e->timer.finish();
     return LZFSE_B200_OK;
 }

@@ -56,6 +56,7 @@ extern "C" {
     pub fn lzfse_b200_encoder_create(cuda_device: c_int, out: *mut *mut lzfse_b200_encoder) -> c_int;
     pub fn lzfse_b200_encoder_destroy(e: *mut lzfse_b200_encoder);
     pub fn lzfse_b200_encode_bound(src_len: usize) -> usize;
+    pub fn lzfse_b200_encode_bound_strict(src_len: usize) -> usize;
     pub fn lzfse_b200_encode_bytes(e: *mut lzfse_b200_encoder, src: *const u8, src_len: usize, dst: *mut u8, dst_cap: usize,
                                    dst_len: *mut usize) -> c_int;
     pub fn lzfse_b200_encode_batch_device(e: *mut lzfse_b200_encoder, src_base: *const u8, src_off: *const u64, src_len: *const u64,

@@ -132,3 +132,50 @@ def test_hostile_announcements_do_not_size_the_batch():
     # with honest capacities the statuses are the reference's
     assert int(st[1]) == ob.decode(liar_vn, cap=len(liar_vn) * dec.MAX_RATIO + dec.MAX_SLACK)[0]
     enc.close(); dec.close()
+
+
+def test_streaming_front_doors_and_cli(tmp_path):
+    """LzfseRingEncoder / LzfseRingDecoder, the reader / writer adaptors and the lzfoo command line produce and accept
+    the frames of encode_bytes (what the reference's test/src/ops.rs checks across its engines)."""
+    import io
+    import subprocess
+    import sys
+
+    import lzfse_rust_b200 as L
+
+    data = tk.synth_text(0x730000, 300000)
+    want = ob.Encoder().encode(data)[1]
+    renc, rdec = L.LzfseRingEncoder(0), L.LzfseRingDecoder(0)
+    dst = io.BytesIO()
+    assert renc.encode(io.BytesIO(data), dst) == (len(data), len(want)) and dst.getvalue() == want
+    out = io.BytesIO()
+    assert rdec.decode(io.BytesIO(want), out) == (len(data), len(want)) and out.getvalue() == data
+    w = renc.writer(io.BytesIO())
+    for k in range(0, len(data), 7777):
+        w.write(data[k:k + 7777])
+    assert w.finalize().getvalue() == want
+    r = rdec.reader(io.BytesIO(want))
+    got = bytearray()
+    while True:
+        c = r.read(10001)
+        if not c:
+            break
+        got += c
+    assert bytes(got) == data
+    bad = bytearray(want); bad[40] ^= 0x55
+    with pytest.raises(L.LzfseError) as ei:
+        rdec.decode(io.BytesIO(bytes(bad)), io.BytesIO())
+    assert ei.value.status == ob.decode(bytes(bad), cap=len(data))[0]
+    renc.close(); rdec.close()
+    # lzfoo: file -> file, stdin -> stdout, -v statistics on stderr, exit code 1 on a bad frame
+    src, enc_f, dec_f = tmp_path / "in.txt", tmp_path / "out.lzfse", tmp_path / "back.txt"
+    src.write_bytes(data)
+    run = lambda args, stdin=None: subprocess.run([sys.executable, "-m", "lzfse_rust_b200"] + args, input=stdin, capture_output=True, timeout=300)
+    p = run(["-encode", "-i", str(src), "-o", str(enc_f), "-v"])
+    assert p.returncode == 0 and enc_f.read_bytes() == want and b"Compression ratio" in p.stderr
+    p = run(["-decode", "-i", str(enc_f), "-o", str(dec_f)])
+    assert p.returncode == 0 and dec_f.read_bytes() == data
+    p = run(["-decode"], stdin=want)
+    assert p.returncode == 0 and p.stdout == data
+    p = run(["-decode"], stdin=bytes(bad))
+    assert p.returncode == 1 and p.stderr.startswith(b"Error: ")
