@@ -111,32 +111,40 @@ SMALL_SLOT = 4096 + 32   # bytes of text generated per small-class stream; its l
 REP_PERIODS = (1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 32, 64)
 
 
+MIX_PARTS = 64   # every class is cut into this many parts; the global order takes one part of each class in turn
+
+
 def mixed_lengths(bytes_per_class):
-    """The ONE global descriptor array of config 5: stream lengths of the four classes, in class order."""
+    """The ONE global descriptor array of config 5: (lens, cls, kidx) = length, class and index inside its class of every
+    stream.  The four classes are interleaved part by part (MIX_PARTS parts each), so that a contiguous range of the
+    array -- what a rank gets from shard_ranges -- holds the same mix as the whole corpus."""
     n64 = bytes_per_class // CHUNK
     rng = np.random.default_rng(0x5EED)
     small = (21 + rng.integers(0, 4076, bytes_per_class // 2048)).astype(np.int64)   # LZVN range, mean ~2 KiB
     small[rng.integers(0, len(small), len(small) // 64)] = rng.integers(0, 21, len(small) // 64)   # a sprinkle of raw-range inputs
-    lens = np.concatenate([np.full(n64, CHUNK, np.int64), np.full(n64, CHUNK, np.int64), small, np.full(n64, CHUNK, np.int64)])
-    cls = np.concatenate([np.zeros(n64, np.int8), np.ones(n64, np.int8), np.full(len(small), 2, np.int8), np.full(n64, 3, np.int8)])
-    return lens, cls
+    per_class = [np.full(n64, CHUNK, np.int64), np.full(n64, CHUNK, np.int64), small, np.full(n64, CHUNK, np.int64)]
+    lens, cls, kidx = [], [], []
+    for part in range(MIX_PARTS):
+        for c, lc in enumerate(per_class):
+            a, b = len(lc) * part // MIX_PARTS, len(lc) * (part + 1) // MIX_PARTS
+            lens.append(lc[a:b]); cls.append(np.full(b - a, c, np.int8)); kidx.append(np.arange(a, b, dtype=np.int64))
+    return np.concatenate(lens), np.concatenate(cls), np.concatenate(kidx)
 
 
-def mixed_data(lens, cls, lo, hi, pool, woff):
-    """Bytes of global streams [lo, hi) of config 5 (every stream's content depends on its global index only)."""
+def mixed_data(lens, cls, kidx, lo, hi, pool, woff):
+    """Bytes of global streams [lo, hi) of config 5 (every stream's content depends on its class and its index there)."""
     from bench_support import workload as W
 
     out = np.empty(int(lens[lo:hi].sum()), np.uint8)
     pos = 0
-    first = {c: int(np.searchsorted(cls, c)) for c in range(4)}   # first global index of each class
     i = lo
     while i < hi:
         c = int(cls[i])
         j = i
-        while j < hi and cls[j] == c:
+        while j < hi and cls[j] == c and kidx[j] == kidx[i] + (j - i):
             j += 1
         n, nbytes = j - i, int(lens[i:j].sum())
-        k0 = i - first[c]
+        k0 = int(kidx[i])
         if c == 0:
             W.text_chunks(pool, woff, n, CHUNK, seed0=0x5EED0000 + k0, out=out[pos:pos + nbytes])
         elif c == 1:
@@ -223,8 +231,8 @@ def sample_workload(a, pool, woff, budget_bytes):
         n, cl = a.streams, a.stream_mib << 20
         raw = np.concatenate([W.text_chunks(pool, woff, 1, cl, seed0=0x16000000 + i) for i in range(n)])
         return raw, np.arange(n, dtype=np.int64) * cl, np.full(n, cl, np.int64), "all %d streams of %d MiB (one host thread per stream)" % (n, a.stream_mib)
-    lens, cls = mixed_lengths(budget_bytes // 4)
-    raw = mixed_data(lens, cls, 0, len(lens), pool, woff)
+    lens, cls, kidx = mixed_lengths(budget_bytes // 4)
+    raw = mixed_data(lens, cls, kidx, 0, len(lens), pool, woff)
     offs = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int64)
     return raw, offs, lens, "the same four classes at %d MiB per class (%d streams)" % (budget_bytes // 4 >> 20, len(lens))
 
@@ -419,7 +427,7 @@ def run_ours(a):
         scaling = "weak"
     else:
         total = int((a.total_gib if a.total_gib else (64 if world > 1 else 8)) * (1 << 30))
-        lens, cls = mixed_lengths(total // 4)
+        lens, cls, kidx = mixed_lengths(total // 4)
         lo, hi = shard_ranges(lens, world)[rank]   # weights: bytes each stream moves (its uncompressed size; C is not known yet)
         wave_bytes = int(a.wave_gib * (1 << 30))
         cum = np.cumsum(lens[lo:hi])
@@ -427,13 +435,13 @@ def run_ours(a):
         cuts = sorted(set(cuts))
         def mk(i0, i1):
             def f():
-                raw = mixed_data(lens, cls, i0, i1, pool, woff)
+                raw = mixed_data(lens, cls, kidx, i0, i1, pool, woff)
                 ln = lens[i0:i1]
                 return raw, np.concatenate([[0], np.cumsum(ln)[:-1]]).astype(np.int64), ln
             return f
         waves = [mk(cuts[k], cuts[k + 1]) for k in range(len(cuts) - 1)]
         extra = {"total_uncompressed_bytes": int(lens.sum()), "global_streams": int(len(lens)), "rank0_range": [int(lo), int(hi)], "waves_per_rank": len(waves),
-                 "sharding": "lzfse_rust_b200.sharding.shard_ranges over one global descriptor array; contiguous ranges, no collective"}
+                 "sharding": "lzfse_rust_b200.sharding.shard_ranges over one global descriptor array (the four classes interleaved in %d parts); contiguous ranges, no collective" % MIX_PARTS}
         scaling = "strong"
 
     sampler = ClockSampler(local)

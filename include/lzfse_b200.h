@@ -12,6 +12,8 @@
  *                                           (and the free fn encode_bytes    src/encode/mod.rs:58)
  *   lzfse_b200_{decode,encode}_batch_* <->  NEW: the same call over n independent LZFSE streams
  *   lzfse_b200_decode_probe_batch_*    <->  decode::probe                    src/decode/probe.rs:11-35
+ *   lzfse_b200_decode_prefix_batch_*   <->  FseCore::decode_n / VnCore::decode_n / RawBlock::decode_n (bounded decode)
+ *                                           src/fse/fse_core.rs:143-198, src/vn/vn_core.rs:67-73, src/raw/block.rs:59-68
  *   status codes                       <->  lzfse_rust::Error                src/error/mod.rs:40-61,
  *                                           FseErrorKind src/fse/error_kind.rs:9-39,
  *                                           VnErrorKind  src/vn/error_kind.rs:9-16
@@ -124,6 +126,24 @@ int lzfse_b200_decode_batch_device_async(lzfse_b200_decoder *d, const uint8_t *s
                                          const uint64_t *dst_cap, uint64_t *out_len, int32_t *status, size_t n,
                                          void *cuda_stream);
 int lzfse_b200_decoder_sync(lzfse_b200_decoder *d);
+
+/* Bounded decode: the first limit[i] bytes of every stream -- the batched counterpart of the reference's incremental
+ * decode_n (src/fse/fse_core.rs:143-198, src/vn/vn_core.rs:67-73, src/raw/block.rs:59-68), which its streaming reader
+ * uses to produce a frame piecewise.  Blocks are decoded (whole) until they cover limit[i] bytes; out_len[i] =
+ * min(limit[i], bytes those blocks produce) bytes are written at dst_base[dst_off[i] ..); more[i] = 1 if the frame goes
+ * on after what was returned (output was cut off, or blocks that produce bytes follow), 0 if it ended there (blocks
+ * that produce nothing and the end-of-stream marker are then still checked as in a full decode).
+ * status[i] covers the decoded blocks only: damage further on is not seen, as with decode_n.  The internal buffer is
+ * sized by what the decoded blocks announce, not by the whole frame, so this is also the safe way to look into frames
+ * of unknown provenance.  `more` is n bytes. */
+int lzfse_b200_decode_prefix_batch_device(lzfse_b200_decoder *d, const uint8_t *src_base, const uint64_t *src_off,
+                                          const uint64_t *src_len, uint8_t *dst_base, const uint64_t *dst_off,
+                                          const uint64_t *limit, uint64_t *out_len, int32_t *status, uint8_t *more,
+                                          size_t n, void *cuda_stream);
+int lzfse_b200_decode_prefix_batch_host(lzfse_b200_decoder *d, const uint8_t *src_base, const uint64_t *src_off,
+                                        const uint64_t *src_len, uint8_t *dst_base, const uint64_t *dst_off,
+                                        const uint64_t *limit, uint64_t *out_len, int32_t *status, uint8_t *more,
+                                        size_t n);
 
 /* Header-only walk: raw_len[i] = sum of the blocks' n_raw_bytes, n_blocks[i] = block count.
  * (Unlike the reference's dead-code probe, LZVN blocks advance by n_payload_bytes; cf. src/vn/ops.rs:13.) */

@@ -13,7 +13,8 @@ SYMBOLS = [
     "lzfse_b200_decoder_last_launches", "lzfse_b200_encoder_create", "lzfse_b200_encoder_destroy", "lzfse_b200_encode_bound",
     "lzfse_b200_encode_bytes", "lzfse_b200_encode_batch_device", "lzfse_b200_encode_batch_host", "lzfse_b200_encoder_last_launches",
     "lzfse_b200_decoder_set_timing", "lzfse_b200_decoder_last_stage_ms", "lzfse_b200_encoder_set_timing", "lzfse_b200_encoder_last_stage_ms",
-    "lzfse_b200_encode_bound_strict", "lzfse_b200_decode_batch_device_async", "lzfse_b200_decoder_sync", "lzfse_b200_encode_batch_device_async", "lzfse_b200_encoder_sync",
+    "lzfse_b200_encode_bound_strict", "lzfse_b200_decode_prefix_batch_device", "lzfse_b200_decode_prefix_batch_host",
+    "lzfse_b200_decode_batch_device_async", "lzfse_b200_decoder_sync", "lzfse_b200_encode_batch_device_async", "lzfse_b200_encoder_sync",
 ]
 
 _lib = None
@@ -60,6 +61,8 @@ def load(build_if_missing=True):
         getattr(lib, "lzfse_b200_%s_batch_host" % n).argtypes = [vp, vp, u64p, u64p, vp, u64p, u64p, u64p, i32p, C.c_size_t]
         getattr(lib, "lzfse_b200_%s_batch_device_async" % n).argtypes = [vp, vp, u64p, u64p, vp, u64p, u64p, u64p, i32p, C.c_size_t, vp]
         getattr(lib, "lzfse_b200_%sr_sync" % n).argtypes = [vp]
+    lib.lzfse_b200_decode_prefix_batch_device.argtypes = [vp, vp, u64p, u64p, vp, u64p, u64p, u64p, i32p, vp, C.c_size_t, vp]
+    lib.lzfse_b200_decode_prefix_batch_host.argtypes = [vp, vp, u64p, u64p, vp, u64p, u64p, u64p, i32p, vp, C.c_size_t]
     lib.lzfse_b200_decode_probe_batch_device.argtypes = [vp, vp, u64p, u64p, u64p, u32p, i32p, C.c_size_t, vp]
     lib.lzfse_b200_decode_probe_batch_host.argtypes = [vp, vp, u64p, u64p, u64p, u32p, i32p, C.c_size_t]
     _lib = lib

@@ -175,6 +175,23 @@ class LzfseDecoder(_Handle):
         outs = [dst[int(doff[i]) : int(doff[i]) + int(out_len[i])].tobytes() if status[i] == 0 else None for i in range(n)]
         return outs, status
 
+    def decode_prefix_batch(self, frames, limits):
+        """Bounded decode (the reference's decode_n as a batch call): the first limits[i] bytes of every frame.
+        Returns (list of bytes-or-None, status array, more array); more[i] = 1 if the frame goes on after what was
+        returned.  Errors beyond the blocks that had to be decoded are not seen."""
+        n = len(frames)
+        lens = np.array([len(f) for f in frames], dtype=np.uint64)
+        offs = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.uint64) if n else np.zeros(0, np.uint64)
+        src = np.frombuffer(b"".join(bytes(f) for f in frames) or b"\0", dtype=np.uint8)
+        limits = _u64(limits)
+        doff = np.concatenate([[0], np.cumsum(limits)[:-1]]).astype(np.uint64) if n else np.zeros(0, np.uint64)
+        dst = np.empty(max(int(limits.sum()), 1), dtype=np.uint8)
+        out_len, status, more = np.zeros(n, np.uint64), np.zeros(n, np.int32), np.zeros(n, np.uint8)
+        self._check(self._lib.lzfse_b200_decode_prefix_batch_host(self._h, _ptr(src), _ptr(offs), _ptr(lens), _ptr(dst), _ptr(doff), _ptr(limits),
+                                                                  _ptr(out_len), _ptr(status), _ptr(more), n))
+        outs = [dst[int(doff[i]) : int(doff[i]) + int(out_len[i])].tobytes() if status[i] == 0 else None for i in range(n)]
+        return outs, status, more
+
     def decode_batch_device(self, src, src_off, src_len, dst, dst_off, dst_cap, stream=None, wait=True):
         """Batched decode on CUDA tensors (uint8 data, int64 descriptors).  Returns (out_len, status) tensors.  The work
         is enqueued on `stream` (default: torch's current stream).  wait=False returns once everything is enqueued; the

@@ -17,9 +17,12 @@ namespace lzb {
 // decode.cu
 uint32_t long_stream_threshold(size_t, int);
 void launch_scan_count(const uint8_t *, const uint64_t *, const uint64_t *, const uint64_t *, size_t, StreamCounts *, uint32_t *, uint64_t *,
-                       uint32_t *, StreamCounts *, uint32_t *, uint32_t, cudaStream_t);
+                       uint32_t *, StreamCounts *, uint32_t *, uint32_t, const uint64_t *, uint8_t *, cudaStream_t);
 void launch_scan_fill(const uint8_t *, const uint64_t *, const uint64_t *, const uint64_t *, const uint64_t *, size_t, StreamCounts *, BlockDesc *, FseDesc *,
-                      uint32_t *, uint64_t *, uint32_t *, uint32_t, uint64_t *, uint32_t *, uint32_t *, cudaStream_t);
+                      uint32_t *, uint64_t *, uint32_t *, uint32_t, uint64_t *, uint32_t *, uint32_t *, const uint64_t *, cudaStream_t);
+void launch_scan_u64(const uint64_t *, uint64_t *, size_t, uint64_t *, cudaStream_t);
+void launch_prefix_copy(const uint8_t *, const uint64_t *, const uint64_t *, const int32_t *, const uint64_t *, uint8_t *, const uint64_t *, uint64_t *,
+                        uint8_t *, size_t, int, cudaStream_t);
 int setup_decode_kernels();
 void launch_fse_stages(const uint8_t *, const uint64_t *, const uint64_t *, const uint64_t *, const uint64_t *, const BlockDesc *, FseDesc *, uint32_t, uint8_t *,
                        LmdRec *, uint32_t *, uint32_t *, int, cudaStream_t, cudaEvent_t);
@@ -46,10 +49,11 @@ using namespace lzb;
 struct DecodeScratch {
     DevBuf counts, err, raw_total, totals_dev, blocks, fse, lits, lmds, work;
     DevBuf long_base, long_blocks, long_streams, image;  // two-pass expansion of long streams (expand_long.cu)
+    DevBuf inner, inner_off;                              // bounded decode: internal output buffer and its layout
     PinnedBuf totals_host;
     cudaStream_t stream = nullptr;  // chains 1.. only
     void release() {
-        for (DevBuf *b : {&counts, &err, &raw_total, &totals_dev, &blocks, &fse, &lits, &lmds, &work, &long_base, &long_blocks, &long_streams, &image}) b->release();
+        for (DevBuf *b : {&counts, &err, &raw_total, &totals_dev, &blocks, &fse, &lits, &lmds, &work, &long_base, &long_blocks, &long_streams, &image, &inner, &inner_off}) b->release();
         totals_host.release();
         if (stream) cudaStreamDestroy(stream);
         stream = nullptr;
@@ -78,19 +82,20 @@ namespace {
 
 // Phase A of a chain: header scan (counts only).  Asynchronous.
 int decode_launch_scan(lzfse_b200_decoder *d, DecodeScratch &c, const uint8_t *src, const uint64_t *src_off, const uint64_t *src_len,
-                       const uint64_t *dst_cap, uint64_t *raw_len, uint32_t *n_blocks, size_t n, cudaStream_t s, bool probe_only) {
+                       const uint64_t *dst_cap, uint64_t *raw_len, uint32_t *n_blocks, size_t n, cudaStream_t s, bool probe_only,
+                       const uint64_t *limit = nullptr, uint8_t *more = nullptr) {
     CK(d, c.counts.reserve((n + 1 + n / 1024 + 2) * sizeof(StreamCounts)));  // + tile sums of the scan
     CK(d, c.err.reserve(n * sizeof(uint32_t)));
     CK(d, c.raw_total.reserve(n * sizeof(uint64_t)));
     CK(d, c.totals_dev.reserve(sizeof(StreamCounts)));
-    CK(d, c.totals_host.reserve(sizeof(StreamCounts) + sizeof(LongTotals)));
+    CK(d, c.totals_host.reserve(sizeof(StreamCounts) + sizeof(LongTotals) + sizeof(uint64_t)));
     CK(d, c.work.reserve(kWorkWords * sizeof(uint32_t)));
     CK(d, cudaMemsetAsync(c.work.p, 0, kWorkWords * sizeof(uint32_t), s));
     uint64_t *raw_total = raw_len ? raw_len : c.raw_total.as<uint64_t>();
     // Totals go straight into pinned host memory (UVA): no device-to-host copy that could queue behind a bulk
     // download on the copy engine.
     launch_scan_count(src, src_off, src_len, probe_only ? nullptr : dst_cap, n, c.counts.as<StreamCounts>(), c.err.as<uint32_t>(), raw_total,
-                      n_blocks, c.totals_host.as<StreamCounts>(), c.work.as<uint32_t>(), long_stream_threshold(n, d->n_sms), s);
+                      n_blocks, c.totals_host.as<StreamCounts>(), c.work.as<uint32_t>(), long_stream_threshold(n, d->n_sms), limit, more, s);
     d->launches += n > 8192 ? 4 : 2;  // k_scan + the exclusive scan (three launches for large batches)
     return LZFSE_B200_OK;
 }
@@ -99,7 +104,7 @@ int decode_launch_scan(lzfse_b200_decoder *d, DecodeScratch &c, const uint8_t *s
 // launches the rest of the chain.  Asynchronous after that; the caller synchronises `s`.
 int decode_launch_rest(lzfse_b200_decoder *d, DecodeScratch &c, const uint8_t *src, const uint64_t *src_off, const uint64_t *src_len, uint8_t *dst,
                        const uint64_t *dst_off, const uint64_t *dst_cap, uint64_t *out_len, int32_t *status, size_t n, cudaStream_t s,
-                       StageTimer *timer) {
+                       StageTimer *timer, const uint64_t *limit = nullptr) {
     uint64_t *raw_total = c.raw_total.as<uint64_t>();
     CK(d, cudaStreamSynchronize(s));
     const StreamCounts tot = *c.totals_host.as<StreamCounts>();
@@ -116,7 +121,7 @@ int decode_launch_rest(lzfse_b200_decoder *d, DecodeScratch &c, const uint8_t *s
 
     launch_scan_fill(src, src_off, src_len, dst_off, dst_cap, n, c.counts.as<StreamCounts>(), c.blocks.as<BlockDesc>(), c.fse.as<FseDesc>(),
                      c.err.as<uint32_t>(), raw_total, c.work.as<uint32_t>(), long_stream_threshold(n, d->n_sms), c.long_base.as<uint64_t>(),
-                     c.long_blocks.as<uint32_t>(), c.long_streams.as<uint32_t>(), s);
+                     c.long_blocks.as<uint32_t>(), c.long_streams.as<uint32_t>(), limit, s);
     d->launches += 1;
     if (timer) timer->mark(s);  // scan (count + host round trip + fill)
     if (tot.n_fse) {
@@ -190,6 +195,34 @@ int decode_batch_device_impl(lzfse_b200_decoder *d, const uint8_t *src, const ui
     }
     CK(d, cudaStreamSynchronize(s));
     d->timer.finish();
+    return LZFSE_B200_OK;
+}
+
+// Bounded decode: the blocks that cover limit[i] bytes are decoded into an internal buffer (the block that crosses the
+// limit is decoded whole, like the reference's decode_n overshoots by one LMD), then the prefix is copied out.
+int decode_prefix_device_impl(lzfse_b200_decoder *d, const uint8_t *src, const uint64_t *src_off, const uint64_t *src_len, uint8_t *dst,
+                              const uint64_t *dst_off, const uint64_t *limit, uint64_t *out_len, int32_t *status, uint8_t *more, size_t n,
+                              cudaStream_t s) {
+    d->launches = 0;
+    d->pending = false;
+    if (n == 0) return LZFSE_B200_OK;
+    DecodeScratch &c = d->chain[0];
+    CK(d, c.inner_off.reserve(n * sizeof(uint64_t)));
+    int rc = decode_launch_scan(d, c, src, src_off, src_len, nullptr, nullptr, nullptr, n, s, false, limit, more);
+    if (rc) return rc;
+    uint64_t *inner_total = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(c.totals_host.p) + sizeof(StreamCounts) + sizeof(LongTotals));
+    launch_scan_u64(c.raw_total.as<uint64_t>(), c.inner_off.as<uint64_t>(), n, inner_total, s);
+    d->launches += 1;
+    CK(d, cudaStreamSynchronize(s));
+    CK(d, c.inner.reserve(*inner_total + 64));
+    // the chain runs against the internal buffer: stream i owns raw_total[i] bytes at inner_off[i]
+    rc = decode_launch_rest(d, c, src, src_off, src_len, c.inner.as<uint8_t>(), c.inner_off.as<uint64_t>(), c.raw_total.as<uint64_t>(), out_len, status, n, s,
+                            nullptr, limit);
+    if (rc) return rc;
+    launch_prefix_copy(c.inner.as<uint8_t>(), c.inner_off.as<uint64_t>(), c.raw_total.as<uint64_t>(), status, limit, dst, dst_off, out_len, more, n, d->n_sms, s);
+    d->launches += 1;
+    CK(d, cudaGetLastError());
+    CK(d, cudaStreamSynchronize(s));
     return LZFSE_B200_OK;
 }
 
@@ -522,6 +555,46 @@ int lzfse_b200_decode_probe_batch_host(lzfse_b200_decoder *d, const uint8_t *src
     CK(d, cudaMemcpyAsync(raw_len, d_raw, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
     CK(d, cudaMemcpyAsync(status, d_status, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     if (n_blocks) CK(d, cudaMemcpyAsync(n_blocks, d_nb, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CK(d, cudaStreamSynchronize(s));
+    return LZFSE_B200_OK;
+}
+
+int lzfse_b200_decode_prefix_batch_device(lzfse_b200_decoder *d, const uint8_t *src, const uint64_t *src_off, const uint64_t *src_len, uint8_t *dst,
+                                          const uint64_t *dst_off, const uint64_t *limit, uint64_t *out_len, int32_t *status, uint8_t *more, size_t n,
+                                          void *stream) {
+    if (!d || (n && (!src_off || !src_len || !dst_off || !limit || !out_len || !status || !more))) return LZFSE_B200_INVALID_ARGUMENT;
+    DeviceGuard g(d->device);
+    if (!g.ok) return LZFSE_B200_CUDA_ERROR;
+    return decode_prefix_device_impl(d, src, src_off, src_len, dst, dst_off, limit, out_len, status, more, n, (cudaStream_t)stream);
+}
+
+int lzfse_b200_decode_prefix_batch_host(lzfse_b200_decoder *d, const uint8_t *src, const uint64_t *src_off, const uint64_t *src_len, uint8_t *dst,
+                                        const uint64_t *dst_off, const uint64_t *limit, uint64_t *out_len, int32_t *status, uint8_t *more, size_t n) {
+    if (!d || (n && (!src || !src_off || !src_len || !dst_off || !limit || !out_len || !status || !more))) return LZFSE_B200_INVALID_ARGUMENT;
+    if (n == 0) return LZFSE_B200_OK;
+    DeviceGuard g(d->device);
+    if (!g.ok) return LZFSE_B200_CUDA_ERROR;
+    cudaStream_t s = d->own_stream;
+    HostStage &st = d->stage;
+    int rc = stage_sources(d, st, src, src_off, src_len, n, 6 * n + 8, s);
+    if (rc) return rc;
+    rc = stage_outputs(d, st, dst_off, limit, n);  // the staged output regions are the limits
+    if (rc) return rc;
+    CK(d, st.desc.reserve(4 * n * sizeof(uint64_t)));
+    CK(d, st.res.reserve(n * (sizeof(uint64_t) + sizeof(int32_t) + 1)));
+    CK(d, cudaMemcpyAsync(st.desc.p, st.pin.p, 4 * n * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    uint64_t *dd = st.desc.as<uint64_t>();
+    uint64_t *d_out_len = st.res.as<uint64_t>();
+    int32_t *d_status = reinterpret_cast<int32_t *>(d_out_len + n);
+    uint8_t *d_more = reinterpret_cast<uint8_t *>(d_status + n);
+    rc = decode_prefix_device_impl(d, st.src.as<uint8_t>(), dd, dd + n, st.dst.as<uint8_t>(), dd + 2 * n, dd + 3 * n, d_out_len, d_status, d_more, n, s);
+    if (rc) return rc;
+    CK(d, cudaMemcpyAsync(out_len, d_out_len, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    CK(d, cudaMemcpyAsync(status, d_status, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    CK(d, cudaMemcpyAsync(more, d_more, n, cudaMemcpyDeviceToHost, s));
+    CK(d, cudaStreamSynchronize(s));
+    rc = fetch_outputs(d, st, dst, dst_off, out_len, status, n, s);
+    if (rc) return rc;
     CK(d, cudaStreamSynchronize(s));
     return LZFSE_B200_OK;
 }

@@ -99,9 +99,11 @@ __global__ void k_scan(const uint8_t *__restrict__ src_base, const uint64_t *__r
                        const uint64_t *__restrict__ dst_cap, size_t n, StreamCounts *counts /* in FILL: scanned bases */,
                        BlockDesc *blocks, FseDesc *fse, uint32_t *err, uint64_t *raw_total, uint32_t *n_blocks_out,
                        uint32_t *work /* kWorkWords counters, or null (probe) */, uint32_t long_fse /* streams with at least this many bvx blocks are long */,
-                       uint64_t *long_base, uint32_t *long_blocks, uint32_t *long_streams) {
+                       uint64_t *long_base, uint32_t *long_blocks, uint32_t *long_streams,
+                       const uint64_t *__restrict__ limit /* bounded decode: stop once this many bytes are covered, or null */, uint8_t *more_out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    bool more = false;
     const uint8_t *s = src_base + src_off[i];
     const uint64_t len = src_len[i];
     uint64_t pos = 0, raw = 0;
@@ -126,6 +128,16 @@ __global__ void k_scan(const uint8_t *__restrict__ src_base, const uint64_t *__r
     for (;;) {
         uint64_t rest = len - pos;
         uint32_t kb = blk < 0x1FFFFFu ? blk : 0x1FFFFFu;
+        // Bounded decode (the reference's decode_n, fse_core.rs:143-198): whole blocks until the limit is covered.  What
+        // follows is not looked at -- unless the frame ends exactly here, which is then checked like any other end.
+        if (limit && raw >= limit[i]) {
+            bool go_on = false;  // blocks that add nothing (and the end-of-stream marker) are still walked and checked
+            if (raw == limit[i] && rest >= 4) {
+                const uint32_t m = ld_u32(s + pos);
+                go_on = m == kMagicEos || (rest >= 8 && (m == kMagicRaw || m == kMagicVxn || m == kMagicVx1 || m == kMagicVx2) && ld_u32(s + pos + 4) == 0);
+            }
+            if (!go_on) { more = true; break; }
+        }
         if (rest < 4) { key = err_key(kb, PH_HEADER, LZFSE_B200_PAYLOAD_UNDERFLOW); break; }
         uint32_t magic = ld_u32(s + pos);
         if (magic == kMagicEos) {
@@ -162,6 +174,14 @@ __global__ void k_scan(const uint8_t *__restrict__ src_base, const uint64_t *__r
             // destination is smaller than that anyway, the block cannot succeed: let the interpreter find the error
             // the reference finds (bad opcode, BufferOverflow at the write that does not fit, VnBadPayload at the
             // end) and keep the positions of the descriptors inside the destination.
+            // Bounded decode sizes its internal buffer from what the blocks announce: an LZVN opcode of at most 3 bytes
+            // produces at most 271, so a header that announces more than 136 bytes per payload byte cannot be honoured
+            // (the interpreter will end with VnBadPayload); it only gets the room its payload could fill.
+            if (limit && (uint64_t)bd.n_raw > 136ull * ld_u32(s + pos + 8) + 16) {
+                stop = true;
+                bd.n_raw = 136u * ld_u32(s + pos + 8) + 16;
+                bd.pad = 1;
+            }
             if (raw + bd.n_raw > kMaxStreamRaw && dst_cap != nullptr && dst_cap[i] < raw + bd.n_raw) {
                 stop = true;
                 bd.n_raw = (uint32_t)(dst_cap[i] > raw ? dst_cap[i] - raw : 0);
@@ -230,6 +250,7 @@ __global__ void k_scan(const uint8_t *__restrict__ src_base, const uint64_t *__r
         err[i] = key;
         raw_total[i] = raw;
         if (n_blocks_out) n_blocks_out[i] = blk;
+        if (more_out) more_out[i] = more ? 1 : 0;
         if (work && n_fse >= long_fse) {  // totals of the long streams: the host sizes their image from these
             atomicAdd(reinterpret_cast<unsigned long long *>(work + 8), (unsigned long long)((raw + 3) & ~3ull));
             atomicAdd(work + 10, blk);
@@ -1330,20 +1351,73 @@ uint32_t long_stream_threshold(size_t n, int n_sms) {
 }
 void launch_scan_count(const uint8_t *src, const uint64_t *src_off, const uint64_t *src_len, const uint64_t *dst_cap, size_t n,
                        StreamCounts *counts, uint32_t *err, uint64_t *raw_total, uint32_t *n_blocks_out, StreamCounts *totals, uint32_t *work,
-                       uint32_t long_fse, cudaStream_t s) {
+                       uint32_t long_fse, const uint64_t *limit, uint8_t *more_out, cudaStream_t s) {
     if (n == 0) return;
     const int tb = 128;
     k_scan<false><<<(unsigned)((n + tb - 1) / tb), tb, 0, s>>>(src, src_off, src_len, nullptr, dst_cap, n, counts, nullptr, nullptr, err, raw_total, n_blocks_out,
-                                                               work, long_fse, nullptr, nullptr, nullptr);
+                                                               work, long_fse, nullptr, nullptr, nullptr, limit, more_out);
     launch_exclusive_scan(counts, n, totals, work, s);
 }
 void launch_scan_fill(const uint8_t *src, const uint64_t *src_off, const uint64_t *src_len, const uint64_t *dst_off, const uint64_t *dst_cap, size_t n,
                       StreamCounts *bases, BlockDesc *blocks, FseDesc *fse, uint32_t *err, uint64_t *raw_total, uint32_t *work, uint32_t long_fse,
-                      uint64_t *long_base, uint32_t *long_blocks, uint32_t *long_streams, cudaStream_t s) {
+                      uint64_t *long_base, uint32_t *long_blocks, uint32_t *long_streams, const uint64_t *limit, cudaStream_t s) {
     if (n == 0) return;
     const int tb = 128;
     k_scan<true><<<(unsigned)((n + tb - 1) / tb), tb, 0, s>>>(src, src_off, src_len, dst_off, dst_cap, n, bases, blocks, fse, err, raw_total, nullptr, work,
-                                                              long_fse, long_base, long_blocks, long_streams);
+                                                              long_fse, long_base, long_blocks, long_streams, limit, nullptr);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Bounded decode (lzfse_b200_decode_prefix_batch_*): the blocks that cover the limit are decoded into an internal buffer
+// laid out by an exclusive scan of their sizes; the prefix each caller asked for is copied out afterwards.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_scan_u64(const uint64_t *__restrict__ in, uint64_t *__restrict__ out, size_t n, uint64_t *total) {
+    // one CTA: thread t owns a contiguous run, the 1024 run sums are scanned in shared memory (16-byte aligned starts)
+    __shared__ uint64_t sums[1024];
+    const size_t per = (n + 1023) / 1024, lo = (size_t)threadIdx.x * per, hi = lo + per < n ? lo + per : n;
+    uint64_t acc = 0;
+    for (size_t i = lo; i < hi; i++) acc += (in[i] + 15) & ~15ull;
+    sums[threadIdx.x] = acc;
+    __syncthreads();
+    for (uint32_t o = 1; o < 1024; o <<= 1) {
+        const uint64_t t = threadIdx.x >= o ? sums[threadIdx.x - o] : 0;
+        __syncthreads();
+        sums[threadIdx.x] += t;
+        __syncthreads();
+    }
+    uint64_t run = sums[threadIdx.x] - acc;
+    for (size_t i = lo; i < hi; i++) { out[i] = run; run += (in[i] + 15) & ~15ull; }
+    if (threadIdx.x == 1023) *total = sums[1023];
+}
+__global__ void __launch_bounds__(256) k_prefix_copy(const uint8_t *__restrict__ inner, const uint64_t *__restrict__ inner_off,
+                                                     const uint64_t *__restrict__ inner_len, const int32_t *__restrict__ status,
+                                                     const uint64_t *__restrict__ limit, uint8_t *__restrict__ dst, const uint64_t *__restrict__ dst_off,
+                                                     uint64_t *out_len, uint8_t *more, size_t n) {
+    for (size_t i = blockIdx.x; i < n; i += gridDim.x) {  // a CTA per stream
+        const uint64_t have = status[i] == 0 ? inner_len[i] : 0, want = limit[i];
+        const uint64_t m = have < want ? have : want;
+        const uint8_t *s = inner + inner_off[i];  // 16-byte aligned
+        uint8_t *d = dst + dst_off[i];
+        if ((reinterpret_cast<uintptr_t>(d) & 15) == 0) {
+            const uint64_t nv = m >> 4;
+            for (uint64_t k = threadIdx.x; k < nv; k += 256) reinterpret_cast<uint4 *>(d)[k] = reinterpret_cast<const uint4 *>(s)[k];
+            for (uint64_t k = (nv << 4) + threadIdx.x; k < m; k += 256) d[k] = s[k];
+        } else {
+            for (uint64_t k = threadIdx.x; k < m; k += 256) d[k] = s[k];
+        }
+        if (threadIdx.x == 0) {
+            out_len[i] = m;
+            if (status[i] != 0) more[i] = 0;
+            else if (have > want) more[i] = 1;  // (otherwise as the scan left it: blocks remain, or the frame ended)
+        }
+    }
+}
+void launch_scan_u64(const uint64_t *in, uint64_t *out, size_t n, uint64_t *total, cudaStream_t s) { k_scan_u64<<<1, 1024, 0, s>>>(in, out, n, total); }
+void launch_prefix_copy(const uint8_t *inner, const uint64_t *inner_off, const uint64_t *inner_len, const int32_t *status, const uint64_t *limit, uint8_t *dst,
+                        const uint64_t *dst_off, uint64_t *out_len, uint8_t *more, size_t n, int n_sms, cudaStream_t s) {
+    if (n == 0) return;
+    const size_t g = n < (size_t)n_sms * 8 ? n : (size_t)n_sms * 8;
+    k_prefix_copy<<<(unsigned)g, 256, 0, s>>>(inner, inner_off, inner_len, status, limit, dst, dst_off, out_len, more, n);
 }
 int setup_decode_kernels() {
     cudaError_t e = cudaFuncSetAttribute(k_fse_literals, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kLitWarps * kLitSmemPerWarp));

@@ -49,6 +49,13 @@ extern "C" {
     pub fn lzfse_b200_decode_probe_batch_host(d: *mut lzfse_b200_decoder, src_base: *const u8, src_off: *const u64,
                                               src_len: *const u64, raw_len: *mut u64, n_blocks: *mut u32, status: *mut i32,
                                               n: usize) -> c_int;
+    pub fn lzfse_b200_decode_prefix_batch_device(d: *mut lzfse_b200_decoder, src_base: *const u8, src_off: *const u64,
+                                                 src_len: *const u64, dst_base: *mut u8, dst_off: *const u64, limit: *const u64,
+                                                 out_len: *mut u64, status: *mut i32, more: *mut u8, n: usize,
+                                                 cuda_stream: *mut c_void) -> c_int;
+    pub fn lzfse_b200_decode_prefix_batch_host(d: *mut lzfse_b200_decoder, src_base: *const u8, src_off: *const u64,
+                                               src_len: *const u64, dst_base: *mut u8, dst_off: *const u64, limit: *const u64,
+                                               out_len: *mut u64, status: *mut i32, more: *mut u8, n: usize) -> c_int;
     pub fn lzfse_b200_decoder_last_launches(d: *const lzfse_b200_decoder) -> u64;
     pub fn lzfse_b200_decoder_set_timing(d: *mut lzfse_b200_decoder, enabled: c_int);
     pub fn lzfse_b200_decoder_last_stage_ms(d: *const lzfse_b200_decoder, stage_ms: *mut f32, cap: c_int) -> c_int;

@@ -179,3 +179,43 @@ def test_streaming_front_doors_and_cli(tmp_path):
     assert p.returncode == 0 and p.stdout == data
     p = run(["-decode"], stdin=bytes(bad))
     assert p.returncode == 1 and p.stderr.startswith(b"Error: ")
+
+
+def test_bounded_decode_matches_prefixes():
+    """lzfse_b200_decode_prefix_batch_host (the reference's decode_n as a batch call): for every fixture and a few
+    generated frames, limits of 0, 1, mid-block, a block boundary, the exact size and beyond must return that prefix of
+    the oracle's output with the right `more`; damage behind the decoded blocks is not seen, damage inside them is."""
+    import lzfse_rust_b200 as L
+
+    enc, dec = L.LzfseEncoder(0), L.LzfseDecoder(0)
+    cases = [(f, ob.decode(f)[1]) for name, f, _ in tk.golden_frames() if name != "special/null.vx2"]
+    gen = [tk.synth_text(0x740000, 300000), bytes(500000), tk.rng_gen_vec(3, 100000), tk.synth_text(0x740001, 3000), b"0123456789", b""]
+    frames, st = enc.encode_batch(gen)
+    assert not st.any()
+    cases += list(zip(frames, gen))
+    batch, limits, want = [], [], []
+    for f, raw in cases:
+        _, _, nb = ob.probe(f)
+        for lim in sorted({0, 1, len(raw) // 3, 40000, 65536, max(len(raw) - 1, 0), len(raw), len(raw) + 1000}):
+            batch.append(f); limits.append(lim); want.append(raw[:lim])
+    outs, st, more = dec.decode_prefix_batch(batch, limits)
+    assert not st.any()
+    for k, (o, w, lim) in enumerate(zip(outs, want, limits)):
+        assert o == w, (k, lim, len(o), len(w))
+        full = len(ob.decode(batch[k])[1])
+        assert int(more[k]) == (1 if lim < full else 0), (k, lim, full, int(more[k]))
+    # a long frame damaged in its last block: a limit inside the first blocks does not see it, the full size does
+    big, raw = cases[-6]
+    bad = big[:-300]   # cut inside its last block
+    es, _ = ob.decode(bytes(bad), cap=len(raw))
+    assert es != 0
+    outs, st, more = dec.decode_prefix_batch([bytes(bad), bytes(bad), big], [50000, len(raw), len(raw)])
+    assert list(st) == [0, es, 0] and outs[0] == raw[:50000] and outs[1] is None and outs[2] == raw and list(more) == [1, 0, 0]
+    # untrusted announcements: a 24-byte frame claiming 0xE0000000 bytes costs nothing and fails like in the reference
+    import struct
+    payload = bytes([0xE3]) + b"abc" + bytes([6, 0, 0, 0, 0, 0, 0, 0])
+    liar = b"bvxn" + struct.pack("<II", 0xE0000000, len(payload)) + payload + b"bvx$"
+    outs, st, more = dec.decode_prefix_batch([liar, big], [10, 10])
+    assert int(st[0]) == 33 and int(st[1]) == 0 and outs[1] == raw[:10]   # VnBadPayload, as the oracle says with room to spare
+    assert ob.decode(liar, cap=1 << 20)[0] == 33
+    enc.close(); dec.close()
