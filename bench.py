@@ -395,6 +395,16 @@ class Batch:
         return (time.perf_counter() - t0) / steps
 
 
+def host_memcpy_gbps(nbytes=256 << 20):
+    """Plain host-to-host copy of pageable memory (numpy): what any staging of a caller's pageable buffer is bound by."""
+    a, b = np.ones(nbytes, np.uint8), np.empty(nbytes, np.uint8)
+    b[:: 4096] = 0
+    best = 1e30
+    for _ in range(3):
+        t0 = time.perf_counter(); np.copyto(b, a); best = min(best, time.perf_counter() - t0)
+    return nbytes / best / 1e9
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
@@ -536,7 +546,9 @@ def run_ours(a):
                                  "what": "plain pinned cudaMemcpyAsync of the same byte counts (H2D of the frames and D2H of the output on two streams at once), all ranks at the same time: the ceiling of the host path"},
                 "frac_of_pcie_control": round(ctl_s / e2e_s, 4),
                 "pageable": {"value": round(e2e_U_all / page_s / 1e9, 3), "unit": UNIT, "ms_per_step": round(page_s * 1e3, 3),
-                             "what": "the same call on pageable caller buffers (what a Vec<u8> is)"}},
+                             "what": "the same call on pageable caller buffers (what a Vec<u8> is)",
+                             "host_memcpy_GBps": round(host_memcpy_gbps(), 2),
+                             "note": "bytes of a pageable buffer cross host memory once more on their way to / from pinned staging: bound by the host's own copy rate (host_memcpy_GBps, one thread; more threads do not raise it on this VM)"}},
         "encode": {"value": round(U_all / (enc_ms * 1e-3) / 1e9, 3), "unit": UNIT, "ms_per_step": round(enc_ms, 3),
                    "stage_ms": {k: round(v, 3) for k, v in enc_stage.items()},
                    "ratio_vs_reference_encoder": round(parity["gpu_bytes"] / parity["oracle_bytes"], 6) if parity else None,

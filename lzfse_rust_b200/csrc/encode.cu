@@ -1133,15 +1133,17 @@ __global__ void __launch_bounds__(kReplayThreads)
 k_enc_replay(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ src_off, const uint64_t *__restrict__ src_len, size_t n_streams,
              EncStream *streams, const StreamCounts *__restrict__ bases, const uint32_t *__restrict__ words, uint2 *pack_scratch, uint32_t *block_ids,
              EncBlock *blocks, uint32_t *block_counter) {
-    // Only every kReplayStride-th lane works: the lanes of a warp run different streams, so a warp executes the union of
-    // their control paths; fewer streams per warp (and more warps) shorten that serial instruction stream.
-    if (threadIdx.x % kReplayStride != 0) return;
-    const size_t si = ((size_t)blockIdx.x * kReplayThreads + threadIdx.x) / kReplayStride;
-    if (si >= n_streams || !streams[si].fast) return;
-    const uint8_t *src = src_base + src_off[si];
-    const uint32_t len = (uint32_t)src_len[si], end = len - 3;
+    // The 32 lanes of a warp (= one CTA) replay 32 different streams.  All of them stay in the loop until the last one
+    // is done, because the ring upkeep below is WARP-WIDE on purpose (see there).
+    static_assert(kReplayStride == 1, "one stream per lane");
+    const size_t si = (size_t)blockIdx.x * kReplayThreads + threadIdx.x;
+    const bool valid = si < n_streams && streams[si < n_streams ? si : 0].fast;
+    bool active = valid;
+    const size_t sj = valid ? si : 0;
+    const uint8_t *src = src_base + src_off[sj];
+    const uint32_t len = valid ? (uint32_t)src_len[sj] : 4u, end = len - 3;
     TEnv env;
-    env.base = bases[si]; env.blocks = blocks; env.block_ids = block_ids; env.block_counter = block_counter; env.src_off = src_off[si];
+    env.base = bases[sj]; env.blocks = blocks; env.block_ids = block_ids; env.block_counter = block_counter; env.src_off = src_off[sj];
     TSink fs;
     fs.packs = pack_scratch + env.base.n_blocks;
     fs.n_packs_total = 0; fs.n_lits_total = 0; fs.blk_pack0 = 0; fs.blk_lit0 = 0; fs.n_match_bytes = 0; fs.match_distance = 0;
@@ -1150,41 +1152,66 @@ k_enc_replay(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ 
     uint32_t cur = 0, literal_index = 0;
     Match pending = {0, 0, 0};
     // Every lane walks its own stream, so a plain load per position costs a memory round trip per step of this serial
-    // loop (and prefetch.global.L1 does not shorten it).  Each lane therefore owns a ring of words in shared memory, two
-    // halves: on entering a half it waits for everything it has requested (cp.async.wait_group 0) and then requests the
-    // half after, which so has half a ring of positions to arrive.  The cursor reads four words at a time into
-    // registers.
-    // Only wait_group 0 is used, on purpose.  The first version kept 16 single-chunk groups in flight and waited with
-    // wait_group 14 ("my 16th newest group is complete"): right by PTX's per-thread wording, but the lanes of this
-    // kernel are divergent and about ten of 16 384 streams per run then read a chunk before it had arrived (frames
-    // still valid, but not the reference's bytes, and different ones from run to run -- found by scripts/enc_words_diff.py:
-    // identical words, different packs; gone with a full drain).
-    __shared__ __align__(16) uint8_t rings[kReplayThreads / kReplayStride * kRingStride];
-    constexpr uint32_t kHalf = kRingWords / 2;
-    static_assert((kRingWords & (kRingWords - 1)) == 0 && kHalf % 4 == 0, "two halves of whole chunks");
-    const uint32_t ring = (uint32_t)__cvta_generic_to_shared(rings) + threadIdx.x / kReplayStride * kRingStride;
-    const uint32_t w_limit = (end + 3u) & ~3u;  // chunks at or beyond this word index are never needed
-    uint32_t wbase = 0xFFFFFFFFu, half = 0xFFFFFFFFu, pre_half = 0xFFFFFFFFu;
+    // loop (and prefetch.global.L1 does not shorten it).  Each lane therefore owns a ring of words in shared memory that
+    // cp.async keeps filled ahead of its cursor; the cursor reads four words at a time into registers.
+    //
+    // How the ring knows that a chunk has arrived -- three versions:
+    //  1. 16 single-chunk groups in flight per lane, `wait_group 14` before reading ("my 16th newest group is complete"):
+    //     right by PTX's per-thread wording, but the lanes are divergent and the hardware keeps ONE group counter per warp;
+    //     about ten of 16 384 streams per run read a chunk before it had arrived (valid frames, but not the reference's
+    //     bytes, and different ones from run to run; found by scripts/enc_words_diff.py).  11.1 ms per GiB, wrong.
+    //  2. two half-ring bursts per lane, `wait_group 0` only: correct, 14.3 ms -- half of all warp instructions were the
+    //     request loops, executed by 1.9 lanes at a time, and every drain also waited for the other lanes' fresh requests.
+    //  3. (this one) the upkeep runs at the top of the loop for the whole, converged warp: every lane requests at most two
+    //     chunks, ONE group is committed per iteration, and `wait_group kLag - 1` then means exactly "everything requested
+    //     kLag iterations ago has arrived" -- per warp, which is how the hardware counts.  Every kLag iterations a lane moves
+    //     its `safe` mark to what it had requested kLag..2 kLag iterations earlier; a lane whose cursor gets ahead of its
+    //     mark (a long jump) asks for a drain, which the whole warp then executes.
+    __shared__ __align__(16) uint8_t rings[kReplayThreads * kRingStride];
+    constexpr uint32_t kLag = 8;
+    static_assert((kRingWords & (kRingWords - 1)) == 0 && (kLag & (kLag - 1)) == 0, "powers of two");
+    const uint32_t ring = (uint32_t)__cvta_generic_to_shared(rings) + threadIdx.x * kRingStride;
+    const uint32_t w_limit = valid ? (end + 3u) & ~3u : 0u;  // chunks at or beyond this word index are never needed
+    uint32_t wbase = 0xFFFFFFFFu, fetched = 0, safe = 0, mark = 0, iter = 0;
     uint4 wq = make_uint4(0, 0, 0, 0);
-    auto request_half = [&](uint32_t h) {  // words [h, h + kHalf) below w_limit, in 16-byte chunks
-        const uint32_t hi = h + kHalf < w_limit ? h + kHalf : w_limit;
-        for (uint32_t c = h; c < hi; c += 4)
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ring + (c & (kRingWords - 1)) * 4), "l"(W + c) : "memory");
-        asm volatile("cp.async.commit_group;" ::: "memory");
+    auto request = [&](bool go) {  // one chunk, predicated: the instruction is the same for all 32 lanes
+        const bool p = go && fetched < w_limit;
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p cp.async.cg.shared.global [%0], [%1], 16;\n\t}"
+                     ::"r"(ring + (fetched & (kRingWords - 1)) * 4), "l"(W + (p ? fetched : 0u)), "r"((uint32_t)p) : "memory");
+        fetched += p ? 4u : 0u;
     };
-    while (cur < end) {
+    for (;;) {
+        __syncwarp();
+        active = active && cur < end;
+        if (!__any_sync(0xFFFFFFFFu, active)) break;
+        {   // ---- ring upkeep, whole warp ----
+            const uint32_t wb = cur & ~3u;
+            // a cursor that jumped past everything requested restarts the ring there; what is still in flight must land first
+            const bool restart = active && wb > fetched;
+            bool drain = __any_sync(0xFFFFFFFFu, restart);
+            if (drain) asm volatile("cp.async.wait_group 0;" ::: "memory");
+            if (restart) fetched = wb;
+            if (drain) { safe = fetched; mark = fetched; }   // (for a restarted lane: nothing of the new range yet)
+            const bool room = active && fetched < wb + kRingWords;
+            request(room);
+            request(active && fetched < wb + kRingWords);
+            if (iter == 0) {  // a few more at the start, while the warp is converged anyway
+#pragma unroll
+                for (int k = 0; k < 6; k++) request(active && fetched < wb + kRingWords);
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group %0;" ::"n"(kLag - 1) : "memory");
+            if ((iter & (kLag - 1)) == 0) { safe = mark; mark = fetched; }  // requested >= kLag iterations ago: arrived
+            const bool need = active && wb + 4 > safe;
+            if (__any_sync(0xFFFFFFFFu, need)) {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                safe = fetched; mark = fetched;
+            }
+            iter++;
+        }
+        if (!active) continue;
         if ((cur & ~3u) != wbase) {
             wbase = cur & ~3u;
-            if ((wbase & ~(kHalf - 1)) != half) {
-                half = wbase & ~(kHalf - 1);
-                if (half != pre_half) {  // first use, or a jump past the half requested ahead: nothing in flight may land on the new requests
-                    asm volatile("cp.async.wait_group 0;" ::: "memory");
-                    request_half(half);
-                }
-                asm volatile("cp.async.wait_group 0;" ::: "memory");
-                pre_half = half + kHalf;
-                if (pre_half < w_limit) request_half(pre_half);  // into the half just left
-            }
             asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(wq.x), "=r"(wq.y), "=r"(wq.z), "=r"(wq.w) : "r"(ring + (wbase & (kRingWords - 1)) * 4) : "memory");
         }
         const uint32_t k4 = cur & 3u;
@@ -1222,12 +1249,13 @@ k_enc_replay(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ 
         if (have) {
             tsink_push_match(fs, env, sel.idx - literal_index, sel.match_len, sel.idx - sel.match_idx);
             literal_index = sel.idx + sel.match_len;
-            if (literal_index >= end) break;
+            if (literal_index >= end) { cur = end; continue; }  // done (the lane stays in the loop: the ring upkeep is warp-wide)
             cur = cur + 1 > literal_index ? cur + 1 : literal_index;
         } else {
             cur++;
         }
     }
+    if (!valid) return;
     if (pending.match_len != 0) {
         tsink_push_match(fs, env, pending.idx - literal_index, pending.match_len, pending.idx - pending.match_idx);
         literal_index = pending.idx + pending.match_len;
@@ -1672,7 +1700,7 @@ int encode_batch_device_impl(lzfse_b200_encoder *e, const uint8_t *src, const ui
     }
     e->timer.mark(s);  // find
     if (n_fast) {
-        k_enc_replay<<<(unsigned)((n * kReplayStride + kReplayThreads - 1) / kReplayThreads), kReplayThreads, 0, s>>>(
+        k_enc_replay<<<(unsigned)((n + kReplayThreads - 1) / kReplayThreads), kReplayThreads, 0, s>>>(
             src, src_off, src_len, n, e->streams.as<EncStream>(), e->counts.as<StreamCounts>(), e->words.as<uint32_t>(), e->packs.as<uint2>(),
             e->block_ids.as<uint32_t>(), e->blocks.as<EncBlock>(), ctr);
         e->launches += 1;
