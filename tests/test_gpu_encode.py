@@ -223,3 +223,22 @@ def test_fast_and_general_parse_agree(dec):
         else:
             os.environ["LZB_ENC_FAST"] = old
     assert (s0 == 0).all() and (s1 == 0).all() and list(f0) == list(f1)
+
+
+def test_reference_frontend_families_all_lengths(enc, dec):
+    """The reference's exhaustive front-end tests (`match_short_zero_n`, `sandwich_n_short`, encode/frontend_bytes.rs:580-625:
+    every n up to 0x1000, ignored there as expensive) plus the same two families on the bvx2 side of the cutoff (4097..4300):
+    one GPU batch, every frame byte-identical to the port's -- whose LMDs for these inputs are pinned to the reference's
+    expected values in tests/test_oracle_encode.py -- and decoded back."""
+    chunks = [bytes(n) for n in range(5, 0x1000)]
+    for n in list(range(12, 0x1000)) + list(range(4097, 4300)):
+        b = bytearray(n); b[0:4] = b"\1\2\3\4"; b[n - 4:n] = b"\1\2\3\4"
+        chunks.append(bytes(b))
+    chunks += [bytes(n) for n in range(4097, 4300)]
+    frames, st = enc.encode_batch(chunks)
+    assert not st.any()
+    oenc = ob.Encoder()
+    for c, f in zip(chunks, frames):
+        assert f == oenc.encode(c)[1], len(c)
+    outs, dst = dec.decode_batch(frames)
+    assert not dst.any() and outs == chunks
