@@ -25,7 +25,7 @@ void launch_prefix_copy(const uint8_t *, const uint64_t *, const uint64_t *, con
                         uint8_t *, size_t, int, cudaStream_t);
 int setup_decode_kernels();
 void launch_fse_stages(const uint8_t *, const uint64_t *, const uint64_t *, const uint64_t *, const uint64_t *, const BlockDesc *, FseDesc *, uint32_t, uint8_t *,
-                       LmdRec *, uint32_t *, uint32_t *, int, cudaStream_t, cudaEvent_t);
+                       LmdRec *, uint32_t *, uint32_t *, int, cudaStream_t, cudaEvent_t, cudaStream_t, cudaEvent_t, cudaEvent_t);
 void launch_expand(const uint8_t *, const uint64_t *, const uint64_t *, uint8_t *, const uint64_t *, const uint64_t *, const StreamCounts *, const BlockDesc *,
                    const FseDesc *, const uint8_t *, const LmdRec *, uint32_t *, size_t, uint32_t *, const uint64_t *, int, cudaStream_t);
 void launch_expand_vn(const uint8_t *, const uint64_t *, const uint64_t *, uint8_t *, const uint64_t *, const uint64_t *, const StreamCounts *,
@@ -37,7 +37,7 @@ void launch_expand_cta(const uint8_t *, const uint64_t *, const uint64_t *, uint
                        const BlockDesc *, const FseDesc *, const uint8_t *, const LmdRec *, const uint64_t *, uint32_t *, size_t, uint32_t *,
                        const uint64_t *, int, cudaStream_t);
 // expand_long.cu
-void launch_expand_long(const uint8_t *, const uint64_t *, const uint64_t *, uint8_t *, const uint64_t *, const uint64_t *, const StreamCounts *,
+int launch_expand_long(const uint8_t *, const uint64_t *, const uint64_t *, uint8_t *, const uint64_t *, const uint64_t *, const StreamCounts *,
                         const BlockDesc *, const FseDesc *, const uint8_t *, const LmdRec *, const uint32_t *, const uint32_t *, const uint64_t *, uint32_t *,
                         uint32_t *, uint32_t, uint32_t, uint32_t *, int, cudaStream_t);
 }  // namespace lzb
@@ -52,7 +52,13 @@ struct DecodeScratch {
     DevBuf inner, inner_off;                              // bounded decode: internal output buffer and its layout
     PinnedBuf totals_host;
     cudaStream_t stream = nullptr;  // chains 1.. only
+    cudaStream_t side = nullptr;    // the literal stage of a small batch runs here, next to the LMD stage
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     void release() {
+        if (side) cudaStreamDestroy(side);
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        if (ev_join) cudaEventDestroy(ev_join);
+        side = nullptr; ev_fork = ev_join = nullptr;
         for (DevBuf *b : {&counts, &err, &raw_total, &totals_dev, &blocks, &fse, &lits, &lmds, &work, &long_base, &long_blocks, &long_streams, &image, &inner, &inner_off}) b->release();
         totals_host.release();
         if (stream) cudaStreamDestroy(stream);
@@ -125,9 +131,14 @@ int decode_launch_rest(lzfse_b200_decoder *d, DecodeScratch &c, const uint8_t *s
     d->launches += 1;
     if (timer) timer->mark(s);  // scan (count + host round trip + fill)
     if (tot.n_fse) {
+        if (!c.side) {
+            CK(d, cudaStreamCreateWithFlags(&c.side, cudaStreamNonBlocking));
+            CK(d, cudaEventCreateWithFlags(&c.ev_fork, cudaEventDisableTiming));
+            CK(d, cudaEventCreateWithFlags(&c.ev_join, cudaEventDisableTiming));
+        }
         launch_fse_stages(src, src_off, src_len, dst_off, dst_cap, c.blocks.as<BlockDesc>(), c.fse.as<FseDesc>(), (uint32_t)tot.n_fse,
                           c.lits.as<uint8_t>(), c.lmds.as<LmdRec>(), c.err.as<uint32_t>(), c.work.as<uint32_t>(), d->n_sms, s,
-                          timer && timer->enabled ? timer->ev[timer->n] : nullptr);
+                          timer && timer->enabled ? timer->ev[timer->n] : nullptr, c.side, c.ev_fork, c.ev_join);
         if (timer && timer->enabled) timer->n++;  // literals
         d->launches += 2;
     } else if (timer) {
@@ -145,10 +156,10 @@ int decode_launch_rest(lzfse_b200_decoder *d, DecodeScratch &c, const uint8_t *s
     // SMs); otherwise a CTA per stream, whose 7 worker warps share one stream through a shared-memory window.
     // Long streams (many blocks): two passes, all their blocks side by side (expand_long.cu); the kernels below skip them.
     if (lt.n_streams) {
-        launch_expand_long(src, src_off, src_len, dst, dst_off, dst_cap, c.counts.as<StreamCounts>(), c.blocks.as<BlockDesc>(), c.fse.as<FseDesc>(),
-                           c.lits.as<uint8_t>(), c.lmds.as<LmdRec>(), c.long_blocks.as<uint32_t>(), c.long_streams.as<uint32_t>(),
-                           c.long_base.as<uint64_t>(), c.image.as<uint32_t>(), c.err.as<uint32_t>(), lt.n_streams, lt.n_blocks, c.work.as<uint32_t>(),
-                           d->n_sms, s);
+        CK(d, (cudaError_t)launch_expand_long(src, src_off, src_len, dst, dst_off, dst_cap, c.counts.as<StreamCounts>(), c.blocks.as<BlockDesc>(),
+                                              c.fse.as<FseDesc>(), c.lits.as<uint8_t>(), c.lmds.as<LmdRec>(), c.long_blocks.as<uint32_t>(),
+                                              c.long_streams.as<uint32_t>(), c.long_base.as<uint64_t>(), c.image.as<uint32_t>(), c.err.as<uint32_t>(),
+                                              lt.n_streams, lt.n_blocks, c.work.as<uint32_t>(), d->n_sms, s));
         d->launches += 2;
     }
     const bool use_cta = d->expand_mode == 2 || (d->expand_mode == 0 && n < (size_t)d->n_sms * 16);

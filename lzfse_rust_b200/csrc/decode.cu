@@ -374,11 +374,27 @@ struct WeightReader {
     uint32_t len, i;
     uint64_t accum;
     int accum_bits;
+    uint32_t T, T_last;  // payload bits consumed so far / before the most recent weight
     bool v1;
-    __device__ void init(const uint8_t *ptr, uint32_t n, bool is_v1) { p = ptr; len = n; i = 0; accum = 0; accum_bits = 0; v1 = is_v1; }
+    __device__ void init(const uint8_t *ptr, uint32_t n, bool is_v1) { p = ptr; len = n; i = 0; accum = 0; accum_bits = 0; T = 0; T_last = 0; v1 = is_v1; }
     __device__ uint32_t next() {
         if (v1) { uint32_t w = ld_u16(p + 2 * i); i++; return w; }
-        while (i != len && accum_bits <= 24) { accum |= (uint64_t)p[i] << accum_bits; accum_bits += 8; i++; }
+        // The reference tops its accumulator up one byte at a time while it holds <= 24 bits; a byte load per weight byte,
+        // each lane in its own cache line, was a sixth of the literal kernel's stall samples.  Four bytes per refill (one
+        // aligned word pair) decode the same weights: past the payload both read zeros.  What differs is how many bytes
+        // have been pulled in at the end, and finish() reconstructs the reference's count from the bits consumed.
+        if (accum_bits <= 32 && i < len) {
+            const uint32_t take = len - i < 4u ? len - i : 4u;
+            const uintptr_t a = reinterpret_cast<uintptr_t>(p + i);
+            const uint32_t r = (uint32_t)a & 3u;
+            const uint32_t *q = reinterpret_cast<const uint32_t *>(a - r);
+            const uint32_t lo = __ldg(q), hi = (r && r + take > 4u) ? __ldg(q + 1) : 0u;  // only words that hold a payload byte
+            uint32_t w = __funnelshift_r(lo, hi, r * 8);
+            if (take < 4u) w &= (1u << (8 * take)) - 1u;
+            accum |= (uint64_t)w << accum_bits;
+            accum_bits += 8 * (int)take;
+            i += take;
+        }
         uint32_t u = (uint32_t)accum;
         uint32_t lo = u & 0x1F, bits, w;
         // WEIGHTS_BITS_TABLE / WEIGHTS_VALUE_TABLE (fse/constants.rs:115-124) in closed form
@@ -389,30 +405,27 @@ struct WeightReader {
         else { bits = 14; w = 24 + ((u >> 4) & 0x3FF); }                    // xxxxxxxxxx1111
         accum >>= bits;
         accum_bits -= (int)bits;
+        T_last = T;
+        T += bits;
         return w;
     }
-    // Weights::load_v2 tail checks (fse/weights.rs:98-103)
+    // Weights::load_v2 tail checks (fse/weights.rs:98-103) on the state the reference's byte-wise reader would be in: before
+    // a weight it has pulled in bytes until it holds more than 24 bits (or the payload ends), so after the last weight it
+    // has read min(len, (T_last + 24) / 8 + 1) bytes and holds that many bits minus what all weights consumed.
     __device__ int finish() const {
         if (v1) return LZFSE_B200_OK;
-        if (accum_bits < 0) return LZFSE_B200_FSE_WEIGHT_PAYLOAD_UNDERFLOW;
-        if (accum_bits >= 8 || i != len) return LZFSE_B200_FSE_WEIGHT_PAYLOAD_OVERFLOW;
+        uint32_t i_ref = (T_last + 24) / 8 + 1;
+        if (i_ref > len) i_ref = len;
+        const int bits_left = 8 * (int)i_ref - (int)T;
+        if (bits_left < 0) return LZFSE_B200_FSE_WEIGHT_PAYLOAD_UNDERFLOW;
+        if (bits_left >= 8 || i_ref != len) return LZFSE_B200_FSE_WEIGHT_PAYLOAD_OVERFLOW;
         return LZFSE_B200_OK;
     }
 };
 
-// Full validation of a block's weight payload: bit accounting, then check_totals (weights.rs:189-201).
-__device__ int validate_weights(const uint8_t *wp, uint32_t n_bytes, bool v1) {
-    WeightReader r;
-    r.init(wp, n_bytes, v1);
-    uint32_t tl = 0, tm = 0, td = 0, tu = 0;
-    for (uint32_t k = 0; k < 20; k++) tl += r.next();
-    for (uint32_t k = 0; k < 20; k++) tm += r.next();
-    for (uint32_t k = 0; k < 64; k++) td += r.next();
-    for (uint32_t k = 0; k < 256; k++) tu += r.next();
-    int e = r.finish();
-    if (e) return e;
-    if (tl <= kLStates && tm <= kMStates && td <= kDStates && tu <= kUStates) return LZFSE_B200_OK;
-    return LZFSE_B200_FSE_BAD_WEIGHT_PAYLOAD;
+// check_totals (weights.rs:189-201)
+__device__ __forceinline__ int check_weight_totals(uint32_t tl, uint32_t tm, uint32_t td, uint32_t tu) {
+    return (tl <= kLStates && tm <= kMStates && td <= kDStates && tu <= kUStates) ? LZFSE_B200_OK : LZFSE_B200_FSE_BAD_WEIGHT_PAYLOAD;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -608,29 +621,37 @@ k_fse_literals(const uint8_t *__restrict__ src_base, const uint64_t *__restrict_
             const bool v1 = fd.flags & FSE_V1;
             const uint8_t *wp = blk + (v1 ? kV1HeaderSize : kV2HeaderSize);
             const uint32_t kb = bd.index < 0x1FFFFFu ? bd.index : 0x1FFFFFu;
-            int e = validate_weights(wp, fd.n_weight_bytes, v1);
+            // One pass over the weight payload: L/M/D weights are only summed here, the literal weights build the U table as
+            // they are read (build_u_table, one lane per block, states in order); the payload's bit accounting and the totals
+            // are checked afterwards, as the reference does before it builds anything -- a payload that fails has at worst
+            // filled this lane's own table with nonsense (writes are clipped to it).
+            WeightReader r;
+            r.init(wp, fd.n_weight_bytes, v1);
+            uint32_t tl = 0, tm = 0, td = 0, total = 0;
+            for (int k = 0; k < 20; k++) tl += r.next();
+            for (int k = 0; k < 20; k++) tm += r.next();
+            for (int k = 0; k < 64; k++) td += r.next();
+            for (uint32_t sym = 0; sym < 256; sym++) {
+                uint32_t w = r.next();
+                if (w == 0) continue;
+                uint32_t k = __clz(w) - 21;  // clz(w) - clz(1024)
+                uint32_t x = (2048u >> k) - w;
+                const uint32_t room = total < 1024u ? 1024u - total : 0u;
+                const uint32_t wn = w < room ? w : room;
+                for (uint32_t j = 0; j < wn; j++) {
+                    uint32_t kk, delta;
+                    if (j < x) { kk = k; delta = ((w + j) << k) - 1024u; }
+                    else { kk = k - 1; delta = (j - x) << (k - 1); }
+                    kd[(total + j) * 32 + lane] = (uint16_t)(delta | (kk << 12));
+                    sy[(total + j) * 32 + lane] = (uint8_t)sym;
+                }
+                total += w;
+            }
+            int e = r.finish();
+            if (!e) e = check_weight_totals(tl, tm, td, total);
             if (e) {
                 atomicMin(&err[bd.stream], err_key(kb, PH_WEIGHTS, e));
             } else if (!(fd.flags & FSE_TRUNC_LIT)) {
-                // build_u_table, one lane per block, states in order
-                WeightReader r;
-                r.init(wp, fd.n_weight_bytes, v1);
-                for (int k = 0; k < 104; k++) r.next();
-                uint32_t total = 0;
-                for (uint32_t sym = 0; sym < 256; sym++) {
-                    uint32_t w = r.next();
-                    if (w == 0) continue;
-                    uint32_t k = __clz(w) - 21;  // clz(w) - clz(1024)
-                    uint32_t x = (2048u >> k) - w;
-                    for (uint32_t j = 0; j < w; j++) {
-                        uint32_t kk, delta;
-                        if (j < x) { kk = k; delta = ((w + j) << k) - 1024u; }
-                        else { kk = k - 1; delta = (j - x) << (k - 1); }
-                        kd[(total + j) * 32 + lane] = (uint16_t)(delta | (kk << 12));
-                        sy[(total + j) * 32 + lane] = (uint8_t)sym;
-                    }
-                    total += w;
-                }
                 for (uint32_t t = total; t < 1024; t++) { kd[t * 32 + lane] = (uint16_t)t; sy[t * 32 + lane] = 0; }
 
                 // Literals::load.  The slice borrows the 8 bytes before the payload as the BitSrc pad
@@ -705,9 +726,9 @@ __device__ __forceinline__ uint32_t l_base(uint32_t s) { return s < 16 ? s : ((0
 __device__ __forceinline__ uint32_t m_base(uint32_t s) { return s < 16 ? s : (uint32_t)((0x0138003800180010ull >> ((s - 16) * 16)) & 0xFFFFu); }
 // D_BASE_VALUE[s] = ((4 + (s & 3)) << (s >> 2)) - 4, D_EXTRA_BITS[s] = s >> 2 (fse/constants.rs:305-321): computed from the entry
 
-template <int KIND>  // 0 = L, 1 = M, 2 = D
-__device__ __forceinline__ void build_v_block(WeightReader &r, uint32_t *tab, uint32_t lane, uint32_t n_sym, uint32_t n_states,
-                                              uint32_t offset) {
+template <int KIND>  // 0 = L, 1 = M, 2 = D; returns the sum of the weights (writes are clipped to the kind's states)
+__device__ __forceinline__ uint32_t build_v_block(WeightReader &r, uint32_t *tab, uint32_t lane, uint32_t n_sym, uint32_t n_states,
+                                                  uint32_t offset) {
     const uint32_t n_clz = __clz(n_states);
     uint32_t total = 0;
     for (uint32_t sym = 0; sym < n_sym; sym++) {
@@ -717,7 +738,9 @@ __device__ __forceinline__ void build_v_block(WeightReader &r, uint32_t *tab, ui
         uint32_t x = ((n_states << 1) >> k) - w;
         const uint32_t vb = KIND == 0 ? l_extra(sym) : (KIND == 1 ? m_extra(sym) : (sym >> 2));
         const uint32_t hi = KIND == 0 ? l_base(sym) : (KIND == 1 ? m_base(sym) : 4u + (sym & 3u));  // D: v_base = (hi << v_bits) - 4
-        for (uint32_t j = 0; j < w; j++) {
+        const uint32_t room = total < n_states ? n_states - total : 0u;
+        const uint32_t wn = w < room ? w : room;
+        for (uint32_t j = 0; j < wn; j++) {
             uint32_t kk, delta;
             if (j < x) { kk = k; delta = ((w + j) << k) - n_states; }
             else { kk = k - 1; delta = (j - x) << (k - 1); }
@@ -727,6 +750,7 @@ __device__ __forceinline__ void build_v_block(WeightReader &r, uint32_t *tab, ui
     }
     // latch (fse/decoder.rs:288-291): k = 0, no value bits, v_base = 0 -- which for D is the field value 4: (4 << 0) - 4
     for (uint32_t t = total; t < n_states; t++) tab[(offset + t) * 32 + lane] = t | (KIND == 2 ? (4u << 16) : 0u);
+    return total;
 }
 
 __global__ void __launch_bounds__(kLmdWarps * 32, 1)
@@ -752,12 +776,21 @@ k_fse_lmds(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ sr
             const uint8_t *wp = blk + (v1 ? kV1HeaderSize : kV2HeaderSize);
             const uint32_t kb = bd.index < 0x1FFFFFu ? bd.index : 0x1FFFFFu;
             // The literal stage reports weight errors; this stage only needs to know the tables are sound.
-            if (!(fd.flags & (FSE_TRUNC_LIT | FSE_TRUNC_LMD)) && validate_weights(wp, fd.n_weight_bytes, v1) == 0) {
+            bool tables_ok = false;
+            if (!(fd.flags & (FSE_TRUNC_LIT | FSE_TRUNC_LMD))) {
+                // one pass over the weight payload: the L/M/D weights build their tables as they are read, the literal
+                // weights are only summed; a payload that fails the reference's checks leaves the block to the literal
+                // stage's error report
                 WeightReader r;
                 r.init(wp, fd.n_weight_bytes, v1);
-                build_v_block<0>(r, tab, lane, kLSymbols, kLStates, 0);
-                build_v_block<1>(r, tab, lane, kMSymbols, kMStates, 64);
-                build_v_block<2>(r, tab, lane, kDSymbols, kDStates, 128);
+                const uint32_t tl = build_v_block<0>(r, tab, lane, kLSymbols, kLStates, 0);
+                const uint32_t tm = build_v_block<1>(r, tab, lane, kMSymbols, kMStates, 64);
+                const uint32_t td = build_v_block<2>(r, tab, lane, kDSymbols, kDStates, 128);
+                uint32_t tu = 0;
+                for (uint32_t k = 0; k < 256; k++) tu += r.next();
+                tables_ok = r.finish() == 0 && check_weight_totals(tl, tm, td, tu) == 0;
+            }
+            if (tables_ok) {
 
                 const uint8_t *s_lo = src_base + src_off[bd.stream], *s_hi = s_lo + src_len[bd.stream];
                 RingWindow br;
@@ -1427,14 +1460,26 @@ int setup_decode_kernels() {
 }
 void launch_fse_stages(const uint8_t *src, const uint64_t *src_off, const uint64_t *src_len, const uint64_t *dst_off, const uint64_t *dst_cap,
                        const BlockDesc *blocks, FseDesc *fse, uint32_t n_fse, uint8_t *lit_scratch, LmdRec *lmd_scratch, uint32_t *err,
-                       uint32_t *work_counters /* kWorkWords zeroed u32 */, int n_sms, cudaStream_t s, cudaEvent_t between) {
+                       uint32_t *work_counters /* kWorkWords zeroed u32 */, int n_sms, cudaStream_t s, cudaEvent_t between,
+                       cudaStream_t side /* or null */, cudaEvent_t fork, cudaEvent_t join) {
     if (n_fse == 0) return;
     unsigned need_lit = (n_fse + 32 * kLitWarps - 1) / (32 * kLitWarps), need_lmd = (n_fse + 32 * kLmdWarps - 1) / (32 * kLmdWarps);
     unsigned g_lit = need_lit < (unsigned)n_sms ? need_lit : (unsigned)n_sms;
     unsigned g_lmd = need_lmd < (unsigned)n_sms ? need_lmd : (unsigned)n_sms;
-    k_fse_literals<<<g_lit, kLitWarps * 32, kLitWarps * kLitSmemPerWarp, s>>>(src, src_off, src_len, blocks, fse, n_fse, lit_scratch, err, work_counters);
+    // The two stages are independent of each other, and each of their CTAs fills an SM's shared memory.  When both grids
+    // fit the machine side by side (batches of few blocks, e.g. 8 streams of 16 MiB) the literal stage runs on a side stream.
+    const bool side_by_side = side != nullptr && g_lit + g_lmd <= (unsigned)n_sms;
+    if (side_by_side) {
+        cudaEventRecord(fork, s);
+        cudaStreamWaitEvent(side, fork, 0);
+        k_fse_literals<<<g_lit, kLitWarps * 32, kLitWarps * kLitSmemPerWarp, side>>>(src, src_off, src_len, blocks, fse, n_fse, lit_scratch, err, work_counters);
+        cudaEventRecord(join, side);
+    } else {
+        k_fse_literals<<<g_lit, kLitWarps * 32, kLitWarps * kLitSmemPerWarp, s>>>(src, src_off, src_len, blocks, fse, n_fse, lit_scratch, err, work_counters);
+    }
     if (between) cudaEventRecord(between, s);
     k_fse_lmds<<<g_lmd, kLmdWarps * 32, kLmdWarps * kLmdSmemPerWarp, s>>>(src, src_off, src_len, dst_off, dst_cap, blocks, fse, n_fse, lmd_scratch, err, work_counters + 1);
+    if (side_by_side) cudaStreamWaitEvent(s, join, 0);
 }
 void launch_expand(const uint8_t *src, const uint64_t *src_off, const uint64_t *src_len, uint8_t *dst, const uint64_t *dst_off,
                    const uint64_t *dst_cap, const StreamCounts *bases, const BlockDesc *blocks, const FseDesc *fse, const uint8_t *lit_scratch,

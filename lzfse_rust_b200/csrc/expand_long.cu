@@ -24,6 +24,7 @@
 // produced before the match (fse_core.rs:104-131), so pass 1 only touches blocks both stages accepted, and pass 2 stops at
 // the first block they did not -- the reference's behaviour.
 #include <cooperative_groups.h>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "lz_blocks.cuh"
@@ -172,9 +173,8 @@ __device__ void p2_gather(const uint32_t *__restrict__ V, uint8_t *__restrict__ 
     if (tid < n - done) O[done + tid] = (uint8_t)p2_byte(__ldcs(V + done + tid), S);
 }
 
-constexpr int kP2Cluster = 8;  // CTAs (SMs) per stream; 8 is the portable cluster size
-
-__global__ void __cluster_dims__(kP2Cluster, 1, 1) __launch_bounds__(kP2Threads, 1)
+// CTAs (SMs) per stream: the cluster size chosen at launch (8, see p2_cluster_size).
+__global__ void __launch_bounds__(kP2Threads, 1)
 k_expand_long_p2(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ src_off, const uint64_t *__restrict__ src_len,
                  uint8_t *__restrict__ dst_base, const uint64_t *__restrict__ dst_off, const uint64_t *__restrict__ dst_cap,
                  const StreamCounts *__restrict__ bases, const BlockDesc *__restrict__ blocks, const FseDesc *__restrict__ fse,
@@ -182,7 +182,7 @@ k_expand_long_p2(const uint8_t *__restrict__ src_base, const uint64_t *__restric
                  uint32_t *err) {
     __shared__ int stop;  // rank 0's copy is the cluster's (read through distributed shared memory)
     cg::cluster_group cluster = cg::this_cluster();
-    const uint32_t tid = threadIdx.x, rank = cluster.block_rank();
+    const uint32_t tid = threadIdx.x, rank = cluster.block_rank(), kP2Cluster = cluster.num_blocks();
     const uint32_t stream = long_streams[blockIdx.x / kP2Cluster];
     uint8_t *S = dst_base + dst_off[stream];
     const uint32_t *img = image + long_base[stream];
@@ -218,17 +218,39 @@ k_expand_long_p2(const uint8_t *__restrict__ src_base, const uint64_t *__restric
     cluster.sync();  // nobody leaves while a sibling may still read its shared memory
 }
 
-void launch_expand_long(const uint8_t *src, const uint64_t *src_off, const uint64_t *src_len, uint8_t *dst, const uint64_t *dst_off,
-                        const uint64_t *dst_cap, const StreamCounts *bases, const BlockDesc *blocks, const FseDesc *fse, const uint8_t *lit_scratch,
-                        const LmdRec *lmd_scratch, const uint32_t *long_blocks, const uint32_t *long_streams, const uint64_t *long_base,
-                        uint32_t *image, uint32_t *err, uint32_t n_long_streams, uint32_t n_long_blocks, uint32_t *work /* kWorkWords */, int n_sms,
-                        cudaStream_t s) {
-    if (n_long_streams == 0) return;
+// Cluster size of pass 2.  8 (the portable maximum) is the default: with 16-CTA clusters the 8 x 16 MiB configuration expands in
+// 3.28 ms instead of 2.36 -- the barrier over 16 SMs costs more than halving the gather saves.  LZB_P2_CLUSTER overrides it for
+// measurements.
+static int p2_cluster_size() {
+    static const int size = [] {
+        const bool big_ok = cudaFuncSetAttribute(k_expand_long_p2, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+        if (!big_ok) cudaGetLastError();
+        if (const char *e = getenv("LZB_P2_CLUSTER")) {
+            const int v = atoi(e);
+            if (v == 1 || v == 2 || v == 4 || v == 8 || (v == 16 && big_ok)) return v;
+        }
+        return 8;
+    }();
+    return size;
+}
+
+int launch_expand_long(const uint8_t *src, const uint64_t *src_off, const uint64_t *src_len, uint8_t *dst, const uint64_t *dst_off,
+                       const uint64_t *dst_cap, const StreamCounts *bases, const BlockDesc *blocks, const FseDesc *fse, const uint8_t *lit_scratch,
+                       const LmdRec *lmd_scratch, const uint32_t *long_blocks, const uint32_t *long_streams, const uint64_t *long_base,
+                       uint32_t *image, uint32_t *err, uint32_t n_long_streams, uint32_t n_long_blocks, uint32_t *work /* kWorkWords */, int n_sms,
+                       cudaStream_t s) {
+    if (n_long_streams == 0) return 0;
     const unsigned need = (n_long_blocks + kP1Warps - 1) / kP1Warps, resident = (unsigned)n_sms * 4;
     k_expand_long_p1<<<need < resident ? need : resident, kP1Warps * 32, 0, s>>>(dst_off, blocks, fse, lit_scratch, lmd_scratch, long_blocks, work + 14, long_base,
                                                                                  image, work + 16);
-    k_expand_long_p2<<<n_long_streams * kP2Cluster, kP2Threads, 0, s>>>(src, src_off, src_len, dst, dst_off, dst_cap, bases, blocks, fse, long_streams, long_base, image,
-                                                           err);
+    const int cl = p2_cluster_size();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(n_long_streams * (unsigned)cl); cfg.blockDim = dim3(kP2Threads); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+    cudaLaunchAttribute at;
+    at.id = cudaLaunchAttributeClusterDimension; at.val.clusterDim.x = (unsigned)cl; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+    cfg.attrs = &at; cfg.numAttrs = 1;
+    return (int)cudaLaunchKernelEx(&cfg, k_expand_long_p2, src, src_off, src_len, dst, dst_off, dst_cap, bases, blocks, fse, long_streams, long_base,
+                                   (const uint32_t *)image, err);
 }
 
 }  // namespace lzb
