@@ -21,7 +21,7 @@ for l in dis.splitlines():
     if m: cur = (os.path.basename(m.group(1)), int(m.group(2))); continue
     m = re.match(r"\s*/\*([0-9a-f]{4,})\*/\s+(.*?);", l)
     if m: line_of[int(m.group(1), 16)] = (cur, m.group(2).strip())
-raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kern], capture_output=True, text=True).stdout
+raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + os.environ.get("NCU_KERNEL_REGEX", kern)], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 hdr = rows[hi]
