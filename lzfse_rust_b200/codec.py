@@ -89,8 +89,8 @@ class _Handle:
     STAGES = ()
 
     def last_stage_ms(self):
-        buf = (C.c_float * 8)()
-        n = getattr(self._lib, "lzfse_b200_%s_last_stage_ms" % self._kind)(self._h, buf, 8)
+        buf = (C.c_float * 16)()
+        n = getattr(self._lib, "lzfse_b200_%s_last_stage_ms" % self._kind)(self._h, buf, 16)
         return dict(zip(self.STAGES, [float(buf[i]) for i in range(n)]))
 
     # ---- shared batch plumbing -------------------------------------------------------------
@@ -204,7 +204,7 @@ class LzfseEncoder(_Handle):
     """LZFSE encoder (lzfse_rust::LzfseEncoder).  Reusable; one call at a time per object."""
 
     _kind = "encoder"
-    STAGES = ("prep", "find", "replay", "parse", "fse_blocks", "assemble")
+    STAGES = ("prep", "find", "replay", "parse", "long_chain", "long_find", "long_replay", "long_stitch", "long_packs", "fse_blocks", "assemble")
 
     def encode_bound(self, n):
         return int(self._lib.lzfse_b200_encode_bound(int(n)))

@@ -33,6 +33,10 @@ constexpr uint32_t kEmptyIdx = 0xC0C0C0C0u;  // history reset marker (encode/his
 constexpr uint32_t kBucketWords = 2 * kHashWidth;
 constexpr uint32_t kTableWords = (1u << kHashBits) * kBucketWords;
 constexpr uint32_t kFastMaxLen = 65536;  // streams up to this long take the shared-memory path (positions fit 16 bits)
+#ifndef LZB_LONG_RSEG
+#define LZB_LONG_RSEG 16384
+#endif
+constexpr uint32_t kLongCSeg = 65536, kLongRSeg = LZB_LONG_RSEG;  // longer bvx2 streams: chain pieces / replay segments (encode_long.cuh)
 
 enum StreamKind : uint32_t { SK_RAW = 0, SK_VN = 1, SK_FSE = 2 };
 
@@ -52,7 +56,11 @@ struct EncStream {       // per stream, written by prep / parse, read by assembl
     uint32_t kind;       // StreamKind
     uint32_t n_blocks;   // FSE blocks produced
     uint32_t vn_size;    // LZVN: bytes of the finished block (header included) in the out scratch
-    uint32_t fast;       // 1: parsed by k_enc_find + k_enc_replay (bvx2 streams of <= kFastMaxLen bytes), 0: by k_enc_parse
+    uint32_t fast;       // 1: parsed by k_enc_find + k_enc_replay (bvx2 streams of <= kFastMaxLen bytes), 2: by the k_long_* kernels
+                         // (longer bvx2 streams, encode_long.cuh), 0: by k_enc_parse
+    uint32_t cseg_base, n_cseg;  // long streams: chain pieces and replay segments (indices into the batch's lists)
+    uint32_t rseg_base, n_rseg;
+    uint64_t long_off;   // long streams: element offset of the stream's prev[] array
 };
 
 struct EncBlock {        // one bvx2 block to encode (compact list, any order)
@@ -63,19 +71,23 @@ struct EncBlock {        // one bvx2 block to encode (compact list, any order)
     uint32_t n_packs, n_lits, n_match_bytes;
     uint32_t out_size;   // filled by k_enc_fse_blocks
     uint32_t gather;     // 1: the literal bytes are not in the literal scratch yet (k_enc_fse_blocks collects them from the source)
-    uint32_t pad;
+    uint32_t pad;        // 1: block of a long stream, copied into the frame by k_long_copy (dst_pos set by k_enc_assemble)
+    uint64_t dst_pos;    // byte offset of the finished block inside dst_base
 };
 
 // ------------------------------------------------------------------------------------------------
 // prep: policy + sizing.  counts[i] = {packs, literal bytes, block slots, out bytes}
 // ------------------------------------------------------------------------------------------------
 __global__ void k_enc_prep(const uint64_t *__restrict__ src_len, size_t n, EncStream *streams, StreamCounts *counts, int32_t *status,
-                           uint32_t *path_counts /* [0] fast streams, [1] streams for k_enc_parse */, int allow_fast) {
+                           uint32_t *path_counts /* [0] fast streams, [1] streams for k_enc_parse, [2] long streams, [3] replay segments,
+                                                    [4] chain pieces, [6..7] prev[] elements (u64) */,
+                           uint32_t *long_list, int allow_fast, int allow_long) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint64_t len = src_len[i];
     EncStream st;
     st.n_blocks = 0; st.vn_size = 0; st.fast = 0;
+    st.cseg_base = st.n_cseg = st.rseg_base = st.n_rseg = 0; st.long_off = 0;
     StreamCounts c = {0, 0, 0, 0};
     status[i] = LZFSE_B200_OK;
     if (len > 0x7FFFFFFFull) {  // BLOCK_GUIDE repositioning (frontend_bytes.rs:348-375) is out of scope
@@ -84,6 +96,15 @@ __global__ void k_enc_prep(const uint64_t *__restrict__ src_len, size_t n, EncSt
     } else if (len > kVnCutoff) {
         st.kind = SK_FSE;
         st.fast = allow_fast && len <= kFastMaxLen;
+        if (allow_long && len > kFastMaxLen) {
+            st.fast = 2;
+            const uint32_t end = (uint32_t)len - 3;
+            st.n_cseg = (end + kLongCSeg - 1) / kLongCSeg; st.n_rseg = (end + kLongRSeg - 1) / kLongRSeg;
+            long_list[atomicAdd(&path_counts[2], 1u)] = (uint32_t)i;
+            st.rseg_base = atomicAdd(&path_counts[3], st.n_rseg);
+            st.cseg_base = atomicAdd(&path_counts[4], st.n_cseg);
+            st.long_off = atomicAdd(reinterpret_cast<unsigned long long *>(path_counts + 6), (unsigned long long)((len + 31) & ~15ull));
+        }
         c.n_blocks = pack_cap(len);                  // packs
         c.n_fse = (len + 31) & ~15ull;               // literal bytes
         c.n_literals = block_cap(len);               // block slots
@@ -96,9 +117,9 @@ __global__ void k_enc_prep(const uint64_t *__restrict__ src_len, size_t n, EncSt
     }
     streams[i] = st;
     counts[i] = c;
-    if (st.kind != SK_RAW) atomicAdd(&path_counts[st.fast ? 0 : 1], 1u);
+    if (st.kind != SK_RAW && st.fast != 2) atomicAdd(&path_counts[st.fast ? 0 : 1], 1u);
 }
-__global__ void k_enc_publish_counts(const uint32_t *path_counts, uint32_t *host_out) { host_out[0] = path_counts[0]; host_out[1] = path_counts[1]; }
+__global__ void k_enc_publish_counts(const uint32_t *path_counts, uint32_t *host_out) { for (int k = 0; k < 8; k++) host_out[k] = path_counts[k]; }
 
 // ------------------------------------------------------------------------------------------------
 // parse: warp per stream
@@ -177,7 +198,7 @@ __device__ __noinline__ void sink_emit_block(FseSink &s, const SinkEnv &env, uin
         b.n_lits = s.n_lits_total - s.blk_lit0;
         b.n_match_bytes = s.n_match_bytes;
         b.out_size = 0;
-        b.src_pos = 0; b.gather = 0; b.pad = 0;
+        b.src_pos = 0; b.gather = 0; b.pad = 0; b.dst_pos = 0;
         const uint32_t id = atomicAdd(env.block_counter, 1u);
         env.blocks[id] = b;
         env.block_ids[base.n_literals + s.n_blocks] = id;
@@ -772,7 +793,7 @@ k_enc_find(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ sr
         __syncthreads();
         const uint32_t si = ctrl->stream;
         if (si >= n_streams) break;
-        if (!streams[si].fast) { __syncthreads(); continue; }
+        if (streams[si].fast != 1) { __syncthreads(); continue; }
         const uint32_t len = (uint32_t)src_len[si], end = len - 3;
         const uint32_t n_units = (end + kFindUnit - 1) / kFindUnit;
         const uint8_t *g = src_base + src_off[si];
@@ -1068,7 +1089,7 @@ __device__ __forceinline__ void tsink_emit_block(TSink &s, const TEnv &env) {
     b.n_packs = s.n_packs_total - s.blk_pack0;
     b.n_lits = s.n_lits_total - s.blk_lit0;
     b.n_match_bytes = s.n_match_bytes;
-    b.out_size = 0; b.gather = 1; b.pad = 0;
+    b.out_size = 0; b.gather = 1; b.pad = 0; b.dst_pos = 0;
     const uint32_t id = atomicAdd(env.block_counter, 1u);
     env.blocks[id] = b;
     env.block_ids[env.base.n_literals + s.n_blocks] = id;
@@ -1137,7 +1158,7 @@ k_enc_replay(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ 
     // is done, because the ring upkeep below is WARP-WIDE on purpose (see there).
     static_assert(kReplayStride == 1, "one stream per lane");
     const size_t si = (size_t)blockIdx.x * kReplayThreads + threadIdx.x;
-    const bool valid = si < n_streams && streams[si < n_streams ? si : 0].fast;
+    const bool valid = si < n_streams && streams[si < n_streams ? si : 0].fast == 1;
     bool active = valid;
     const size_t sj = valid ? si : 0;
     const uint8_t *src = src_base + src_off[sj];
@@ -1264,6 +1285,8 @@ k_enc_replay(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ 
     tsink_emit_block(fs, env);
     streams[si].n_blocks = fs.n_blocks;
 }
+
+#include "encode_long.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // FSE block encode: warp per block.
@@ -1583,7 +1606,7 @@ __global__ void __launch_bounds__(kAsmWarps * 32)
 k_enc_assemble(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ src_off, const uint64_t *__restrict__ src_len,
                uint8_t *__restrict__ dst_base, const uint64_t *__restrict__ dst_off, const uint64_t *__restrict__ dst_cap, size_t n_streams,
                const EncStream *__restrict__ streams, const StreamCounts *__restrict__ bases, const uint32_t *__restrict__ block_ids,
-               const EncBlock *__restrict__ blocks, const uint8_t *__restrict__ out_scratch, uint64_t *out_len, int32_t *status) {
+               EncBlock *blocks, const uint8_t *__restrict__ out_scratch, uint64_t *out_len, int32_t *status) {
     const uint32_t lane = lane_id();
     const size_t si = (size_t)blockIdx.x * kAsmWarps + (threadIdx.x >> 5);
     if (si >= n_streams) return;
@@ -1599,7 +1622,11 @@ k_enc_assemble(const uint8_t *__restrict__ src_base, const uint64_t *__restrict_
         if (len < kRawLimit && len + 8 <= st.vn_size) raw = true;
         else total += st.vn_size;
     } else if (st.kind == SK_FSE) {
-        for (uint32_t k = 0; k < st.n_blocks; k++) total += blocks[block_ids[bases[si].n_literals + k]].out_size;
+        uint64_t part = 0;
+        for (uint32_t k = lane; k < st.n_blocks; k += 32) part += blocks[block_ids[bases[si].n_literals + k]].out_size;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, o);
+        total += part;
     }
     if (raw) total += 8 + len;
     if (total > cap) {  // the reference would grow its Vec; a fixed buffer reports BufferOverflow
@@ -1614,6 +1641,21 @@ k_enc_assemble(const uint8_t *__restrict__ src_base, const uint64_t *__restrict_
     } else if (st.kind == SK_VN) {
         warp_copy_bytes(dst, out_scratch + bases[si].n_lmds, st.vn_size, lane);
         pos = st.vn_size;
+    } else if (st.fast == 2) {
+        // a long stream's blocks are copied side by side by k_long_copy; here only where each of them goes
+        for (uint32_t k0 = 0; k0 < st.n_blocks; k0 += 32) {
+            const uint32_t k = k0 + lane;
+            const uint32_t id = k < st.n_blocks ? block_ids[bases[si].n_literals + k] : 0u;
+            const uint32_t sz = k < st.n_blocks ? blocks[id].out_size : 0u;
+            uint64_t inc = sz;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint64_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+                if (lane >= (uint32_t)o) inc += t;
+            }
+            if (k < st.n_blocks) { blocks[id].dst_pos = dst_off[si] + pos + inc - sz; blocks[id].pad = 1; }
+            pos += __shfl_sync(0xFFFFFFFFu, inc, 31);
+        }
     } else {
         for (uint32_t k = 0; k < st.n_blocks; k++) {
             const EncBlock b = blocks[block_ids[bases[si].n_literals + k]];
@@ -1635,6 +1677,9 @@ struct lzfse_b200_encoder {
     std::string last_error;
     uint64_t launches = 0;
     DevBuf streams, counts, totals_dev, tables, packs, lits, block_ids, blocks, out, counters, words;
+    DevBuf long_list, l_prev, l_heads, l_cseg, l_rseg, l_out, l_spec, l_fix, l_states, l_tail;  // long streams (encode_long.cuh)
+    int allow_long = 1;  // LZB_ENC_LONG=0 sends streams > 64 KiB through k_enc_parse (measurements, tests)
+    uint32_t last_long_redo = 0;
     bool pending = false;             // an *_async call has been enqueued and not yet synchronised
     cudaStream_t pending_stream = nullptr;
     bool tables_dirty = false;        // a call that ran k_enc_parse did not complete: entries of unknown epochs may be in the tables
@@ -1659,12 +1704,16 @@ int encode_batch_device_impl(lzfse_b200_encoder *e, const uint8_t *src, const ui
     LZB_CK(e, e->counts.reserve((n + 1 + n / 1024 + 2) * sizeof(StreamCounts)));  // + tile sums of the scan
     LZB_CK(e, e->totals_dev.reserve(sizeof(StreamCounts)));
     LZB_CK(e, e->totals_host.reserve(2 * sizeof(StreamCounts)));
-    LZB_CK(e, e->counters.reserve(8 * sizeof(uint32_t)));
+    LZB_CK(e, e->counters.reserve(16 * sizeof(uint32_t)));
+    LZB_CK(e, e->long_list.reserve(n * sizeof(uint32_t)));
     const int tb = 128;
     e->timer.begin(s);
-    LZB_CK(e, cudaMemsetAsync(e->counters.p, 0, 8 * sizeof(uint32_t), s));
-    uint32_t *ctr = e->counters.as<uint32_t>();  // [0] blocks produced, [1] parse cursor, [2] fse-encode cursor, [3] find cursor, [4] fast streams, [5] k_enc_parse streams
-    k_enc_prep<<<(unsigned)((n + tb - 1) / tb), tb, 0, s>>>(src_len, n, e->streams.as<EncStream>(), e->counts.as<StreamCounts>(), status, ctr + 4, e->allow_fast);
+    LZB_CK(e, cudaMemsetAsync(e->counters.p, 0, 16 * sizeof(uint32_t), s));
+    // [0] blocks produced, [1] parse cursor, [2] fse-encode cursor, [3] find cursor, [4] fast streams, [5] k_enc_parse streams,
+    // [6] long streams, [7] replay segments, [8] chain pieces, [10..11] prev[] elements, [12] chain cursor, [13] segments stitched again
+    uint32_t *ctr = e->counters.as<uint32_t>();
+    k_enc_prep<<<(unsigned)((n + tb - 1) / tb), tb, 0, s>>>(src_len, n, e->streams.as<EncStream>(), e->counts.as<StreamCounts>(), status, ctr + 4,
+                                                           e->long_list.as<uint32_t>(), e->allow_fast, e->allow_long);
     launch_exclusive_scan(e->counts.as<StreamCounts>(), n, e->totals_host.as<StreamCounts>(), nullptr, s);  // pinned host memory (UVA)
     k_enc_publish_counts<<<1, 1, 0, s>>>(ctr + 4, reinterpret_cast<uint32_t *>(e->totals_host.as<StreamCounts>() + 1));
     e->launches += n > 8192 ? 5 : 3;  // prep + the exclusive scan (three launches for large batches) + publish
@@ -1672,6 +1721,10 @@ int encode_batch_device_impl(lzfse_b200_encoder *e, const uint8_t *src, const ui
     const StreamCounts tot = *e->totals_host.as<StreamCounts>();  // {packs, literal bytes, block slots, out bytes}
     const uint32_t n_fast = reinterpret_cast<const uint32_t *>(e->totals_host.as<StreamCounts>() + 1)[0];
     const uint32_t n_slow = reinterpret_cast<const uint32_t *>(e->totals_host.as<StreamCounts>() + 1)[1];
+    const uint32_t n_long = reinterpret_cast<const uint32_t *>(e->totals_host.as<StreamCounts>() + 1)[2];
+    const uint32_t n_rseg = reinterpret_cast<const uint32_t *>(e->totals_host.as<StreamCounts>() + 1)[3];
+    const uint32_t n_cseg = reinterpret_cast<const uint32_t *>(e->totals_host.as<StreamCounts>() + 1)[4];
+    const uint64_t long_elems = reinterpret_cast<const uint64_t *>(e->totals_host.as<StreamCounts>() + 1)[3];
     if (tot.n_literals > 0xFFFFFFF0ull) { e->last_error = "too many blocks in one batch"; return LZFSE_B200_INVALID_ARGUMENT; }
     const unsigned parse_ctas = (unsigned)e->n_sms * kParseWarpsPerSm / kParseWarps;
     const size_t n_slots = (size_t)parse_ctas * kParseWarps;
@@ -1684,7 +1737,18 @@ int encode_batch_device_impl(lzfse_b200_encoder *e, const uint8_t *src, const ui
         if (e->tables.p != before || e->tables_dirty) LZB_CK(e, cudaMemsetAsync(e->tables.p, 0, e->tables.cap, s));
         e->tables_dirty = true;
     }
-    if (n_fast) LZB_CK(e, e->words.reserve((tot.n_fse + 256) * sizeof(uint32_t)));  // one word per position (k_enc_find -> k_enc_replay)
+    if (n_fast || n_long) LZB_CK(e, e->words.reserve((tot.n_fse + 256) * sizeof(uint32_t)));  // one word per position (k_enc_find -> k_enc_replay)
+    if (n_long) {
+        LZB_CK(e, e->l_prev.reserve((long_elems + 64) * sizeof(uint32_t)));
+        LZB_CK(e, e->l_heads.reserve((size_t)n_cseg * (1u << kHashBits) * sizeof(uint32_t)));
+        LZB_CK(e, e->l_cseg.reserve((size_t)n_cseg * sizeof(LongSeg)));
+        LZB_CK(e, e->l_rseg.reserve((size_t)n_rseg * sizeof(LongSeg)));
+        LZB_CK(e, e->l_out.reserve((size_t)n_rseg * sizeof(LongSegOut)));
+        LZB_CK(e, e->l_spec.reserve((size_t)n_rseg * kEmitCap * sizeof(uint4)));
+        LZB_CK(e, e->l_fix.reserve((size_t)n_rseg * kEmitCap * sizeof(uint4)));
+        LZB_CK(e, e->l_states.reserve((size_t)n_rseg * kSpecStates * sizeof(uint4)));
+        LZB_CK(e, e->l_tail.reserve((size_t)n_long * 2 * sizeof(uint4)));
+    }
     LZB_CK(e, e->packs.reserve((tot.n_blocks + 1) * sizeof(uint2)));
     LZB_CK(e, e->lits.reserve(tot.n_fse + 64));
     LZB_CK(e, e->block_ids.reserve((tot.n_literals + 1) * sizeof(uint32_t)));
@@ -1714,6 +1778,36 @@ int encode_batch_device_impl(lzfse_b200_encoder *e, const uint8_t *src, const ui
         e->launches += 1;
     }
     e->timer.mark(s);  // parse
+    if (n_long) {
+        const EncStream *st = e->streams.as<EncStream>();
+        const StreamCounts *bs = e->counts.as<StreamCounts>();
+        const uint32_t *ll = e->long_list.as<uint32_t>();
+        LongSeg *cseg = e->l_cseg.as<LongSeg>(), *rseg = e->l_rseg.as<LongSeg>();
+        LongSegOut *so = e->l_out.as<LongSegOut>();
+        uint32_t *words = e->words.as<uint32_t>();
+        k_long_segs<<<n_long, 256, 0, s>>>(ll, n_long, st, cseg, rseg);
+        k_long_chain<<<n_cseg < (unsigned)e->n_sms ? n_cseg : (unsigned)e->n_sms, kChainThreads, kChainSmem, s>>>(
+            src, src_off, src_len, st, cseg, n_cseg, e->l_prev.as<uint32_t>(), e->l_heads.as<uint32_t>(), ctr + 12);
+        k_long_carry<<<n_long * ((1u << kHashBits) / 256), 256, 0, s>>>(ll, n_long, st, e->l_heads.as<uint32_t>());
+        e->timer.mark(s);  // long_chain
+        k_long_find<<<n_cseg * (kCSeg / kLFindThreads), kLFindThreads, 0, s>>>(src, src_off, src_len, st, bs, cseg, e->l_prev.as<uint32_t>(),
+                                                                                  e->l_heads.as<uint32_t>(), words);
+        e->timer.mark(s);  // long_find
+        k_long_replay<<<(n_rseg + kReplayThreads - 1) / kReplayThreads, kReplayThreads, 0, s>>>(src, src_off, src_len, bs, rseg, n_rseg, words,
+                                                                                                 e->l_spec.as<uint4>(), e->l_states.as<uint4>(), so);
+        e->timer.mark(s);  // long_replay
+        k_long_stitch_a<<<(n_rseg + 63) / 64, 64, 0, s>>>(src, src_off, src_len, bs, rseg, n_rseg, words, e->l_spec.as<uint4>(), e->l_states.as<uint4>(),
+                                                           e->l_fix.as<uint4>(), so);
+        k_long_stitch_b<<<(n_long + 31) / 32, 32, 0, s>>>(src, src_off, src_len, st, bs, ll, n_long, words, e->l_spec.as<uint4>(), e->l_states.as<uint4>(),
+                                                           e->l_fix.as<uint4>(), so, e->l_tail.as<uint4>(), ctr + 13);
+        e->timer.mark(s);  // long_stitch
+        k_long_packs<<<n_long, 32, 0, s>>>(src_off, src_len, e->streams.as<EncStream>(), bs, ll, n_long, e->l_spec.as<uint4>(), e->l_fix.as<uint4>(), so,
+                                            e->l_tail.as<uint4>(), e->packs.as<uint2>(), e->block_ids.as<uint32_t>(), e->blocks.as<EncBlock>(), ctr);
+        e->timer.mark(s);  // long_packs
+        e->launches += 8;
+    } else {
+        for (int k = 0; k < 5; k++) e->timer.mark(s);
+    }
     if (tot.n_literals) {
         unsigned g = (unsigned)((tot.n_literals + kFseEncWarps - 1) / kFseEncWarps);
         if (g > (unsigned)e->n_sms * 4) g = (unsigned)e->n_sms * 4;
@@ -1726,6 +1820,10 @@ int encode_batch_device_impl(lzfse_b200_encoder *e, const uint8_t *src, const ui
         src, src_off, src_len, dst, dst_off, dst_cap, n, e->streams.as<EncStream>(), e->counts.as<StreamCounts>(), e->block_ids.as<uint32_t>(),
         e->blocks.as<EncBlock>(), e->out.as<uint8_t>(), out_len, status);
     e->launches += 1;
+    if (n_long) {
+        k_long_copy<<<(unsigned)e->n_sms * 8, 256, 0, s>>>(e->blocks.as<EncBlock>(), ctr, e->out.as<uint8_t>(), dst);
+        e->launches += 1;
+    }
     e->timer.mark(s);  // assemble
     LZB_CK(e, cudaGetLastError());
     if (!wait) {  // lzfse_b200_encoder_sync (or the caller's own wait on `s`) completes the call
@@ -1758,9 +1856,11 @@ int lzfse_b200_encoder_create(int device, lzfse_b200_encoder **out) {
     e->n_sms = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete e; return LZFSE_B200_CUDA_ERROR; }
     if (const char *ef = getenv("LZB_ENC_FAST")) e->allow_fast = atoi(ef) != 0;
+    if (const char *ef = getenv("LZB_ENC_LONG")) e->allow_long = atoi(ef) != 0;
     cudaFuncAttributes fa;
     if (cudaFuncGetAttributes(&fa, k_enc_fse_blocks) != cudaSuccess ||
-        cudaFuncSetAttribute(k_enc_find, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFindSmemBytes) != cudaSuccess) {
+        cudaFuncSetAttribute(k_enc_find, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFindSmemBytes) != cudaSuccess ||
+        cudaFuncSetAttribute(k_long_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmem) != cudaSuccess) {
         cudaGetLastError();  // no sm_100a image for this device: there is no fallback path
         cudaStreamDestroy(e->own_stream);
         delete e;
@@ -1773,7 +1873,8 @@ int lzfse_b200_encoder_create(int device, lzfse_b200_encoder **out) {
 void lzfse_b200_encoder_destroy(lzfse_b200_encoder *e) {
     if (!e) return;
     DeviceGuard g(e->device);
-    for (DevBuf *b : {&e->streams, &e->counts, &e->totals_dev, &e->tables, &e->packs, &e->lits, &e->block_ids, &e->blocks, &e->out, &e->counters, &e->words}) b->release();
+    for (DevBuf *b : {&e->streams, &e->counts, &e->totals_dev, &e->tables, &e->packs, &e->lits, &e->block_ids, &e->blocks, &e->out, &e->counters, &e->words,
+                      &e->long_list, &e->l_prev, &e->l_heads, &e->l_cseg, &e->l_rseg, &e->l_out, &e->l_spec, &e->l_fix, &e->l_states, &e->l_tail}) b->release();
     e->totals_host.release();
     e->stage.release();
     e->timer.release();

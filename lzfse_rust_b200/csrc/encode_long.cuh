@@ -1,0 +1,623 @@
+// encode_long.cuh -- the front end for bvx2 streams longer than kFastMaxLen (BASELINE configs[3]: 16 MiB streams).
+// Included by encode.cu inside namespace lzb, after k_enc_replay (it uses Match, TSink, hash_u, ld4u, ld8u).
+//
+// Round 1 parsed such a stream with ONE warp (k_enc_parse): 16 MiB in 3 s.  Two facts let a single stream use the
+// whole machine without changing one byte of the frame:
+//
+//  1. What a position finds in the history does not depend on the parse (top of encode.cu).  The reference's
+//     HistoryTable (encode/history.rs:24-31,101-131) is the hash chain prev[p] = newest q < p in p's bucket, and
+//     that chain can be built for all 64 Ki-position pieces of a stream at once: k_long_chain links the positions
+//     inside a piece (bucket heads in shared memory) and leaves the newest position per bucket, k_long_carry turns
+//     those into "newest position before this piece" per bucket (a running maximum over the pieces, one thread per
+//     bucket), and a hop that leaves its piece continues in that table.  k_long_find then evaluates find_match
+//     (frontend_bytes.rs:214-244) for EVERY position, one thread each, and writes the same per-position word
+//     k_enc_find writes.
+//  2. The sequential part (backward limit, Match::select, frontend_bytes.rs:160-211,261-302) started from a clean
+//     state at an arbitrary position falls into step with the true parse after a few matches.  k_long_replay runs
+//     it for every kRSeg-position segment on its own (thread per segment, speculative), recording each pushed
+//     match with the state it leaves behind; k_long_stitch walks a stream's segments in order with the TRUE state,
+//     replays from it until that state equals a recorded one (or takes the segment whole when the true state at
+//     its border is equivalent to a clean start), and from there on the speculative output IS the true output.
+//     tests/model/long_parse_model.c is this algorithm on the CPU, checked against the oracle's front end.
+//
+//  k_long_packs finally turns a stream's match list into packs and block records (Buffer::push with its L / M
+//  splits and block closing, fse/buffer.rs:45-117), 32 matches per step while nothing irregular happens.
+//  Everything downstream (k_enc_fse_blocks, k_enc_assemble) is shared with the other paths.
+
+constexpr uint32_t kNoPos = 0xFFFFFFFFu;
+constexpr uint32_t kCSeg = kLongCSeg;         // positions per chain piece (16-bit bucket heads)
+constexpr uint32_t kRSeg = kLongRSeg;         // positions per speculative replay segment
+static_assert(kRSeg % 32 == 0 && kCSeg % kRSeg == 0, "segments are whole 32-position groups");
+constexpr uint32_t kEmitCap = kRSeg / 4 + 8;  // matches are >= 4 bytes and do not overlap
+constexpr uint32_t kSpecStates = 256;         // pushed matches per segment that carry the state they leave behind
+constexpr uint32_t kLongLaneCap = 64;
+
+struct LongSeg { uint32_t stream, k; };
+struct FrontState { uint32_t cur, lit, p_idx, p_midx, p_len; };
+struct LongSegOut {
+    uint32_t n_spec;     // matches pushed by the speculative replay
+    uint32_t lim0;       // a backward extension before the first push stopped at the literal limit
+    uint32_t good0;      // the first candidate met was >= GOOD_MATCH_LEN long
+    uint32_t cand0;      // position of the first candidate met (kNoPos: none)
+    FrontState exit;     // state when the cursor left the segment
+    uint32_t n_fix;      // matches the stitch pushed before it fell into step
+    uint32_t from;       // first speculative match that is part of the true parse (n_spec: none)
+    FrontState a_out;    // k_long_stitch_a: true state behind this segment IF the previous segment's exit state was true
+    uint32_t pad;
+};
+
+// ---- segment descriptors -----------------------------------------------------------------------
+__global__ void k_long_segs(const uint32_t *__restrict__ long_list, uint32_t n_long, const EncStream *__restrict__ streams, LongSeg *cseg, LongSeg *rseg) {
+    const uint32_t slot = blockIdx.x;
+    if (slot >= n_long) return;
+    const uint32_t si = long_list[slot];
+    const EncStream st = streams[si];
+    for (uint32_t k = threadIdx.x; k < st.n_cseg; k += blockDim.x) cseg[st.cseg_base + k] = LongSeg{si, k};
+    for (uint32_t k = threadIdx.x; k < st.n_rseg; k += blockDim.x) rseg[st.rseg_base + k] = LongSeg{si, k};
+}
+
+// ---- chain inside a piece ----------------------------------------------------------------------
+// Phase A, all warps: bucket index of every position and which lanes of a 32-position step share a bucket (the info
+// word of k_enc_find, parked in shared memory).  Phase B, warp 0: the ordered pass over the bucket heads.
+constexpr int kChainThreads = 1024;
+constexpr uint32_t kChainSmem = kCSeg * 2 + (1u << kHashBits) * 4;  // info words + bucket heads (32-bit: a piece has 65 536 positions AND "none")
+__global__ void __launch_bounds__(kChainThreads, 1)
+k_long_chain(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ src_off, const uint64_t *__restrict__ src_len,
+             const EncStream *__restrict__ streams, const LongSeg *__restrict__ cseg, uint32_t n_cseg, uint32_t *__restrict__ prev,
+             uint32_t *__restrict__ seg_head, uint32_t *work_counter) {
+    extern __shared__ __align__(16) uint8_t csm[];
+    uint16_t *info = reinterpret_cast<uint16_t *>(csm);
+    uint32_t *head = reinterpret_cast<uint32_t *>(csm + kCSeg * 2);
+    __shared__ uint32_t s_seg;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_seg = atomicAdd(work_counter, 1u);
+        __syncthreads();
+        const uint32_t cs = s_seg;
+        if (cs >= n_cseg) break;
+        const LongSeg sg = cseg[cs];
+        const EncStream st = streams[sg.stream];
+        const uint8_t *src = src_base + src_off[sg.stream];
+        const uint32_t len = (uint32_t)src_len[sg.stream], end = len - 3;
+        const uint32_t B = sg.k * kCSeg, n_pos = end - B < kCSeg ? end - B : kCSeg;
+        uint32_t *pv = prev + st.long_off + B;
+        for (uint32_t t = tid; t < (1u << kHashBits); t += kChainThreads) head[t] = kNoPos;
+        for (uint32_t b0 = warp * 32; b0 < n_pos; b0 += kChainThreads) {
+            const uint32_t p = b0 + lane;
+            const bool act = p < n_pos;
+            const uint32_t h = hash_u(ld4u(src + B + (act ? p : n_pos - 1)), false);
+            const uint32_t m = __match_any_sync(0xFFFFFFFFu, act ? h : 0xFFFF0000u + lane);
+            const uint32_t lower = m & lanemask_lt();
+            const uint32_t newest = (m >> lane) == 1u ? 0x4000u : 0u;
+            const uint32_t iw = lower ? (0x8000u | newest | ((uint32_t)(__ffs(m) - 1) << 5) | (31 - __clz(lower))) : (newest | h);
+            if (act) info[p] = (uint16_t)iw;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            // Only the bucket heads carry a dependency from one step to the next, and program order satisfies it (a step's
+            // head stores are issued before the next step's head loads); nothing in the pass consumes the loaded values
+            // before the global stores.  So eight steps issue their loads and stores back to back (k_enc_find's chain).
+            constexpr uint32_t kSteps = 8;
+            for (uint32_t u0 = 0; u0 < n_pos; u0 += 32 * kSteps) {
+                uint32_t iw[kSteps], h[kSteps], old[kSteps];
+#pragma unroll
+                for (uint32_t k = 0; k < kSteps; k++) { const uint32_t p = u0 + k * 32 + lane; iw[k] = p < n_pos ? info[p] : 0u; }
+#pragma unroll
+                for (uint32_t k = 0; k < kSteps; k++) {
+                    const uint32_t hb = __shfl_sync(0xFFFFFFFFu, iw[k], (iw[k] >> 5) & 31u);  // the bucket index lives in the group's lowest lane
+                    h[k] = ((iw[k] & 0x8000u) ? hb : iw[k]) & 0x3FFFu;
+                }
+#pragma unroll
+                for (uint32_t k = 0; k < kSteps; k++) {
+                    const uint32_t p = u0 + k * 32 + lane;
+                    const bool act = p < n_pos;
+                    old[k] = act ? *reinterpret_cast<volatile uint32_t *>(&head[h[k]]) : kNoPos;
+                    __syncwarp();
+                    if (act && (iw[k] & 0x4000u)) *reinterpret_cast<volatile uint32_t *>(&head[h[k]]) = p;  // newest position of its bucket in this step
+                    __syncwarp();
+                }
+#pragma unroll
+                for (uint32_t k = 0; k < kSteps; k++) {
+                    const uint32_t b0 = u0 + k * 32, p = b0 + lane;
+                    if (p < n_pos) pv[p] = (iw[k] & 0x8000u) ? B + b0 + (iw[k] & 31u) : (old[k] == kNoPos ? kNoPos : B + old[k]);
+                }
+            }
+        }
+        __syncthreads();
+        uint32_t *sh = seg_head + ((size_t)st.cseg_base + sg.k) * (1u << kHashBits);
+        for (uint32_t t = tid; t < (1u << kHashBits); t += kChainThreads) sh[t] = head[t] == kNoPos ? kNoPos : B + head[t];
+    }
+}
+
+// seg_head[piece][bucket]: newest position of the bucket inside the piece  ->  newest position BEFORE the piece.
+__global__ void k_long_carry(const uint32_t *__restrict__ long_list, uint32_t n_long, const EncStream *__restrict__ streams, uint32_t *seg_head) {
+    const uint32_t slot = blockIdx.x / ((1u << kHashBits) / 256);
+    const uint32_t h = (blockIdx.x % ((1u << kHashBits) / 256)) * 256 + threadIdx.x;
+    if (slot >= n_long) return;
+    const EncStream st = streams[long_list[slot]];
+    uint32_t run = kNoPos;
+    uint32_t *q = seg_head + (size_t)st.cseg_base * (1u << kHashBits) + h;
+    for (uint32_t k = 0; k < st.n_cseg; k++, q += (1u << kHashBits)) {
+        const uint32_t t = *q;
+        *q = run;
+        if (t != kNoPos) run = t;
+    }
+}
+
+// ---- find_match for every position ---------------------------------------------------------------
+// Forward length of src[a..] against src[b..], whole warp, 8 bytes per lane and step, from `l` up to `lim`.
+__device__ __forceinline__ uint32_t gwarp_match_inc(const uint8_t *src, uint32_t a, uint32_t b, uint32_t l, uint32_t lim, uint32_t lane) {
+    while (l < lim) {
+        const uint32_t off = l + lane * 8;
+        uint64_t y = 0;
+        if (off + 8 <= lim) y = ld8u(src + a + off) ^ ld8u(src + b + off);
+        else for (uint32_t k = 0; off + k < lim; k++) y |= (uint64_t)(src[a + off + k] ^ src[b + off + k]) << (8 * k);
+        const uint32_t diff = __ballot_sync(0xFFFFFFFFu, y != 0);
+        if (diff) {
+            const int j = __ffs(diff) - 1;
+            const uint64_t yj = __shfl_sync(0xFFFFFFFFu, y, j);
+            return l + j * 8 + ((__ffsll((long long)yj) - 1) >> 3);
+        }
+        l += 256;
+    }
+    return lim;
+}
+
+constexpr int kLFindThreads = 256;
+__global__ void __launch_bounds__(kLFindThreads)
+k_long_find(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ src_off, const uint64_t *__restrict__ src_len,
+            const EncStream *__restrict__ streams, const StreamCounts *__restrict__ bases, const LongSeg *__restrict__ cseg,
+            const uint32_t *__restrict__ prev, const uint32_t *__restrict__ seg_head, uint32_t *__restrict__ words) {
+    const uint32_t lane = threadIdx.x & 31;
+    const LongSeg sg = cseg[blockIdx.x / (kCSeg / kLFindThreads)];
+    const EncStream st = streams[sg.stream];
+    const uint8_t *src = src_base + src_off[sg.stream];
+    asm volatile("" : "+l"(src));
+    const uint32_t len = (uint32_t)src_len[sg.stream], end = len - 3;
+    const uint32_t p = sg.k * kCSeg + (blockIdx.x % (kCSeg / kLFindThreads)) * kLFindThreads + threadIdx.x;
+    if (p - lane >= end) return;  // whole warp beyond the last position
+    const bool act = p < end;
+    const uint32_t *pv = prev + st.long_off;
+    const uint32_t *sh = seg_head + (size_t)st.cseg_base * (1u << kHashBits);
+    uint32_t best_len = 0, best_c = 0, n_sat = 0;
+    uint32_t cs[4] = {0, 0, 0, 0}, ls[4] = {0, 0, 0, 0};
+    const uint32_t maxl = act ? len - p : 0;
+    if (act) {
+        const uint32_t val = ld4u(src + p), h = hash_u(val, false);
+        const uint32_t lim = maxl < kLongLaneCap ? maxl : kLongLaneCap;
+        uint32_t c = pv[p];
+        if (c == kNoPos) c = sh[(size_t)(p >> 16) * (1u << kHashBits) + h];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (c == kNoPos || p - c > kMaxDValue) break;  // newest first, up to the first one out of range (frontend_bytes.rs:214-244)
+            uint32_t cn = pv[c];
+            if (cn == kNoPos) cn = sh[(size_t)(c >> 16) * (1u << kHashBits) + h];
+            if (ld4u(src + c) == val) {
+                uint32_t l = 4;
+                while (l + 8 <= lim) {
+                    const uint64_t y = ld8u(src + p + l) ^ ld8u(src + c + l);
+                    if (y) { l += (__ffsll((long long)y) - 1) >> 3; goto ext_done; }
+                    l += 8;
+                }
+                while (l < lim && src[p + l] == src[c + l]) l++;
+            ext_done:
+                if (l == kLongLaneCap && l < maxl) { cs[n_sat] = c; n_sat++; }
+                if (l > best_len) { best_len = l; best_c = c; }
+            }
+            c = cn;
+        }
+    }
+    // Candidates that reached the per-lane cap: their lengths up to what the word can hold, measured by the whole warp.
+    // Strictly longest wins, newest first.  Two candidates that both pass the word's limit are compared further; once both
+    // have matched as many bytes as the larger of their distances the source is periodic with both distances and the two
+    // lengths are equal (Fine & Wilf), so the comparison stops there and the newer one wins.
+    uint32_t todo = __ballot_sync(0xFFFFFFFFu, n_sat != 0);
+    while (todo) {
+        const int j = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const uint32_t pj = __shfl_sync(0xFFFFFFFFu, p, j), nj = __shfl_sync(0xFFFFFFFFu, n_sat, j), mj = len - pj;
+        const uint32_t wl = mj < kWordLenSat ? mj : kWordLenSat;
+        uint32_t lj[4] = {0, 0, 0, 0}, cj[4];
+        uint32_t n_full = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            cj[k] = __shfl_sync(0xFFFFFFFFu, cs[k], j);
+            if ((uint32_t)k < nj) { lj[k] = gwarp_match_inc(src, pj, cj[k], kLongLaneCap, wl, lane); n_full += lj[k] == wl; }
+        }
+        if (n_full >= 2 && wl < mj) {
+            // lockstep beyond the word's limit, 256 bytes per round, only among those still matching
+            uint32_t alive = 0, maxd = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) if ((uint32_t)k < nj && lj[k] == wl) { alive |= 1u << k; maxd = max(maxd, pj - cj[k]); }
+            uint32_t off = wl;
+            while (__popc(alive) >= 2 && off < mj && off < maxd) {
+                const uint32_t hi = off + 256 < mj ? off + 256 : mj;
+#pragma unroll
+                for (int k = 0; k < 4; k++) if (alive & (1u << k)) {
+                    const uint32_t e = gwarp_match_inc(src, pj, cj[k], off, hi, lane);
+                    lj[k] = e;
+                    if (e < hi) alive &= ~(1u << k);
+                }
+                off = hi;
+            }
+            // the survivors are the longest (equal among themselves): make the newest of them win outright
+            if (alive) { const int w = __ffs(alive) - 1;
+#pragma unroll
+                for (int k = 0; k < 4; k++) if (k == w) lj[k] = 0xFFFFFFFFu; }
+        }
+        if (lane == (uint32_t)j) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) ls[k] = lj[k];
+        }
+    }
+    uint32_t word = 0;
+    if (act && best_len) {
+        if (n_sat) {
+            uint32_t bl = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) if ((uint32_t)k < n_sat && ls[k] > bl) { bl = ls[k]; best_c = cs[k]; }
+            best_len = bl;
+        }
+        uint32_t bw = 0;
+        const uint32_t blim = best_c < kWordBwSat ? best_c : kWordBwSat;
+        while (bw < blim && src[p - bw - 1] == src[best_c - bw - 1]) bw++;
+        word = (p - best_c) | ((best_len < kWordLenSat ? best_len : kWordLenSat) << 18) | (bw << 28);
+    }
+    {   // positions without a candidate carry the distance to the next position of their 32-group that has one
+        const uint32_t nz = __ballot_sync(0xFFFFFFFFu, word != 0);
+        if (word == 0) {
+            const uint32_t next = lane == 31 ? 0u : nz & (0xFFFFFFFEu << lane);
+            word = (next ? (uint32_t)__ffs(next) - 1u - lane : 32u - lane) << 18;
+        }
+    }
+    if (act) words[bases[sg.stream].n_fse + p] = word;
+}
+
+// ---- one position of the sequential front end ------------------------------------------------------
+// FrontendBytes::match_any's loop body (frontend_bytes.rs:185-211,261-302) over the per-position words.  Returns true
+// when a match is pushed to the back end (sel).  `lim_flag` is set when a backward extension stopped at the literal
+// limit although the candidate's own start would have allowed more; `cand`/`good` describe the first candidate met.
+struct StepOut { Match sel; };
+__device__ __forceinline__ bool front_step(const uint8_t *src, uint32_t len, uint32_t end, uint32_t w, FrontState &s, Match &sel, uint32_t &lim_flag,
+                                           uint32_t &cand, uint32_t &good) {
+    const uint32_t cur = s.cur;
+    if ((w & 0x3FFFFu) == 0) { s.cur = cur + ((w >> 18) & 0x3FFu); return false; }
+    Match inc;
+    inc.idx = cur;
+    inc.match_idx = cur - (w & 0x3FFFFu);
+    inc.match_len = (w >> 18) & 0x3FFu;
+    if (inc.match_len == kWordLenSat) {  // the word's length field is saturated: finish the extension here
+        const uint32_t maxl = len - cur;
+        while (inc.match_len + 8 <= maxl) {
+            const uint64_t y = ld8u(src + cur + inc.match_len) ^ ld8u(src + inc.match_idx + inc.match_len);
+            if (y) { inc.match_len += (__ffsll((long long)y) - 1) >> 3; goto fwd_done; }
+            inc.match_len += 8;
+        }
+        while (inc.match_len < maxl && src[cur + inc.match_len] == src[inc.match_idx + inc.match_len]) inc.match_len++;
+    fwd_done:;
+    }
+    {   // match_dec (:261-268)
+        const uint32_t lit = cur - s.lit;
+        const uint32_t lim = lit < inc.match_idx ? lit : inc.match_idx;
+        const uint32_t bw = w >> 28;
+        uint32_t dec = bw < lim ? bw : lim;
+        if (bw == kWordBwSat) while (dec < lim && src[inc.idx - dec - 1] == src[inc.match_idx - dec - 1]) dec++;
+        if (dec == lit && dec < inc.match_idx) lim_flag = 1;
+        inc.idx -= dec; inc.match_idx -= dec; inc.match_len += dec;
+    }
+    if (cand == kNoPos) { cand = cur; good = inc.match_len >= kGoodMatchLen; }
+    bool have = true;
+    sel.idx = s.p_idx; sel.match_idx = s.p_midx; sel.match_len = s.p_len;
+    if (inc.match_len >= kGoodMatchLen) { sel = inc; s.p_len = 0; }
+    else if (s.p_len == 0) { s.p_idx = inc.idx; s.p_midx = inc.match_idx; s.p_len = inc.match_len; have = false; }
+    else if ((int32_t)(s.p_idx + s.p_len - inc.idx) <= 0) { s.p_idx = inc.idx; s.p_midx = inc.match_idx; s.p_len = inc.match_len; }
+    else if (inc.match_len > s.p_len) { sel = inc; s.p_len = 0; }
+    else { s.p_len = 0; }
+    if (!have) { s.cur = cur + 1; return false; }
+    s.lit = sel.idx + sel.match_len;
+    s.cur = s.lit >= end ? end : (cur + 1 > s.lit ? cur + 1 : s.lit);
+    return true;
+}
+
+// ---- speculative replay, one THREAD per segment ----------------------------------------------------
+// Same loop and the same word ring as k_enc_replay (see there for the ring's rules); starts clean at the segment's first
+// position and stops when the cursor leaves the segment.
+__global__ void __launch_bounds__(kReplayThreads)
+k_long_replay(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ src_off, const uint64_t *__restrict__ src_len,
+              const StreamCounts *__restrict__ bases, const LongSeg *__restrict__ rseg, uint32_t n_rseg, const uint32_t *__restrict__ words,
+              uint4 *__restrict__ spec, uint4 *__restrict__ states, LongSegOut *__restrict__ seg_out) {
+    const uint32_t rs = blockIdx.x * kReplayThreads + threadIdx.x;
+    const bool valid = rs < n_rseg;
+    const LongSeg sg = rseg[valid ? rs : 0];
+    const uint8_t *src = src_base + src_off[sg.stream];
+    const uint32_t len = (uint32_t)src_len[sg.stream], end = len - 3;
+    const uint32_t B = sg.k * kRSeg, se = !valid ? 0u : (end - B < kRSeg ? end : B + kRSeg);
+    const uint32_t *W = words + bases[sg.stream].n_fse;
+    uint4 *out = spec + (size_t)rs * kEmitCap;
+    uint4 *sto = states + (size_t)rs * kSpecStates;
+    FrontState s = {B, B, 0, 0, 0};
+    uint32_t n_out = 0, lim_flag = 0, lim0 = 0, cand = kNoPos, good = 0;
+    bool active = valid;
+
+    __shared__ __align__(16) uint8_t rings[kReplayThreads * kRingStride];
+    constexpr uint32_t kLag = 8;
+    const uint32_t ring = (uint32_t)__cvta_generic_to_shared(rings) + threadIdx.x * kRingStride;
+    const uint32_t w_limit = valid ? (se + 3u) & ~3u : 0u;
+    uint32_t wbase = 0xFFFFFFFFu, fetched = 0, safe = 0, mark = 0, iter = 0;
+    uint4 wq = make_uint4(0, 0, 0, 0);
+    auto request = [&](bool go) {
+        const bool p = go && fetched < w_limit;
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p cp.async.cg.shared.global [%0], [%1], 16;\n\t}"
+                     ::"r"(ring + (fetched & (kRingWords - 1)) * 4), "l"(W + (p ? fetched : 0u)), "r"((uint32_t)p) : "memory");
+        fetched += p ? 4u : 0u;
+    };
+    for (;;) {
+        __syncwarp();
+        active = active && s.cur < se;
+        if (!__any_sync(0xFFFFFFFFu, active)) break;
+        {   // ---- ring upkeep, whole warp (k_enc_replay) ----
+            const uint32_t wb = s.cur & ~3u;
+            const bool restart = active && wb > fetched;
+            const bool drain = __any_sync(0xFFFFFFFFu, restart);
+            if (drain) asm volatile("cp.async.wait_group 0;" ::: "memory");
+            if (restart) fetched = wb;
+            if (drain) { safe = fetched; mark = fetched; }
+            request(active && fetched < wb + kRingWords);
+            request(active && fetched < wb + kRingWords);
+            if (iter == 0) {
+#pragma unroll
+                for (int k = 0; k < 6; k++) request(active && fetched < wb + kRingWords);
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group %0;" ::"n"(kLag - 1) : "memory");
+            if ((iter & (kLag - 1)) == 0) { safe = mark; mark = fetched; }
+            const bool need = active && wb + 4 > safe;
+            if (__any_sync(0xFFFFFFFFu, need)) {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                safe = fetched; mark = fetched;
+            }
+            iter++;
+        }
+        if (!active) continue;
+        if ((s.cur & ~3u) != wbase) {
+            wbase = s.cur & ~3u;
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(wq.x), "=r"(wq.y), "=r"(wq.z), "=r"(wq.w) : "r"(ring + (wbase & (kRingWords - 1)) * 4) : "memory");
+        }
+        const uint32_t k4 = s.cur & 3u;
+        const uint32_t w = k4 == 0 ? wq.x : (k4 == 1 ? wq.y : (k4 == 2 ? wq.z : wq.w));
+        Match sel;
+        if (front_step(src, len, end, w, s, sel, lim_flag, cand, good)) {
+            if (n_out == 0) lim0 = lim_flag;
+            out[n_out] = make_uint4(sel.idx, sel.match_len, sel.idx - sel.match_idx, s.cur);
+            if (n_out < kSpecStates) sto[n_out] = make_uint4(s.p_idx, s.p_midx, s.p_len, 0);
+            n_out++;
+        }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (!valid) return;
+    if (n_out == 0) lim0 = lim_flag;
+    LongSegOut o;
+    o.n_spec = n_out; o.lim0 = lim0; o.good0 = good; o.cand0 = cand; o.exit = s;
+    o.n_fix = 0; o.from = sg.k == 0 ? 0u : n_out; o.a_out = s; o.pad = 0;
+    seg_out[rs] = o;
+}
+
+// ---- stitch ----------------------------------------------------------------------------------------
+// The true state T arrives at segment k of a stream; on return T is the true state behind it, n_fix matches have been
+// written to the segment's fix list and `from` says where the speculative list joins the true parse.
+__device__ void stitch_segment(const uint8_t *src, uint32_t len, uint32_t end, const uint32_t *W, uint32_t k, FrontState &T, LongSegOut &o,
+                               const uint4 *sp, const uint4 *stt, uint4 *fix) {
+    const uint32_t B = k * kRSeg, se = end - B < kRSeg ? end : B + kRSeg;
+    o.n_fix = 0; o.from = o.n_spec;
+    if (T.cur >= se) return;  // a match of an earlier segment covers this one
+    if (T.cur == B && !o.lim0) {
+        // The true parse stands at the segment's first position like the speculative one did, with a literal run at least
+        // as long, and no backward extension of the speculative replay before its first push was cut by its shorter run:
+        // both see the same candidates with the same lengths.
+        if (T.p_len == 0) {
+            const uint32_t keep = T.lit;
+            o.from = 0; T = o.exit;
+            if (o.n_spec == 0) T.lit = keep;
+            return;
+        }
+        if (T.p_idx + T.p_len <= B) {
+            // ... and a pending match that ends before the segment: the first candidate either replaces it (>= GOOD) or
+            // pushes it out unchanged (Match::select); after that the two parses are in step.
+            if (o.cand0 == kNoPos) { T.cur = se; return; }
+            uint32_t keep = T.lit;
+            if (!o.good0) { fix[0] = make_uint4(T.p_idx, T.p_len, T.p_idx - T.p_midx, 0); o.n_fix = 1; keep = T.p_idx + T.p_len; }
+            o.from = 0; T = o.exit;
+            if (o.n_spec == 0) T.lit = keep;
+            return;
+        }
+    }
+    if (T.cur < o.cand0) T.cur = o.cand0 < se ? o.cand0 : se;  // nothing happens before the segment's first candidate
+    uint32_t j = 0, n_fix = 0, dummy0 = 0, dummy1 = 0, dummy2 = 0;
+    const uint32_t n_cmp = o.n_spec < kSpecStates ? o.n_spec : kSpecStates;
+    uint4 sj = n_cmp ? sp[0] : make_uint4(0, 0, 0, 0);
+    while (T.cur < se) {
+        Match sel;
+        if (!front_step(src, len, end, W[T.cur], T, sel, dummy0, dummy1, dummy2)) continue;
+        fix[n_fix++] = make_uint4(sel.idx, sel.match_len, sel.idx - sel.match_idx, T.cur);
+        while (j < n_cmp && sj.x + sj.y < T.lit) { j++; if (j < n_cmp) sj = sp[j]; }
+        if (j < n_cmp && sj.x + sj.y == T.lit && sj.w == T.cur) {
+            const uint4 ps = stt[j];
+            if (ps.z == T.p_len && (T.p_len == 0 || (ps.x == T.p_idx && ps.y == T.p_midx))) {  // the same state: in step from here
+                o.n_fix = n_fix; o.from = j + 1; T = o.exit;
+                return;
+            }
+        }
+    }
+    o.n_fix = n_fix;
+}
+__device__ __forceinline__ bool same_state(const FrontState &a, const FrontState &b) {
+    return a.cur == b.cur && a.lit == b.lit && a.p_len == b.p_len && (a.p_len == 0 || (a.p_idx == b.p_idx && a.p_midx == b.p_midx));
+}
+// a: every segment at once, ASSUMING the exit state of the segment before it is true (it is, once that segment is in step).
+__global__ void k_long_stitch_a(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ src_off, const uint64_t *__restrict__ src_len,
+                                const StreamCounts *__restrict__ bases, const LongSeg *__restrict__ rseg, uint32_t n_rseg, const uint32_t *__restrict__ words,
+                                const uint4 *__restrict__ spec, const uint4 *__restrict__ states, uint4 *__restrict__ fix, LongSegOut *seg_out) {
+    const uint32_t rs = blockIdx.x * blockDim.x + threadIdx.x;
+    if (rs >= n_rseg) return;
+    const LongSeg sg = rseg[rs];
+    if (sg.k == 0) return;
+    const uint32_t len = (uint32_t)src_len[sg.stream];
+    LongSegOut o = seg_out[rs];
+    FrontState T = seg_out[rs - 1].exit;
+    stitch_segment(src_base + src_off[sg.stream], len, len - 3, words + bases[sg.stream].n_fse, sg.k, T, o, spec + (size_t)rs * kEmitCap,
+                   states + (size_t)rs * kSpecStates, fix + (size_t)rs * kEmitCap);
+    seg_out[rs].n_fix = o.n_fix; seg_out[rs].from = o.from; seg_out[rs].a_out = T;  // (.exit is being read by the neighbour)
+}
+// b: one thread per stream walks the segments in order with the true state; a segment whose assumption held is taken
+// as k_long_stitch_a left it, any other is stitched again from the true state.  Leaves the stream's tail (pending match,
+// final literals; frontend_bytes.rs:121-131,271-317) in tail[2 * slot ..].
+__global__ void k_long_stitch_b(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ src_off, const uint64_t *__restrict__ src_len,
+                                const EncStream *__restrict__ streams, const StreamCounts *__restrict__ bases, const uint32_t *__restrict__ long_list,
+                                uint32_t n_long, const uint32_t *__restrict__ words, const uint4 *__restrict__ spec, const uint4 *__restrict__ states,
+                                uint4 *__restrict__ fix, LongSegOut *seg_out, uint4 *tail, uint32_t *redo_count) {
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= n_long) return;
+    const uint32_t si = long_list[slot];
+    const EncStream st = streams[si];
+    const uint8_t *src = src_base + src_off[si];
+    const uint32_t len = (uint32_t)src_len[si], end = len - 3;
+    const uint32_t *W = words + bases[si].n_fse;
+    FrontState T = seg_out[st.rseg_base].exit;
+    uint32_t redo = 0;
+    for (uint32_t k = 1; k < st.n_rseg; k++) {
+        const uint32_t rs = st.rseg_base + k;
+        if (same_state(T, seg_out[rs - 1].exit)) { T = seg_out[rs].a_out; continue; }
+        LongSegOut o = seg_out[rs];
+        stitch_segment(src, len, end, W, k, T, o, spec + (size_t)rs * kEmitCap, states + (size_t)rs * kSpecStates, fix + (size_t)rs * kEmitCap);
+        seg_out[rs].n_fix = o.n_fix; seg_out[rs].from = o.from;
+        redo++;
+    }
+    uint32_t lit = T.lit, n_tail = 0;
+    if (T.p_len != 0) { tail[2 * slot + n_tail++] = make_uint4(T.p_idx, T.p_len, T.p_idx - T.p_midx, 0); lit = T.p_idx + T.p_len; }
+    if (len - lit != 0) tail[2 * slot + n_tail++] = make_uint4(len, 0, 1, 0);  // push_literals: (L, 0, 1)
+    if (n_tail < 2) tail[2 * slot + 1] = make_uint4(0, 0, 0, 0xFFFFFFFFu);
+    if (n_tail < 1) tail[2 * slot] = make_uint4(0, 0, 0, 0xFFFFFFFFu);
+    if (redo) atomicAdd(redo_count, redo);
+}
+
+// ---- matches -> packs and block records, one WARP per stream ------------------------------------------
+__device__ __forceinline__ void wsink_emit_block(TSink &s, uint64_t &out_used, const TEnv &env, uint32_t lane) {
+    const uint32_t n_packs = s.n_packs_total - s.blk_pack0, n_lits = s.n_lits_total - s.blk_lit0;
+    if (lane == 0) {
+        EncBlock b;
+        b.pack_off = env.base.n_blocks + s.blk_pack0;
+        b.lit_off = env.base.n_fse + s.blk_lit0;
+        b.out_off = env.base.n_lmds + out_used;
+        b.src_pos = env.src_off + s.blk_src0;
+        b.n_packs = n_packs; b.n_lits = n_lits; b.n_match_bytes = s.n_match_bytes;
+        b.out_size = 0; b.gather = 1; b.pad = 0; b.dst_pos = 0;
+        const uint32_t id = atomicAdd(env.block_counter, 1u);
+        env.blocks[id] = b;
+        env.block_ids[env.base.n_literals + s.n_blocks] = id;
+    }
+    out_used += (block_bound(n_lits, n_packs) + 15) & ~15ull;
+    s.n_blocks++;
+    s.blk_src0 += n_lits + s.n_match_bytes;
+    s.blk_pack0 = s.n_packs_total; s.blk_lit0 = s.n_lits_total;
+    s.n_match_bytes = 0; s.match_distance = 0;
+}
+__global__ void __launch_bounds__(32)
+k_long_packs(const uint64_t *__restrict__ src_off, const uint64_t *__restrict__ src_len, EncStream *streams, const StreamCounts *__restrict__ bases,
+             const uint32_t *__restrict__ long_list, uint32_t n_long, const uint4 *__restrict__ spec, const uint4 *__restrict__ fix,
+             const LongSegOut *__restrict__ seg_out, const uint4 *__restrict__ tail, uint2 *pack_scratch, uint32_t *block_ids, EncBlock *blocks,
+             uint32_t *block_counter) {
+    const uint32_t slot = blockIdx.x, lane = threadIdx.x;
+    if (slot >= n_long) return;
+    const uint32_t si = long_list[slot];
+    const EncStream st = streams[si];
+    TEnv env;
+    env.base = bases[si]; env.blocks = blocks; env.block_ids = block_ids; env.block_counter = block_counter; env.src_off = src_off[si];
+    TSink fs;
+    fs.packs = pack_scratch + env.base.n_blocks;
+    fs.n_packs_total = 0; fs.n_lits_total = 0; fs.blk_pack0 = 0; fs.blk_lit0 = 0; fs.n_match_bytes = 0; fs.match_distance = 0;
+    fs.n_blocks = 0; fs.out_used = 0; fs.blk_src0 = 0;
+    uint32_t prev_end = 0;
+    uint64_t out_used = 0;  // (a 2 GiB stream's blocks pass 4 GiB of scratch)
+    auto run = [&](const uint4 *list, uint32_t count) {
+        uint4 nx = make_uint4(0, 0, 0, 0);
+        if (lane < count) nx = list[lane];
+        for (uint32_t i0 = 0; i0 < count; i0 += 32) {
+            const uint32_t n = count - i0 < 32 ? count - i0 : 32;
+            const uint4 r = nx;
+            nx = make_uint4(0, 0, 0, 0);
+            if (i0 + 32 + lane < count) nx = list[i0 + 32 + lane];  // the next step's records are on their way while this one is worked on
+            const uint32_t my_end = r.x + r.y;
+            uint32_t pe = __shfl_up_sync(0xFFFFFFFFu, my_end, 1);
+            if (lane == 0) pe = prev_end;
+            const uint32_t lit_len = lane < n ? r.x - pe : 0u;
+            const bool simple = lit_len <= kMaxLValue && r.y <= kMaxMValue;
+            const uint32_t sum_lit = __reduce_add_sync(0xFFFFFFFFu, lit_len);
+            const bool room = fs.n_packs_total - fs.blk_pack0 + n <= kLmdsPerBlock && fs.n_lits_total - fs.blk_lit0 + sum_lit <= kLiteralsPerBlock;
+            if (__all_sync(0xFFFFFFFFu, simple) && room) {
+                uint32_t dp = __shfl_up_sync(0xFFFFFFFFu, r.z, 1);
+                if (lane == 0) dp = fs.match_distance;
+                if (lane < n) fs.packs[fs.n_packs_total + lane] = make_uint2(lit_len | (r.y << 16), r.z == dp ? 0u : r.z);
+                fs.n_packs_total += n; fs.n_lits_total += sum_lit;
+                fs.n_match_bytes += __reduce_add_sync(0xFFFFFFFFu, lane < n ? r.y : 0u);
+                fs.match_distance = __shfl_sync(0xFFFFFFFFu, r.z, n - 1);
+            } else {
+                for (uint32_t i = 0; i < n; i++) {  // Buffer::push one match at a time, the warp in step (lane 0's stores count)
+                    uint32_t l = __shfl_sync(0xFFFFFFFFu, lit_len, i), m = __shfl_sync(0xFFFFFFFFu, r.y, i);
+                    const uint32_t d = __shfl_sync(0xFFFFFFFFu, r.z, i);
+                    if (l <= kMaxLValue && m <= kMaxMValue && fs.n_packs_total - fs.blk_pack0 < kLmdsPerBlock &&
+                        fs.n_lits_total - fs.blk_lit0 + l <= kLiteralsPerBlock) {
+                        fs.n_lits_total += l;
+                        tsink_push_lmd(fs, l, m, d);
+                    } else {
+                        while (!tsink_buffer_push(fs, l, m, d)) wsink_emit_block(fs, out_used, env, lane);
+                    }
+                }
+            }
+            prev_end = __shfl_sync(0xFFFFFFFFu, my_end, n - 1);
+        }
+    };
+    for (uint32_t k = 0; k < st.n_rseg; k++) {
+        const uint32_t rs = st.rseg_base + k;
+        const LongSegOut o = seg_out[rs];
+        run(fix + (size_t)rs * kEmitCap, o.n_fix);
+        run(spec + (size_t)rs * kEmitCap + o.from, o.n_spec - o.from);
+    }
+    for (uint32_t t = 0; t < 2; t++) {
+        const uint4 r = tail[2 * slot + t];
+        if (r.w != 0xFFFFFFFFu) run(tail + 2 * slot + t, 1);
+    }
+    wsink_emit_block(fs, out_used, env, lane);  // finalize
+    if (lane == 0) streams[si].n_blocks = fs.n_blocks;
+}
+
+// ---- the blocks of long streams are copied into the frame side by side -------------------------------------
+__global__ void __launch_bounds__(256)
+k_long_copy(const EncBlock *__restrict__ blocks, const uint32_t *__restrict__ n_blocks_p, const uint8_t *__restrict__ out_scratch, uint8_t *__restrict__ dst_base) {
+    const uint32_t n_blocks = *n_blocks_p;
+    for (uint32_t bi = blockIdx.x; bi < n_blocks; bi += gridDim.x) {
+        const EncBlock b = blocks[bi];
+        if (b.pad != 1) continue;
+        const uint8_t *s = out_scratch + b.out_off;
+        uint8_t *d = dst_base + b.dst_pos;
+        const uint32_t n = b.out_size;
+        const uint32_t head = (uint32_t)((16 - (reinterpret_cast<uintptr_t>(d) & 15)) & 15);
+        if (n >= head + 16) {
+            // the scratch side is 16-byte aligned; the frame side is reached through aligned 16-byte stores assembled from
+            // two neighbouring scratch words when the two are skewed
+            for (uint32_t t = threadIdx.x; t < head; t += blockDim.x) d[t] = s[t];
+            const uint32_t nv = (n - head) / 16;
+            if (((reinterpret_cast<uintptr_t>(s) + head) & 15) == 0) {
+                const uint4 *s4 = reinterpret_cast<const uint4 *>(s + head);
+                uint4 *d4 = reinterpret_cast<uint4 *>(d + head);
+                for (uint32_t t = threadIdx.x; t < nv; t += blockDim.x) d4[t] = s4[t];
+            } else {
+                uint32_t *d32 = reinterpret_cast<uint32_t *>(d + head);
+                for (uint32_t t = threadIdx.x; t < nv * 4; t += blockDim.x) d32[t] = ld4u(s + head + t * 4);
+            }
+            for (uint32_t t = head + nv * 16 + threadIdx.x; t < n; t += blockDim.x) d[t] = s[t];
+        } else {
+            for (uint32_t t = threadIdx.x; t < n; t += blockDim.x) d[t] = s[t];
+        }
+    }
+}

@@ -63,7 +63,7 @@ struct DeviceGuard {
 
 // Optional per-stage CUDA-event timing on the launching stream (measurement aid for bench.py).
 struct StageTimer {
-    static constexpr int kMax = 8;
+    static constexpr int kMax = 16;
     bool enabled = false;
     cudaEvent_t ev[kMax + 1] = {};
     int n = 0;          // events recorded in the current call

@@ -40,6 +40,52 @@ def test_large_streams(codec):
     assert not dst.any() and outs == streams
 
 
+def _assorted_long_inputs():
+    rng = np.random.default_rng(1)
+    t = tk.synth_text(9, 1 << 20)
+    patch = bytearray()
+    while len(patch) < 700000:
+        k = int(rng.integers(0, 5)); n = int(rng.integers(1, 3000))
+        if k == 0: patch += t[int(rng.integers(0, len(t) - n * 10)):][:n * 10]
+        elif k == 1: patch += bytes([int(rng.integers(0, 256))]) * n               # byte runs (M > 2359 splits)
+        elif k == 2: patch += rng.integers(0, 256, n * 10, dtype=np.uint8).tobytes()  # noise (L > 315 splits)
+        elif k == 3: patch += (rng.integers(0, 4, n * 10, dtype=np.uint8) * 16).tobytes()
+        else:
+            d = int(rng.integers(1, min(len(patch), 300000) + 1)) if patch else 1
+            for _ in range(n): patch.append(patch[-d] if len(patch) >= d else 0)
+    sparse = bytearray(rng.integers(0, 256, 1 << 20, dtype=np.uint8).tobytes())
+    for _ in range(2000):  # short repeats in noise: matches stay pending across segment borders
+        a = int(rng.integers(100000, len(sparse) - 100)); d = int(rng.integers(8, 90000)); n = int(rng.integers(4, 30))
+        sparse[a:a + n] = sparse[a - d:a - d + n]
+    return {"text200k": t[:200000], "text1m": t, "text65537": t[:65537], "text70001": t[5:70006], "zeros300k": bytes(300000),
+            "noise300k": tk.rng_gen_vec(3, 300000), "period1000": (tk.rng_gen_vec(5, 1000) * 400)[:333333], "period3": (b"abc" * 50000)[:140001],
+            "patch": bytes(patch), "sparse": bytes(sparse), "far": (tk.rng_gen_vec(5, 300000) * 4)[:1 << 20], "lits": tk.seq_bytes(1, 500000, 0x0F0F0F0F)}
+
+
+def test_long_encoder_assorted(codec):
+    """Streams longer than 64 KiB take the segmented front end (encode_long.cuh: hash chain per 64 Ki positions, find_match for
+    every position, speculative replay per segment, stitch, packs).  Frames must equal the oracle's byte for byte on inputs that
+    stress each piece: lengths around the segment sizes, one match covering the whole stream, no matches at all, long periods
+    (several candidates longer than the per-position word can say), L / M splits and block closes in odd places, matches pending
+    across many segments, distances beyond the window."""
+    enc, dec = codec
+    data = _assorted_long_inputs()
+    names = list(data)
+    frames, st = enc.encode_batch([data[k] for k in names])
+    assert not st.any()
+    oenc = ob.Encoder()
+    for k, f in zip(names, frames):
+        assert f == oenc.encode(data[k])[1], k
+    outs, dst = dec.decode_batch(frames)
+    assert not dst.any() and outs == [data[k] for k in names]
+    # the same streams next to short ones (all three parse paths in one batch)
+    mixed = [data["text200k"], tk.synth_text(1, 3000), data["zeros300k"], tk.synth_text(2, 65536), b"", data["text70001"], tk.synth_text(3, 20000)]
+    frames, st = enc.encode_batch(mixed)
+    assert not st.any()
+    for s, f in zip(mixed, frames):
+        assert f == oenc.encode(s)[1]
+
+
 def test_mixed_corpus(codec):
     enc, dec = codec
     rng = np.random.default_rng(2024)
