@@ -1677,7 +1677,7 @@ struct lzfse_b200_encoder {
     std::string last_error;
     uint64_t launches = 0;
     DevBuf streams, counts, totals_dev, tables, packs, lits, block_ids, blocks, out, counters, words;
-    DevBuf long_list, l_prev, l_heads, l_cseg, l_rseg, l_out, l_spec, l_fix, l_states, l_tail;  // long streams (encode_long.cuh)
+    DevBuf long_list, l_prev, l_heads, l_cseg, l_rseg, l_out, l_spec, l_fix, l_states, l_tail, l_agg, l_pre, l_entry;  // long streams (encode_long.cuh)
     int allow_long = 1;  // LZB_ENC_LONG=0 sends streams > 64 KiB through k_enc_parse (measurements, tests)
     uint32_t last_long_redo = 0;
     bool pending = false;             // an *_async call has been enqueued and not yet synchronised
@@ -1710,7 +1710,7 @@ int encode_batch_device_impl(lzfse_b200_encoder *e, const uint8_t *src, const ui
     e->timer.begin(s);
     LZB_CK(e, cudaMemsetAsync(e->counters.p, 0, 16 * sizeof(uint32_t), s));
     // [0] blocks produced, [1] parse cursor, [2] fse-encode cursor, [3] find cursor, [4] fast streams, [5] k_enc_parse streams,
-    // [6] long streams, [7] replay segments, [8] chain pieces, [10..11] prev[] elements, [12] chain cursor, [13] segments stitched again
+    // [6] long streams, [7] replay segments, [8] chain pieces, [10..11] prev[] elements, [12] chain cursor, [13] segments stitched again, [14] segments whose packs were pushed one by one
     uint32_t *ctr = e->counters.as<uint32_t>();
     k_enc_prep<<<(unsigned)((n + tb - 1) / tb), tb, 0, s>>>(src_len, n, e->streams.as<EncStream>(), e->counts.as<StreamCounts>(), status, ctr + 4,
                                                            e->long_list.as<uint32_t>(), e->allow_fast, e->allow_long);
@@ -1748,6 +1748,9 @@ int encode_batch_device_impl(lzfse_b200_encoder *e, const uint8_t *src, const ui
         LZB_CK(e, e->l_fix.reserve((size_t)n_rseg * kEmitCap * sizeof(uint4)));
         LZB_CK(e, e->l_states.reserve((size_t)n_rseg * kSpecStates * sizeof(uint4)));
         LZB_CK(e, e->l_tail.reserve((size_t)n_long * 2 * sizeof(uint4)));
+        LZB_CK(e, e->l_agg.reserve((size_t)n_rseg * sizeof(SegAgg)));
+        LZB_CK(e, e->l_pre.reserve((size_t)n_rseg * kEmitCap * sizeof(uint2)));
+        LZB_CK(e, e->l_entry.reserve((size_t)n_rseg * sizeof(SegEntry)));
     }
     LZB_CK(e, e->packs.reserve((tot.n_blocks + 1) * sizeof(uint2)));
     LZB_CK(e, e->lits.reserve(tot.n_fse + 64));
@@ -1801,10 +1804,14 @@ int encode_batch_device_impl(lzfse_b200_encoder *e, const uint8_t *src, const ui
         k_long_stitch_b<<<(n_long + 31) / 32, 32, 0, s>>>(src, src_off, src_len, st, bs, ll, n_long, words, e->l_spec.as<uint4>(), e->l_states.as<uint4>(),
                                                            e->l_fix.as<uint4>(), so, e->l_tail.as<uint4>(), ctr + 13);
         e->timer.mark(s);  // long_stitch
-        k_long_packs<<<n_long, 32, 0, s>>>(src_off, src_len, e->streams.as<EncStream>(), bs, ll, n_long, e->l_spec.as<uint4>(), e->l_fix.as<uint4>(), so,
-                                            e->l_tail.as<uint4>(), e->packs.as<uint2>(), e->block_ids.as<uint32_t>(), e->blocks.as<EncBlock>(), ctr);
+        k_long_seg_stats<<<(n_rseg + 3) / 4, 128, 0, s>>>(e->l_spec.as<uint4>(), e->l_fix.as<uint4>(), so, n_rseg, e->l_agg.as<SegAgg>(), e->l_pre.as<uint2>());
+        k_long_blocks<<<n_long, 32, 0, s>>>(src_off, src_len, e->streams.as<EncStream>(), bs, ll, n_long, e->l_spec.as<uint4>(), e->l_fix.as<uint4>(), so,
+                                             e->l_agg.as<SegAgg>(), e->l_pre.as<uint2>(), e->l_entry.as<SegEntry>(), e->l_tail.as<uint4>(), e->packs.as<uint2>(),
+                                             e->block_ids.as<uint32_t>(), e->blocks.as<EncBlock>(), ctr, ctr + 14);
+        k_long_write_packs<<<(n_rseg + 3) / 4, 128, 0, s>>>(bs, rseg, n_rseg, e->l_spec.as<uint4>(), e->l_fix.as<uint4>(), so, e->l_agg.as<SegAgg>(),
+                                                             e->l_entry.as<SegEntry>(), e->packs.as<uint2>());
         e->timer.mark(s);  // long_packs
-        e->launches += 8;
+        e->launches += 10;
     } else {
         for (int k = 0; k < 5; k++) e->timer.mark(s);
     }
@@ -1874,7 +1881,7 @@ void lzfse_b200_encoder_destroy(lzfse_b200_encoder *e) {
     if (!e) return;
     DeviceGuard g(e->device);
     for (DevBuf *b : {&e->streams, &e->counts, &e->totals_dev, &e->tables, &e->packs, &e->lits, &e->block_ids, &e->blocks, &e->out, &e->counters, &e->words,
-                      &e->long_list, &e->l_prev, &e->l_heads, &e->l_cseg, &e->l_rseg, &e->l_out, &e->l_spec, &e->l_fix, &e->l_states, &e->l_tail}) b->release();
+                      &e->long_list, &e->l_prev, &e->l_heads, &e->l_cseg, &e->l_rseg, &e->l_out, &e->l_spec, &e->l_fix, &e->l_states, &e->l_tail, &e->l_agg, &e->l_pre, &e->l_entry}) b->release();
     e->totals_host.release();
     e->stage.release();
     e->timer.release();

@@ -20,8 +20,8 @@
 //     its border is equivalent to a clean start), and from there on the speculative output IS the true output.
 //     tests/model/long_parse_model.c is this algorithm on the CPU, checked against the oracle's front end.
 //
-//  k_long_packs finally turns a stream's match list into packs and block records (Buffer::push with its L / M
-//  splits and block closing, fse/buffer.rs:45-117), 32 matches per step while nothing irregular happens.
+//  k_long_seg_stats / k_long_blocks / k_long_write_packs finally turn a stream's match list into packs and block records
+//  (Buffer::push with its L / M splits and block closing, fse/buffer.rs:45-117); see there.
 //  Everything downstream (k_enc_fse_blocks, k_enc_assemble) is shared with the other paths.
 
 constexpr uint32_t kNoPos = 0xFFFFFFFFu;
@@ -112,7 +112,8 @@ k_long_chain(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ 
                 for (uint32_t k = 0; k < kSteps; k++) {
                     const uint32_t p = u0 + k * 32 + lane;
                     const bool act = p < n_pos;
-                    old[k] = act ? *reinterpret_cast<volatile uint32_t *>(&head[h[k]]) : kNoPos;
+                    old[k] = 0xFFFFFFFFu;
+                    if (act) old[k] = *reinterpret_cast<volatile uint32_t *>(&head[h[k]]);
                     __syncwarp();
                     if (act && (iw[k] & 0x4000u)) *reinterpret_cast<volatile uint32_t *>(&head[h[k]]) = p;  // newest position of its bucket in this step
                     __syncwarp();
@@ -522,11 +523,66 @@ __device__ __forceinline__ void wsink_emit_block(TSink &s, uint64_t &out_used, c
     s.blk_pack0 = s.n_packs_total; s.blk_lit0 = s.n_lits_total;
     s.n_match_bytes = 0; s.match_distance = 0;
 }
+// The conversion is sequential only at block borders, so it is split in three:
+//   k_long_seg_stats   warp / segment: what the segment's matches add up to (count, literal and match bytes, all of them
+//                      single packs?) and the running sums per match;
+//   k_long_blocks      warp / stream: walks the segments in order over those sums -- a segment of plain packs that stays
+//                      inside the open block, or crosses into the next one because the block's 10 000 packs are full, costs
+//                      a few instructions and only fixes where its packs go; anything else (L > 315, M > 2359, a block
+//                      that fills up with literals) is pushed match by match right here (Buffer::push);
+//   k_long_write_packs warp / segment: writes the packs of the plain segments.
+struct SegAgg {
+    uint32_t n;          // matches of the segment that are part of the true parse (fix list, then the speculative list from `from`)
+    uint32_t sum_lit;    // literal bytes of matches 1..n-1 (the first one's depend on where the previous segment ended)
+    uint32_t sum_m;      // match bytes
+    uint32_t simple;     // every L (but the first) <= 315 and every M <= 2359
+    uint32_t first_idx, last_end, last_dist, pad;
+};
+struct SegEntry { uint32_t pack_base, d_prev, split, first_lit; };  // split: first match of the segment that opens a new block (n: none; kNoPos: packs already written)
+
+__device__ __forceinline__ uint4 seg_record(const uint4 *fixl, const uint4 *specl, uint32_t n_fix, uint32_t i) { return i < n_fix ? fixl[i] : specl[i - n_fix]; }
+
+__global__ void __launch_bounds__(128)
+k_long_seg_stats(const uint4 *__restrict__ spec, const uint4 *__restrict__ fix, const LongSegOut *__restrict__ seg_out, uint32_t n_rseg, SegAgg *agg,
+                 uint2 *__restrict__ pre) {
+    const uint32_t rs = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (rs >= n_rseg) return;
+    const LongSegOut o = seg_out[rs];
+    const uint4 *fixl = fix + (size_t)rs * kEmitCap, *specl = spec + (size_t)rs * kEmitCap + o.from;
+    uint2 *pr = pre + (size_t)rs * kEmitCap;
+    const uint32_t n = o.n_fix + (o.n_spec - o.from);
+    uint32_t run_lit = 0, run_m = 0, carry_end = 0, simple = 1, first_idx = 0, last_end = 0, last_dist = 0;
+    for (uint32_t i0 = 0; i0 < n; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        uint4 r = make_uint4(0, 0, 0, 0);
+        if (i < n) r = seg_record(fixl, specl, o.n_fix, i);
+        const uint32_t my_end = r.x + r.y;
+        uint32_t pe = __shfl_up_sync(0xFFFFFFFFu, my_end, 1);
+        if (lane == 0) pe = carry_end;
+        const uint32_t lit = (i < n && i != 0) ? r.x - pe : 0u;
+        if (i < n && (lit > kMaxLValue || r.y > kMaxMValue)) simple = 0;
+        uint32_t il = lit, im = i < n ? r.y : 0u;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t a = __shfl_up_sync(0xFFFFFFFFu, il, d), b = __shfl_up_sync(0xFFFFFFFFu, im, d);
+            if (lane >= (uint32_t)d) { il += a; im += b; }
+        }
+        if (i < n) pr[i] = make_uint2(run_lit + il, run_m + im);
+        const uint32_t nn = n - i0 < 32 ? n - i0 : 32;
+        run_lit += __shfl_sync(0xFFFFFFFFu, il, 31); run_m += __shfl_sync(0xFFFFFFFFu, im, 31);
+        carry_end = __shfl_sync(0xFFFFFFFFu, my_end, nn - 1);
+        if (i0 == 0) first_idx = __shfl_sync(0xFFFFFFFFu, r.x, 0);
+        last_end = carry_end; last_dist = __shfl_sync(0xFFFFFFFFu, r.z, nn - 1);
+    }
+    simple = __all_sync(0xFFFFFFFFu, simple != 0);
+    if (lane == 0) agg[rs] = SegAgg{n, run_lit, run_m, simple, first_idx, last_end, last_dist, 0};
+}
+
 __global__ void __launch_bounds__(32)
-k_long_packs(const uint64_t *__restrict__ src_off, const uint64_t *__restrict__ src_len, EncStream *streams, const StreamCounts *__restrict__ bases,
-             const uint32_t *__restrict__ long_list, uint32_t n_long, const uint4 *__restrict__ spec, const uint4 *__restrict__ fix,
-             const LongSegOut *__restrict__ seg_out, const uint4 *__restrict__ tail, uint2 *pack_scratch, uint32_t *block_ids, EncBlock *blocks,
-             uint32_t *block_counter) {
+k_long_blocks(const uint64_t *__restrict__ src_off, const uint64_t *__restrict__ src_len, EncStream *streams, const StreamCounts *__restrict__ bases,
+              const uint32_t *__restrict__ long_list, uint32_t n_long, const uint4 *__restrict__ spec, const uint4 *__restrict__ fix,
+              const LongSegOut *__restrict__ seg_out, const SegAgg *__restrict__ agg, const uint2 *__restrict__ pre, SegEntry *entry,
+              const uint4 *__restrict__ tail, uint2 *pack_scratch, uint32_t *block_ids, EncBlock *blocks, uint32_t *block_counter, uint32_t *exact_count) {
     const uint32_t slot = blockIdx.x, lane = threadIdx.x;
     if (slot >= n_long) return;
     const uint32_t si = long_list[slot];
@@ -537,16 +593,14 @@ k_long_packs(const uint64_t *__restrict__ src_off, const uint64_t *__restrict__ 
     fs.packs = pack_scratch + env.base.n_blocks;
     fs.n_packs_total = 0; fs.n_lits_total = 0; fs.blk_pack0 = 0; fs.blk_lit0 = 0; fs.n_match_bytes = 0; fs.match_distance = 0;
     fs.n_blocks = 0; fs.out_used = 0; fs.blk_src0 = 0;
-    uint32_t prev_end = 0;
+    uint32_t prev_end = 0, n_exact = 0;
     uint64_t out_used = 0;  // (a 2 GiB stream's blocks pass 4 GiB of scratch)
-    auto run = [&](const uint4 *list, uint32_t count) {
-        uint4 nx = make_uint4(0, 0, 0, 0);
-        if (lane < count) nx = list[lane];
+    // Buffer::push for a list of matches, 32 per step while all of them are single packs that fit the open block
+    auto run = [&](const uint4 *fixl, const uint4 *specl, uint32_t n_fix, uint32_t count) {
         for (uint32_t i0 = 0; i0 < count; i0 += 32) {
             const uint32_t n = count - i0 < 32 ? count - i0 : 32;
-            const uint4 r = nx;
-            nx = make_uint4(0, 0, 0, 0);
-            if (i0 + 32 + lane < count) nx = list[i0 + 32 + lane];  // the next step's records are on their way while this one is worked on
+            uint4 r = make_uint4(0, 0, 0, 0);
+            if (lane < n) r = seg_record(fixl, specl, n_fix, i0 + lane);
             const uint32_t my_end = r.x + r.y;
             uint32_t pe = __shfl_up_sync(0xFFFFFFFFu, my_end, 1);
             if (lane == 0) pe = prev_end;
@@ -562,7 +616,7 @@ k_long_packs(const uint64_t *__restrict__ src_off, const uint64_t *__restrict__ 
                 fs.n_match_bytes += __reduce_add_sync(0xFFFFFFFFu, lane < n ? r.y : 0u);
                 fs.match_distance = __shfl_sync(0xFFFFFFFFu, r.z, n - 1);
             } else {
-                for (uint32_t i = 0; i < n; i++) {  // Buffer::push one match at a time, the warp in step (lane 0's stores count)
+                for (uint32_t i = 0; i < n; i++) {  // one match at a time, the warp in step (every lane stores the same values)
                     uint32_t l = __shfl_sync(0xFFFFFFFFu, lit_len, i), m = __shfl_sync(0xFFFFFFFFu, r.y, i);
                     const uint32_t d = __shfl_sync(0xFFFFFFFFu, r.z, i);
                     if (l <= kMaxLValue && m <= kMaxMValue && fs.n_packs_total - fs.blk_pack0 < kLmdsPerBlock &&
@@ -577,18 +631,83 @@ k_long_packs(const uint64_t *__restrict__ src_off, const uint64_t *__restrict__ 
             prev_end = __shfl_sync(0xFFFFFFFFu, my_end, n - 1);
         }
     };
-    for (uint32_t k = 0; k < st.n_rseg; k++) {
-        const uint32_t rs = st.rseg_base + k;
-        const LongSegOut o = seg_out[rs];
-        run(fix + (size_t)rs * kEmitCap, o.n_fix);
-        run(spec + (size_t)rs * kEmitCap + o.from, o.n_spec - o.from);
+    for (uint32_t k0 = 0; k0 < st.n_rseg; k0 += 32) {
+        SegAgg mine = SegAgg{0, 0, 0, 1, 0, 0, 0, 0};
+        if (k0 + lane < st.n_rseg) mine = agg[st.rseg_base + k0 + lane];
+        const uint32_t kn = st.n_rseg - k0 < 32 ? st.n_rseg - k0 : 32;
+        for (uint32_t t = 0; t < kn; t++) {
+            const uint32_t rs = st.rseg_base + k0 + t;
+            const uint32_t n = __shfl_sync(0xFFFFFFFFu, mine.n, t);
+            if (n == 0) continue;
+            const uint32_t sum_lit = __shfl_sync(0xFFFFFFFFu, mine.sum_lit, t), sum_m = __shfl_sync(0xFFFFFFFFu, mine.sum_m, t);
+            const uint32_t simple = __shfl_sync(0xFFFFFFFFu, mine.simple, t), first_idx = __shfl_sync(0xFFFFFFFFu, mine.first_idx, t);
+            const uint32_t last_end = __shfl_sync(0xFFFFFFFFu, mine.last_end, t), last_dist = __shfl_sync(0xFFFFFFFFu, mine.last_dist, t);
+            const uint32_t first_lit = first_idx - prev_end;
+            const uint32_t cnt = fs.n_packs_total - fs.blk_pack0, lits = fs.n_lits_total - fs.blk_lit0;
+            bool done = false;
+            if (simple && first_lit <= kMaxLValue) {
+                if (cnt + n <= kLmdsPerBlock && lits + first_lit + sum_lit <= kLiteralsPerBlock) {
+                    if (lane == 0) entry[rs] = SegEntry{fs.n_packs_total, fs.match_distance, n, first_lit};
+                    fs.n_packs_total += n; fs.n_lits_total += first_lit + sum_lit; fs.n_match_bytes += sum_m;
+                    done = true;
+                } else if (cnt + n > kLmdsPerBlock) {
+                    // the open block takes its 10 000th pack inside this segment: matches [0, j) finish it, match j opens the next one
+                    const uint32_t j = kLmdsPerBlock - cnt;
+                    uint2 pj = make_uint2(0, 0);
+                    uint32_t lit_a = 0;  // literal bytes of matches [0, j)
+                    if (j != 0) { pj = pre[(size_t)rs * kEmitCap + j - 1]; lit_a = first_lit + pj.x; }
+                    const uint32_t lit_b = first_lit + sum_lit - lit_a;
+                    if (lits + lit_a <= kLiteralsPerBlock && lit_b <= kLiteralsPerBlock && n - j <= kLmdsPerBlock) {
+                        if (lane == 0) entry[rs] = SegEntry{fs.n_packs_total, fs.match_distance, j, first_lit};
+                        fs.n_packs_total += j; fs.n_lits_total += lit_a; fs.n_match_bytes += pj.y;
+                        wsink_emit_block(fs, out_used, env, lane);
+                        fs.n_packs_total += n - j; fs.n_lits_total += lit_b; fs.n_match_bytes += sum_m - pj.y;
+                        done = true;
+                    }
+                }
+            }
+            if (done) { fs.match_distance = last_dist; prev_end = last_end; continue; }
+            const LongSegOut o = seg_out[rs];
+            if (lane == 0) entry[rs] = SegEntry{0, 0, kNoPos, 0};
+            run(fix + (size_t)rs * kEmitCap, spec + (size_t)rs * kEmitCap + o.from, o.n_fix, n);
+            n_exact++;
+        }
     }
     for (uint32_t t = 0; t < 2; t++) {
         const uint4 r = tail[2 * slot + t];
-        if (r.w != 0xFFFFFFFFu) run(tail + 2 * slot + t, 1);
+        if (r.w != 0xFFFFFFFFu) run(tail + 2 * slot + t, nullptr, 1, 1);
     }
     wsink_emit_block(fs, out_used, env, lane);  // finalize
-    if (lane == 0) streams[si].n_blocks = fs.n_blocks;
+    if (lane == 0) { streams[si].n_blocks = fs.n_blocks; if (n_exact) atomicAdd(exact_count, n_exact); }
+}
+
+__global__ void __launch_bounds__(128)
+k_long_write_packs(const StreamCounts *__restrict__ bases, const LongSeg *__restrict__ rseg, uint32_t n_rseg, const uint4 *__restrict__ spec,
+                   const uint4 *__restrict__ fix, const LongSegOut *__restrict__ seg_out, const SegAgg *__restrict__ agg, const SegEntry *__restrict__ entry,
+                   uint2 *pack_scratch) {
+    const uint32_t rs = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (rs >= n_rseg) return;
+    const uint32_t n = agg[rs].n;
+    if (n == 0) return;
+    const SegEntry en = entry[rs];
+    if (en.split == kNoPos) return;
+    const LongSegOut o = seg_out[rs];
+    const uint4 *fixl = fix + (size_t)rs * kEmitCap, *specl = spec + (size_t)rs * kEmitCap + o.from;
+    uint2 *packs = pack_scratch + bases[rseg[rs].stream].n_blocks + en.pack_base;
+    uint32_t carry_end = 0, carry_d = en.d_prev;
+    for (uint32_t i0 = 0; i0 < n; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        uint4 r = make_uint4(0, 0, 0, 0);
+        if (i < n) r = seg_record(fixl, specl, o.n_fix, i);
+        const uint32_t my_end = r.x + r.y;
+        uint32_t pe = __shfl_up_sync(0xFFFFFFFFu, my_end, 1), dp = __shfl_up_sync(0xFFFFFFFFu, r.z, 1);
+        if (lane == 0) { pe = carry_end; dp = carry_d; }
+        if (i == en.split) dp = 0;  // first pack of a block: nothing to repeat (Buffer::reset)
+        const uint32_t lit = i == 0 ? en.first_lit : r.x - pe;
+        if (i < n) packs[i] = make_uint2(lit | (r.y << 16), r.z == dp ? 0u : r.z);
+        const uint32_t nn = n - i0 < 32 ? n - i0 : 32;
+        carry_end = __shfl_sync(0xFFFFFFFFu, my_end, nn - 1); carry_d = __shfl_sync(0xFFFFFFFFu, r.z, nn - 1);
+    }
 }
 
 // ---- the blocks of long streams are copied into the frame side by side -------------------------------------
