@@ -34,9 +34,9 @@ constexpr uint32_t kBucketWords = 2 * kHashWidth;
 constexpr uint32_t kTableWords = (1u << kHashBits) * kBucketWords;
 constexpr uint32_t kFastMaxLen = 65536;  // streams up to this long take the shared-memory path (positions fit 16 bits)
 #ifndef LZB_LONG_RSEG
-#define LZB_LONG_RSEG 16384
+#define LZB_LONG_RSEG 4096
 #endif
-constexpr uint32_t kLongCSeg = 65536, kLongRSeg = LZB_LONG_RSEG;  // longer bvx2 streams: chain pieces / replay segments (encode_long.cuh)
+constexpr uint32_t kLongCSeg = 32768, kLongRSeg = LZB_LONG_RSEG;  // longer bvx2 streams: chain pieces / replay segments (encode_long.cuh)
 
 enum StreamKind : uint32_t { SK_RAW = 0, SK_VN = 1, SK_FSE = 2 };
 
@@ -60,6 +60,7 @@ struct EncStream {       // per stream, written by prep / parse, read by assembl
                          // (longer bvx2 streams, encode_long.cuh), 0: by k_enc_parse
     uint32_t cseg_base, n_cseg;  // long streams: chain pieces and replay segments (indices into the batch's lists)
     uint32_t rseg_base, n_rseg;
+    uint32_t seg, pad;   // seg = 1: the sequential front end runs per segment (k_long_replay + stitch) instead of per stream
     uint64_t long_off;   // long streams: element offset of the stream's prev[] array
 };
 
@@ -80,14 +81,14 @@ struct EncBlock {        // one bvx2 block to encode (compact list, any order)
 // ------------------------------------------------------------------------------------------------
 __global__ void k_enc_prep(const uint64_t *__restrict__ src_len, size_t n, EncStream *streams, StreamCounts *counts, int32_t *status,
                            uint32_t *path_counts /* [0] fast streams, [1] streams for k_enc_parse, [2] long streams, [3] replay segments,
-                                                    [4] chain pieces, [6..7] prev[] elements (u64) */,
-                           uint32_t *long_list, int allow_fast, int allow_long) {
+                                                    [4] chain pieces, [5] streams replayed by segments, [6..7] prev[] elements (u64) */,
+                           uint32_t *long_list, uint32_t *seg_list, int allow_fast, int allow_long, int allow_seg) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint64_t len = src_len[i];
     EncStream st;
     st.n_blocks = 0; st.vn_size = 0; st.fast = 0;
-    st.cseg_base = st.n_cseg = st.rseg_base = st.n_rseg = 0; st.long_off = 0;
+    st.cseg_base = st.n_cseg = st.rseg_base = st.n_rseg = 0; st.long_off = 0; st.seg = 0; st.pad = 0;
     StreamCounts c = {0, 0, 0, 0};
     status[i] = LZFSE_B200_OK;
     if (len > 0x7FFFFFFFull) {  // BLOCK_GUIDE repositioning (frontend_bytes.rs:348-375) is out of scope
@@ -97,13 +98,16 @@ __global__ void k_enc_prep(const uint64_t *__restrict__ src_len, size_t n, EncSt
         st.kind = SK_FSE;
         st.fast = allow_fast && len <= kFastMaxLen;
         if (allow_long && len > kFastMaxLen) {
-            st.fast = 2;
-            const uint32_t end = (uint32_t)len - 3;
-            st.n_cseg = (end + kLongCSeg - 1) / kLongCSeg; st.n_rseg = (end + kLongRSeg - 1) / kLongRSeg;
+            st.fast = 2; st.seg = 1;
+            st.n_cseg = ((uint32_t)len - 3 + kLongCSeg - 1) / kLongCSeg;
             long_list[atomicAdd(&path_counts[2], 1u)] = (uint32_t)i;
-            st.rseg_base = atomicAdd(&path_counts[3], st.n_rseg);
             st.cseg_base = atomicAdd(&path_counts[4], st.n_cseg);
             st.long_off = atomicAdd(reinterpret_cast<unsigned long long *>(path_counts + 6), (unsigned long long)((len + 31) & ~15ull));
+        } else if (st.fast == 1 && allow_seg) st.seg = 1;
+        if (st.seg) {
+            st.n_rseg = ((uint32_t)len - 3 + kLongRSeg - 1) / kLongRSeg;
+            st.rseg_base = atomicAdd(&path_counts[3], st.n_rseg);
+            seg_list[atomicAdd(&path_counts[5], 1u)] = (uint32_t)i;
         }
         c.n_blocks = pack_cap(len);                  // packs
         c.n_fse = (len + 31) & ~15ull;               // literal bytes
@@ -1158,7 +1162,7 @@ k_enc_replay(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ 
     // is done, because the ring upkeep below is WARP-WIDE on purpose (see there).
     static_assert(kReplayStride == 1, "one stream per lane");
     const size_t si = (size_t)blockIdx.x * kReplayThreads + threadIdx.x;
-    const bool valid = si < n_streams && streams[si < n_streams ? si : 0].fast == 1;
+    const bool valid = si < n_streams && streams[si < n_streams ? si : 0].fast == 1 && !streams[si < n_streams ? si : 0].seg;
     bool active = valid;
     const size_t sj = valid ? si : 0;
     const uint8_t *src = src_base + src_off[sj];
@@ -1677,8 +1681,9 @@ struct lzfse_b200_encoder {
     std::string last_error;
     uint64_t launches = 0;
     DevBuf streams, counts, totals_dev, tables, packs, lits, block_ids, blocks, out, counters, words;
-    DevBuf long_list, l_prev, l_heads, l_cseg, l_rseg, l_out, l_spec, l_fix, l_states, l_tail, l_agg, l_pre, l_entry;  // long streams (encode_long.cuh)
+    DevBuf long_list, seg_list, l_prev, l_info, l_heads, l_cseg, l_rseg, l_out, l_spec, l_fix, l_states, l_tail, l_agg, l_csum, l_entry;  // long streams (encode_long.cuh)
     int allow_long = 1;  // LZB_ENC_LONG=0 sends streams > 64 KiB through k_enc_parse (measurements, tests)
+    int allow_seg = 1;   // LZB_ENC_SEG=0: streams <= 64 KiB are replayed whole by k_enc_replay (one thread per stream) instead of per segment
     uint32_t last_long_redo = 0;
     bool pending = false;             // an *_async call has been enqueued and not yet synchronised
     cudaStream_t pending_stream = nullptr;
@@ -1706,6 +1711,7 @@ int encode_batch_device_impl(lzfse_b200_encoder *e, const uint8_t *src, const ui
     LZB_CK(e, e->totals_host.reserve(2 * sizeof(StreamCounts)));
     LZB_CK(e, e->counters.reserve(16 * sizeof(uint32_t)));
     LZB_CK(e, e->long_list.reserve(n * sizeof(uint32_t)));
+    LZB_CK(e, e->seg_list.reserve(n * sizeof(uint32_t)));
     const int tb = 128;
     e->timer.begin(s);
     LZB_CK(e, cudaMemsetAsync(e->counters.p, 0, 16 * sizeof(uint32_t), s));
@@ -1713,7 +1719,7 @@ int encode_batch_device_impl(lzfse_b200_encoder *e, const uint8_t *src, const ui
     // [6] long streams, [7] replay segments, [8] chain pieces, [10..11] prev[] elements, [12] chain cursor, [13] segments stitched again, [14] segments whose packs were pushed one by one
     uint32_t *ctr = e->counters.as<uint32_t>();
     k_enc_prep<<<(unsigned)((n + tb - 1) / tb), tb, 0, s>>>(src_len, n, e->streams.as<EncStream>(), e->counts.as<StreamCounts>(), status, ctr + 4,
-                                                           e->long_list.as<uint32_t>(), e->allow_fast, e->allow_long);
+                                                           e->long_list.as<uint32_t>(), e->seg_list.as<uint32_t>(), e->allow_fast, e->allow_long, e->allow_seg);
     launch_exclusive_scan(e->counts.as<StreamCounts>(), n, e->totals_host.as<StreamCounts>(), nullptr, s);  // pinned host memory (UVA)
     k_enc_publish_counts<<<1, 1, 0, s>>>(ctr + 4, reinterpret_cast<uint32_t *>(e->totals_host.as<StreamCounts>() + 1));
     e->launches += n > 8192 ? 5 : 3;  // prep + the exclusive scan (three launches for large batches) + publish
@@ -1724,6 +1730,7 @@ int encode_batch_device_impl(lzfse_b200_encoder *e, const uint8_t *src, const ui
     const uint32_t n_long = reinterpret_cast<const uint32_t *>(e->totals_host.as<StreamCounts>() + 1)[2];
     const uint32_t n_rseg = reinterpret_cast<const uint32_t *>(e->totals_host.as<StreamCounts>() + 1)[3];
     const uint32_t n_cseg = reinterpret_cast<const uint32_t *>(e->totals_host.as<StreamCounts>() + 1)[4];
+    const uint32_t n_segl = reinterpret_cast<const uint32_t *>(e->totals_host.as<StreamCounts>() + 1)[5];
     const uint64_t long_elems = reinterpret_cast<const uint64_t *>(e->totals_host.as<StreamCounts>() + 1)[3];
     if (tot.n_literals > 0xFFFFFFF0ull) { e->last_error = "too many blocks in one batch"; return LZFSE_B200_INVALID_ARGUMENT; }
     const unsigned parse_ctas = (unsigned)e->n_sms * kParseWarpsPerSm / kParseWarps;
@@ -1739,18 +1746,21 @@ int encode_batch_device_impl(lzfse_b200_encoder *e, const uint8_t *src, const ui
     }
     if (n_fast || n_long) LZB_CK(e, e->words.reserve((tot.n_fse + 256) * sizeof(uint32_t)));  // one word per position (k_enc_find -> k_enc_replay)
     if (n_long) {
-        LZB_CK(e, e->l_prev.reserve((long_elems + 64) * sizeof(uint32_t)));
+        LZB_CK(e, e->l_prev.reserve((long_elems + 64) * sizeof(uint2)));   // {chain link, four bytes} per position
+        LZB_CK(e, e->l_info.reserve((long_elems + 64) * sizeof(uint16_t)));
         LZB_CK(e, e->l_heads.reserve((size_t)n_cseg * (1u << kHashBits) * sizeof(uint32_t)));
         LZB_CK(e, e->l_cseg.reserve((size_t)n_cseg * sizeof(LongSeg)));
+    }
+    if (n_segl) {
         LZB_CK(e, e->l_rseg.reserve((size_t)n_rseg * sizeof(LongSeg)));
         LZB_CK(e, e->l_out.reserve((size_t)n_rseg * sizeof(LongSegOut)));
         LZB_CK(e, e->l_spec.reserve((size_t)n_rseg * kEmitCap * sizeof(uint4)));
         LZB_CK(e, e->l_fix.reserve((size_t)n_rseg * kEmitCap * sizeof(uint4)));
         LZB_CK(e, e->l_states.reserve((size_t)n_rseg * kSpecStates * sizeof(uint4)));
-        LZB_CK(e, e->l_tail.reserve((size_t)n_long * 2 * sizeof(uint4)));
+        LZB_CK(e, e->l_tail.reserve((size_t)n_segl * 2 * sizeof(uint4)));
         LZB_CK(e, e->l_agg.reserve((size_t)n_rseg * sizeof(SegAgg)));
-        LZB_CK(e, e->l_pre.reserve((size_t)n_rseg * kEmitCap * sizeof(uint2)));
         LZB_CK(e, e->l_entry.reserve((size_t)n_rseg * sizeof(SegEntry)));
+        LZB_CK(e, e->l_csum.reserve((size_t)n_rseg * kSegChunks * sizeof(uint2)));
     }
     LZB_CK(e, e->packs.reserve((tot.n_blocks + 1) * sizeof(uint2)));
     LZB_CK(e, e->lits.reserve(tot.n_fse + 64));
@@ -1766,7 +1776,7 @@ int encode_batch_device_impl(lzfse_b200_encoder *e, const uint8_t *src, const ui
         e->launches += 1;
     }
     e->timer.mark(s);  // find
-    if (n_fast) {
+    if (n_fast && !e->allow_seg) {
         k_enc_replay<<<(unsigned)((n + kReplayThreads - 1) / kReplayThreads), kReplayThreads, 0, s>>>(
             src, src_off, src_len, n, e->streams.as<EncStream>(), e->counts.as<StreamCounts>(), e->words.as<uint32_t>(), e->packs.as<uint2>(),
             e->block_ids.as<uint32_t>(), e->blocks.as<EncBlock>(), ctr);
@@ -1781,39 +1791,63 @@ int encode_batch_device_impl(lzfse_b200_encoder *e, const uint8_t *src, const ui
         e->launches += 1;
     }
     e->timer.mark(s);  // parse
-    if (n_long) {
+    {
         const EncStream *st = e->streams.as<EncStream>();
         const StreamCounts *bs = e->counts.as<StreamCounts>();
-        const uint32_t *ll = e->long_list.as<uint32_t>();
+        const uint32_t *ll = e->long_list.as<uint32_t>(), *sl = e->seg_list.as<uint32_t>();
         LongSeg *cseg = e->l_cseg.as<LongSeg>(), *rseg = e->l_rseg.as<LongSeg>();
         LongSegOut *so = e->l_out.as<LongSegOut>();
         uint32_t *words = e->words.as<uint32_t>();
-        k_long_segs<<<n_long, 256, 0, s>>>(ll, n_long, st, cseg, rseg);
-        k_long_chain<<<n_cseg < (unsigned)e->n_sms ? n_cseg : (unsigned)e->n_sms, kChainThreads, kChainSmem, s>>>(
-            src, src_off, src_len, st, cseg, n_cseg, e->l_prev.as<uint32_t>(), e->l_heads.as<uint32_t>(), ctr + 12);
-        k_long_carry<<<n_long * ((1u << kHashBits) / 256), 256, 0, s>>>(ll, n_long, st, e->l_heads.as<uint32_t>());
+        static const bool dbg = getenv("LZB_ENC_DEBUG_SYNC") != nullptr;  // measurements / fault finding: name the kernel that failed
+#define LZB_DBG(name) do { if (dbg) { cudaError_t de = cudaStreamSynchronize(s); if (de != cudaSuccess) { e->last_error = std::string(name) + ": " + cudaGetErrorString(de); return LZFSE_B200_CUDA_ERROR; } } } while (0)
+        LZB_DBG("before the segment kernels");
+        if (n_segl) { k_long_segs<<<n_segl, 64, 0, s>>>(sl, n_segl, st, cseg, rseg); e->launches += 1; }
+        LZB_DBG("k_long_segs");
+        if (n_long) {
+            k_long_info<<<n_cseg * (kCSeg / 256), 256, 0, s>>>(src, src_off, src_len, st, cseg, e->l_prev.as<uint2>(), e->l_info.as<uint16_t>());
+            const unsigned cg = (unsigned)e->n_sms * kChainPerSm;
+            k_long_chain<<<n_cseg < cg ? n_cseg : cg, 32, kChainSmem, s>>>(src_len, st, cseg, n_cseg, e->l_info.as<uint16_t>(), e->l_prev.as<uint2>(),
+                                                                             e->l_heads.as<uint32_t>(), ctr + 12);
+            k_long_carry<<<n_long * ((1u << kHashBits) / 256), 256, 0, s>>>(ll, n_long, st, e->l_heads.as<uint32_t>());
+            e->launches += 3;
+        }
+        LZB_DBG("k_long_info / chain / carry");
         e->timer.mark(s);  // long_chain
-        k_long_find<<<n_cseg * (kCSeg / kLFindThreads), kLFindThreads, 0, s>>>(src, src_off, src_len, st, bs, cseg, e->l_prev.as<uint32_t>(),
-                                                                                  e->l_heads.as<uint32_t>(), words);
+        if (n_long) {
+            k_long_find<<<n_cseg * (kCSeg / kLFindThreads), kLFindThreads, 0, s>>>(src, src_off, src_len, st, bs, cseg, e->l_prev.as<uint2>(),
+                                                                                      e->l_heads.as<uint32_t>(), words);
+            e->launches += 1;
+        }
+        LZB_DBG("k_long_find");
         e->timer.mark(s);  // long_find
-        k_long_replay<<<(n_rseg + kReplayThreads - 1) / kReplayThreads, kReplayThreads, 0, s>>>(src, src_off, src_len, bs, rseg, n_rseg, words,
-                                                                                                 e->l_spec.as<uint4>(), e->l_states.as<uint4>(), so);
+        if (n_segl)
+            k_long_replay<<<(n_rseg + kReplayThreads - 1) / kReplayThreads, kReplayThreads, 0, s>>>(src, src_off, src_len, bs, rseg, n_rseg, words,
+                                                                                                     e->l_spec.as<uint4>(), e->l_states.as<uint4>(), so);
+        LZB_DBG("k_long_replay");
         e->timer.mark(s);  // long_replay
-        k_long_stitch_a<<<(n_rseg + 63) / 64, 64, 0, s>>>(src, src_off, src_len, bs, rseg, n_rseg, words, e->l_spec.as<uint4>(), e->l_states.as<uint4>(),
-                                                           e->l_fix.as<uint4>(), so);
-        k_long_stitch_b<<<(n_long + 31) / 32, 32, 0, s>>>(src, src_off, src_len, st, bs, ll, n_long, words, e->l_spec.as<uint4>(), e->l_states.as<uint4>(),
-                                                           e->l_fix.as<uint4>(), so, e->l_tail.as<uint4>(), ctr + 13);
+        if (n_segl) {
+            k_long_stitch_a<<<(n_rseg + 63) / 64, 64, 0, s>>>(src, src_off, src_len, bs, rseg, n_rseg, words, e->l_spec.as<uint4>(), e->l_states.as<uint4>(),
+                                                               e->l_fix.as<uint4>(), so);
+            LZB_DBG("k_long_stitch_a");
+            k_long_stitch_b<<<(n_segl + 3) / 4, 128, 0, s>>>(src, src_off, src_len, st, bs, sl, n_segl, words, e->l_spec.as<uint4>(), e->l_states.as<uint4>(),
+                                                              e->l_fix.as<uint4>(), so, e->l_tail.as<uint4>(), ctr + 13);
+        }
+        LZB_DBG("k_long_stitch_b");
         e->timer.mark(s);  // long_stitch
-        k_long_seg_stats<<<(n_rseg + 3) / 4, 128, 0, s>>>(e->l_spec.as<uint4>(), e->l_fix.as<uint4>(), so, n_rseg, e->l_agg.as<SegAgg>(), e->l_pre.as<uint2>());
-        k_long_blocks<<<n_long, 32, 0, s>>>(src_off, src_len, e->streams.as<EncStream>(), bs, ll, n_long, e->l_spec.as<uint4>(), e->l_fix.as<uint4>(), so,
-                                             e->l_agg.as<SegAgg>(), e->l_pre.as<uint2>(), e->l_entry.as<SegEntry>(), e->l_tail.as<uint4>(), e->packs.as<uint2>(),
-                                             e->block_ids.as<uint32_t>(), e->blocks.as<EncBlock>(), ctr, ctr + 14);
-        k_long_write_packs<<<(n_rseg + 3) / 4, 128, 0, s>>>(bs, rseg, n_rseg, e->l_spec.as<uint4>(), e->l_fix.as<uint4>(), so, e->l_agg.as<SegAgg>(),
-                                                             e->l_entry.as<SegEntry>(), e->packs.as<uint2>());
+        if (n_segl) {
+            k_long_seg_stats<<<(n_rseg + 3) / 4, 128, 0, s>>>(e->l_spec.as<uint4>(), e->l_fix.as<uint4>(), so, n_rseg, e->l_agg.as<SegAgg>(), e->l_csum.as<uint2>());
+            LZB_DBG("k_long_seg_stats");
+            static const int bw = getenv("LZB_BLOCKS_WARPS") ? atoi(getenv("LZB_BLOCKS_WARPS")) : 4;
+            k_long_blocks<<<(n_segl + bw - 1) / bw, bw * 32, 0, s>>>(src_off, src_len, e->streams.as<EncStream>(), bs, sl, n_segl, e->l_spec.as<uint4>(), e->l_fix.as<uint4>(), so,
+                                                            e->l_agg.as<SegAgg>(), e->l_csum.as<uint2>(), e->l_entry.as<SegEntry>(), e->l_tail.as<uint4>(), e->packs.as<uint2>(),
+                                                            e->block_ids.as<uint32_t>(), e->blocks.as<EncBlock>(), ctr, ctr + 14);
+            LZB_DBG("k_long_blocks");
+            k_long_write_packs<<<(n_rseg + 3) / 4, 128, 0, s>>>(bs, rseg, n_rseg, e->l_spec.as<uint4>(), e->l_fix.as<uint4>(), so, e->l_agg.as<SegAgg>(),
+                                                                 e->l_entry.as<SegEntry>(), e->packs.as<uint2>());
+            e->launches += 6;
+        }
+        LZB_DBG("k_long_write_packs");
         e->timer.mark(s);  // long_packs
-        e->launches += 10;
-    } else {
-        for (int k = 0; k < 5; k++) e->timer.mark(s);
     }
     if (tot.n_literals) {
         unsigned g = (unsigned)((tot.n_literals + kFseEncWarps - 1) / kFseEncWarps);
@@ -1864,6 +1898,7 @@ int lzfse_b200_encoder_create(int device, lzfse_b200_encoder **out) {
     if (cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete e; return LZFSE_B200_CUDA_ERROR; }
     if (const char *ef = getenv("LZB_ENC_FAST")) e->allow_fast = atoi(ef) != 0;
     if (const char *ef = getenv("LZB_ENC_LONG")) e->allow_long = atoi(ef) != 0;
+    if (const char *ef = getenv("LZB_ENC_SEG")) e->allow_seg = atoi(ef) != 0;
     cudaFuncAttributes fa;
     if (cudaFuncGetAttributes(&fa, k_enc_fse_blocks) != cudaSuccess ||
         cudaFuncSetAttribute(k_enc_find, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFindSmemBytes) != cudaSuccess ||
@@ -1881,7 +1916,7 @@ void lzfse_b200_encoder_destroy(lzfse_b200_encoder *e) {
     if (!e) return;
     DeviceGuard g(e->device);
     for (DevBuf *b : {&e->streams, &e->counts, &e->totals_dev, &e->tables, &e->packs, &e->lits, &e->block_ids, &e->blocks, &e->out, &e->counters, &e->words,
-                      &e->long_list, &e->l_prev, &e->l_heads, &e->l_cseg, &e->l_rseg, &e->l_out, &e->l_spec, &e->l_fix, &e->l_states, &e->l_tail, &e->l_agg, &e->l_pre, &e->l_entry}) b->release();
+                      &e->long_list, &e->seg_list, &e->l_prev, &e->l_info, &e->l_heads, &e->l_cseg, &e->l_rseg, &e->l_out, &e->l_spec, &e->l_fix, &e->l_states, &e->l_tail, &e->l_agg, &e->l_csum, &e->l_entry}) b->release();
     e->totals_host.release();
     e->stage.release();
     e->timer.release();

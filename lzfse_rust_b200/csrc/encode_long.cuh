@@ -6,7 +6,7 @@
 //
 //  1. What a position finds in the history does not depend on the parse (top of encode.cu).  The reference's
 //     HistoryTable (encode/history.rs:24-31,101-131) is the hash chain prev[p] = newest q < p in p's bucket, and
-//     that chain can be built for all 64 Ki-position pieces of a stream at once: k_long_chain links the positions
+//     that chain can be built for all 32 Ki-position pieces of a stream at once: k_long_chain links the positions
 //     inside a piece (bucket heads in shared memory) and leaves the newest position per bucket, k_long_carry turns
 //     those into "newest position before this piece" per bucket (a running maximum over the pieces, one thread per
 //     bucket), and a hop that leaves its piece continues in that table.  k_long_find then evaluates find_match
@@ -29,7 +29,8 @@ constexpr uint32_t kCSeg = kLongCSeg;         // positions per chain piece (16-b
 constexpr uint32_t kRSeg = kLongRSeg;         // positions per speculative replay segment
 static_assert(kRSeg % 32 == 0 && kCSeg % kRSeg == 0, "segments are whole 32-position groups");
 constexpr uint32_t kEmitCap = kRSeg / 4 + 8;  // matches are >= 4 bytes and do not overlap
-constexpr uint32_t kSpecStates = 256;         // pushed matches per segment that carry the state they leave behind
+constexpr uint32_t kSpecStates = kRSeg / 64 < 256 ? kRSeg / 64 : 256;  // pushed matches per segment that carry the state they leave behind
+constexpr uint32_t kSegChunks = (kEmitCap + 31) / 32;  // 32-match chunks of a segment's list (k_long_seg_stats leaves their sums)
 constexpr uint32_t kLongLaneCap = 64;
 
 struct LongSeg { uint32_t stream, k; };
@@ -43,7 +44,7 @@ struct LongSegOut {
     uint32_t n_fix;      // matches the stitch pushed before it fell into step
     uint32_t from;       // first speculative match that is part of the true parse (n_spec: none)
     FrontState a_out;    // k_long_stitch_a: true state behind this segment IF the previous segment's exit state was true
-    uint32_t pad;
+    uint32_t a_ok;       // k_long_stitch_a: ... and the segment fell into step (a_out == exit)
 };
 
 // ---- segment descriptors -----------------------------------------------------------------------
@@ -57,77 +58,92 @@ __global__ void k_long_segs(const uint32_t *__restrict__ long_list, uint32_t n_l
 }
 
 // ---- chain inside a piece ----------------------------------------------------------------------
-// Phase A, all warps: bucket index of every position and which lanes of a 32-position step share a bucket (the info
-// word of k_enc_find, parked in shared memory).  Phase B, warp 0: the ordered pass over the bucket heads.
-constexpr int kChainThreads = 1024;
-constexpr uint32_t kChainSmem = kCSeg * 2 + (1u << kHashBits) * 4;  // info words + bucket heads (32-bit: a piece has 65 536 positions AND "none")
-__global__ void __launch_bounds__(kChainThreads, 1)
-k_long_chain(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ src_off, const uint64_t *__restrict__ src_len,
-             const EncStream *__restrict__ streams, const LongSeg *__restrict__ cseg, uint32_t n_cseg, uint32_t *__restrict__ prev,
-             uint32_t *__restrict__ seg_head, uint32_t *work_counter) {
+// k_long_info, one thread per position: the position's four bytes (kept next to its chain link, so that a candidate is
+// accepted or rejected by the same load that yields the next hop) and the info word of k_enc_find -- bucket index, and
+// which lanes of a 32-position step share a bucket.
+// k_long_chain, one WARP per piece, six of them per SM: the ordered pass over the bucket heads (16-bit, shared memory).
+constexpr uint32_t kCSegShift = 15;
+static_assert(kCSeg == 1u << kCSegShift, "chain piece size");
+constexpr uint32_t kChainSmem = (1u << kHashBits) * 2;
+constexpr uint32_t kChainPerSm = 6;
+__global__ void __launch_bounds__(256)
+k_long_info(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ src_off, const uint64_t *__restrict__ src_len,
+            const EncStream *__restrict__ streams, const LongSeg *__restrict__ cseg, uint2 *__restrict__ pairs, uint16_t *__restrict__ info) {
+    const uint32_t lane = threadIdx.x & 31;
+    const LongSeg sg = cseg[blockIdx.x / (kCSeg / 256)];
+    const EncStream st = streams[sg.stream];
+    const uint8_t *src = src_base + src_off[sg.stream];
+    const uint32_t end = (uint32_t)src_len[sg.stream] - 3;
+    const uint32_t p = sg.k * kCSeg + (blockIdx.x % (kCSeg / 256)) * 256 + threadIdx.x;
+    if (p - lane >= end) return;
+    const bool act = p < end;
+    const uint32_t val = ld4u(src + (act ? p : end - 1)), h = hash_u(val, false);
+    const uint32_t m = __match_any_sync(0xFFFFFFFFu, act ? h : 0xFFFF0000u + lane);
+    const uint32_t lower = m & lanemask_lt();
+    const uint32_t newest = (m >> lane) == 1u ? 0x4000u : 0u;
+    const uint32_t iw = lower ? (0x8000u | newest | ((uint32_t)(__ffs(m) - 1) << 5) | (31 - __clz(lower))) : (newest | h);
+    if (act) { info[st.long_off + p] = (uint16_t)iw; pairs[st.long_off + p].y = val; }
+}
+__global__ void __launch_bounds__(32)
+k_long_chain(const uint64_t *__restrict__ src_len, const EncStream *__restrict__ streams, const LongSeg *__restrict__ cseg, uint32_t n_cseg,
+             const uint16_t *__restrict__ info, uint2 *__restrict__ pairs, uint32_t *__restrict__ seg_head, uint32_t *work_counter) {
     extern __shared__ __align__(16) uint8_t csm[];
-    uint16_t *info = reinterpret_cast<uint16_t *>(csm);
-    uint32_t *head = reinterpret_cast<uint32_t *>(csm + kCSeg * 2);
-    __shared__ uint32_t s_seg;
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint16_t *head = reinterpret_cast<uint16_t *>(csm);
+    const uint32_t lane = threadIdx.x;
     for (;;) {
-        __syncthreads();
-        if (tid == 0) s_seg = atomicAdd(work_counter, 1u);
-        __syncthreads();
-        const uint32_t cs = s_seg;
+        uint32_t cs = 0;
+        if (lane == 0) cs = atomicAdd(work_counter, 1u);
+        cs = __shfl_sync(0xFFFFFFFFu, cs, 0);
         if (cs >= n_cseg) break;
         const LongSeg sg = cseg[cs];
         const EncStream st = streams[sg.stream];
-        const uint8_t *src = src_base + src_off[sg.stream];
-        const uint32_t len = (uint32_t)src_len[sg.stream], end = len - 3;
+        const uint32_t end = (uint32_t)src_len[sg.stream] - 3;
         const uint32_t B = sg.k * kCSeg, n_pos = end - B < kCSeg ? end - B : kCSeg;
-        uint32_t *pv = prev + st.long_off + B;
-        for (uint32_t t = tid; t < (1u << kHashBits); t += kChainThreads) head[t] = kNoPos;
-        for (uint32_t b0 = warp * 32; b0 < n_pos; b0 += kChainThreads) {
-            const uint32_t p = b0 + lane;
-            const bool act = p < n_pos;
-            const uint32_t h = hash_u(ld4u(src + B + (act ? p : n_pos - 1)), false);
-            const uint32_t m = __match_any_sync(0xFFFFFFFFu, act ? h : 0xFFFF0000u + lane);
-            const uint32_t lower = m & lanemask_lt();
-            const uint32_t newest = (m >> lane) == 1u ? 0x4000u : 0u;
-            const uint32_t iw = lower ? (0x8000u | newest | ((uint32_t)(__ffs(m) - 1) << 5) | (31 - __clz(lower))) : (newest | h);
-            if (act) info[p] = (uint16_t)iw;
-        }
-        __syncthreads();
-        if (warp == 0) {
-            // Only the bucket heads carry a dependency from one step to the next, and program order satisfies it (a step's
-            // head stores are issued before the next step's head loads); nothing in the pass consumes the loaded values
-            // before the global stores.  So eight steps issue their loads and stores back to back (k_enc_find's chain).
-            constexpr uint32_t kSteps = 8;
-            for (uint32_t u0 = 0; u0 < n_pos; u0 += 32 * kSteps) {
-                uint32_t iw[kSteps], h[kSteps], old[kSteps];
+        const uint16_t *inf = info + st.long_off + B;
+        uint2 *pv = pairs + st.long_off + B;
+        for (uint32_t t = lane; t < (1u << kHashBits) * 2 / 16; t += 32) reinterpret_cast<uint4 *>(csm)[t] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+        __syncwarp();
+        // Only the bucket heads carry a dependency from one step to the next, and program order satisfies it (a step's
+        // head stores are issued before the next step's head loads); nothing consumes the loaded values before the global
+        // stores.  So eight steps issue their loads and stores back to back, with the next eight info words on their way.
+        constexpr uint32_t kSteps = 8;
+        uint32_t nxt[kSteps];
 #pragma unroll
-                for (uint32_t k = 0; k < kSteps; k++) { const uint32_t p = u0 + k * 32 + lane; iw[k] = p < n_pos ? info[p] : 0u; }
+        for (uint32_t k = 0; k < kSteps; k++) { const uint32_t p = k * 32 + lane; nxt[k] = p < n_pos ? inf[p] : 0u; }
+        for (uint32_t u0 = 0; u0 < n_pos; u0 += 32 * kSteps) {
+            uint32_t iw[kSteps], h[kSteps], old[kSteps];
 #pragma unroll
-                for (uint32_t k = 0; k < kSteps; k++) {
-                    const uint32_t hb = __shfl_sync(0xFFFFFFFFu, iw[k], (iw[k] >> 5) & 31u);  // the bucket index lives in the group's lowest lane
-                    h[k] = ((iw[k] & 0x8000u) ? hb : iw[k]) & 0x3FFFu;
-                }
+            for (uint32_t k = 0; k < kSteps; k++) { iw[k] = nxt[k]; const uint32_t p = u0 + (kSteps + k) * 32 + lane; nxt[k] = p < n_pos ? inf[p] : 0u; }
 #pragma unroll
-                for (uint32_t k = 0; k < kSteps; k++) {
-                    const uint32_t p = u0 + k * 32 + lane;
-                    const bool act = p < n_pos;
-                    old[k] = 0xFFFFFFFFu;
-                    if (act) old[k] = *reinterpret_cast<volatile uint32_t *>(&head[h[k]]);
-                    __syncwarp();
-                    if (act && (iw[k] & 0x4000u)) *reinterpret_cast<volatile uint32_t *>(&head[h[k]]) = p;  // newest position of its bucket in this step
-                    __syncwarp();
-                }
+            for (uint32_t k = 0; k < kSteps; k++) {
+                const uint32_t hb = __shfl_sync(0xFFFFFFFFu, iw[k], (iw[k] >> 5) & 31u);  // the bucket index lives in the group's lowest lane
+                h[k] = ((iw[k] & 0x8000u) ? hb : iw[k]) & 0x3FFFu;
+            }
 #pragma unroll
-                for (uint32_t k = 0; k < kSteps; k++) {
-                    const uint32_t b0 = u0 + k * 32, p = b0 + lane;
-                    if (p < n_pos) pv[p] = (iw[k] & 0x8000u) ? B + b0 + (iw[k] & 31u) : (old[k] == kNoPos ? kNoPos : B + old[k]);
-                }
+            for (uint32_t k = 0; k < kSteps; k++) {
+                const uint32_t p = u0 + k * 32 + lane;
+                const bool act = p < n_pos;
+                old[k] = 0xFFFFu;
+                if (act) old[k] = *reinterpret_cast<volatile uint16_t *>(&head[h[k]]);
+                __syncwarp();
+                if (act && (iw[k] & 0x4000u)) *reinterpret_cast<volatile uint16_t *>(&head[h[k]]) = (uint16_t)p;  // newest position of its bucket in this step
+                __syncwarp();
+            }
+#pragma unroll
+            for (uint32_t k = 0; k < kSteps; k++) {
+                const uint32_t b0 = u0 + k * 32, p = b0 + lane;
+                if (p < n_pos) pv[p].x = (iw[k] & 0x8000u) ? B + b0 + (iw[k] & 31u) : (old[k] == 0xFFFFu ? kNoPos : B + old[k]);
             }
         }
-        __syncthreads();
+        __syncwarp();
         uint32_t *sh = seg_head + ((size_t)st.cseg_base + sg.k) * (1u << kHashBits);
-        for (uint32_t t = tid; t < (1u << kHashBits); t += kChainThreads) sh[t] = head[t] == kNoPos ? kNoPos : B + head[t];
+        for (uint32_t t = lane * 4; t < (1u << kHashBits); t += 128) {
+            uint4 v;
+            v.x = head[t] == 0xFFFFu ? kNoPos : B + head[t]; v.y = head[t + 1] == 0xFFFFu ? kNoPos : B + head[t + 1];
+            v.z = head[t + 2] == 0xFFFFu ? kNoPos : B + head[t + 2]; v.w = head[t + 3] == 0xFFFFu ? kNoPos : B + head[t + 3];
+            *reinterpret_cast<uint4 *>(sh + t) = v;
+        }
+        __syncwarp();
     }
 }
 
@@ -169,7 +185,7 @@ constexpr int kLFindThreads = 256;
 __global__ void __launch_bounds__(kLFindThreads)
 k_long_find(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ src_off, const uint64_t *__restrict__ src_len,
             const EncStream *__restrict__ streams, const StreamCounts *__restrict__ bases, const LongSeg *__restrict__ cseg,
-            const uint32_t *__restrict__ prev, const uint32_t *__restrict__ seg_head, uint32_t *__restrict__ words) {
+            const uint2 *__restrict__ pairs, const uint32_t *__restrict__ seg_head, uint32_t *__restrict__ words) {
     const uint32_t lane = threadIdx.x & 31;
     const LongSeg sg = cseg[blockIdx.x / (kCSeg / kLFindThreads)];
     const EncStream st = streams[sg.stream];
@@ -179,22 +195,24 @@ k_long_find(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ s
     const uint32_t p = sg.k * kCSeg + (blockIdx.x % (kCSeg / kLFindThreads)) * kLFindThreads + threadIdx.x;
     if (p - lane >= end) return;  // whole warp beyond the last position
     const bool act = p < end;
-    const uint32_t *pv = prev + st.long_off;
+    const uint2 *pv = pairs + st.long_off;  // {newest earlier position of the bucket inside the piece, the four bytes at this position}
     const uint32_t *sh = seg_head + (size_t)st.cseg_base * (1u << kHashBits);
     uint32_t best_len = 0, best_c = 0, n_sat = 0;
     uint32_t cs[4] = {0, 0, 0, 0}, ls[4] = {0, 0, 0, 0};
     const uint32_t maxl = act ? len - p : 0;
     if (act) {
-        const uint32_t val = ld4u(src + p), h = hash_u(val, false);
+        const uint2 me = pv[p];
+        const uint32_t val = me.y, h = hash_u(val, false);
         const uint32_t lim = maxl < kLongLaneCap ? maxl : kLongLaneCap;
-        uint32_t c = pv[p];
-        if (c == kNoPos) c = sh[(size_t)(p >> 16) * (1u << kHashBits) + h];
+        uint32_t c = me.x;
+        if (c == kNoPos) c = sh[(size_t)(p >> kCSegShift) * (1u << kHashBits) + h];
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             if (c == kNoPos || p - c > kMaxDValue) break;  // newest first, up to the first one out of range (frontend_bytes.rs:214-244)
-            uint32_t cn = pv[c];
-            if (cn == kNoPos) cn = sh[(size_t)(c >> 16) * (1u << kHashBits) + h];
-            if (ld4u(src + c) == val) {
+            const uint2 ce = pv[c];
+            uint32_t cn = ce.x;
+            if (cn == kNoPos) cn = sh[(size_t)(c >> kCSegShift) * (1u << kHashBits) + h];
+            if (ce.y == val) {
                 uint32_t l = 4;
                 while (l + 8 <= lim) {
                     const uint64_t y = ld8u(src + p + l) ^ ld8u(src + c + l);
@@ -400,10 +418,13 @@ k_long_replay(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__
     if (n_out == 0) lim0 = lim_flag;
     LongSegOut o;
     o.n_spec = n_out; o.lim0 = lim0; o.good0 = good; o.cand0 = cand; o.exit = s;
-    o.n_fix = 0; o.from = sg.k == 0 ? 0u : n_out; o.a_out = s; o.pad = 0;
+    o.n_fix = 0; o.from = sg.k == 0 ? 0u : n_out; o.a_out = s; o.a_ok = 0;
     seg_out[rs] = o;
 }
 
+__device__ __forceinline__ bool same_state(const FrontState &a, const FrontState &b) {
+    return a.cur == b.cur && a.lit == b.lit && a.p_len == b.p_len && (a.p_len == 0 || (a.p_idx == b.p_idx && a.p_midx == b.p_midx));
+}
 // ---- stitch ----------------------------------------------------------------------------------------
 // The true state T arrives at segment k of a stream; on return T is the true state behind it, n_fix matches have been
 // written to the segment's fix list and `from` says where the speculative list joins the true parse.
@@ -452,9 +473,6 @@ __device__ void stitch_segment(const uint8_t *src, uint32_t len, uint32_t end, c
     }
     o.n_fix = n_fix;
 }
-__device__ __forceinline__ bool same_state(const FrontState &a, const FrontState &b) {
-    return a.cur == b.cur && a.lit == b.lit && a.p_len == b.p_len && (a.p_len == 0 || (a.p_idx == b.p_idx && a.p_midx == b.p_midx));
-}
 // a: every segment at once, ASSUMING the exit state of the segment before it is true (it is, once that segment is in step).
 __global__ void k_long_stitch_a(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ src_off, const uint64_t *__restrict__ src_len,
                                 const StreamCounts *__restrict__ bases, const LongSeg *__restrict__ rseg, uint32_t n_rseg, const uint32_t *__restrict__ words,
@@ -469,37 +487,54 @@ __global__ void k_long_stitch_a(const uint8_t *__restrict__ src_base, const uint
     stitch_segment(src_base + src_off[sg.stream], len, len - 3, words + bases[sg.stream].n_fse, sg.k, T, o, spec + (size_t)rs * kEmitCap,
                    states + (size_t)rs * kSpecStates, fix + (size_t)rs * kEmitCap);
     seg_out[rs].n_fix = o.n_fix; seg_out[rs].from = o.from; seg_out[rs].a_out = T;  // (.exit is being read by the neighbour)
+    seg_out[rs].a_ok = same_state(T, o.exit);
 }
-// b: one thread per stream walks the segments in order with the true state; a segment whose assumption held is taken
-// as k_long_stitch_a left it, any other is stitched again from the true state.  Leaves the stream's tail (pending match,
-// final literals; frontend_bytes.rs:121-131,271-317) in tail[2 * slot ..].
-__global__ void k_long_stitch_b(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ src_off, const uint64_t *__restrict__ src_len,
-                                const EncStream *__restrict__ streams, const StreamCounts *__restrict__ bases, const uint32_t *__restrict__ long_list,
-                                uint32_t n_long, const uint32_t *__restrict__ words, const uint4 *__restrict__ spec, const uint4 *__restrict__ states,
-                                uint4 *__restrict__ fix, LongSegOut *seg_out, uint4 *tail, uint32_t *redo_count) {
-    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot >= n_long) return;
-    const uint32_t si = long_list[slot];
+// b: one warp per stream walks the segments in order with the true state.  While the true state entering a segment is the exit
+// state of the one before, what k_long_stitch_a left is right: the lanes look at 32 segments at a time and the walk jumps to
+// the first that did not fall into step; its a_out is still the truth behind it.  Any other segment is stitched again from
+// the true state (lane 0).  Leaves the stream's tail (pending match, final literals; frontend_bytes.rs:121-131,271-317).
+__global__ void __launch_bounds__(128)
+k_long_stitch_b(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ src_off, const uint64_t *__restrict__ src_len,
+                const EncStream *__restrict__ streams, const StreamCounts *__restrict__ bases, const uint32_t *__restrict__ seg_list,
+                uint32_t n_segl, const uint32_t *__restrict__ words, const uint4 *__restrict__ spec, const uint4 *__restrict__ states,
+                uint4 *__restrict__ fix, LongSegOut *seg_out, uint4 *tail, uint32_t *redo_count) {
+    const uint32_t slot = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (slot >= n_segl) return;
+    const uint32_t si = seg_list[slot];
     const EncStream st = streams[si];
     const uint8_t *src = src_base + src_off[si];
     const uint32_t len = (uint32_t)src_len[si], end = len - 3;
     const uint32_t *W = words + bases[si].n_fse;
     FrontState T = seg_out[st.rseg_base].exit;
-    uint32_t redo = 0;
-    for (uint32_t k = 1; k < st.n_rseg; k++) {
+    uint32_t redo = 0, k = 1;
+    while (k < st.n_rseg) {
         const uint32_t rs = st.rseg_base + k;
-        if (same_state(T, seg_out[rs - 1].exit)) { T = seg_out[rs].a_out; continue; }
-        LongSegOut o = seg_out[rs];
-        stitch_segment(src, len, end, W, k, T, o, spec + (size_t)rs * kEmitCap, states + (size_t)rs * kSpecStates, fix + (size_t)rs * kEmitCap);
-        seg_out[rs].n_fix = o.n_fix; seg_out[rs].from = o.from;
-        redo++;
+        if (same_state(T, seg_out[rs - 1].exit)) {
+            bool ok = false;
+            if (k + lane < st.n_rseg) ok = seg_out[rs + lane].a_ok != 0;
+            const uint32_t nb = ~__ballot_sync(0xFFFFFFFFu, ok);
+            const uint32_t m = nb ? (uint32_t)__ffs(nb) - 1u : 32u;  // segments k .. k+m-1 fell into step
+            if (m == 32 || k + m >= st.n_rseg) { T = seg_out[rs + m - 1].exit; k += m; }
+            else { T = seg_out[rs + m].a_out; k += m + 1; }
+            continue;
+        }
+        if (lane == 0) {
+            LongSegOut o = seg_out[rs];
+            stitch_segment(src, len, end, W, k, T, o, spec + (size_t)rs * kEmitCap, states + (size_t)rs * kSpecStates, fix + (size_t)rs * kEmitCap);
+            seg_out[rs].n_fix = o.n_fix; seg_out[rs].from = o.from;
+        }
+        T.cur = __shfl_sync(0xFFFFFFFFu, T.cur, 0); T.lit = __shfl_sync(0xFFFFFFFFu, T.lit, 0); T.p_idx = __shfl_sync(0xFFFFFFFFu, T.p_idx, 0);
+        T.p_midx = __shfl_sync(0xFFFFFFFFu, T.p_midx, 0); T.p_len = __shfl_sync(0xFFFFFFFFu, T.p_len, 0);
+        redo++; k++;
     }
-    uint32_t lit = T.lit, n_tail = 0;
-    if (T.p_len != 0) { tail[2 * slot + n_tail++] = make_uint4(T.p_idx, T.p_len, T.p_idx - T.p_midx, 0); lit = T.p_idx + T.p_len; }
-    if (len - lit != 0) tail[2 * slot + n_tail++] = make_uint4(len, 0, 1, 0);  // push_literals: (L, 0, 1)
-    if (n_tail < 2) tail[2 * slot + 1] = make_uint4(0, 0, 0, 0xFFFFFFFFu);
-    if (n_tail < 1) tail[2 * slot] = make_uint4(0, 0, 0, 0xFFFFFFFFu);
-    if (redo) atomicAdd(redo_count, redo);
+    if (lane == 0) {
+        uint32_t lit = T.lit, n_tail = 0;
+        if (T.p_len != 0) { tail[2 * slot + n_tail++] = make_uint4(T.p_idx, T.p_len, T.p_idx - T.p_midx, 0); lit = T.p_idx + T.p_len; }
+        if (len - lit != 0) tail[2 * slot + n_tail++] = make_uint4(len, 0, 1, 0);  // push_literals: (L, 0, 1)
+        if (n_tail < 2) tail[2 * slot + 1] = make_uint4(0, 0, 0, 0xFFFFFFFFu);
+        if (n_tail < 1) tail[2 * slot] = make_uint4(0, 0, 0, 0xFFFFFFFFu);
+        if (redo) atomicAdd(redo_count, redo);
+    }
 }
 
 // ---- matches -> packs and block records, one WARP per stream ------------------------------------------
@@ -525,7 +560,7 @@ __device__ __forceinline__ void wsink_emit_block(TSink &s, uint64_t &out_used, c
 }
 // The conversion is sequential only at block borders, so it is split in three:
 //   k_long_seg_stats   warp / segment: what the segment's matches add up to (count, literal and match bytes, all of them
-//                      single packs?) and the running sums per match;
+//                      single packs?) 
 //   k_long_blocks      warp / stream: walks the segments in order over those sums -- a segment of plain packs that stays
 //                      inside the open block, or crosses into the next one because the block's 10 000 packs are full, costs
 //                      a few instructions and only fixes where its packs go; anything else (L > 315, M > 2359, a block
@@ -544,12 +579,11 @@ __device__ __forceinline__ uint4 seg_record(const uint4 *fixl, const uint4 *spec
 
 __global__ void __launch_bounds__(128)
 k_long_seg_stats(const uint4 *__restrict__ spec, const uint4 *__restrict__ fix, const LongSegOut *__restrict__ seg_out, uint32_t n_rseg, SegAgg *agg,
-                 uint2 *__restrict__ pre) {
+                 uint2 *__restrict__ csum) {
     const uint32_t rs = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (rs >= n_rseg) return;
     const LongSegOut o = seg_out[rs];
     const uint4 *fixl = fix + (size_t)rs * kEmitCap, *specl = spec + (size_t)rs * kEmitCap + o.from;
-    uint2 *pr = pre + (size_t)rs * kEmitCap;
     const uint32_t n = o.n_fix + (o.n_spec - o.from);
     uint32_t run_lit = 0, run_m = 0, carry_end = 0, simple = 1, first_idx = 0, last_end = 0, last_dist = 0;
     for (uint32_t i0 = 0; i0 < n; i0 += 32) {
@@ -561,15 +595,10 @@ k_long_seg_stats(const uint4 *__restrict__ spec, const uint4 *__restrict__ fix, 
         if (lane == 0) pe = carry_end;
         const uint32_t lit = (i < n && i != 0) ? r.x - pe : 0u;
         if (i < n && (lit > kMaxLValue || r.y > kMaxMValue)) simple = 0;
-        uint32_t il = lit, im = i < n ? r.y : 0u;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t a = __shfl_up_sync(0xFFFFFFFFu, il, d), b = __shfl_up_sync(0xFFFFFFFFu, im, d);
-            if (lane >= (uint32_t)d) { il += a; im += b; }
-        }
-        if (i < n) pr[i] = make_uint2(run_lit + il, run_m + im);
+        const uint32_t cl = __reduce_add_sync(0xFFFFFFFFu, lit), cm = __reduce_add_sync(0xFFFFFFFFu, i < n ? r.y : 0u);
+        if (lane == 0) csum[(size_t)rs * kSegChunks + (i0 >> 5)] = make_uint2(cl, cm);  // literal (without match 0's) and match bytes of this chunk
+        run_lit += cl; run_m += cm;
         const uint32_t nn = n - i0 < 32 ? n - i0 : 32;
-        run_lit += __shfl_sync(0xFFFFFFFFu, il, 31); run_m += __shfl_sync(0xFFFFFFFFu, im, 31);
         carry_end = __shfl_sync(0xFFFFFFFFu, my_end, nn - 1);
         if (i0 == 0) first_idx = __shfl_sync(0xFFFFFFFFu, r.x, 0);
         last_end = carry_end; last_dist = __shfl_sync(0xFFFFFFFFu, r.z, nn - 1);
@@ -578,14 +607,14 @@ k_long_seg_stats(const uint4 *__restrict__ spec, const uint4 *__restrict__ fix, 
     if (lane == 0) agg[rs] = SegAgg{n, run_lit, run_m, simple, first_idx, last_end, last_dist, 0};
 }
 
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(128)
 k_long_blocks(const uint64_t *__restrict__ src_off, const uint64_t *__restrict__ src_len, EncStream *streams, const StreamCounts *__restrict__ bases,
-              const uint32_t *__restrict__ long_list, uint32_t n_long, const uint4 *__restrict__ spec, const uint4 *__restrict__ fix,
-              const LongSegOut *__restrict__ seg_out, const SegAgg *__restrict__ agg, const uint2 *__restrict__ pre, SegEntry *entry,
+              const uint32_t *__restrict__ seg_list, uint32_t n_segl, const uint4 *__restrict__ spec, const uint4 *__restrict__ fix,
+              const LongSegOut *__restrict__ seg_out, const SegAgg *__restrict__ agg, const uint2 *__restrict__ csum, SegEntry *entry,
               const uint4 *__restrict__ tail, uint2 *pack_scratch, uint32_t *block_ids, EncBlock *blocks, uint32_t *block_counter, uint32_t *exact_count) {
-    const uint32_t slot = blockIdx.x, lane = threadIdx.x;
-    if (slot >= n_long) return;
-    const uint32_t si = long_list[slot];
+    const uint32_t slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (slot >= n_segl) return;
+    const uint32_t si = seg_list[slot];
     const EncStream st = streams[si];
     TEnv env;
     env.base = bases[si]; env.blocks = blocks; env.block_ids = block_ids; env.block_counter = block_counter; env.src_off = src_off[si];
@@ -642,6 +671,13 @@ k_long_blocks(const uint64_t *__restrict__ src_off, const uint64_t *__restrict__
             const uint32_t sum_lit = __shfl_sync(0xFFFFFFFFu, mine.sum_lit, t), sum_m = __shfl_sync(0xFFFFFFFFu, mine.sum_m, t);
             const uint32_t simple = __shfl_sync(0xFFFFFFFFu, mine.simple, t), first_idx = __shfl_sync(0xFFFFFFFFu, mine.first_idx, t);
             const uint32_t last_end = __shfl_sync(0xFFFFFFFFu, mine.last_end, t), last_dist = __shfl_sync(0xFFFFFFFFu, mine.last_dist, t);
+#ifdef LZB_LONG_DEBUG
+            if (first_idx < prev_end || n > kEmitCap) {
+                if (lane == 0) printf("k_long_blocks: stream %u seg %u/%u: first_idx %u prev_end %u n %u n_fix %u from %u n_spec %u\n", si, k0 + t, st.n_rseg, first_idx, prev_end, n,
+                                      seg_out[rs].n_fix, seg_out[rs].from, seg_out[rs].n_spec);
+                return;
+            }
+#endif
             const uint32_t first_lit = first_idx - prev_end;
             const uint32_t cnt = fs.n_packs_total - fs.blk_pack0, lits = fs.n_lits_total - fs.blk_lit0;
             bool done = false;
@@ -653,9 +689,25 @@ k_long_blocks(const uint64_t *__restrict__ src_off, const uint64_t *__restrict__
                 } else if (cnt + n > kLmdsPerBlock) {
                     // the open block takes its 10 000th pack inside this segment: matches [0, j) finish it, match j opens the next one
                     const uint32_t j = kLmdsPerBlock - cnt;
-                    uint2 pj = make_uint2(0, 0);
-                    uint32_t lit_a = 0;  // literal bytes of matches [0, j)
-                    if (j != 0) { pj = pre[(size_t)rs * kEmitCap + j - 1]; lit_a = first_lit + pj.x; }
+                    uint2 pj = make_uint2(0, 0);  // literal bytes (without the first match's) and match bytes of matches [0, j)
+                    uint32_t lit_a = 0;           // literal bytes of matches [0, j)
+                    if (j != 0) {
+                        const LongSegOut o = seg_out[rs];
+                        const uint4 *fixl = fix + (size_t)rs * kEmitCap, *specl = spec + (size_t)rs * kEmitCap + o.from;
+                        // whole chunks from k_long_seg_stats' sums, the rest from the records of the chunk j lies in
+                        uint32_t sl = 0, sm = 0;
+                        const uint32_t cf = j >> 5, i = (cf << 5) + lane;
+                        for (uint32_t c = lane; c < cf; c += 32) { const uint2 v = csum[(size_t)rs * kSegChunks + c]; sl += v.x; sm += v.y; }
+                        uint4 r = make_uint4(0, 0, 0, 0), rp = make_uint4(0, 0, 0, 0);
+                        if (i < j) r = seg_record(fixl, specl, o.n_fix, i);
+                        if (lane == 0 && i != 0 && i < j) rp = seg_record(fixl, specl, o.n_fix, i - 1);
+                        uint32_t pe = __shfl_up_sync(0xFFFFFFFFu, r.x + r.y, 1);
+                        if (lane == 0) pe = rp.x + rp.y;
+                        if (i < j && i != 0) sl += r.x - pe;
+                        if (i < j) sm += r.y;
+                        pj.x = __reduce_add_sync(0xFFFFFFFFu, sl); pj.y = __reduce_add_sync(0xFFFFFFFFu, sm);
+                        lit_a = first_lit + pj.x;
+                    }
                     const uint32_t lit_b = first_lit + sum_lit - lit_a;
                     if (lits + lit_a <= kLiteralsPerBlock && lit_b <= kLiteralsPerBlock && n - j <= kLmdsPerBlock) {
                         if (lane == 0) entry[rs] = SegEntry{fs.n_packs_total, fs.match_distance, j, first_lit};
