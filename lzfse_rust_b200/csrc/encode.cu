@@ -1681,7 +1681,7 @@ struct lzfse_b200_encoder {
     std::string last_error;
     uint64_t launches = 0;
     DevBuf streams, counts, totals_dev, tables, packs, lits, block_ids, blocks, out, counters, words;
-    DevBuf long_list, seg_list, l_prev, l_info, l_heads, l_cseg, l_rseg, l_out, l_spec, l_fix, l_states, l_tail, l_agg, l_csum, l_entry;  // long streams (encode_long.cuh)
+    DevBuf long_list, seg_list, l_prev, l_heads, l_cseg, l_rseg, l_out, l_spec, l_fix, l_states, l_tail, l_agg, l_csum, l_entry;  // long streams (encode_long.cuh)
     int allow_long = 1;  // LZB_ENC_LONG=0 sends streams > 64 KiB through k_enc_parse (measurements, tests)
     int allow_seg = 1;   // LZB_ENC_SEG=0: streams <= 64 KiB are replayed whole by k_enc_replay (one thread per stream) instead of per segment
     uint32_t last_long_redo = 0;
@@ -1747,7 +1747,6 @@ int encode_batch_device_impl(lzfse_b200_encoder *e, const uint8_t *src, const ui
     if (n_fast || n_long) LZB_CK(e, e->words.reserve((tot.n_fse + 256) * sizeof(uint32_t)));  // one word per position (k_enc_find -> k_enc_replay)
     if (n_long) {
         LZB_CK(e, e->l_prev.reserve((long_elems + 64) * sizeof(uint2)));   // {chain link, four bytes} per position
-        LZB_CK(e, e->l_info.reserve((long_elems + 64) * sizeof(uint16_t)));
         LZB_CK(e, e->l_heads.reserve((size_t)n_cseg * (1u << kHashBits) * sizeof(uint32_t)));
         LZB_CK(e, e->l_cseg.reserve((size_t)n_cseg * sizeof(LongSeg)));
     }
@@ -1804,18 +1803,17 @@ int encode_batch_device_impl(lzfse_b200_encoder *e, const uint8_t *src, const ui
         if (n_segl) { k_long_segs<<<n_segl, 64, 0, s>>>(sl, n_segl, st, cseg, rseg); e->launches += 1; }
         LZB_DBG("k_long_segs");
         if (n_long) {
-            k_long_info<<<n_cseg * (kCSeg / 256), 256, 0, s>>>(src, src_off, src_len, st, cseg, e->l_prev.as<uint2>(), e->l_info.as<uint16_t>());
             const unsigned cg = (unsigned)e->n_sms * kChainPerSm;
-            k_long_chain<<<n_cseg < cg ? n_cseg : cg, 32, kChainSmem, s>>>(src_len, st, cseg, n_cseg, e->l_info.as<uint16_t>(), e->l_prev.as<uint2>(),
+            k_long_chain<<<n_cseg < cg ? n_cseg : cg, 32, kChainSmem, s>>>(src, src_off, src_len, st, cseg, n_cseg, e->l_prev.as<uint2>(),
                                                                              e->l_heads.as<uint32_t>(), ctr + 12);
             k_long_carry<<<n_long * ((1u << kHashBits) / 256), 256, 0, s>>>(ll, n_long, st, e->l_heads.as<uint32_t>());
+            k_long_link<<<n_cseg * (kCSeg / 256), 256, 0, s>>>(src_len, st, cseg, e->l_prev.as<uint2>(), e->l_heads.as<uint32_t>());
             e->launches += 3;
         }
-        LZB_DBG("k_long_info / chain / carry");
+        LZB_DBG("k_long_chain / carry / link");
         e->timer.mark(s);  // long_chain
         if (n_long) {
-            k_long_find<<<n_cseg * (kCSeg / kLFindThreads), kLFindThreads, 0, s>>>(src, src_off, src_len, st, bs, cseg, e->l_prev.as<uint2>(),
-                                                                                      e->l_heads.as<uint32_t>(), words);
+            k_long_find<<<n_cseg * (kCSeg / kLFindThreads), kLFindThreads, 0, s>>>(src, src_off, src_len, st, bs, cseg, e->l_prev.as<uint2>(), words);
             e->launches += 1;
         }
         LZB_DBG("k_long_find");
@@ -1916,7 +1914,7 @@ void lzfse_b200_encoder_destroy(lzfse_b200_encoder *e) {
     if (!e) return;
     DeviceGuard g(e->device);
     for (DevBuf *b : {&e->streams, &e->counts, &e->totals_dev, &e->tables, &e->packs, &e->lits, &e->block_ids, &e->blocks, &e->out, &e->counters, &e->words,
-                      &e->long_list, &e->seg_list, &e->l_prev, &e->l_info, &e->l_heads, &e->l_cseg, &e->l_rseg, &e->l_out, &e->l_spec, &e->l_fix, &e->l_states, &e->l_tail, &e->l_agg, &e->l_csum, &e->l_entry}) b->release();
+                      &e->long_list, &e->seg_list, &e->l_prev, &e->l_heads, &e->l_cseg, &e->l_rseg, &e->l_out, &e->l_spec, &e->l_fix, &e->l_states, &e->l_tail, &e->l_agg, &e->l_csum, &e->l_entry}) b->release();
     e->totals_host.release();
     e->stage.release();
     e->timer.release();

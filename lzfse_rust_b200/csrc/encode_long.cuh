@@ -9,7 +9,7 @@
 //     that chain can be built for all 32 Ki-position pieces of a stream at once: k_long_chain links the positions
 //     inside a piece (bucket heads in shared memory) and leaves the newest position per bucket, k_long_carry turns
 //     those into "newest position before this piece" per bucket (a running maximum over the pieces, one thread per
-//     bucket), and a hop that leaves its piece continues in that table.  k_long_find then evaluates find_match
+//     bucket), and k_long_link lets every link that would leave its piece continue there.  k_long_find then evaluates find_match
 //     (frontend_bytes.rs:214-244) for EVERY position, one thread each, and writes the same per-position word
 //     k_enc_find writes.
 //  2. The sequential part (backward limit, Match::select, frontend_bytes.rs:160-211,261-302) started from a clean
@@ -58,37 +58,23 @@ __global__ void k_long_segs(const uint32_t *__restrict__ long_list, uint32_t n_l
 }
 
 // ---- chain inside a piece ----------------------------------------------------------------------
-// k_long_info, one thread per position: the position's four bytes (kept next to its chain link, so that a candidate is
-// accepted or rejected by the same load that yields the next hop) and the info word of k_enc_find -- bucket index, and
-// which lanes of a 32-position step share a bucket.
-// k_long_chain, one WARP per piece, six of them per SM: the ordered pass over the bucket heads (16-bit, shared memory).
+// One WARP per piece, six of them per SM, bucket heads (16-bit) in shared memory, 32 positions per step in order.  Two
+// positions of a step share a bucket in ~3 % of the steps; instead of finding the peers of every step (match.any costs
+// ~350 cycles when all 32 values differ, which made a separate info kernel 1.2 ms per 128 MiB) every lane stores its
+// position into its bucket head and reads it back: if all 32 read their own position there were no peers and the heads are
+// right; otherwise this step is redone with match.any (newest lane owns the head, lanes with a lower peer link to it).
+// Writes {link, the four bytes at the position} per position: find_match accepts or rejects a candidate with the same load
+// that yields the next hop.
 constexpr uint32_t kCSegShift = 15;
 static_assert(kCSeg == 1u << kCSegShift, "chain piece size");
 constexpr uint32_t kChainSmem = (1u << kHashBits) * 2;
 constexpr uint32_t kChainPerSm = 6;
-__global__ void __launch_bounds__(256)
-k_long_info(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ src_off, const uint64_t *__restrict__ src_len,
-            const EncStream *__restrict__ streams, const LongSeg *__restrict__ cseg, uint2 *__restrict__ pairs, uint16_t *__restrict__ info) {
-    const uint32_t lane = threadIdx.x & 31;
-    const LongSeg sg = cseg[blockIdx.x / (kCSeg / 256)];
-    const EncStream st = streams[sg.stream];
-    const uint8_t *src = src_base + src_off[sg.stream];
-    const uint32_t end = (uint32_t)src_len[sg.stream] - 3;
-    const uint32_t p = sg.k * kCSeg + (blockIdx.x % (kCSeg / 256)) * 256 + threadIdx.x;
-    if (p - lane >= end) return;
-    const bool act = p < end;
-    const uint32_t val = ld4u(src + (act ? p : end - 1)), h = hash_u(val, false);
-    const uint32_t m = __match_any_sync(0xFFFFFFFFu, act ? h : 0xFFFF0000u + lane);
-    const uint32_t lower = m & lanemask_lt();
-    const uint32_t newest = (m >> lane) == 1u ? 0x4000u : 0u;
-    const uint32_t iw = lower ? (0x8000u | newest | ((uint32_t)(__ffs(m) - 1) << 5) | (31 - __clz(lower))) : (newest | h);
-    if (act) { info[st.long_off + p] = (uint16_t)iw; pairs[st.long_off + p].y = val; }
-}
 __global__ void __launch_bounds__(32)
-k_long_chain(const uint64_t *__restrict__ src_len, const EncStream *__restrict__ streams, const LongSeg *__restrict__ cseg, uint32_t n_cseg,
-             const uint16_t *__restrict__ info, uint2 *__restrict__ pairs, uint32_t *__restrict__ seg_head, uint32_t *work_counter) {
+k_long_chain(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ src_off, const uint64_t *__restrict__ src_len,
+             const EncStream *__restrict__ streams, const LongSeg *__restrict__ cseg, uint32_t n_cseg, uint2 *__restrict__ pairs,
+             uint32_t *__restrict__ seg_head, uint32_t *work_counter) {
     extern __shared__ __align__(16) uint8_t csm[];
-    uint16_t *head = reinterpret_cast<uint16_t *>(csm);
+    volatile uint16_t *head = reinterpret_cast<volatile uint16_t *>(csm);
     const uint32_t lane = threadIdx.x;
     for (;;) {
         uint32_t cs = 0;
@@ -99,40 +85,43 @@ k_long_chain(const uint64_t *__restrict__ src_len, const EncStream *__restrict__
         const EncStream st = streams[sg.stream];
         const uint32_t end = (uint32_t)src_len[sg.stream] - 3;
         const uint32_t B = sg.k * kCSeg, n_pos = end - B < kCSeg ? end - B : kCSeg;
-        const uint16_t *inf = info + st.long_off + B;
+        const uint8_t *src = src_base + src_off[sg.stream] + B;
+        asm volatile("" : "+l"(src));
         uint2 *pv = pairs + st.long_off + B;
         for (uint32_t t = lane; t < (1u << kHashBits) * 2 / 16; t += 32) reinterpret_cast<uint4 *>(csm)[t] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
         __syncwarp();
-        // Only the bucket heads carry a dependency from one step to the next, and program order satisfies it (a step's
-        // head stores are issued before the next step's head loads); nothing consumes the loaded values before the global
-        // stores.  So eight steps issue their loads and stores back to back, with the next eight info words on their way.
-        constexpr uint32_t kSteps = 8;
+        constexpr uint32_t kSteps = 8;  // the bytes of the next eight steps are on their way while eight are worked on
         uint32_t nxt[kSteps];
 #pragma unroll
-        for (uint32_t k = 0; k < kSteps; k++) { const uint32_t p = k * 32 + lane; nxt[k] = p < n_pos ? inf[p] : 0u; }
+        for (uint32_t k = 0; k < kSteps; k++) { const uint32_t p = k * 32 + lane; nxt[k] = ld4u(src + (p < n_pos ? p : n_pos - 1)); }
         for (uint32_t u0 = 0; u0 < n_pos; u0 += 32 * kSteps) {
-            uint32_t iw[kSteps], h[kSteps], old[kSteps];
-#pragma unroll
-            for (uint32_t k = 0; k < kSteps; k++) { iw[k] = nxt[k]; const uint32_t p = u0 + (kSteps + k) * 32 + lane; nxt[k] = p < n_pos ? inf[p] : 0u; }
+            uint32_t val[kSteps];
 #pragma unroll
             for (uint32_t k = 0; k < kSteps; k++) {
-                const uint32_t hb = __shfl_sync(0xFFFFFFFFu, iw[k], (iw[k] >> 5) & 31u);  // the bucket index lives in the group's lowest lane
-                h[k] = ((iw[k] & 0x8000u) ? hb : iw[k]) & 0x3FFFu;
-            }
-#pragma unroll
-            for (uint32_t k = 0; k < kSteps; k++) {
-                const uint32_t p = u0 + k * 32 + lane;
-                const bool act = p < n_pos;
-                old[k] = 0xFFFFu;
-                if (act) old[k] = *reinterpret_cast<volatile uint16_t *>(&head[h[k]]);
-                __syncwarp();
-                if (act && (iw[k] & 0x4000u)) *reinterpret_cast<volatile uint16_t *>(&head[h[k]]) = (uint16_t)p;  // newest position of its bucket in this step
-                __syncwarp();
+                val[k] = nxt[k];
+                const uint32_t p = u0 + (kSteps + k) * 32 + lane;
+                nxt[k] = ld4u(src + (p < n_pos ? p : n_pos - 1));
             }
 #pragma unroll
             for (uint32_t k = 0; k < kSteps; k++) {
                 const uint32_t b0 = u0 + k * 32, p = b0 + lane;
-                if (p < n_pos) pv[p].x = (iw[k] & 0x8000u) ? B + b0 + (iw[k] & 31u) : (old[k] == 0xFFFFu ? kNoPos : B + old[k]);
+                if (b0 >= n_pos) break;
+                const bool act = p < n_pos;
+                const uint32_t h = hash_u(val[k], false);
+                uint32_t link = 0xFFFFu;
+                if (act) link = head[h];
+                __syncwarp();
+                if (act) head[h] = (uint16_t)p;
+                __syncwarp();
+                const bool lost = act && head[h] != p;
+                if (__any_sync(0xFFFFFFFFu, lost)) {  // peers in this step: HistoryTable::push in order
+                    const uint32_t m = __match_any_sync(0xFFFFFFFFu, act ? h : 0xFFFF0000u + lane);
+                    const uint32_t lower = m & lanemask_lt();
+                    if (act && (m >> lane) == 1u) head[h] = (uint16_t)p;  // the newest position of the bucket
+                    if (lower) link = b0 + (31 - __clz(lower));
+                    __syncwarp();
+                }
+                if (act) pv[p] = make_uint2(link == 0xFFFFu ? kNoPos : B + link, val[k]);
             }
         }
         __syncwarp();
@@ -162,6 +151,24 @@ __global__ void k_long_carry(const uint32_t *__restrict__ long_list, uint32_t n_
     }
 }
 
+// A link that leaves its piece continues with the newest position of the bucket before the piece: written into the link
+// itself, so that a hop of find_match is ONE load wherever it leads.
+__global__ void __launch_bounds__(256)
+k_long_link(const uint64_t *__restrict__ src_len, const EncStream *__restrict__ streams, const LongSeg *__restrict__ cseg, uint2 *__restrict__ pairs,
+            const uint32_t *__restrict__ seg_head) {
+    const LongSeg sg = cseg[blockIdx.x / (kCSeg / 256)];
+    if (sg.k == 0) return;  // nothing before the first piece
+    const EncStream st = streams[sg.stream];
+    const uint32_t end = (uint32_t)src_len[sg.stream] - 3;
+    const uint32_t p = sg.k * kCSeg + (blockIdx.x % (kCSeg / 256)) * 256 + threadIdx.x;
+    if (p >= end) return;
+    uint2 *pv = pairs + st.long_off;
+    const uint2 e = pv[p];
+    if (e.x != kNoPos) return;
+    const uint32_t c = seg_head[((size_t)st.cseg_base + sg.k) * (1u << kHashBits) + hash_u(e.y, false)];
+    if (c != kNoPos) pv[p].x = c;
+}
+
 // ---- find_match for every position ---------------------------------------------------------------
 // Forward length of src[a..] against src[b..], whole warp, 8 bytes per lane and step, from `l` up to `lim`.
 __device__ __forceinline__ uint32_t gwarp_match_inc(const uint8_t *src, uint32_t a, uint32_t b, uint32_t l, uint32_t lim, uint32_t lane) {
@@ -185,7 +192,7 @@ constexpr int kLFindThreads = 256;
 __global__ void __launch_bounds__(kLFindThreads)
 k_long_find(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ src_off, const uint64_t *__restrict__ src_len,
             const EncStream *__restrict__ streams, const StreamCounts *__restrict__ bases, const LongSeg *__restrict__ cseg,
-            const uint2 *__restrict__ pairs, const uint32_t *__restrict__ seg_head, uint32_t *__restrict__ words) {
+            const uint2 *__restrict__ pairs, uint32_t *__restrict__ words) {
     const uint32_t lane = threadIdx.x & 31;
     const LongSeg sg = cseg[blockIdx.x / (kCSeg / kLFindThreads)];
     const EncStream st = streams[sg.stream];
@@ -196,22 +203,19 @@ k_long_find(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ s
     if (p - lane >= end) return;  // whole warp beyond the last position
     const bool act = p < end;
     const uint2 *pv = pairs + st.long_off;  // {newest earlier position of the bucket inside the piece, the four bytes at this position}
-    const uint32_t *sh = seg_head + (size_t)st.cseg_base * (1u << kHashBits);
     uint32_t best_len = 0, best_c = 0, n_sat = 0;
     uint32_t cs[4] = {0, 0, 0, 0}, ls[4] = {0, 0, 0, 0};
     const uint32_t maxl = act ? len - p : 0;
     if (act) {
         const uint2 me = pv[p];
-        const uint32_t val = me.y, h = hash_u(val, false);
+        const uint32_t val = me.y;
         const uint32_t lim = maxl < kLongLaneCap ? maxl : kLongLaneCap;
         uint32_t c = me.x;
-        if (c == kNoPos) c = sh[(size_t)(p >> kCSegShift) * (1u << kHashBits) + h];
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             if (c == kNoPos || p - c > kMaxDValue) break;  // newest first, up to the first one out of range (frontend_bytes.rs:214-244)
             const uint2 ce = pv[c];
-            uint32_t cn = ce.x;
-            if (cn == kNoPos) cn = sh[(size_t)(c >> kCSegShift) * (1u << kHashBits) + h];
+            const uint32_t cn = ce.x;
             if (ce.y == val) {
                 uint32_t l = 4;
                 while (l + 8 <= lim) {
@@ -278,9 +282,17 @@ k_long_find(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ s
             for (int k = 0; k < 4; k++) if ((uint32_t)k < n_sat && ls[k] > bl) { bl = ls[k]; best_c = cs[k]; }
             best_len = bl;
         }
+        // backward length (match_kit/match_fast.rs:61-89) up to what the word can hold: the 16 bytes before the two positions
         uint32_t bw = 0;
         const uint32_t blim = best_c < kWordBwSat ? best_c : kWordBwSat;
-        while (bw < blim && src[p - bw - 1] == src[best_c - bw - 1]) bw++;
+        if (best_c >= 16) {
+            const uint64_t y1 = ld8u(src + p - 8) ^ ld8u(src + best_c - 8);
+            if (y1) bw = (uint32_t)__clzll((long long)y1) >> 3;
+            else { const uint64_t y2 = ld8u(src + p - 16) ^ ld8u(src + best_c - 16); bw = 8 + (y2 ? (uint32_t)__clzll((long long)y2) >> 3 : 8u); }
+            bw = bw < blim ? bw : blim;
+        } else {
+            while (bw < blim && src[p - bw - 1] == src[best_c - bw - 1]) bw++;
+        }
         word = (p - best_c) | ((best_len < kWordLenSat ? best_len : kWordLenSat) << 18) | (bw << 28);
     }
     {   // positions without a candidate carry the distance to the next position of their 32-group that has one

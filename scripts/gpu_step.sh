@@ -1,7 +1,3 @@
 mkdir -p gpurun_out
-for v in lzfse_rust_b200/liblzfse_b200.so gpurun_tmp_r8192.so gpurun_tmp_r4096.so; do
-echo "== $v"
-LZB_SO=$PWD/$v timeout 300 python scripts/try_long.py > gpurun_out/try_long.log 2>&1; grep -v "^ok " gpurun_out/try_long.log | tail -5 | cut -c1-400
-LZB_SO=$PWD/$v timeout 300 python scripts/prof_encode.py --chunks 16384 --iters 3 2>&1 | tail -1 | cut -c1-600
-done
-timeout 900 python -m pytest tests/test_gpu_encode.py tests/test_gpu_configs.py -x -q 2>&1 | tail -5
+timeout 600 ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum,sm__warps_active.avg.pct_of_peak_sustained_active,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:'k_long_|k_enc_' --csv --log-file gpurun_out/long_launches.csv python scripts/prof_large.py --iters 1 > gpurun_out/ncu_ll.log 2>&1
+tail -2 gpurun_out/ncu_ll.log
