@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.environ.get("LZB_SO") or os.path.join(HERE, "liblzfse_b200.so")
 SOURCES = ["decode.cu", "expand.cu", "expand_long.cu", "encode.cu", "api.cu"]
-HEADERS = ["common.cuh", "lz_blocks.cuh", "host_util.h", os.path.join("..", "..", "include", "lzfse_b200.h")]
+HEADERS = ["common.cuh", "lz_blocks.cuh", "encode_long.cuh", "host_util.h", os.path.join("..", "..", "include", "lzfse_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-O2,-Wall", "-Xptxas", "-v", "--use_fast_math",

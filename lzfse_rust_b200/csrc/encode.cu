@@ -1803,14 +1803,14 @@ int encode_batch_device_impl(lzfse_b200_encoder *e, const uint8_t *src, const ui
         if (n_segl) { k_long_segs<<<n_segl, 64, 0, s>>>(sl, n_segl, st, cseg, rseg); e->launches += 1; }
         LZB_DBG("k_long_segs");
         if (n_long) {
+            k_long_heads<<<n_cseg, 512, kHeadsSmem, s>>>(src, src_off, src_len, st, cseg, e->l_heads.as<uint32_t>());
+            k_long_carry<<<n_long * ((1u << kHashBits) / 256), 256, 0, s>>>(ll, n_long, st, e->l_heads.as<uint32_t>());
             const unsigned cg = (unsigned)e->n_sms * kChainPerSm;
             k_long_chain<<<n_cseg < cg ? n_cseg : cg, 32, kChainSmem, s>>>(src, src_off, src_len, st, cseg, n_cseg, e->l_prev.as<uint2>(),
                                                                              e->l_heads.as<uint32_t>(), ctr + 12);
-            k_long_carry<<<n_long * ((1u << kHashBits) / 256), 256, 0, s>>>(ll, n_long, st, e->l_heads.as<uint32_t>());
-            k_long_link<<<n_cseg * (kCSeg / 256), 256, 0, s>>>(src_len, st, cseg, e->l_prev.as<uint2>(), e->l_heads.as<uint32_t>());
             e->launches += 3;
         }
-        LZB_DBG("k_long_chain / carry / link");
+        LZB_DBG("k_long_heads / carry / chain");
         e->timer.mark(s);  // long_chain
         if (n_long) {
             k_long_find<<<n_cseg * (kCSeg / kLFindThreads), kLFindThreads, 0, s>>>(src, src_off, src_len, st, bs, cseg, e->l_prev.as<uint2>(), words);
@@ -1900,7 +1900,8 @@ int lzfse_b200_encoder_create(int device, lzfse_b200_encoder **out) {
     cudaFuncAttributes fa;
     if (cudaFuncGetAttributes(&fa, k_enc_fse_blocks) != cudaSuccess ||
         cudaFuncSetAttribute(k_enc_find, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFindSmemBytes) != cudaSuccess ||
-        cudaFuncSetAttribute(k_long_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmem) != cudaSuccess) {
+        cudaFuncSetAttribute(k_long_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmem) != cudaSuccess ||
+        cudaFuncSetAttribute(k_long_heads, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHeadsSmem) != cudaSuccess) {
         cudaGetLastError();  // no sm_100a image for this device: there is no fallback path
         cudaStreamDestroy(e->own_stream);
         delete e;

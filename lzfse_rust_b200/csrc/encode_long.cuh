@@ -9,7 +9,7 @@
 //     that chain can be built for all 32 Ki-position pieces of a stream at once: k_long_chain links the positions
 //     inside a piece (bucket heads in shared memory) and leaves the newest position per bucket, k_long_carry turns
 //     those into "newest position before this piece" per bucket (a running maximum over the pieces, one thread per
-//     bucket), and k_long_link lets every link that would leave its piece continue there.  k_long_find then evaluates find_match
+//     bucket; computed first, from an order-free maximum per piece), and a link that would leave its piece continues there.  k_long_find then evaluates find_match
 //     (frontend_bytes.rs:214-244) for EVERY position, one thread each, and writes the same per-position word
 //     k_enc_find writes.
 //  2. The sequential part (backward limit, Match::select, frontend_bytes.rs:160-211,261-302) started from a clean
@@ -18,7 +18,7 @@
 //     match with the state it leaves behind; k_long_stitch walks a stream's segments in order with the TRUE state,
 //     replays from it until that state equals a recorded one (or takes the segment whole when the true state at
 //     its border is equivalent to a clean start), and from there on the speculative output IS the true output.
-//     tests/model/long_parse_model.c is this algorithm on the CPU, checked against the oracle's front end.
+//     tests/model/long_parse_model.c is this algorithm on the CPU, checked against the reference port's sequential front end.
 //
 //  k_long_seg_stats / k_long_blocks / k_long_write_packs finally turn a stream's match list into packs and block records
 //  (Buffer::push with its L / M splits and block closing, fse/buffer.rs:45-117); see there.
@@ -69,10 +69,30 @@ constexpr uint32_t kCSegShift = 15;
 static_assert(kCSeg == 1u << kCSegShift, "chain piece size");
 constexpr uint32_t kChainSmem = (1u << kHashBits) * 2;
 constexpr uint32_t kChainPerSm = 6;
+constexpr uint32_t kHeadsSmem = (1u << kHashBits) * 4;
+// Newest position per bucket and piece, order-free (a maximum): lets k_long_carry run BEFORE the chain, so that the chain
+// can write finished links (a link that leaves its piece continues with the newest position of the bucket before the piece).
+__global__ void __launch_bounds__(512)
+k_long_heads(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ src_off, const uint64_t *__restrict__ src_len,
+             const EncStream *__restrict__ streams, const LongSeg *__restrict__ cseg, uint32_t *__restrict__ seg_head) {
+    extern __shared__ __align__(16) uint8_t csm[];
+    uint32_t *hd = reinterpret_cast<uint32_t *>(csm);
+    const LongSeg sg = cseg[blockIdx.x];
+    const EncStream st = streams[sg.stream];
+    const uint32_t end = (uint32_t)src_len[sg.stream] - 3;
+    const uint32_t B = sg.k * kCSeg, n_pos = end - B < kCSeg ? end - B : kCSeg;
+    const uint8_t *src = src_base + src_off[sg.stream] + B;
+    for (uint32_t t = threadIdx.x; t < (1u << kHashBits); t += 512) hd[t] = 0;
+    __syncthreads();
+    for (uint32_t t = threadIdx.x; t < n_pos; t += 512) atomicMax(&hd[hash_u(ld4u(src + t), false)], t + 1);
+    __syncthreads();
+    uint32_t *sh = seg_head + ((size_t)st.cseg_base + sg.k) * (1u << kHashBits);
+    for (uint32_t t = threadIdx.x; t < (1u << kHashBits); t += 512) sh[t] = hd[t] ? B + hd[t] - 1 : kNoPos;
+}
 __global__ void __launch_bounds__(32)
 k_long_chain(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ src_off, const uint64_t *__restrict__ src_len,
              const EncStream *__restrict__ streams, const LongSeg *__restrict__ cseg, uint32_t n_cseg, uint2 *__restrict__ pairs,
-             uint32_t *__restrict__ seg_head, uint32_t *work_counter) {
+             const uint32_t *__restrict__ seg_head, uint32_t *work_counter) {
     extern __shared__ __align__(16) uint8_t csm[];
     volatile uint16_t *head = reinterpret_cast<volatile uint16_t *>(csm);
     const uint32_t lane = threadIdx.x;
@@ -88,14 +108,17 @@ k_long_chain(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ 
         const uint8_t *src = src_base + src_off[sg.stream] + B;
         asm volatile("" : "+l"(src));
         uint2 *pv = pairs + st.long_off + B;
+        const uint32_t *before = seg_head + ((size_t)st.cseg_base + sg.k) * (1u << kHashBits);  // (after k_long_carry) newest position before the piece
         for (uint32_t t = lane; t < (1u << kHashBits) * 2 / 16; t += 32) reinterpret_cast<uint4 *>(csm)[t] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
         __syncwarp();
-        constexpr uint32_t kSteps = 8;  // the bytes of the next eight steps are on their way while eight are worked on
-        uint32_t nxt[kSteps];
+        // The bytes of the next eight steps are on their way while eight are worked on, and the links of eight steps are
+        // stored while the next eight are worked on (a link that leaves the piece is a load from `before`).
+        constexpr uint32_t kSteps = 8;
+        uint32_t nxt[kSteps], dval[kSteps], dlink[kSteps];
 #pragma unroll
-        for (uint32_t k = 0; k < kSteps; k++) { const uint32_t p = k * 32 + lane; nxt[k] = ld4u(src + (p < n_pos ? p : n_pos - 1)); }
-        for (uint32_t u0 = 0; u0 < n_pos; u0 += 32 * kSteps) {
-            uint32_t val[kSteps];
+        for (uint32_t k = 0; k < kSteps; k++) { const uint32_t p = k * 32 + lane; nxt[k] = ld4u(src + (p < n_pos ? p : n_pos - 1)); dval[k] = 0; dlink[k] = 0; }
+        for (uint32_t u0 = 0; u0 < n_pos + 32 * kSteps; u0 += 32 * kSteps) {
+            uint32_t val[kSteps], link[kSteps];
 #pragma unroll
             for (uint32_t k = 0; k < kSteps; k++) {
                 val[k] = nxt[k];
@@ -105,11 +128,12 @@ k_long_chain(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ 
 #pragma unroll
             for (uint32_t k = 0; k < kSteps; k++) {
                 const uint32_t b0 = u0 + k * 32, p = b0 + lane;
-                if (b0 >= n_pos) break;
+                link[k] = kNoPos;
+                if (b0 >= n_pos) continue;
                 const bool act = p < n_pos;
                 const uint32_t h = hash_u(val[k], false);
-                uint32_t link = 0xFFFFu;
-                if (act) link = head[h];
+                uint32_t l16 = 0xFFFFu;
+                if (act) l16 = head[h];
                 __syncwarp();
                 if (act) head[h] = (uint16_t)p;
                 __syncwarp();
@@ -118,19 +142,21 @@ k_long_chain(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ 
                     const uint32_t m = __match_any_sync(0xFFFFFFFFu, act ? h : 0xFFFF0000u + lane);
                     const uint32_t lower = m & lanemask_lt();
                     if (act && (m >> lane) == 1u) head[h] = (uint16_t)p;  // the newest position of the bucket
-                    if (lower) link = b0 + (31 - __clz(lower));
+                    if (lower) l16 = b0 + (31 - __clz(lower));
                     __syncwarp();
                 }
-                if (act) pv[p] = make_uint2(link == 0xFFFFu ? kNoPos : B + link, val[k]);
+                if (act) link[k] = l16 != 0xFFFFu ? B + l16 : before[h];
             }
-        }
-        __syncwarp();
-        uint32_t *sh = seg_head + ((size_t)st.cseg_base + sg.k) * (1u << kHashBits);
-        for (uint32_t t = lane * 4; t < (1u << kHashBits); t += 128) {
-            uint4 v;
-            v.x = head[t] == 0xFFFFu ? kNoPos : B + head[t]; v.y = head[t + 1] == 0xFFFFu ? kNoPos : B + head[t + 1];
-            v.z = head[t + 2] == 0xFFFFu ? kNoPos : B + head[t + 2]; v.w = head[t + 3] == 0xFFFFu ? kNoPos : B + head[t + 3];
-            *reinterpret_cast<uint4 *>(sh + t) = v;
+            // the previous eight steps' pairs
+            if (u0 != 0) {
+#pragma unroll
+                for (uint32_t k = 0; k < kSteps; k++) {
+                    const uint32_t p = u0 - 32 * kSteps + k * 32 + lane;
+                    if (p < n_pos) pv[p] = make_uint2(dlink[k], dval[k]);
+                }
+            }
+#pragma unroll
+            for (uint32_t k = 0; k < kSteps; k++) { dval[k] = val[k]; dlink[k] = link[k]; }
         }
         __syncwarp();
     }
@@ -149,24 +175,6 @@ __global__ void k_long_carry(const uint32_t *__restrict__ long_list, uint32_t n_
         *q = run;
         if (t != kNoPos) run = t;
     }
-}
-
-// A link that leaves its piece continues with the newest position of the bucket before the piece: written into the link
-// itself, so that a hop of find_match is ONE load wherever it leads.
-__global__ void __launch_bounds__(256)
-k_long_link(const uint64_t *__restrict__ src_len, const EncStream *__restrict__ streams, const LongSeg *__restrict__ cseg, uint2 *__restrict__ pairs,
-            const uint32_t *__restrict__ seg_head) {
-    const LongSeg sg = cseg[blockIdx.x / (kCSeg / 256)];
-    if (sg.k == 0) return;  // nothing before the first piece
-    const EncStream st = streams[sg.stream];
-    const uint32_t end = (uint32_t)src_len[sg.stream] - 3;
-    const uint32_t p = sg.k * kCSeg + (blockIdx.x % (kCSeg / 256)) * 256 + threadIdx.x;
-    if (p >= end) return;
-    uint2 *pv = pairs + st.long_off;
-    const uint2 e = pv[p];
-    if (e.x != kNoPos) return;
-    const uint32_t c = seg_head[((size_t)st.cseg_base + sg.k) * (1u << kHashBits) + hash_u(e.y, false)];
-    if (c != kNoPos) pv[p].x = c;
 }
 
 // ---- find_match for every position ---------------------------------------------------------------
@@ -189,7 +197,10 @@ __device__ __forceinline__ uint32_t gwarp_match_inc(const uint8_t *src, uint32_t
 }
 
 constexpr int kLFindThreads = 256;
-__global__ void __launch_bounds__(kLFindThreads)
+#ifndef LZB_LFIND_MINB
+#define LZB_LFIND_MINB 8   // resident CTAs per SM: 5 / 6 / 8 (47 / 40 / 32 registers) measured 4.03 / 3.76 / 3.64 ms
+#endif
+__global__ void __launch_bounds__(kLFindThreads, LZB_LFIND_MINB)
 k_long_find(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ src_off, const uint64_t *__restrict__ src_len,
             const EncStream *__restrict__ streams, const StreamCounts *__restrict__ bases, const LongSeg *__restrict__ cseg,
             const uint2 *__restrict__ pairs, uint32_t *__restrict__ words) {
@@ -211,6 +222,7 @@ k_long_find(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ s
         const uint32_t val = me.y;
         const uint32_t lim = maxl < kLongLaneCap ? maxl : kLongLaneCap;
         uint32_t c = me.x;
+        const uint64_t p8 = maxl >= 12 ? ld8u(src + p + 4) : 0ull;  // bytes 4..11 of this position, shared by its candidates
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             if (c == kNoPos || p - c > kMaxDValue) break;  // newest first, up to the first one out of range (frontend_bytes.rs:214-244)
@@ -218,6 +230,11 @@ k_long_find(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ s
             const uint32_t cn = ce.x;
             if (ce.y == val) {
                 uint32_t l = 4;
+                if (maxl >= 12) {  // most matches end inside the next eight bytes: one load of the candidate decides
+                    const uint64_t y0 = p8 ^ ld8u(src + c + 4);
+                    if (y0) { l = 4 + ((__ffsll((long long)y0) - 1) >> 3); goto ext_done; }
+                    l = 12;
+                }
                 while (l + 8 <= lim) {
                     const uint64_t y = ld8u(src + p + l) ^ ld8u(src + c + l);
                     if (y) { l += (__ffsll((long long)y) - 1) >> 3; goto ext_done; }
@@ -583,7 +600,9 @@ struct SegAgg {
     uint32_t sum_lit;    // literal bytes of matches 1..n-1 (the first one's depend on where the previous segment ended)
     uint32_t sum_m;      // match bytes
     uint32_t simple;     // every L (but the first) <= 315 and every M <= 2359
-    uint32_t first_idx, last_end, last_dist, pad;
+    uint32_t first_idx, last_end, last_dist;
+    uint32_t n_fix, from;  // copied from the segment's LongSegOut: the block walk forms record addresses without another load
+    uint32_t pad;
 };
 struct SegEntry { uint32_t pack_base, d_prev, split, first_lit; };  // split: first match of the segment that opens a new block (n: none; kNoPos: packs already written)
 
@@ -616,7 +635,7 @@ k_long_seg_stats(const uint4 *__restrict__ spec, const uint4 *__restrict__ fix, 
         last_end = carry_end; last_dist = __shfl_sync(0xFFFFFFFFu, r.z, nn - 1);
     }
     simple = __all_sync(0xFFFFFFFFu, simple != 0);
-    if (lane == 0) agg[rs] = SegAgg{n, run_lit, run_m, simple, first_idx, last_end, last_dist, 0};
+    if (lane == 0) agg[rs] = SegAgg{n, run_lit, run_m, simple, first_idx, last_end, last_dist, o.n_fix, o.from, 0};
 }
 
 __global__ void __launch_bounds__(128)
@@ -673,7 +692,7 @@ k_long_blocks(const uint64_t *__restrict__ src_off, const uint64_t *__restrict__
         }
     };
     for (uint32_t k0 = 0; k0 < st.n_rseg; k0 += 32) {
-        SegAgg mine = SegAgg{0, 0, 0, 1, 0, 0, 0, 0};
+        SegAgg mine = SegAgg{0, 0, 0, 1, 0, 0, 0, 0, 0, 0};
         if (k0 + lane < st.n_rseg) mine = agg[st.rseg_base + k0 + lane];
         const uint32_t kn = st.n_rseg - k0 < 32 ? st.n_rseg - k0 : 32;
         for (uint32_t t = 0; t < kn; t++) {
@@ -704,15 +723,15 @@ k_long_blocks(const uint64_t *__restrict__ src_off, const uint64_t *__restrict__
                     uint2 pj = make_uint2(0, 0);  // literal bytes (without the first match's) and match bytes of matches [0, j)
                     uint32_t lit_a = 0;           // literal bytes of matches [0, j)
                     if (j != 0) {
-                        const LongSegOut o = seg_out[rs];
-                        const uint4 *fixl = fix + (size_t)rs * kEmitCap, *specl = spec + (size_t)rs * kEmitCap + o.from;
+                        const uint32_t o_n_fix = __shfl_sync(0xFFFFFFFFu, mine.n_fix, t), o_from = __shfl_sync(0xFFFFFFFFu, mine.from, t);
+                        const uint4 *fixl = fix + (size_t)rs * kEmitCap, *specl = spec + (size_t)rs * kEmitCap + o_from;
                         // whole chunks from k_long_seg_stats' sums, the rest from the records of the chunk j lies in
                         uint32_t sl = 0, sm = 0;
                         const uint32_t cf = j >> 5, i = (cf << 5) + lane;
                         for (uint32_t c = lane; c < cf; c += 32) { const uint2 v = csum[(size_t)rs * kSegChunks + c]; sl += v.x; sm += v.y; }
                         uint4 r = make_uint4(0, 0, 0, 0), rp = make_uint4(0, 0, 0, 0);
-                        if (i < j) r = seg_record(fixl, specl, o.n_fix, i);
-                        if (lane == 0 && i != 0 && i < j) rp = seg_record(fixl, specl, o.n_fix, i - 1);
+                        if (i < j) r = seg_record(fixl, specl, o_n_fix, i);
+                        if (lane == 0 && i != 0 && i < j) rp = seg_record(fixl, specl, o_n_fix, i - 1);
                         uint32_t pe = __shfl_up_sync(0xFFFFFFFFu, r.x + r.y, 1);
                         if (lane == 0) pe = rp.x + rp.y;
                         if (i < j && i != 0) sl += r.x - pe;

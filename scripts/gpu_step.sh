@@ -1,13 +1,5 @@
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
-timeout 600 python bench.py --config 4 --steps 5 --warmup 3 > gpurun_out/bench_c4.json 2> gpurun_out/bench_c4.err; echo c4_rc=$?
-python bench.py > gpurun_out/bench_ours.json 2> gpurun_out/bench_ours.err; echo bench_rc=$?
-for f in ours c4; do python - <<PY
-import json
-try:
-    d = json.load(open("gpurun_out/bench_$f.json"))
-    print("$f", d["value"], d["ms_per_step"], d.get("stage_ms"), "e2e", d["e2e"].get("value"), "enc", d.get("encode", {}).get("value"), d.get("encode", {}).get("stage_ms"), d["cpu_baseline"])
-except Exception as e:
-    print("$f", "ERR", e)
-PY
+for v in lzfse_rust_b200/liblzfse_b200.so gpurun_tmp_m6.so gpurun_tmp_m8.so; do
+echo "== $v"
+LZB_SO=$PWD/$v timeout 300 python scripts/try_long.py > gpurun_out/try_long.log 2>&1; grep -v "^ok " gpurun_out/try_long.log | tail -4 | cut -c1-400
 done
