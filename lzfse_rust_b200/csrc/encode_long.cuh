@@ -32,6 +32,7 @@ constexpr uint32_t kEmitCap = kRSeg / 4 + 8;  // matches are >= 4 bytes and do n
 constexpr uint32_t kSpecStates = kRSeg / 64 < 256 ? kRSeg / 64 : 256;  // pushed matches per segment that carry the state they leave behind
 constexpr uint32_t kSegChunks = (kEmitCap + 31) / 32;  // 32-match chunks of a segment's list (k_long_seg_stats leaves their sums)
 constexpr uint32_t kLongLaneCap = 64;
+constexpr uint32_t kSpecFwdCap = kRSeg;       // a speculative replay (not the stream's first segment) gives up on matches longer than this
 
 struct LongSeg { uint32_t stream, k; };
 struct FrontState { uint32_t cur, lit, p_idx, p_midx, p_len; };
@@ -327,8 +328,10 @@ k_long_find(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ s
 // when a match is pushed to the back end (sel).  `lim_flag` is set when a backward extension stopped at the literal
 // limit although the candidate's own start would have allowed more; `cand`/`good` describe the first candidate met.
 struct StepOut { Match sel; };
+// `fwd_cap`: a speculative replay gives up (returns false with s.cur = kNoPos) when a match runs on for more than this many
+// bytes -- such a match usually covers the following segments, whose replays would each measure it to its end again.
 __device__ __forceinline__ bool front_step(const uint8_t *src, uint32_t len, uint32_t end, uint32_t w, FrontState &s, Match &sel, uint32_t &lim_flag,
-                                           uint32_t &cand, uint32_t &good) {
+                                           uint32_t &cand, uint32_t &good, const uint32_t fwd_cap = 0xFFFFFFFFu) {
     const uint32_t cur = s.cur;
     if ((w & 0x3FFFFu) == 0) { s.cur = cur + ((w >> 18) & 0x3FFu); return false; }
     Match inc;
@@ -341,6 +344,7 @@ __device__ __forceinline__ bool front_step(const uint8_t *src, uint32_t len, uin
             const uint64_t y = ld8u(src + cur + inc.match_len) ^ ld8u(src + inc.match_idx + inc.match_len);
             if (y) { inc.match_len += (__ffsll((long long)y) - 1) >> 3; goto fwd_done; }
             inc.match_len += 8;
+            if (inc.match_len > fwd_cap) { if (cand == kNoPos) cand = cur; s.cur = kNoPos; return false; }  // (this position IS a candidate: the stitch may not jump over it)
         }
         while (inc.match_len < maxl && src[cur + inc.match_len] == src[inc.match_idx + inc.match_len]) inc.match_len++;
     fwd_done:;
@@ -435,7 +439,7 @@ k_long_replay(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__
         const uint32_t k4 = s.cur & 3u;
         const uint32_t w = k4 == 0 ? wq.x : (k4 == 1 ? wq.y : (k4 == 2 ? wq.z : wq.w));
         Match sel;
-        if (front_step(src, len, end, w, s, sel, lim_flag, cand, good)) {
+        if (front_step(src, len, end, w, s, sel, lim_flag, cand, good, sg.k == 0 ? 0xFFFFFFFFu : kSpecFwdCap)) {
             if (n_out == 0) lim0 = lim_flag;
             out[n_out] = make_uint4(sel.idx, sel.match_len, sel.idx - sel.match_idx, s.cur);
             if (n_out < kSpecStates) sto[n_out] = make_uint4(s.p_idx, s.p_midx, s.p_len, 0);
@@ -445,6 +449,7 @@ k_long_replay(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     if (!valid) return;
     if (n_out == 0) lim0 = lim_flag;
+    if (s.cur == kNoPos) { n_out = 0; lim0 = 1; }  // given up: nothing of this segment is taken over, the stitch replays it if the true parse gets here
     LongSegOut o;
     o.n_spec = n_out; o.lim0 = lim0; o.good0 = good; o.cand0 = cand; o.exit = s;
     o.n_fix = 0; o.from = sg.k == 0 ? 0u : n_out; o.a_out = s; o.a_ok = 0;
@@ -513,6 +518,7 @@ __global__ void k_long_stitch_a(const uint8_t *__restrict__ src_base, const uint
     const uint32_t len = (uint32_t)src_len[sg.stream];
     LongSegOut o = seg_out[rs];
     FrontState T = seg_out[rs - 1].exit;
+    if (T.cur == kNoPos) return;  // the segment before gave up: no state to start from (k_long_stitch_b replays from the true one)
     stitch_segment(src_base + src_off[sg.stream], len, len - 3, words + bases[sg.stream].n_fse, sg.k, T, o, spec + (size_t)rs * kEmitCap,
                    states + (size_t)rs * kSpecStates, fix + (size_t)rs * kEmitCap);
     seg_out[rs].n_fix = o.n_fix; seg_out[rs].from = o.from; seg_out[rs].a_out = T;  // (.exit is being read by the neighbour)

@@ -56,11 +56,14 @@ static void build_words(void) { /* HistoryTable::push + find_match's candidate l
 
 /* one position of FrontendBytes::match_any's loop; returns 1 and fills *e when a match is pushed to the back end */
 static uint32_t first_cand, first_good; /* position of the first candidate a replay met, and whether its length was >= GOOD */
+static uint32_t fwd_cap = 0xFFFFFFFFu; /* speculative replays give up on matches longer than this (encode_long.cuh: kSpecFwdCap) */
+static int gave_up;
 static int lit_limited; /* set when a backward extension stopped at the literal limit (a longer literal run could have gone on) */
 static int step(state_t *s, emit_t *e) {
     const uint32_t cur = s->cur;
     if (wdist[cur] == 0) { s->cur++; return 0; }
     uint32_t i_idx = cur, i_midx = cur - wdist[cur], i_len = wlen[cur];
+    if (i_len >= 1023 && i_len > fwd_cap) { if (first_cand == NONE) first_cand = cur; gave_up = 1; s->cur = NONE; return 0; }
     { uint32_t lit = cur - s->lit, lim = lit < i_midx ? lit : i_midx, dec = 0;
       while (dec < lim && src[i_idx - dec - 1] == src[i_midx - dec - 1]) dec++;
       if (dec == lit && dec < i_midx) lit_limited = 1;
@@ -99,12 +102,14 @@ int main(int argc, char **argv) {
         state_t s = {k * R, k * R, 0, 0, 0};
         const uint32_t se = (k + 1) * R < end_ ? (k + 1) * R : end_;
         emit_t e;
-        lit_limited = 0; first_cand = NONE;
+        lit_limited = 0; first_cand = NONE; gave_up = 0; fwd_cap = k == 0 ? 0xFFFFFFFFu : R;
         while (s.cur < se) if (step(&s, &e)) { if (n_spec[k] == 0) lim0[k] = (uint8_t)lit_limited; if (n_spec[k] >= cap) { printf("spec overflow\n"); return 1; } spec[(size_t)k * cap + n_spec[k]++] = e; }
         if (n_spec[k] == 0) lim0[k] = (uint8_t)lit_limited;
+        if (gave_up) { n_spec[k] = 0; lim0[k] = 1; }
         exit_[k] = s; cand0[k] = first_cand; good0[k] = (uint8_t)first_good;
     }
     /* stitch */
+    fwd_cap = 0xFFFFFFFFu;
     state_t T = exit_[0];
     uint64_t fix_total = 0, fix_steps = 0, max_steps = 0, unsynced = 0, soft = 0;
     for (uint32_t k = 1; k < n_seg; k++) {

@@ -39,7 +39,8 @@ def _inputs():
         elif k == 1: mix += bytes([int(rng.integers(0, 256))]) * min(n, 300)
         elif k == 2: mix += rng.integers(0, 256, n * 5, dtype=np.uint8).tobytes()
         else: mix += (rng.integers(0, 4, n * 5, dtype=np.uint8) * 16).tobytes()
-    return {"text": t, "noise": tk.rng_gen_vec(3, 200000), "sparse": bytes(r), "mix": bytes(mix), "zeros": bytes(70000)}
+    far = tk.rng_gen_vec(3, 90000)
+    return {"far_repeat": far + far + t[:30000] + far[:50000], "text": t, "noise": tk.rng_gen_vec(3, 200000), "sparse": bytes(r), "mix": bytes(mix), "zeros": bytes(70000)}
 
 
 @pytest.mark.parametrize("seg", [4096, 16384, 65536])
