@@ -185,7 +185,11 @@ size_t lzfse_b200_encode_bound_strict(size_t src_len);
 int lzfse_b200_encode_bytes(lzfse_b200_encoder *e, const uint8_t *src, size_t src_len, uint8_t *dst,
                             size_t dst_cap, size_t *dst_len);
 
-/* Batched encode: n independent inputs -> n independent frames (same layout rules as decode). */
+/* Batched encode: n independent inputs -> n independent frames (same layout rules as decode).
+ * Device memory: the handle's scratch grows to about 19 bytes per input byte of the largest batch it has seen (a 32-bit word per
+ * position, the per-segment match lists of the front end, packs, literals and the blocks' output scratch; 27 bytes per input
+ * byte for streams longer than 64 KiB, whose hash chain lives in HBM) and is kept until the handle is destroyed; a batch that does
+ * not fit returns LZFSE_B200_OUT_OF_MEMORY as the call's status -- split it.  A stream may be as long as 0x7FFFFFFF bytes. */
 int lzfse_b200_encode_batch_device(lzfse_b200_encoder *e, const uint8_t *src_base, const uint64_t *src_off,
                                    const uint64_t *src_len, uint8_t *dst_base, const uint64_t *dst_off,
                                    const uint64_t *dst_cap, uint64_t *out_len, int32_t *status, size_t n,

@@ -1309,6 +1309,7 @@ struct FseEncSmem {
     uint32_t bitbuf[72];   // chunk bit buffer (<= 31 carried + 32 * 54 bits)
     uint16_t chain[128];   // (count | bits << 4) per symbol, in emission order
     uint8_t sym[128];      // chunk symbols for the chain lanes
+    int2 ent[128];         // the chunk's table entries {t_k, t_w}, looked up and unpacked by all lanes before the chain lanes run
 };
 
 __device__ __forceinline__ uint32_t l_sym(uint32_t v) { return v < 16 ? v : (v < 20 ? 16u : (v < 28 ? 17u : (v < 60 ? 18u : 19u))); }   // L_BASE_FROM_VALUE
@@ -1376,6 +1377,13 @@ __device__ void build_e_table(const uint32_t *w, uint32_t *e, uint32_t n_sym, ui
     }
 }
 // EEntry::encode (fse/encoder.rs:190-200): returns count | bits << 4
+__device__ __forceinline__ int2 e_unpack(uint32_t entry) { return make_int2((int16_t)(entry & 0xFFFF), (int16_t)(entry >> 16)); }
+__device__ __forceinline__ uint32_t e_step2(int2 e, uint32_t &state) {  // the same with the entry already unpacked
+    const uint32_t s = state;
+    const uint32_t nb = (uint32_t)(e.x + (int32_t)s) >> 10;
+    state = (uint32_t)(e.y + (int32_t)(s >> nb));
+    return nb | ((s & ((1u << nb) - 1u)) << 4);
+}
 __device__ __forceinline__ uint32_t e_step(uint32_t entry, uint32_t &state) {
     const int32_t t_k = (int16_t)(entry & 0xFFFF), t_w = (int16_t)(entry >> 16);
     const uint32_t s = state;
@@ -1508,12 +1516,13 @@ k_enc_fse_blocks(EncBlock *blocks, const uint32_t *__restrict__ n_blocks_p, cons
             const uint32_t n = hi < 128 ? hi : 128;  // literals [hi - n, hi), emitted from hi - 1 downwards
             for (uint32_t t = lane; t < n; t += 32) {  // emission slot t holds literal hi - 1 - t
                 const uint32_t idx = hi - 1 - t;
-                sm.sym[t] = (uint8_t)(idx < b.n_lits ? lits[idx] : pad);
+                sm.ent[t] = e_unpack(sm.E[104 + (idx < b.n_lits ? lits[idx] : pad)]);
             }
             __syncwarp();
             if (lane < 4) {  // literal idx uses state idx & 3 (the loop encodes i-1 with state 3 ... i-4 with state 0)
                 const uint32_t first = 3 - lane;  // slots first, first + 4, ... belong to this state
-                for (uint32_t t = first; t < n; t += 4) sm.chain[t] = (uint16_t)e_step(sm.E[104 + sm.sym[t]], ust);
+#pragma unroll 4
+                for (uint32_t t = first; t < n; t += 4) sm.chain[t] = (uint16_t)e_step2(sm.ent[t], ust);
             }
             __syncwarp();
             {   // each lane packs four consecutive slots
@@ -1545,12 +1554,12 @@ k_enc_fse_blocks(EncBlock *blocks, const uint32_t *__restrict__ n_blocks_p, cons
                 const uint2 p = packs[hi - 1 - lane];
                 l = p.x & 0xFFFF; m = p.x >> 16; d = p.y;
                 sl = l_sym(l); smm = m_sym(m); sd = d_sym(d);
-                sm.sym[lane] = (uint8_t)sl; sm.sym[32 + lane] = (uint8_t)smm; sm.sym[64 + lane] = (uint8_t)sd;
+                sm.ent[lane] = e_unpack(sm.E[sl]); sm.ent[32 + lane] = e_unpack(sm.E[20 + smm]); sm.ent[64 + lane] = e_unpack(sm.E[40 + sd]);
             }
             __syncwarp();
             if (lane < 3) {
-                const uint32_t off = lane == 0 ? 0u : (lane == 1 ? 20u : 40u);
-                for (uint32_t t = 0; t < n; t++) sm.chain[lane * 32 + t] = (uint16_t)e_step(sm.E[off + sm.sym[lane * 32 + t]], st);
+#pragma unroll 4
+                for (uint32_t t = 0; t < n; t++) sm.chain[lane * 32 + t] = (uint16_t)e_step2(sm.ent[lane * 32 + t], st);
             }
             __syncwarp();
             uint64_t v = 0; uint32_t nb = 0;

@@ -76,6 +76,26 @@ def test_frames_equal_oracle(enc, dec):
     assert (dstat == 0).all() and list(outs) == list(datas)
 
 
+def test_all_front_ends_agree(enc):
+    """The encoder has three front ends for bvx2 streams -- per segment (default), per stream (`LZB_ENC_SEG=0`: k_enc_replay for
+    streams <= 64 KiB) and one warp per stream (`LZB_ENC_LONG=0`: k_enc_parse for longer ones).  All must emit the same frames."""
+    import lzfse_rust_b200 as L
+
+    datas = [d for n, d in _patterns() if n in ("zeros", "seq_masked", "text64k", "period3", "period64", "lits_then_far_match", "len40001", "noise_fse")]
+    datas += [tk.synth_text(0x77, 200000), tk.synth_text(0x78, 65536)]
+    ref, st = enc.encode_batch(datas)
+    assert not st.any()
+    for var in ("LZB_ENC_SEG", "LZB_ENC_LONG"):
+        os.environ[var] = "0"
+        try:
+            e2 = L.LzfseEncoder(0)
+            frames, st = e2.encode_batch(datas)
+            e2.close()
+        finally:
+            del os.environ[var]
+        assert not st.any() and list(frames) == list(ref), var
+
+
 def test_text_chunk_batch(enc):
     chunks = [tk.synth_text(0x5EED0000 + i, 65536) for i in range(64)]
     frames, status = enc.encode_batch(chunks)
