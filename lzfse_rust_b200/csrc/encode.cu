@@ -17,6 +17,7 @@
 #include <cstdlib>
 #include <new>
 #include <string>
+#include <type_traits>
 
 #include "common.cuh"
 #include "host_util.h"
@@ -706,12 +707,14 @@ constexpr uint32_t kFindUnit = 256;       // positions a find warp takes at a ti
 constexpr uint32_t kNone = 0xFFFFu;       // chain end (positions are < kFastMaxLen - 3)
 constexpr uint32_t kLaneCap = 64;         // per-lane forward extension stops here; longer ones are finished warp-wide (or inherited from a run already measured)
 constexpr uint32_t kWordLenSat = 1023, kWordBwSat = 15;
+constexpr uint32_t kRunProbeAfter = 4096;  // cache hits after which a stream's positions ask the run cache before comparing bytes
 constexpr uint32_t kRunSlots = 64;        // (distance, start, end) of long runs already measured, per stream
 constexpr uint32_t kFsSrc = 16, kFsSrcBytes = kFastMaxLen + 48;  // 16 bytes below the stream (backward reads), up to 15 of alignment, over-read slack behind
 constexpr uint32_t kFsHead = kFsSrc + kFsSrcBytes + 16, kFsPrev = kFsHead + (1u << kHashBits) * 2, kFsCtrl = kFsPrev + kFastMaxLen * 2;
 struct FindCtrl {
     unsigned long long mbar;
-    uint32_t chain_done, next_ticket, stream, pad;
+    uint32_t chain_done, next_ticket, stream;
+    uint32_t run_hits;  // positions of this stream that found their length in the run cache (saturates at kRunProbeAfter)
     unsigned long long runs[kRunSlots];
     uint8_t pre_done[kFastMaxLen / kFindUnit];  // per unit: peer info written
 };
@@ -812,7 +815,7 @@ k_enc_find(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ sr
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sm0 + kFsSrc),
                          "l"(g - mis), "r"(bytes), "r"(mbar)
                          : "memory");
-            ctrl->chain_done = 0; ctrl->next_ticket = 0;
+            ctrl->chain_done = 0; ctrl->next_ticket = 0; ctrl->run_hits = 0;
         }
         // meanwhile: empty bucket heads, run cache, unit flags
         for (uint32_t t = tid; t < (1u << kHashBits) * 2 / 16; t += kFindThreads)
@@ -963,11 +966,18 @@ k_enc_find(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ sr
                 for (uint32_t b0 = p0; b0 < p1; b0 += 32) {
                     const uint32_t p = b0 + lane;
                     const bool act = p < p1;
+                    // Once a stream has shown itself to be periodic (its positions keep finding their lengths in the run cache),
+                    // the cache is asked BEFORE the bytes are compared; on text that question would only cost (measured +14 %).
+                    const uint32_t hits_seen = *reinterpret_cast<volatile uint32_t *>(&ctrl->run_hits);
+                    const bool probe_first = hits_seen >= kRunProbeAfter;
                     uint32_t best_len = 0, best_c = 0;
                     uint32_t cs[4], ls[4];  // candidates whose length reached kLaneCap
                     uint32_t n_sat = 0;
                     const uint32_t maxl = len - p;
-                    if (act) {
+                    // (two copies of the candidate loop: the one that asks the run cache first is only entered by periodic streams,
+                    // so that text runs exactly the loop it ran before)
+                    auto candidates = [&](auto probe_tag) {
+                        constexpr bool kProbe = decltype(probe_tag)::value;
                         const uint32_t val = lds4u(s + p);
                         uint32_t c = lds_u16(s_prev + p * 2);
                         if (c != kNone) {
@@ -978,18 +988,33 @@ k_enc_find(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ sr
                                 // (the distance limit 262 139 cannot be exceeded inside 64 KiB)
                                 const uint32_t cn = lds_u16(s_prev + c * 2);
                                 if (lds4u(s + c) == val) {
-                                    const uint64_t y = p8 ^ lds8u(s + c + 4);
                                     uint32_t l;
-                                    if (y) { l = 4 + ((__ffsll((long long)y) - 1) >> 3); l = l < lim ? l : lim; }
-                                    else l = lim >= 12 ? smem_match_inc(s, p, c, 12, lim) : lim;
-                                    if (l == kLaneCap && l < maxl) { cs[n_sat] = c; ls[n_sat] = 0; n_sat++; }
+                                    bool known = false;
+                                    if constexpr (kProbe) {
+                                        // a position well inside a run that was already measured at this distance knows its length
+                                        // without looking at the bytes (periodic data: every position has four such candidates)
+                                        const uint32_t d = p - c;
+                                        const unsigned long long e = *reinterpret_cast<volatile unsigned long long *>(&ctrl->runs[(d * 0x9E3779B1u) >> 26]);
+                                        const uint32_t ed = (uint32_t)(e & 0x3FFFF), es = (uint32_t)(e >> 18) & 0x1FFFFF, ee = (uint32_t)(e >> 39);
+                                        if (ed == d && es <= p && p + kLaneCap < ee) { known = true; cs[n_sat] = c; ls[n_sat] = ee - p; n_sat++; }
+                                    }
+                                    if (known) {
+                                        l = kLaneCap;
+                                    } else {
+                                        const uint64_t y = p8 ^ lds8u(s + c + 4);
+                                        if (y) { l = 4 + ((__ffsll((long long)y) - 1) >> 3); l = l < lim ? l : lim; }
+                                        else l = lim >= 12 ? smem_match_inc(s, p, c, 12, lim) : lim;
+                                        if (l == kLaneCap && l < maxl) { cs[n_sat] = c; ls[n_sat] = 0; n_sat++; }
+                                    }
                                     if (l > best_len) { best_len = l; best_c = c; }
                                 }
                                 c = cn;
                                 if (c == kNone) break;
                             }
                         }
-                    }
+                    };
+                    if (probe_first) { if (act) candidates(std::true_type{}); }
+                    else if (act) candidates(std::false_type{});
                     // Candidates beyond the per-lane cap need their exact lengths (strictly longest wins, newest first, and the
                     // word stores up to 1023).  Runs are measured once per (distance, start) with the whole warp and remembered:
                     // inside a run every later position inherits end - p, which keeps periodic data linear.
@@ -1002,7 +1027,7 @@ k_enc_find(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ sr
                                 const uint32_t d = p - cs[k];
                                 const unsigned long long e = *reinterpret_cast<volatile unsigned long long *>(&ctrl->runs[(d * 0x9E3779B1u) >> 26]);
                                 const uint32_t ed = (uint32_t)(e & 0x3FFFF), es = (uint32_t)(e >> 18) & 0x1FFFFF, ee = (uint32_t)(e >> 39);
-                                if (ed == d && es <= p && p + kLaneCap <= ee) ls[k] = ee - p;
+                                if (ed == d && es <= p && p + kLaneCap <= ee) { ls[k] = ee - p; if (hits_seen < kRunProbeAfter) atomicAdd(&ctrl->run_hits, 1u); }
                                 else open = true;
                             }
                             need = open;

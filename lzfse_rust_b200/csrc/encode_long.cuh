@@ -32,7 +32,8 @@ constexpr uint32_t kEmitCap = kRSeg / 4 + 8;  // matches are >= 4 bytes and do n
 constexpr uint32_t kSpecStates = kRSeg / 64 < 256 ? kRSeg / 64 : 256;  // pushed matches per segment that carry the state they leave behind
 constexpr uint32_t kSegChunks = (kEmitCap + 31) / 32;  // 32-match chunks of a segment's list (k_long_seg_stats leaves their sums)
 constexpr uint32_t kLongLaneCap = 64;
-constexpr uint32_t kSpecFwdCap = kRSeg;       // a speculative replay (not the stream's first segment) gives up on matches longer than this
+constexpr uint32_t kSpecFwdCap = 0;           // a speculative replay (not the stream's first segment) gives up on a match whose length the word cannot hold
+                                              // (>= 1023 bytes; measured with a cap of one segment: 5.3 instead of 4.6 ms on 8 192 periodic streams)
 
 struct LongSeg { uint32_t stream, k; };
 struct FrontState { uint32_t cur, lit, p_idx, p_midx, p_len; };
@@ -340,6 +341,7 @@ __device__ __forceinline__ bool front_step(const uint8_t *src, uint32_t len, uin
     inc.match_len = (w >> 18) & 0x3FFu;
     if (inc.match_len == kWordLenSat) {  // the word's length field is saturated: finish the extension here
         const uint32_t maxl = len - cur;
+        if (inc.match_len > fwd_cap) { if (cand == kNoPos) cand = cur; s.cur = kNoPos; return false; }
         while (inc.match_len + 8 <= maxl) {
             const uint64_t y = ld8u(src + cur + inc.match_len) ^ ld8u(src + inc.match_idx + inc.match_len);
             if (y) { inc.match_len += (__ffsll((long long)y) - 1) >> 3; goto fwd_done; }

@@ -100,6 +100,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     enc, dec = L.LzfseEncoder(local), L.LzfseDecoder(local)
+    enc.set_timing(True); dec.set_timing(True)
     pool, woff = W.word_pool(dec)
     total = a.mib_per_class << 20
     t = lambda x: torch.from_numpy(np.asarray(x, np.int64)).to(dev)
@@ -127,6 +128,7 @@ def main():
                 c_len, st = enc.encode_batch_device(d_raw, d_offs, d_lens, d_comp, d_coff, d_caps)
                 e1.record(); torch.cuda.synchronize()
             enc_ms[kind] += e0.elapsed_time(e1)
+            if rank == 0: sys.stderr.write("%s encode stages %s\n" % (kind, {k: round(v, 2) for k, v in enc.last_stage_ms().items() if v > 0.01}))
             launches += enc.last_launches
             assert int((st != 0).sum()) == 0, "encode status"
             d_out = torch.zeros(len(raw), dtype=torch.uint8, device=dev)
@@ -137,6 +139,7 @@ def main():
                 out_len, dst = dec.decode_batch_device(d_comp, d_coff, d_clen, d_out, d_offs, d_lens)
                 e1.record(); torch.cuda.synchronize()
             dec_ms[kind] += e0.elapsed_time(e1)
+            if rank == 0: sys.stderr.write("%s decode stages %s\n" % (kind, {k: round(v, 2) for k, v in dec.last_stage_ms().items() if v > 0.01}))
             launches += dec.last_launches
             assert int((dst != 0).sum()) == 0 and bool(torch.equal(d_out, d_raw)) and bool(torch.equal(out_len.to(torch.int64), d_lens)), "round trip"
             u_bytes[kind] += len(raw); c_bytes[kind] += int(c_len.sum()); n_streams[kind] += n

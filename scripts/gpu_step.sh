@@ -1,3 +1,3 @@
-mkdir -p gpurun_out
-timeout 300 python scripts/try_long.py --no-time > gpurun_out/try_long.log 2>&1; grep -v "^ok " gpurun_out/try_long.log | tail -3 | cut -c1-400
-timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+timeout 900 python -m pytest tests/test_gpu_encode.py tests/test_gpu_configs.py -x -q 2>&1 | tail -3
+timeout 300 python scripts/prof_encode.py --chunks 16384 --iters 2 2>&1 | tail -1 | cut -c1-150
+timeout 600 python scripts/bench_mixed.py --mib-per-class 512 2>&1 | grep "encode stages" | cut -c1-300
