@@ -32,8 +32,6 @@ constexpr uint32_t kEmitCap = kRSeg / 4 + 8;  // matches are >= 4 bytes and do n
 constexpr uint32_t kSpecStates = kRSeg / 64 < 256 ? kRSeg / 64 : 256;  // pushed matches per segment that carry the state they leave behind
 constexpr uint32_t kSegChunks = (kEmitCap + 31) / 32;  // 32-match chunks of a segment's list (k_long_seg_stats leaves their sums)
 constexpr uint32_t kLongLaneCap = 64;
-constexpr uint32_t kSpecFwdCap = 0;           // a speculative replay (not the stream's first segment) gives up on a match whose length the word cannot hold
-                                              // (>= 1023 bytes; measured with a cap of one segment: 5.3 instead of 4.6 ms on 8 192 periodic streams)
 
 struct LongSeg { uint32_t stream, k; };
 struct FrontState { uint32_t cur, lit, p_idx, p_midx, p_len; };
@@ -329,27 +327,32 @@ k_long_find(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ s
 // when a match is pushed to the back end (sel).  `lim_flag` is set when a backward extension stopped at the literal
 // limit although the candidate's own start would have allowed more; `cand`/`good` describe the first candidate met.
 struct StepOut { Match sel; };
-// `fwd_cap`: a speculative replay gives up (returns false with s.cur = kNoPos) when a match runs on for more than this many
-// bytes -- such a match usually covers the following segments, whose replays would each measure it to its end again.
+// A word whose length field is saturated (>= 1 023 bytes) needs the match measured to its end.  `ext_len` != 0 is that
+// length, already known; otherwise the caller either lets the step measure it (one thread, 8 bytes per iteration: the stitch,
+// where it is rare) or, with kCoop, gets the request back (`need_ext`, state untouched) and has its whole warp measure it --
+// on periodic data EVERY segment's clean start finds a match that runs to the end of the stream.
+template <bool kCoop>
 __device__ __forceinline__ bool front_step(const uint8_t *src, uint32_t len, uint32_t end, uint32_t w, FrontState &s, Match &sel, uint32_t &lim_flag,
-                                           uint32_t &cand, uint32_t &good, const uint32_t fwd_cap = 0xFFFFFFFFu) {
+                                           uint32_t &cand, uint32_t &good, uint32_t ext_len, bool &need_ext) {
     const uint32_t cur = s.cur;
     if ((w & 0x3FFFFu) == 0) { s.cur = cur + ((w >> 18) & 0x3FFu); return false; }
     Match inc;
     inc.idx = cur;
     inc.match_idx = cur - (w & 0x3FFFFu);
     inc.match_len = (w >> 18) & 0x3FFu;
-    if (inc.match_len == kWordLenSat) {  // the word's length field is saturated: finish the extension here
-        const uint32_t maxl = len - cur;
-        if (inc.match_len > fwd_cap) { if (cand == kNoPos) cand = cur; s.cur = kNoPos; return false; }
-        while (inc.match_len + 8 <= maxl) {
-            const uint64_t y = ld8u(src + cur + inc.match_len) ^ ld8u(src + inc.match_idx + inc.match_len);
-            if (y) { inc.match_len += (__ffsll((long long)y) - 1) >> 3; goto fwd_done; }
-            inc.match_len += 8;
-            if (inc.match_len > fwd_cap) { if (cand == kNoPos) cand = cur; s.cur = kNoPos; return false; }  // (this position IS a candidate: the stitch may not jump over it)
+    if (inc.match_len == kWordLenSat) {  // the word's length field is saturated
+        if (ext_len) inc.match_len = ext_len;
+        else if (kCoop) { need_ext = true; return false; }
+        else {
+            const uint32_t maxl = len - cur;
+            while (inc.match_len + 8 <= maxl) {
+                const uint64_t y = ld8u(src + cur + inc.match_len) ^ ld8u(src + inc.match_idx + inc.match_len);
+                if (y) { inc.match_len += (__ffsll((long long)y) - 1) >> 3; goto fwd_done; }
+                inc.match_len += 8;
+            }
+            while (inc.match_len < maxl && src[cur + inc.match_len] == src[inc.match_idx + inc.match_len]) inc.match_len++;
+        fwd_done:;
         }
-        while (inc.match_len < maxl && src[cur + inc.match_len] == src[inc.match_idx + inc.match_len]) inc.match_len++;
-    fwd_done:;
     }
     {   // match_dec (:261-268)
         const uint32_t lit = cur - s.lit;
@@ -374,10 +377,14 @@ __device__ __forceinline__ bool front_step(const uint8_t *src, uint32_t len, uin
     return true;
 }
 
+// (out of line: the replay loop is register-bound and only needs this on long matches)
+__device__ __noinline__ uint32_t gwarp_match_inc_far(const uint8_t *src, uint32_t a, uint32_t b, uint32_t l, uint32_t lim, uint32_t lane) {
+    return gwarp_match_inc(src, a, b, l, lim, lane);
+}
 // ---- speculative replay, one THREAD per segment ----------------------------------------------------
 // Same loop and the same word ring as k_enc_replay (see there for the ring's rules); starts clean at the segment's first
 // position and stops when the cursor leaves the segment.
-__global__ void __launch_bounds__(kReplayThreads)
+__global__ void __launch_bounds__(kReplayThreads, 32)
 k_long_replay(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ src_off, const uint64_t *__restrict__ src_len,
               const StreamCounts *__restrict__ bases, const LongSeg *__restrict__ rseg, uint32_t n_rseg, const uint32_t *__restrict__ words,
               uint4 *__restrict__ spec, uint4 *__restrict__ states, LongSegOut *__restrict__ seg_out) {
@@ -391,8 +398,8 @@ k_long_replay(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__
     uint4 *out = spec + (size_t)rs * kEmitCap;
     uint4 *sto = states + (size_t)rs * kSpecStates;
     FrontState s = {B, B, 0, 0, 0};
-    uint32_t n_out = 0, lim_flag = 0, lim0 = 0, cand = kNoPos, good = 0;
-    bool active = valid;
+    uint32_t n_out = 0, lim_flag = 0, lim0 = 0, cand = kNoPos, good = 0, ext_len = 0, w_req = 0;
+    bool active = valid, need_ext = false;
 
     __shared__ __align__(16) uint8_t rings[kReplayThreads * kRingStride];
     constexpr uint32_t kLag = 8;
@@ -433,6 +440,19 @@ k_long_replay(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__
             }
             iter++;
         }
+        {   // ---- matches longer than the word can say are measured by the whole warp, 256 bytes per round ----
+            const uint32_t lane = threadIdx.x;  // (one warp per CTA)
+            uint32_t rm = __ballot_sync(0xFFFFFFFFu, need_ext);
+            while (rm) {
+                const int j = __ffs(rm) - 1;
+                rm &= rm - 1;
+                const uint8_t *sj = reinterpret_cast<const uint8_t *>(__shfl_sync(0xFFFFFFFFu, reinterpret_cast<unsigned long long>(src), j));
+                const uint32_t a = __shfl_sync(0xFFFFFFFFu, s.cur, j), lj = __shfl_sync(0xFFFFFFFFu, len, j);
+                const uint32_t b = a - (__shfl_sync(0xFFFFFFFFu, w_req, j) & 0x3FFFFu);
+                const uint32_t e = gwarp_match_inc_far(sj, a, b, kWordLenSat, lj - a, lane);
+                if (lane == (uint32_t)j) { ext_len = e; need_ext = false; }
+            }
+        }
         if (!active) continue;
         if ((s.cur & ~3u) != wbase) {
             wbase = s.cur & ~3u;
@@ -441,7 +461,10 @@ k_long_replay(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__
         const uint32_t k4 = s.cur & 3u;
         const uint32_t w = k4 == 0 ? wq.x : (k4 == 1 ? wq.y : (k4 == 2 ? wq.z : wq.w));
         Match sel;
-        if (front_step(src, len, end, w, s, sel, lim_flag, cand, good, sg.k == 0 ? 0xFFFFFFFFu : kSpecFwdCap)) {
+        const bool pushed = front_step<true>(src, len, end, w, s, sel, lim_flag, cand, good, ext_len, need_ext);
+        w_req = w;
+        if (!need_ext) ext_len = 0;
+        if (pushed) {
             if (n_out == 0) lim0 = lim_flag;
             out[n_out] = make_uint4(sel.idx, sel.match_len, sel.idx - sel.match_idx, s.cur);
             if (n_out < kSpecStates) sto[n_out] = make_uint4(s.p_idx, s.p_midx, s.p_len, 0);
@@ -451,7 +474,6 @@ k_long_replay(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     if (!valid) return;
     if (n_out == 0) lim0 = lim_flag;
-    if (s.cur == kNoPos) { n_out = 0; lim0 = 1; }  // given up: nothing of this segment is taken over, the stitch replays it if the true parse gets here
     LongSegOut o;
     o.n_spec = n_out; o.lim0 = lim0; o.good0 = good; o.cand0 = cand; o.exit = s;
     o.n_fix = 0; o.from = sg.k == 0 ? 0u : n_out; o.a_out = s; o.a_ok = 0;
@@ -496,7 +518,8 @@ __device__ void stitch_segment(const uint8_t *src, uint32_t len, uint32_t end, c
     uint4 sj = n_cmp ? sp[0] : make_uint4(0, 0, 0, 0);
     while (T.cur < se) {
         Match sel;
-        if (!front_step(src, len, end, W[T.cur], T, sel, dummy0, dummy1, dummy2)) continue;
+        bool dummy3 = false;
+        if (!front_step<false>(src, len, end, W[T.cur], T, sel, dummy0, dummy1, dummy2, 0u, dummy3)) continue;
         fix[n_fix++] = make_uint4(sel.idx, sel.match_len, sel.idx - sel.match_idx, T.cur);
         while (j < n_cmp && sj.x + sj.y < T.lit) { j++; if (j < n_cmp) sj = sp[j]; }
         if (j < n_cmp && sj.x + sj.y == T.lit && sj.w == T.cur) {
@@ -520,7 +543,6 @@ __global__ void k_long_stitch_a(const uint8_t *__restrict__ src_base, const uint
     const uint32_t len = (uint32_t)src_len[sg.stream];
     LongSegOut o = seg_out[rs];
     FrontState T = seg_out[rs - 1].exit;
-    if (T.cur == kNoPos) return;  // the segment before gave up: no state to start from (k_long_stitch_b replays from the true one)
     stitch_segment(src_base + src_off[sg.stream], len, len - 3, words + bases[sg.stream].n_fse, sg.k, T, o, spec + (size_t)rs * kEmitCap,
                    states + (size_t)rs * kSpecStates, fix + (size_t)rs * kEmitCap);
     seg_out[rs].n_fix = o.n_fix; seg_out[rs].from = o.from; seg_out[rs].a_out = T;  // (.exit is being read by the neighbour)

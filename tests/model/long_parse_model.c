@@ -102,7 +102,7 @@ int main(int argc, char **argv) {
         state_t s = {k * R, k * R, 0, 0, 0};
         const uint32_t se = (k + 1) * R < end_ ? (k + 1) * R : end_;
         emit_t e;
-        lit_limited = 0; first_cand = NONE; gave_up = 0; fwd_cap = k == 0 ? 0xFFFFFFFFu : 0;
+        lit_limited = 0; first_cand = NONE; gave_up = 0; fwd_cap = 0xFFFFFFFFu; /* (the give-up rule is kept for experiments: the CUDA replay now measures long matches with its whole warp instead) */
         while (s.cur < se) if (step(&s, &e)) { if (n_spec[k] == 0) lim0[k] = (uint8_t)lit_limited; if (n_spec[k] >= cap) { printf("spec overflow\n"); return 1; } spec[(size_t)k * cap + n_spec[k]++] = e; }
         if (n_spec[k] == 0) lim0[k] = (uint8_t)lit_limited;
         if (gave_up) { n_spec[k] = 0; lim0[k] = 1; }
