@@ -34,7 +34,7 @@ fn main() {
         assert!(st.success(), "nvcc failed on {}", src);
         objs.push(o);
     }
-    for h in ["common.cuh", "lz_blocks.cuh", "host_util.h", "../../include/lzfse_b200.h"].iter() {
+    for h in ["common.cuh", "lz_blocks.cuh", "encode_long.cuh", "host_util.h", "../../include/lzfse_b200.h"].iter() {
         println!("cargo:rerun-if-changed={}", csrc.join(h).display());
     }
     let so = out.join("liblzfse_b200.so");
