@@ -726,6 +726,44 @@ k_long_blocks(const uint64_t *__restrict__ src_off, const uint64_t *__restrict__
         if (k0 + lane < st.n_rseg) mine = agg[st.rseg_base + k0 + lane];
         const uint32_t kn = st.n_rseg - k0 < 32 ? st.n_rseg - k0 : 32;
         for (uint32_t t = 0; t < kn; t++) {
+            {   // ---- all segments from t on that stay inside the open block as plain packs, in one go ----
+                // Lane l looks at segment l: where the previous non-empty segment ended (its first literal run), running
+                // sums over the lanes, first lane that does not fit.  What follows handles that one segment in order.
+                const bool in = lane >= t && lane < kn;
+                const uint32_t ne = __ballot_sync(0xFFFFFFFFu, in && mine.n != 0);
+                const uint32_t before = ne & ((1u << lane) - 1u);
+                const int src_l = before ? 31 - __clz(before) : (int)lane;
+                const uint32_t pe_s = __shfl_sync(0xFFFFFFFFu, mine.last_end, src_l), dp_s = __shfl_sync(0xFFFFFFFFu, mine.last_dist, src_l);
+                const uint32_t pe = before ? pe_s : prev_end, dp = before ? dp_s : fs.match_distance;
+                const bool has = in && mine.n != 0;
+                const uint32_t fl = has ? mine.first_idx - pe : 0u;
+                const bool okl = !has || (mine.simple && fl <= kMaxLValue);
+                uint32_t cn = has ? mine.n : 0u, cl = has ? fl + mine.sum_lit : 0u, cm = has ? mine.sum_m : 0u;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t a = __shfl_up_sync(0xFFFFFFFFu, cn, o), b = __shfl_up_sync(0xFFFFFFFFu, cl, o), c = __shfl_up_sync(0xFFFFFFFFu, cm, o);
+                    if (lane >= (uint32_t)o) { cn += a; cl += b; cm += c; }
+                }
+                const uint32_t cnt0 = fs.n_packs_total - fs.blk_pack0, lits0 = fs.n_lits_total - fs.blk_lit0;
+                // (sums of 32 segments stay far below 2^32: a segment has at most kEmitCap matches; its literal bytes may be large
+                // when a pending match lies far back, hence the saturating test on cl through the per-lane flag below)
+                const bool fit = okl && cnt0 + cn <= kLmdsPerBlock && cl <= kLiteralsPerBlock && lits0 + cl <= kLiteralsPerBlock;
+                const uint32_t bad = __ballot_sync(0xFFFFFFFFu, in && !fit);
+                const uint32_t t_stop = bad ? (uint32_t)__ffs(bad) - 1u : kn;  // segments [t, t_stop) are plain
+                if (t_stop > t) {
+                    if (has && lane < t_stop) entry[st.rseg_base + k0 + lane] = SegEntry{fs.n_packs_total + cn - mine.n, dp, mine.n, fl};
+                    const uint32_t last = t_stop - 1;
+                    const uint32_t tn = __shfl_sync(0xFFFFFFFFu, cn, last), tl = __shfl_sync(0xFFFFFFFFu, cl, last), tm = __shfl_sync(0xFFFFFFFFu, cm, last);
+                    const uint32_t ne_run = ne & ((2u << last) - 1u);
+                    if (ne_run) {
+                        const int ll = 31 - __clz(ne_run);
+                        fs.match_distance = __shfl_sync(0xFFFFFFFFu, mine.last_dist, ll); prev_end = __shfl_sync(0xFFFFFFFFu, mine.last_end, ll);
+                    }
+                    fs.n_packs_total += tn; fs.n_lits_total += tl; fs.n_match_bytes += tm;
+                    t = t_stop;
+                    if (t >= kn) break;
+                }
+            }
             const uint32_t rs = st.rseg_base + k0 + t;
             const uint32_t n = __shfl_sync(0xFFFFFFFFu, mine.n, t);
             if (n == 0) continue;
