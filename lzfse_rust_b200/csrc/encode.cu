@@ -780,6 +780,44 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t phase) {
         "DONE_%=:\n\t}" ::"r"(mbar), "r"(phase) : "memory");
 }
 
+// find_match's candidate loop for a position of a PERIODIC stream (see k_enc_find): the run cache is asked before any byte is
+// compared; a position well inside a run that was already measured at this distance knows its length without looking at the
+// bytes.  res = {best_len, best_c, n_sat, cs[4], ls[4]}.
+__device__ __noinline__ void find_candidates_probe(uint32_t s, uint32_t s_prev, const FindCtrl *ctrl, uint32_t p, uint32_t maxl, uint32_t *res) {
+    uint32_t best_len = 0, best_c = 0, n_sat = 0;
+    uint32_t cs[4] = {0, 0, 0, 0}, ls[4] = {0, 0, 0, 0};
+    const uint32_t val = lds4u(s + p);
+    uint32_t c = lds_u16(s_prev + p * 2);
+    if (c != kNone) {
+        const uint64_t p8 = lds8u(s + p + 4);
+        const uint32_t lim = maxl < kLaneCap ? maxl : kLaneCap;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t cn = lds_u16(s_prev + c * 2);
+            if (lds4u(s + c) == val) {
+                uint32_t l;
+                const uint32_t d = p - c;
+                const unsigned long long e = *reinterpret_cast<const volatile unsigned long long *>(&ctrl->runs[(d * 0x9E3779B1u) >> 26]);
+                const uint32_t ed = (uint32_t)(e & 0x3FFFF), es = (uint32_t)(e >> 18) & 0x1FFFFF, ee = (uint32_t)(e >> 39);
+                if (ed == d && es <= p && p + kLaneCap < ee) {
+                    l = kLaneCap; cs[n_sat] = c; ls[n_sat] = ee - p; n_sat++;
+                } else {
+                    const uint64_t y = p8 ^ lds8u(s + c + 4);
+                    if (y) { l = 4 + ((__ffsll((long long)y) - 1) >> 3); l = l < lim ? l : lim; }
+                    else l = lim >= 12 ? smem_match_inc(s, p, c, 12, lim) : lim;
+                    if (l == kLaneCap && l < maxl) { cs[n_sat] = c; ls[n_sat] = 0; n_sat++; }
+                }
+                if (l > best_len) { best_len = l; best_c = c; }
+            }
+            c = cn;
+            if (c == kNone) break;
+        }
+    }
+    res[0] = best_len; res[1] = best_c; res[2] = n_sat;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { res[3 + k] = cs[k]; res[7 + k] = ls[k]; }
+}
+
 __global__ void __launch_bounds__(kFindThreads, 1)
 k_enc_find(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ src_off, const uint64_t *__restrict__ src_len, size_t n_streams,
            const EncStream *__restrict__ streams, const StreamCounts *__restrict__ bases, uint32_t *__restrict__ words, uint32_t *stream_counter) {
@@ -974,10 +1012,17 @@ k_enc_find(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ sr
                     uint32_t cs[4], ls[4];  // candidates whose length reached kLaneCap
                     uint32_t n_sat = 0;
                     const uint32_t maxl = len - p;
-                    // (two copies of the candidate loop: the one that asks the run cache first is only entered by periodic streams,
-                    // so that text runs exactly the loop it ran before)
-                    auto candidates = [&](auto probe_tag) {
-                        constexpr bool kProbe = decltype(probe_tag)::value;
+                    // (two copies of the candidate loop: the one that asks the run cache first is out of line and only entered by
+                    // periodic streams, so that text runs exactly the loop it ran before)
+                    if (probe_first) {
+                        if (act) {
+                            uint32_t res[11];
+                            find_candidates_probe(s, s_prev, ctrl, p, maxl, res);
+                            best_len = res[0]; best_c = res[1]; n_sat = res[2];
+#pragma unroll
+                            for (int k = 0; k < 4; k++) { cs[k] = res[3 + k]; ls[k] = res[7 + k]; }
+                        }
+                    } else if (act) {
                         const uint32_t val = lds4u(s + p);
                         uint32_t c = lds_u16(s_prev + p * 2);
                         if (c != kNone) {
@@ -988,33 +1033,18 @@ k_enc_find(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ sr
                                 // (the distance limit 262 139 cannot be exceeded inside 64 KiB)
                                 const uint32_t cn = lds_u16(s_prev + c * 2);
                                 if (lds4u(s + c) == val) {
+                                    const uint64_t y = p8 ^ lds8u(s + c + 4);
                                     uint32_t l;
-                                    bool known = false;
-                                    if constexpr (kProbe) {
-                                        // a position well inside a run that was already measured at this distance knows its length
-                                        // without looking at the bytes (periodic data: every position has four such candidates)
-                                        const uint32_t d = p - c;
-                                        const unsigned long long e = *reinterpret_cast<volatile unsigned long long *>(&ctrl->runs[(d * 0x9E3779B1u) >> 26]);
-                                        const uint32_t ed = (uint32_t)(e & 0x3FFFF), es = (uint32_t)(e >> 18) & 0x1FFFFF, ee = (uint32_t)(e >> 39);
-                                        if (ed == d && es <= p && p + kLaneCap < ee) { known = true; cs[n_sat] = c; ls[n_sat] = ee - p; n_sat++; }
-                                    }
-                                    if (known) {
-                                        l = kLaneCap;
-                                    } else {
-                                        const uint64_t y = p8 ^ lds8u(s + c + 4);
-                                        if (y) { l = 4 + ((__ffsll((long long)y) - 1) >> 3); l = l < lim ? l : lim; }
-                                        else l = lim >= 12 ? smem_match_inc(s, p, c, 12, lim) : lim;
-                                        if (l == kLaneCap && l < maxl) { cs[n_sat] = c; ls[n_sat] = 0; n_sat++; }
-                                    }
+                                    if (y) { l = 4 + ((__ffsll((long long)y) - 1) >> 3); l = l < lim ? l : lim; }
+                                    else l = lim >= 12 ? smem_match_inc(s, p, c, 12, lim) : lim;
+                                    if (l == kLaneCap && l < maxl) { cs[n_sat] = c; ls[n_sat] = 0; n_sat++; }
                                     if (l > best_len) { best_len = l; best_c = c; }
                                 }
                                 c = cn;
                                 if (c == kNone) break;
                             }
                         }
-                    };
-                    if (probe_first) { if (act) candidates(std::true_type{}); }
-                    else if (act) candidates(std::false_type{});
+                    }
                     // Candidates beyond the per-lane cap need their exact lengths (strictly longest wins, newest first, and the
                     // word stores up to 1023).  Runs are measured once per (distance, start) with the whole warp and remembered:
                     // inside a run every later position inherits end - p, which keeps periodic data linear.
