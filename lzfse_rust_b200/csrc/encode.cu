@@ -6,13 +6,18 @@
 // (encode/frontend_bytes.rs:185-207,336-344), so the candidates a position sees do not depend on the parse.
 //
 // Pipeline (one CUDA stream):
-//   k_enc_prep        thread / stream   block-type policy (frontend_bytes.rs:63-77) + scratch sizing
-//   k_exclusive_scan                    per-stream scratch bases (decode.cu)
-//   k_enc_parse       warp / stream     hash-table match finder (warp-wide candidate compares and batched
-//                                       history inserts), Match::select, FSE block buffering or LZVN opcodes
-//   k_enc_fse_blocks  lane / block      histogram, normalize_m1, weight varints, encode tables, 4-state
-//                                       literal stream, L/M/D stream, bvx2 header
-//   k_enc_assemble    warp / stream     compaction of the blocks into the caller's frame + bvx$
+//   k_enc_prep          thread / stream    block-type policy (frontend_bytes.rs:63-77), scratch sizing, which front end
+//   k_exclusive_scan                       per-stream scratch bases (decode.cu)
+//   bvx2 streams <= 64 KiB:  k_enc_find    CTA / stream       find_match for every position in shared memory -> one word per position
+//   bvx2 streams  > 64 KiB:  k_long_heads / carry / chain / find (encode_long.cuh)   the same words, hash chain over the stream in HBM
+//   every bvx2 stream:       k_long_replay / stitch_a / stitch_b (encode_long.cuh)    the sequential front end (backward limit,
+//                            Match::select) per 4 Ki-position segment, speculative, stitched where the states meet
+//                            k_long_seg_stats / blocks / write_packs                  Buffer::push: packs and block records
+//   LZVN-sized inputs:       k_enc_parse   warp / stream      hash table in HBM, 32 positions per step, LZVN opcodes
+//   k_enc_fse_blocks    warp / block       histogram, normalize_m1, weight varints, encode tables, 4-state literal stream,
+//                                          L/M/D stream, bvx2 header
+//   k_enc_assemble (+ k_long_copy)         compaction of the blocks into the caller's frame + bvx$
+// (LZB_ENC_SEG=0: k_enc_replay, one thread per <= 64 KiB stream, instead of the segments; LZB_ENC_LONG=0: k_enc_parse for > 64 KiB.)
 #include <cstdio>
 #include <cstdlib>
 #include <new>
@@ -1363,7 +1368,6 @@ struct FseEncSmem {
     uint32_t E[360];       // encode table: t_k (low 16) | t_w (high 16)
     uint32_t bitbuf[72];   // chunk bit buffer (<= 31 carried + 32 * 54 bits)
     uint16_t chain[128];   // (count | bits << 4) per symbol, in emission order
-    uint8_t sym[128];      // chunk symbols for the chain lanes
     int2 ent[128];         // the chunk's table entries {t_k, t_w}, looked up and unpacked by all lanes before the chain lanes run
 };
 

@@ -326,7 +326,6 @@ k_long_find(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ s
 // FrontendBytes::match_any's loop body (frontend_bytes.rs:185-211,261-302) over the per-position words.  Returns true
 // when a match is pushed to the back end (sel).  `lim_flag` is set when a backward extension stopped at the literal
 // limit although the candidate's own start would have allowed more; `cand`/`good` describe the first candidate met.
-struct StepOut { Match sel; };
 // A word whose length field is saturated (>= 1 023 bytes) needs the match measured to its end.  `ext_len` != 0 is that
 // length, already known; otherwise the caller either lets the step measure it (one thread, 8 bytes per iteration: the stitch,
 // where it is rare) or, with kCoop, gets the request back (`need_ext`, state untouched) and has its whole warp measure it --
@@ -513,13 +512,13 @@ __device__ void stitch_segment(const uint8_t *src, uint32_t len, uint32_t end, c
         }
     }
     if (T.cur < o.cand0) T.cur = o.cand0 < se ? o.cand0 : se;  // nothing happens before the segment's first candidate
-    uint32_t j = 0, n_fix = 0, dummy0 = 0, dummy1 = 0, dummy2 = 0;
+    uint32_t j = 0, n_fix = 0, lim_unused = 0, cand_unused = 0, good_unused = 0;  // (what only a speculative replay records)
     const uint32_t n_cmp = o.n_spec < kSpecStates ? o.n_spec : kSpecStates;
     uint4 sj = n_cmp ? sp[0] : make_uint4(0, 0, 0, 0);
     while (T.cur < se) {
         Match sel;
-        bool dummy3 = false;
-        if (!front_step<false>(src, len, end, W[T.cur], T, sel, dummy0, dummy1, dummy2, 0u, dummy3)) continue;
+        bool need_unused = false;
+        if (!front_step<false>(src, len, end, W[T.cur], T, sel, lim_unused, cand_unused, good_unused, 0u, need_unused)) continue;
         fix[n_fix++] = make_uint4(sel.idx, sel.match_len, sel.idx - sel.match_idx, T.cur);
         while (j < n_cmp && sj.x + sj.y < T.lit) { j++; if (j < n_cmp) sj = sp[j]; }
         if (j < n_cmp && sj.x + sj.y == T.lit && sj.w == T.cur) {
@@ -770,13 +769,6 @@ k_long_blocks(const uint64_t *__restrict__ src_off, const uint64_t *__restrict__
             const uint32_t sum_lit = __shfl_sync(0xFFFFFFFFu, mine.sum_lit, t), sum_m = __shfl_sync(0xFFFFFFFFu, mine.sum_m, t);
             const uint32_t simple = __shfl_sync(0xFFFFFFFFu, mine.simple, t), first_idx = __shfl_sync(0xFFFFFFFFu, mine.first_idx, t);
             const uint32_t last_end = __shfl_sync(0xFFFFFFFFu, mine.last_end, t), last_dist = __shfl_sync(0xFFFFFFFFu, mine.last_dist, t);
-#ifdef LZB_LONG_DEBUG
-            if (first_idx < prev_end || n > kEmitCap) {
-                if (lane == 0) printf("k_long_blocks: stream %u seg %u/%u: first_idx %u prev_end %u n %u n_fix %u from %u n_spec %u\n", si, k0 + t, st.n_rseg, first_idx, prev_end, n,
-                                      seg_out[rs].n_fix, seg_out[rs].from, seg_out[rs].n_spec);
-                return;
-            }
-#endif
             const uint32_t first_lit = first_idx - prev_end;
             const uint32_t cnt = fs.n_packs_total - fs.blk_pack0, lits = fs.n_lits_total - fs.blk_lit0;
             bool done = false;
