@@ -485,8 +485,12 @@ __device__ __forceinline__ bool same_state(const FrontState &a, const FrontState
 // ---- stitch ----------------------------------------------------------------------------------------
 // The true state T arrives at segment k of a stream; on return T is the true state behind it, n_fix matches have been
 // written to the segment's fix list and `from` says where the speculative list joins the true parse.
+// kWarp: called by a whole converged warp with identical arguments (k_long_stitch_b): the words are then fetched 32 at a time
+// and handed round by shuffle -- one memory round trip per 32 positions instead of one per position, which is what the
+// fallback costs when a segment never falls into step.
+template <bool kWarp>
 __device__ void stitch_segment(const uint8_t *src, uint32_t len, uint32_t end, const uint32_t *W, uint32_t k, FrontState &T, LongSegOut &o,
-                               const uint4 *sp, const uint4 *stt, uint4 *fix) {
+                               const uint4 *sp, const uint4 *stt, uint4 *fix, uint32_t lane = 0) {
     const uint32_t B = k * kRSeg, se = end - B < kRSeg ? end : B + kRSeg;
     o.n_fix = 0; o.from = o.n_spec;
     if (T.cur >= se) return;  // a match of an earlier segment covers this one
@@ -515,10 +519,19 @@ __device__ void stitch_segment(const uint8_t *src, uint32_t len, uint32_t end, c
     uint32_t j = 0, n_fix = 0, lim_unused = 0, cand_unused = 0, good_unused = 0;  // (what only a speculative replay records)
     const uint32_t n_cmp = o.n_spec < kSpecStates ? o.n_spec : kSpecStates;
     uint4 sj = n_cmp ? sp[0] : make_uint4(0, 0, 0, 0);
+    uint32_t wreg = 0, wbase = kNoPos;
     while (T.cur < se) {
         Match sel;
         bool need_unused = false;
-        if (!front_step<false>(src, len, end, W[T.cur], T, sel, lim_unused, cand_unused, good_unused, 0u, need_unused)) continue;
+        uint32_t w;
+        if (kWarp) {
+            const uint32_t b = T.cur & ~31u;
+            if (b != wbase) { wbase = b; wreg = W[b + lane]; }  // (may read up to 31 words past the stream's last position: scratch, never used)
+            w = __shfl_sync(0xFFFFFFFFu, wreg, T.cur & 31u);
+        } else {
+            w = W[T.cur];
+        }
+        if (!front_step<false>(src, len, end, w, T, sel, lim_unused, cand_unused, good_unused, 0u, need_unused)) continue;
         fix[n_fix++] = make_uint4(sel.idx, sel.match_len, sel.idx - sel.match_idx, T.cur);
         while (j < n_cmp && sj.x + sj.y < T.lit) { j++; if (j < n_cmp) sj = sp[j]; }
         if (j < n_cmp && sj.x + sj.y == T.lit && sj.w == T.cur) {
@@ -542,7 +555,7 @@ __global__ void k_long_stitch_a(const uint8_t *__restrict__ src_base, const uint
     const uint32_t len = (uint32_t)src_len[sg.stream];
     LongSegOut o = seg_out[rs];
     FrontState T = seg_out[rs - 1].exit;
-    stitch_segment(src_base + src_off[sg.stream], len, len - 3, words + bases[sg.stream].n_fse, sg.k, T, o, spec + (size_t)rs * kEmitCap,
+    stitch_segment<false>(src_base + src_off[sg.stream], len, len - 3, words + bases[sg.stream].n_fse, sg.k, T, o, spec + (size_t)rs * kEmitCap,
                    states + (size_t)rs * kSpecStates, fix + (size_t)rs * kEmitCap);
     seg_out[rs].n_fix = o.n_fix; seg_out[rs].from = o.from; seg_out[rs].a_out = T;  // (.exit is being read by the neighbour)
     seg_out[rs].a_ok = same_state(T, o.exit);
@@ -550,7 +563,7 @@ __global__ void k_long_stitch_a(const uint8_t *__restrict__ src_base, const uint
 // b: one warp per stream walks the segments in order with the true state.  While the true state entering a segment is the exit
 // state of the one before, what k_long_stitch_a left is right: the lanes look at 32 segments at a time and the walk jumps to
 // the first that did not fall into step; its a_out is still the truth behind it.  Any other segment is stitched again from
-// the true state (lane 0).  Leaves the stream's tail (pending match, final literals; frontend_bytes.rs:121-131,271-317).
+// the true state (the warp in step, words fetched 32 at a time).  Leaves the stream's tail (pending match, final literals; frontend_bytes.rs:121-131,271-317).
 __global__ void __launch_bounds__(128)
 k_long_stitch_b(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ src_off, const uint64_t *__restrict__ src_len,
                 const EncStream *__restrict__ streams, const StreamCounts *__restrict__ bases, const uint32_t *__restrict__ seg_list,
@@ -576,13 +589,12 @@ k_long_stitch_b(const uint8_t *__restrict__ src_base, const uint64_t *__restrict
             else { T = seg_out[rs + m].a_out; k += m + 1; }
             continue;
         }
-        if (lane == 0) {
+        {   // the whole warp in step (identical state in every lane; every lane stores the same values)
             LongSegOut o = seg_out[rs];
-            stitch_segment(src, len, end, W, k, T, o, spec + (size_t)rs * kEmitCap, states + (size_t)rs * kSpecStates, fix + (size_t)rs * kEmitCap);
-            seg_out[rs].n_fix = o.n_fix; seg_out[rs].from = o.from;
+            stitch_segment<true>(src, len, end, W, k, T, o, spec + (size_t)rs * kEmitCap, states + (size_t)rs * kSpecStates, fix + (size_t)rs * kEmitCap, lane);
+            __syncwarp();
+            if (lane == 0) { seg_out[rs].n_fix = o.n_fix; seg_out[rs].from = o.from; }
         }
-        T.cur = __shfl_sync(0xFFFFFFFFu, T.cur, 0); T.lit = __shfl_sync(0xFFFFFFFFu, T.lit, 0); T.p_idx = __shfl_sync(0xFFFFFFFFu, T.p_idx, 0);
-        T.p_midx = __shfl_sync(0xFFFFFFFFu, T.p_midx, 0); T.p_len = __shfl_sync(0xFFFFFFFFu, T.p_len, 0);
         redo++; k++;
     }
     if (lane == 0) {
